@@ -1,0 +1,303 @@
+"""
+oracle -- TEST INFRASTRUCTURE ONLY (see oracle/ct_oracle.c header).
+
+ctypes front-end of the plain-C CPU restatement.  Takes and returns CPU torch
+tensors so that the parity tests read like the reference's own tests.  Only
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this package; the product (compressed_tensors_b200/) never does.
+
+The strategy -> scale-addressing mapping and the compute-dtype rule are
+restated here independently of the product so that a bug in the product's host
+logic cannot hide in a shared helper:
+  * strategies: quantization/lifecycle/forward.py:184-241,
+    forward_helpers.py:62-177 (reference paths under src/compressed_tensors)
+  * compute dtype = torch type promotion of `x / scale`
+    (forward_helpers.py:538), SURVEY.md Appendix B1
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+import subprocess
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libct_oracle.so")
+_SRC = os.path.join(_HERE, "ct_oracle.c")
+
+INT64_MAX = (1 << 63) - 1
+
+DT = {
+    torch.float32: 0,
+    torch.float16: 1,
+    torch.bfloat16: 2,
+    torch.int8: 3,
+    torch.float8_e4m3fn: 4,
+    torch.int32: 5,
+    torch.uint8: 6,
+    torch.int64: 7,
+    torch.bool: 6,
+}
+
+
+def build(force: bool = False) -> str:
+    """Compile ct_oracle.c -> libct_oracle.so with gcc (OpenMP if available)."""
+    if (
+        not force
+        and os.path.exists(_SO)
+        and os.path.getmtime(_SO) >= os.path.getmtime(_SRC)
+    ):
+        return _SO
+    cmd = ["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-fno-fast-math", "-o", _SO, _SRC, "-lm"]
+    subprocess.run(cmd, check=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+        for name in (
+            "orc_pack_int32 orc_unpack_int32 orc_quantize orc_dequantize orc_fake_quantize "
+            "orc_pack_bitmasks orc_unpack_bitmasks orc_sparse24_compress orc_sparse24_decompress "
+            "orc_bitmask_compress orc_bitmask_decompress orc_quantize_pack orc_unpack_dequantize "
+            "orc_num_threads"
+        ).split():
+            getattr(_lib, name).restype = ctypes.c_int
+    return _lib
+
+
+def num_threads() -> int:
+    return lib().orc_num_threads()
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return ctypes.c_void_p(0)
+    assert t.device.type == "cpu" and t.is_contiguous()
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _i64(v) -> ctypes.c_int64:
+    return ctypes.c_int64(int(v))
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"oracle {what} failed rc={rc}")
+
+
+# --------------------------------------------------------------------------- #
+# pack / unpack
+# --------------------------------------------------------------------------- #
+def pack_to_int32(value: torch.Tensor, num_bits: int, packed_dim: int = 1) -> torch.Tensor:
+    """helpers.py:20-101.  For packed_dim=0 returns the same transposed *view*
+    shape as the reference (non-contiguous), built from a contiguous buffer."""
+    if value.dtype is not torch.int8:
+        raise ValueError("Tensor must be quantized to torch.int8 before packing")
+    if not 1 <= num_bits <= 8:
+        raise ValueError(f"Packing is only supported for num_bits in [1, 8], got {num_bits}")
+    if value.ndim > 2:
+        return torch.stack([pack_to_int32(v, num_bits, packed_dim) for v in value])
+    value = value.contiguous()
+    rows, cols = value.shape
+    if packed_dim == 1:
+        out = torch.empty(rows, math.ceil(cols * num_bits / 32), dtype=torch.int32)
+    else:
+        out = torch.empty(math.ceil(rows * num_bits / 32), cols, dtype=torch.int32)
+    _check(lib().orc_pack_int32(_p(value), _p(out), _i64(rows), _i64(cols), num_bits, packed_dim), "pack")
+    return out
+
+
+def unpack_from_int32(value: torch.Tensor, num_bits: int, shape: Sequence[int], packed_dim: int = 1) -> torch.Tensor:
+    """helpers.py:104-180"""
+    if value.dtype is not torch.int32:
+        raise ValueError(f"Expected {torch.int32} but got {value.dtype}, Aborting unpack.")
+    if not 1 <= num_bits <= 8:
+        raise ValueError(f"Unpacking is only supported for num_bits in [1, 8], got {num_bits}")
+    if value.ndim > 2:
+        return torch.stack([unpack_from_int32(v, num_bits, tuple(shape)[1:], packed_dim) for v in value])
+    value = value.contiguous()
+    rows, cols = int(shape[0]), int(shape[1])
+    out = torch.empty(rows, cols, dtype=torch.int8)
+    _check(lib().orc_unpack_int32(_p(value), _p(out), _i64(rows), _i64(cols), num_bits, packed_dim), "unpack")
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# quantize / dequantize / fake_quantize
+# --------------------------------------------------------------------------- #
+def _addressing(x2d_shape, scale: torch.Tensor, strategy: str, group_size, block_structure):
+    """-> (rdiv, cdiv, s_row_stride, n_scale_expected)"""
+    rows, cols = x2d_shape
+    if strategy in ("tensor",):
+        return INT64_MAX, INT64_MAX, 0
+    if strategy in ("channel", "token", "attn_head"):
+        if scale.numel() == 1:
+            return INT64_MAX, INT64_MAX, 0
+        return 1, INT64_MAX, 1
+    if strategy in ("group", "tensor_group"):
+        g = int(group_size)
+        if cols >= g and cols % g != 0:
+            raise ValueError(
+                "tensor column shape must be divisble " f"by the given group_size {g} but got {cols}"
+            )
+        ngroups = scale.shape[-1] if scale.ndim >= 1 else 1
+        srows = scale.numel() // max(ngroups, 1)
+        return 1, g, (ngroups if srows > 1 else 0)
+    if strategy == "block":
+        bh, bw = block_structure
+        ncb = math.ceil(cols / bw)
+        return bh, bw, ncb
+    raise ValueError(strategy)
+
+
+def _prep(x, scale, zero_point, g_idx, strategy):
+    x2 = x.reshape(-1, x.shape[-1]).contiguous() if x.ndim != 2 else x.contiguous()
+    s = scale.contiguous()
+    z = zero_point.contiguous() if zero_point is not None else None
+    gi = None
+    if g_idx is not None and strategy in ("group", "tensor_group") and g_idx.device.type != "meta" and not bool((g_idx == -1).any()):
+        gi = g_idx.to(torch.int32).contiguous()
+    return x2, s, z, gi
+
+
+def quantize(x, scale, zero_point=None, *, strategy="tensor", group_size=None, block_structure=None,
+             num_bits=8, qtype="int", dtype=None, g_idx=None, global_scale=None) -> torch.Tensor:
+    """forward.py:36-73 -> _process_quantization(do_quantize=True, do_dequantize=False)."""
+    if global_scale is not None:
+        scale = scale / global_scale
+    cd = torch.result_type(x, scale)
+    x2, s, z, gi = _prep(x, scale, zero_point, g_idx, strategy)
+    rdiv, cdiv, srs = _addressing(x2.shape, s, strategy, group_size, block_structure)
+    if strategy in ("group", "tensor_group"):
+        # _process_group: flatten().to(output_dtype); output_dtype = dtype or x.dtype (forward_helpers.py:134,171)
+        out_dtype = dtype if dtype is not None else x.dtype
+    else:
+        out_dtype = dtype if dtype is not None else cd
+    # when the group path casts compute-dtype values to x.dtype no extra rounding occurs
+    # for integers / fp8 grid values, so storing straight to out_dtype is exact.
+    out = torch.empty(x2.shape, dtype=out_dtype)
+    rc = lib().orc_quantize(_p(x2), DT[x2.dtype], _p(s), DT[s.dtype], _p(z), DT[z.dtype] if z is not None else -1,
+                            _p(gi), _p(out), DT[out_dtype], _i64(x2.shape[0]), _i64(x2.shape[1]),
+                            _i64(rdiv), _i64(cdiv), _i64(srs), DT[cd], 0 if qtype == "int" else 1, int(num_bits))
+    _check(rc, "quantize")
+    return out.reshape(x.shape)
+
+
+def dequantize(x_q, scale, zero_point=None, *, strategy=None, group_size=None, block_structure=None,
+               dtype=None, g_idx=None, global_scale=None) -> torch.Tensor:
+    """forward.py:76-145 (strategy inferred from the scale shape when not given)."""
+    if strategy is None:
+        if scale.ndim in (0, 1):
+            strategy = "tensor"
+        elif scale.ndim == 2:
+            if scale.shape[1] == 1:
+                strategy = "channel"
+            elif scale.shape[0] == 1 or scale.shape[0] == x_q.shape[0]:
+                strategy = "group"
+                group_size = int(x_q.shape[1] / scale.shape[1])
+            else:
+                strategy = "block"
+                block_structure = [x_q.shape[-2] // scale.shape[0], x_q.shape[-1] // scale.shape[1]]
+        else:
+            raise ValueError(
+                f"Could not infer a quantization strategy from scale with {scale.ndim} "
+                "dimmensions. Expected 0 or 2 dimmensions."
+            )
+    if dtype is None:
+        dtype = scale.dtype
+    if global_scale is not None:
+        scale = scale / global_scale
+    x2, s, z, gi = _prep(x_q, scale, zero_point, g_idx, strategy)
+    rdiv, cdiv, srs = _addressing(x2.shape, s, strategy, group_size, block_structure)
+    # dtype= is honoured only on the group path
+    out_dtype = dtype if strategy in ("group", "tensor_group") else s.dtype
+    out = torch.empty(x2.shape, dtype=out_dtype)
+    rc = lib().orc_dequantize(_p(x2), DT[x2.dtype], _p(s), DT[s.dtype], _p(z), DT[z.dtype] if z is not None else -1,
+                              _p(gi), _p(out), DT[out_dtype], _i64(x2.shape[0]), _i64(x2.shape[1]),
+                              _i64(rdiv), _i64(cdiv), _i64(srs))
+    _check(rc, "dequantize")
+    return out.reshape(x_q.shape)
+
+
+def fake_quantize(x, scale, zero_point=None, *, strategy="tensor", group_size=None, block_structure=None,
+                  num_bits=8, qtype="int", g_idx=None, global_scale=None) -> torch.Tensor:
+    """forward.py:148-181 -> _quantize_dequantize (forward_helpers.py:180-215)."""
+    if global_scale is not None:
+        scale = scale / global_scale
+    cd = torch.result_type(x, scale)
+    x2, s, z, gi = _prep(x, scale, zero_point, g_idx, strategy)
+    rdiv, cdiv, srs = _addressing(x2.shape, s, strategy, group_size, block_structure)
+    out_dtype = x.dtype if strategy in ("group", "tensor_group") else s.dtype
+    out = torch.empty(x2.shape, dtype=out_dtype)
+    rc = lib().orc_fake_quantize(_p(x2), DT[x2.dtype], _p(s), DT[s.dtype], _p(z), DT[z.dtype] if z is not None else -1,
+                                 _p(gi), _p(out), DT[out_dtype], _i64(x2.shape[0]), _i64(x2.shape[1]),
+                                 _i64(rdiv), _i64(cdiv), _i64(srs), DT[cd], 0 if qtype == "int" else 1, int(num_bits))
+    _check(rc, "fake_quantize")
+    return out.reshape(x.shape)
+
+
+# --------------------------------------------------------------------------- #
+# bitmasks and sparse formats
+# --------------------------------------------------------------------------- #
+def pack_bitmasks(bytemasks: torch.Tensor) -> torch.Tensor:
+    """utils/helpers.py:306-317"""
+    bm = bytemasks.to(torch.uint8).reshape(-1, bytemasks.shape[-1]).contiguous()
+    rows, cols = bm.shape
+    out = torch.empty(rows, (cols + 7) // 8, dtype=torch.uint8)
+    _check(lib().orc_pack_bitmasks(_p(bm), _p(out), _i64(rows), _i64(cols)), "pack_bitmasks")
+    return out.reshape(*bytemasks.shape[:-1], (cols + 7) // 8)
+
+
+def unpack_bitmasks(packed: torch.Tensor, original_shape: Sequence[int]) -> torch.Tensor:
+    """utils/helpers.py:320-343"""
+    cols = int(original_shape[-1])
+    pk = packed.reshape(-1, packed.shape[-1]).contiguous()
+    rows = pk.shape[0]
+    out = torch.empty(rows, cols, dtype=torch.uint8)
+    _check(lib().orc_unpack_bitmasks(_p(pk), _p(out), _i64(rows), _i64(cols)), "unpack_bitmasks")
+    return out.reshape(tuple(original_shape)).to(torch.bool)
+
+
+def sparse24_compress(x: torch.Tensor):
+    """restated Sparse24BitMaskCompressor.compress (parity unpinned) -> (values [R,C/2], bitmask u8 [R,C/8])"""
+    x = x.contiguous()
+    rows, cols = x.shape
+    values = torch.empty(rows, cols // 2, dtype=x.dtype)
+    bitmask = torch.empty(rows, (cols + 7) // 8, dtype=torch.uint8)
+    _check(lib().orc_sparse24_compress(_p(x), DT[x.dtype], _p(values), _p(bitmask), _i64(rows), _i64(cols)), "s24c")
+    return values, bitmask
+
+
+def sparse24_decompress(values: torch.Tensor, bitmask: torch.Tensor, shape) -> torch.Tensor:
+    rows, cols = int(shape[0]), int(shape[1])
+    out = torch.empty(rows, cols, dtype=values.dtype)
+    _check(lib().orc_sparse24_decompress(_p(values.contiguous()), DT[values.dtype], _p(bitmask.contiguous()), _p(out), _i64(rows), _i64(cols)), "s24d")
+    return out
+
+
+def bitmask_compress(x: torch.Tensor):
+    """restated BitmaskCompressor.compress (parity unpinned) -> (values [nnz], bitmask, row_offsets i64 [R])"""
+    x = x.contiguous()
+    rows, cols = x.shape
+    values = torch.empty(rows * cols, dtype=x.dtype)
+    bitmask = torch.empty(rows, (cols + 7) // 8, dtype=torch.uint8)
+    row_offsets = torch.empty(rows, dtype=torch.int64)
+    nnz = ctypes.c_int64(0)
+    _check(lib().orc_bitmask_compress(_p(x), DT[x.dtype], _p(values), _p(bitmask), _p(row_offsets), ctypes.byref(nnz), _i64(rows), _i64(cols)), "bmc")
+    return values[: nnz.value].clone(), bitmask, row_offsets
+
+
+def bitmask_decompress(values: torch.Tensor, bitmask: torch.Tensor, shape) -> torch.Tensor:
+    rows, cols = int(shape[0]), int(shape[1])
+    out = torch.empty(rows, cols, dtype=values.dtype)
+    _check(lib().orc_bitmask_decompress(_p(values.contiguous()), DT[values.dtype], _p(bitmask.contiguous()), _p(out), _i64(rows), _i64(cols)), "bmd")
+    return out

@@ -1,0 +1,35 @@
+"""shared helpers for the parity tests"""
+import torch
+
+
+def okw(args: dict) -> dict:
+    """reference QuantizationArgs.model_dump() -> oracle keyword arguments"""
+    return dict(
+        strategy=args["strategy"],
+        group_size=args.get("group_size"),
+        block_structure=args.get("block_structure"),
+        num_bits=args["num_bits"],
+        qtype=args["type"],
+    )
+
+
+def bits_equal(a: torch.Tensor, b: torch.Tensor) -> bool:
+    """bit-for-bit equality (distinguishes -0.0 from 0.0, compares NaN payloads)"""
+    if a.dtype != b.dtype or a.shape != b.shape:
+        return False
+    a = a.contiguous()
+    b = b.contiguous()
+    if a.dtype.is_floating_point:
+        width = {1: torch.uint8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[a.element_size()]
+        return torch.equal(a.view(width), b.view(width))
+    return torch.equal(a, b)
+
+
+def diff_report(a: torch.Tensor, b: torch.Tensor) -> str:
+    if a.dtype != b.dtype or a.shape != b.shape:
+        return f"dtype/shape {a.dtype}{tuple(a.shape)} vs {b.dtype}{tuple(b.shape)}"
+    af, bf = a.float().flatten(), b.float().flatten()
+    bad = (af != bf) & ~(af.isnan() & bf.isnan())
+    n = int(bad.sum())
+    idx = bad.nonzero().flatten()[:5].tolist()
+    return f"{n}/{af.numel()} differ; first {[(i, af[i].item(), bf[i].item()) for i in idx]}"
