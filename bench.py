@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the compress/decompress hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--layers L]
+
+Workload (configs[1] of BASELINE.json): W4A16 group_size=128 quantize + pack_to_int32 over every
+Linear weight of a Llama-3-8B-shaped model (32 layers x {q,k,v,o,gate,up,down} = 224 bf16 tensors,
+6.98 G elements, 13.96 GB), synthetic N(0, 0.02^2) weights, scales from the min/max observer rule.
+One "step" = one pass of the hot path over all 224 tensors (a single multi-tensor launch).
+`value` = weight bytes processed per second with tensors resident in HBM; `e2e` = the same pass
+through the compressor plugin API on HOST (pinned) state dicts, H2D and D2H inside the timed region.
+The inputs (14 GB) are far larger than the 126 MB L2, so every step streams from HBM.
+
+Under torchrun (N > 1) every rank owns its own full-size tensor set (weak scaling, no data-path
+collective); timing = max over ranks.
+
+--impl reference times the CPU restatement of the reference path (oracle/, plain C + OpenMP on all
+host threads; the reference itself is Python and cannot travel to the GPU box) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "weight_GBps_w4a16_g128_quantize_pack_llama3_8b"
+UNIT = "GB/s"
+LAYER_SHAPES = [(4096, 4096), (1024, 4096), (1024, 4096), (4096, 4096), (14336, 4096), (14336, 4096), (4096, 14336)]
+GROUP = 128
+BITS = 4
+ALG_BYTES_PER_ELEM = 2 + BITS / 8 + 2 / GROUP          # bf16 in + packed out + bf16 scale = 2.515625
+FALLBACK_HBM_GBS = 6650.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def profile_traffic(kernel: str):
+    """per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if any"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for k, nm in enumerate(names):
+                if len(s) > 3 + k and s[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def make_weights(device, layers: int, seed0: int):
+    """bf16 weights + observer scales, generated on the device"""
+    ws, scs = [], []
+    for li in range(layers):
+        for ti, (r, c) in enumerate(LAYER_SHAPES):
+            g = torch.Generator(device=device).manual_seed(seed0 + li * len(LAYER_SHAPES) + ti)
+            w = torch.empty(r, c, dtype=torch.bfloat16, device=device)
+            step = 2048
+            for r0 in range(0, r, step):  # bounded fp32 temporaries
+                w[r0:r0 + step] = (torch.randn(min(step, r - r0), c, device=device, generator=g) * 0.02).bfloat16()
+            # calculate_qparams, symmetric int4: scale = max|w| / 7.5 in the weight dtype (utils/helpers.py:79-87)
+            sc = (w.unflatten(-1, (-1, GROUP)).abs().amax(-1).float() / 7.5).bfloat16()
+            ws.append(w)
+            scs.append(sc)
+    return ws, scs
+
+
+def args_w4():
+    from types import SimpleNamespace
+    return SimpleNamespace(strategy="group", group_size=GROUP, block_structure=None, num_bits=BITS, type="int", symmetric=True)
+
+
+def time_steps(fn, steps: int, warmup: int, dist_on: bool):
+    """W untimed steps, then exactly K steps bracketed by barrier + synchronize; CUDA events on the launching stream"""
+    import torch.distributed as dist
+
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def run_b200(a):
+    import torch.distributed as dist
+
+    from compressed_tensors_b200 import _native as N
+    from compressed_tensors_b200 import ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist_on = world > 1
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if dist_on:
+        dist.init_process_group("nccl", device_id=dev)
+    if a.gpus != world:
+        print(f"[bench] note: --gpus {a.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+
+    layers = a.layers
+    ws, scs = make_weights(dev, layers, 1000 + rank * 100000)
+    n_elems = sum(w.numel() for w in ws)
+    weight_bytes = n_elems * 2
+    alg_bytes = n_elems * ALG_BYTES_PER_ELEM
+    qargs = args_w4()
+
+    # device-resident problem table for the multi-tensor launch
+    outs = [torch.empty(w.shape[0], w.shape[1] * BITS // 32, dtype=torch.int32, device=dev) for w in ws]
+    probs = []
+    for w, sc, o in zip(ws, scs, outs):
+        p = ops._resolve(w, sc, None, qargs, None)
+        d = ops._desc(p, w.dtype, sc.dtype, None, torch.bfloat16, torch.int8, None, N.Q_INT, BITS)
+        probs.append((d, w, sc, None, o))
+
+    def step():
+        ops.batched(N.OP_QUANTIZE_PACK, probs, local)
+
+    l0 = N.launch_count()
+    with ClockSampler(local) as cs:
+        ms = time_steps(step, a.steps, a.warmup, dist_on)
+    launches = (N.launch_count() - l0) - a.warmup  # one launch per step
+    clocks = cs.summary()
+    ms_per_step = ms / a.steps
+    value = world * weight_bytes / (ms_per_step * 1e-3) / 1e9
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # secondary ops of the metric (same tensors), device-resident, reported beside the headline
+    extra = {}
+    if not a.no_extra:
+        def rate(fn, bytes_alg, nelem_bytes):
+            t = time_steps(fn, max(3, a.steps // 2), 3, False) / max(3, a.steps // 2)
+            return {"weight_GBps": round(nelem_bytes / (t * 1e-3) / 1e9, 1), "hbm_GBps": round(bytes_alg / (t * 1e-3) / 1e9, 1),
+                    "frac_of_peak": round(bytes_alg / (t * 1e-3) / 1e9 / peak, 3), "ms": round(t, 3)}
+
+        # decompress: unpack + dequantize
+        dq = [torch.empty_like(w) for w in ws]
+        dprobs = []
+        for w, sc, o, dst in zip(ws, scs, outs, dq):
+            p = ops._resolve(torch.empty(w.shape, dtype=torch.int8, device="meta"), sc, None, qargs, None)
+            d = ops._desc(p, None, sc.dtype, None, None, torch.int8, torch.bfloat16, N.Q_INT, BITS)
+            dprobs.append((d, o, sc, None, dst))
+        extra["w4a16_unpack_dequantize"] = rate(lambda: ops.batched(N.OP_UNPACK_DEQUANTIZE, dprobs, local), alg_bytes, weight_bytes)
+        del dq, dprobs
+        # FP8 per-tensor quantize / dequantize (configs[2])
+        from types import SimpleNamespace
+        f8 = SimpleNamespace(strategy="tensor", group_size=None, block_structure=None, num_bits=8, type="float", symmetric=True)
+        s8 = [(w.abs().max().float() / 448).bfloat16().reshape(1) for w in ws]
+        q8 = [torch.empty(w.shape, dtype=torch.float8_e4m3fn, device=dev) for w in ws]
+        qprobs, dqprobs = [], []
+        back = [torch.empty_like(w) for w in ws]
+        for w, sc, q, b in zip(ws, s8, q8, back):
+            p = ops._resolve(w, sc, None, f8, None)
+            qprobs.append((ops._desc(p, w.dtype, sc.dtype, None, torch.bfloat16, torch.float8_e4m3fn, None, N.Q_FLOAT, 8), w, sc, None, q))
+            dqprobs.append((ops._desc(p, None, sc.dtype, None, None, torch.float8_e4m3fn, torch.bfloat16, N.Q_INT, 8), q, sc, None, b))
+        extra["fp8_quantize"] = rate(lambda: ops.batched(N.OP_QUANTIZE, qprobs, local), n_elems * 3.0, weight_bytes)
+        extra["fp8_dequantize"] = rate(lambda: ops.batched(N.OP_DEQUANTIZE, dqprobs, local), n_elems * 3.0, weight_bytes)
+        del q8, back, qprobs, dqprobs
+        # standalone int4 pack / unpack on int8 codes (one big tensor set: largest shape x 8)
+        codes = [torch.randint(-8, 8, (14336, 4096), dtype=torch.int8, device=dev) for _ in range(8)]
+        nel = sum(c.numel() for c in codes)
+        pk = [torch.empty(c.shape[0], c.shape[1] // 8, dtype=torch.int32, device=dev) for c in codes]
+        lib = N.lib()
+
+        def pack_all():
+            for c, o in zip(codes, pk):
+                lib.ct_pack_int32(N.ptr(c), N.ptr(o), c.shape[0], c.shape[1], 4, 1, local, N.stream_ptr(local))
+
+        def unpack_all():
+            for c, o in zip(codes, pk):
+                lib.ct_unpack_int32(N.ptr(o), N.ptr(c), c.shape[0], c.shape[1], 4, 1, local, N.stream_ptr(local))
+
+        extra["int4_pack"] = rate(pack_all, nel * 1.5, nel)
+        extra["int4_unpack"] = rate(unpack_all, nel * 1.5, nel)
+        del codes, pk
+
+    # end to end through the plugin API on host (pinned) state dicts
+    e2e = None
+    if not a.no_e2e:
+        e2e = run_e2e(ws, scs, a, dist_on, world)
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        cpu = cpu_baseline(max_seconds=20.0)
+
+    if dist_on:
+        dist.barrier()
+    if rank == 0:
+        tn = N.lib()
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"W4A16 g128 symmetric quantize+pack_to_int32, Llama-3-8B-shaped Linear weights, {layers} layers x 7 = {len(ws)} bf16 tensors per GPU, {n_elems/1e9:.3f} G elements",
+                       "l2": "inputs (%.1f GB per step) >> 126 MB L2, no flush needed" % (weight_bytes / 1e9),
+                       "launch": "one multi-tensor persistent launch per step", "pipe": os.environ.get("CT_B200_PIPE", "tma")},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": profile_traffic("quantize_pack"), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "frac_of_8TBps_nominal": round(achieved / 8000.0, 4)},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if extra:
+            line["ops"] = extra
+        print(json.dumps(line))
+    if dist_on:
+        dist.destroy_process_group()
+
+
+def run_e2e(ws, scs, a, dist_on, world):
+    """the same pass through the public compressor API with HOST buffers (pinned), copies inside the timed region"""
+    from compressed_tensors_b200 import ops
+
+    try:
+        from compressed_tensors_b200.compressors import PackedQuantizationCompressor
+        from compressed_tensors_b200.quantization import preset_name_to_scheme
+        scheme = preset_name_to_scheme("W4A16", ["Linear"])
+
+        def compress_one(w, sc):
+            return PackedQuantizationCompressor.compress({"weight": w, "weight_scale": sc}, scheme)["weight_packed"]
+        api = "PackedQuantizationCompressor.compress(state_dict, scheme) on pinned CPU tensors"
+    except ImportError:
+        qa = args_w4()
+
+        def compress_one(w, sc):
+            return ops.quantize_pack(w, sc, None, qa)
+        api = "ops.quantize_pack on pinned CPU tensors"
+
+    layers = min(a.e2e_layers, len(ws) // len(LAYER_SHAPES))
+    n = layers * len(LAYER_SHAPES)
+    hw = [w.cpu().pin_memory() for w in ws[:n]]
+    hs = [s.cpu().pin_memory() for s in scs[:n]]
+    wbytes = sum(t.numel() * 2 for t in hw)
+    h2d = wbytes + sum(t.numel() * 2 for t in hs)
+    d2h = sum(t.numel() // 8 * 4 for t in hw)
+    res = [None]
+
+    def step():
+        for w, sc in zip(hw, hs):
+            res[0] = compress_one(w, sc)
+
+    steps = max(2, min(a.steps, 5))
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    if dist_on:
+        import torch.distributed as dist
+        t = torch.tensor([dt], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    assert res[0] is not None and not res[0].is_cuda
+    return {"value": round(world * wbytes / dt / 1e9, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "api": api, "tensors_per_step": n, "steps": steps, "ms_per_step": round(dt * 1e3, 2)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port (plain C + OpenMP), bounded sample of the workload
+# ------------------------------------------------------------------------------------------------
+def oracle_compress_layer(ws, scs, tmp):
+    """quantize(int8) -> pack_to_int32 for each tensor of the sample, through the C oracle"""
+    import ctypes
+
+    import oracle
+
+    L = oracle.lib()
+    for w, sc, (q8, out) in zip(ws, scs, tmp):
+        r, c = w.shape
+        L.orc_quantize_pack(oracle._p(w), 2, oracle._p(sc), 2, ctypes.c_void_p(0), -1, ctypes.c_void_p(0), oracle._p(out), oracle._p(q8),
+                            ctypes.c_int64(r), ctypes.c_int64(c), ctypes.c_int64(1), ctypes.c_int64(GROUP), ctypes.c_int64(c // GROUP), 2, BITS)
+
+
+def cpu_sample():
+    """one layer of the workload (7 tensors, 218 M elements, 436 MB of bf16)"""
+    ws, scs, tmp = [], [], []
+    for ti, (r, c) in enumerate(LAYER_SHAPES):
+        g = torch.Generator().manual_seed(1000 + ti)
+        w = (torch.randn(r, c, generator=g) * 0.02).bfloat16()
+        sc = (w.unflatten(-1, (-1, GROUP)).abs().amax(-1).float() / 7.5).bfloat16()
+        ws.append(w)
+        scs.append(sc)
+        tmp.append((torch.empty(r, c, dtype=torch.int8), torch.empty(r, c // 8, dtype=torch.int32)))
+    return ws, scs, tmp
+
+
+def cpu_baseline(max_seconds: float):
+    import oracle
+
+    ws, scs, tmp = cpu_sample()
+    wbytes = sum(w.numel() * 2 for w in ws)
+    oracle_compress_layer(ws, scs, tmp)  # warm-up (also builds the .so)
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        oracle_compress_layer(ws, scs, tmp)
+        reps += 1
+        if time.perf_counter() - t0 > max_seconds / 2 or reps >= 20:
+            break
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": round(wbytes / dt / 1e9, 3), "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+            "sample": f"oracle/ct_oracle.c (C + OpenMP) on 1 of 32 layers (7 tensors, {wbytes/1e6:.0f} MB bf16), {reps} reps, {dt*1e3:.0f} ms each"}
+
+
+def run_reference(a):
+    """reference arm: the CPU restatement of the reference path on the host cores"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+
+    ws, scs, tmp = cpu_sample()
+    wbytes = sum(w.numel() * 2 for w in ws)
+    for _ in range(max(1, min(a.warmup, 3))):
+        oracle_compress_layer(ws, scs, tmp)
+    steps = max(1, a.steps)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        oracle_compress_layer(ws, scs, tmp)
+        done += 1
+        if time.perf_counter() - t0 > 150:
+            break
+    dt = (time.perf_counter() - t0) / done
+    v = round(wbytes / dt / 1e9, 3)
+    sample = f"1 of 32 Llama-3-8B layers per step (7 tensors, {wbytes/1e6:.0f} MB bf16), oracle/ct_oracle.c C+OpenMP port of the reference's torch-eager path"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": done, "warmup": a.warmup,
+        "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "W4A16 g128 symmetric quantize+pack_to_int32, Llama-3-8B-shaped Linear weights (bounded sample: 1 layer per step)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--layers", type=int, default=32, help="Llama-3-8B layers per GPU (32 = the full model)")
+    ap.add_argument("--e2e-layers", type=int, default=32)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    a = ap.parse_args()
+    if a.warmup < 3:
+        a.warmup = 3
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,327 @@
+// dispatch.cu -- decides, per tensor, between the streaming fast path and the generic kernels,
+// builds the job tables for multi-tensor launches, and implements the C ABI compute entry points.
+#include <cstring>
+#include <vector>
+
+#include "engine.h"
+
+namespace ctb {
+
+static bool is_inf(int64_t v) { return v == CT_DIV_INF; }
+
+// flat scale divisor D (elements per scale element) if scale index == flat_index / D
+static bool flat_divisor(const ct_quant_desc& d, int64_t& D) {
+    if (is_inf(d.rdiv) && is_inf(d.cdiv)) { D = CT_DIV_INF; return true; }          // TENSOR
+    if (d.rdiv == 1 && d.s_row_stride == 1 && (is_inf(d.cdiv) || d.cdiv >= d.cols)) {  // CHANNEL / one group per row
+        D = d.cols;
+        return true;
+    }
+    if (d.rdiv == 1 && !is_inf(d.cdiv) && d.cdiv > 0 && d.cols % d.cdiv == 0 && d.s_row_stride == d.cols / d.cdiv) {
+        D = d.cdiv;                                                                  // GROUP, full rows of scales
+        return true;
+    }
+    return false;
+}
+
+static int validate_desc(const ct_quant_desc* d) {
+    if (!d) { set_error("null descriptor"); return CT_E_ARG; }
+    if (d->rows < 0 || d->cols < 0) { set_error("negative shape"); return CT_E_SHAPE; }
+    if (d->qtype == CT_Q_INT && (d->num_bits < 1 || d->num_bits > 8)) {
+        set_error("num_bits %d outside [1, 8]", d->num_bits);
+        return CT_E_BITS;
+    }
+    if (d->qtype == CT_Q_FLOAT && d->num_bits != 8) { set_error("float quantization supports num_bits == 8 only"); return CT_E_BITS; }
+    if (d->rdiv <= 0 || d->cdiv <= 0) { set_error("rdiv/cdiv must be positive"); return CT_E_SHAPE; }
+    return CT_OK;
+}
+
+struct Plan {
+    bool fast;
+    FastSig sig;
+    Job job;        // tile_begin/end filled by the caller
+    Common cm;
+};
+
+static uint32_t bits_of(int dt, float v) {
+    // v as a 16-bit float pattern duplicated in both halves (host-side conversion, RNE; v is exact)
+    if (dt == CT_BF16) {
+        uint32_t u; memcpy(&u, &v, 4);
+        uint32_t h = u >> 16;
+        return h | (h << 16);
+    }
+    if (dt == CT_F16) {
+        __half hv = __float2half_rn(v);
+        uint16_t h; memcpy(&h, &hv, 2);
+        return (uint32_t)h | ((uint32_t)h << 16);
+    }
+    return 0;
+}
+
+static Common make_common(int p_dt, int qtype, int bits) {
+    Common cm;
+    if (qtype == CT_Q_INT) {
+        const float r = (float)(1 << bits);
+        cm.qmax = r / 2 - 1;
+        cm.qmin = -r / 2;
+    } else {
+        cm.qmax = 448.f;
+        cm.qmin = -448.f;
+    }
+    cm.qmin2 = bits_of(p_dt, cm.qmin);
+    cm.qmax2 = bits_of(p_dt, cm.qmax);
+    cm.bits = bits;
+    return cm;
+}
+
+// Try to express (op, desc) as a streaming job.  in/out are the streamed tensors of the op.
+static Plan plan_one(int op, const ct_quant_desc& d, const void* in, const void* scale, const void* zp,
+                     const int32_t* g_idx, void* out) {
+    Plan p;
+    p.fast = false;
+    memset(&p.job, 0, sizeof(p.job));
+    memset(&p.cm, 0, sizeof(p.cm));
+    p.sig = FastSig{0, 0, 0, 0};
+    const int64_t n = d.rows * d.cols;
+    if (g_idx || n == 0 || n % 8 != 0 || (n / 8) >= 0x7fffffffLL) return p;
+    if (!aligned16(in) || !aligned16(out)) return p;
+    int64_t D;
+    if (!flat_divisor(d, D)) return p;
+    if (!is_inf(D) && D % 8 != 0) return p;
+    if (zp && d.zp_dtype != CT_I8) return p;
+    const int zpk = zp ? 1 : 0;
+
+    int p_dt, in_bytes_per_chunk;
+    FastSig sig;
+    sig.zp = zpk;
+    switch (op) {
+    case CT_OP_QUANTIZE_PACK:
+        if (d.qtype != CT_Q_INT || (d.num_bits != 4 && d.num_bits != 8)) return p;
+        if ((d.cols * d.num_bits) % 32 != 0) return p;
+        if (d.x_dtype != d.scale_dtype || d.x_dtype != d.compute_dtype || !is_float_dt(d.x_dtype)) return p;
+        p_dt = d.x_dtype; sig.op = F_QUANTPACK; sig.sel = d.num_bits; in_bytes_per_chunk = 8 * dt_size(p_dt);
+        break;
+    case CT_OP_UNPACK_DEQUANTIZE:
+        if (d.num_bits != 4 && d.num_bits != 8) return p;
+        if ((d.cols * d.num_bits) % 32 != 0) return p;
+        if (d.out_dtype != d.scale_dtype || !is_float_dt(d.out_dtype)) return p;
+        p_dt = d.scale_dtype; sig.op = F_UNPACKDEQ; sig.sel = d.num_bits; in_bytes_per_chunk = d.num_bits;
+        break;
+    case CT_OP_QUANTIZE:
+        if (d.x_dtype != d.scale_dtype || d.x_dtype != d.compute_dtype || !is_float_dt(d.x_dtype)) return p;
+        if (d.qtype == CT_Q_INT && d.q_dtype != CT_I8) return p;
+        if (d.qtype == CT_Q_FLOAT && d.q_dtype != CT_F8E4M3) return p;
+        p_dt = d.x_dtype; sig.op = F_QUANT; sig.sel = (d.qtype == CT_Q_FLOAT) ? 2 : 1; in_bytes_per_chunk = 8 * dt_size(p_dt);
+        break;
+    case CT_OP_DEQUANTIZE:
+        if (d.out_dtype != d.scale_dtype || !is_float_dt(d.out_dtype)) return p;
+        if (d.q_dtype != CT_I8 && d.q_dtype != CT_F8E4M3) return p;
+        p_dt = d.scale_dtype; sig.op = F_DEQUANT; sig.sel = (d.q_dtype == CT_F8E4M3) ? 2 : 1; in_bytes_per_chunk = 8;
+        break;
+    case CT_OP_FAKE_QUANTIZE:
+        if (d.x_dtype != d.scale_dtype || d.x_dtype != d.compute_dtype || d.out_dtype != d.x_dtype || !is_float_dt(d.x_dtype)) return p;
+        p_dt = d.x_dtype; sig.op = F_FAKE;
+        if (d.qtype == CT_Q_FLOAT) sig.sel = 2;
+        else sig.sel = (p_dt == CT_F32 || d.num_bits > (p_dt == CT_BF16 ? 7 : 8)) ? 1 : 0;
+        in_bytes_per_chunk = 8 * dt_size(p_dt);
+        break;
+    default:
+        return p;
+    }
+    sig.p_dt = p_dt;
+    // a partial last tile must still be a multiple of 16 bytes for the bulk copy
+    if (((n / 8) * in_bytes_per_chunk) % 16 != 0) return p;
+
+    p.fast = true;
+    p.sig = sig;
+    p.job.in = reinterpret_cast<const uint8_t*>(in);
+    p.job.scale = scale;
+    p.job.zp = zp;
+    p.job.out = reinterpret_cast<uint8_t*>(out);
+    p.job.n_chunks = (uint32_t)(n / 8);
+    p.job.dc = make_fastdiv(is_inf(D) ? (uint64_t)0x7FFFFFFFull : (uint64_t)(D / 8));
+    p.cm = make_common(p_dt, d.qtype, d.num_bits);
+    return p;
+}
+
+static int launch_sig(const FastSig& s, const LaunchPlan& lp, int device, cudaStream_t st) {
+    switch (s.op) {
+    case F_QUANTPACK: return launch_fast_quantpack(s, lp, device, st);
+    case F_UNPACKDEQ: return launch_fast_unpackdeq(s, lp, device, st);
+    case F_QUANT: return launch_fast_quant(s, lp, device, st);
+    case F_DEQUANT: return launch_fast_dequant(s, lp, device, st);
+    case F_FAKE: return launch_fast_fake(s, lp, device, st);
+    default: return launch_fast_bits(s, lp, device, st);
+    }
+}
+
+static int run_generic(int op, const ct_quant_desc& d, const void* in, const void* scale, const void* zp,
+                       const int32_t* g_idx, void* out, cudaStream_t st) {
+    switch (op) {
+    case CT_OP_QUANTIZE_PACK:
+        if (d.qtype != CT_Q_INT) { set_error("quantize_pack needs integer quantization"); return CT_E_DTYPE; }
+        return launch_generic_quantpack(d, in, scale, zp, g_idx, reinterpret_cast<int32_t*>(out), st);
+    case CT_OP_UNPACK_DEQUANTIZE:
+        return launch_generic_unpackdeq(d, reinterpret_cast<const int32_t*>(in), scale, zp, g_idx, out, st);
+    case CT_OP_QUANTIZE: return launch_generic_quant(G_QUANTIZE, d, in, scale, zp, g_idx, out, st);
+    case CT_OP_DEQUANTIZE: return launch_generic_quant(G_DEQUANTIZE, d, in, scale, zp, g_idx, out, st);
+    case CT_OP_FAKE_QUANTIZE: return launch_generic_quant(G_FAKE, d, in, scale, zp, g_idx, out, st);
+    }
+    set_error("unknown op %d", op);
+    return CT_E_ARG;
+}
+
+static int check_dtypes(int op, const ct_quant_desc& d, bool has_zp) {
+    const bool quantizing = (op == CT_OP_QUANTIZE_PACK || op == CT_OP_QUANTIZE || op == CT_OP_FAKE_QUANTIZE);
+    if (!is_float_dt(d.scale_dtype)) { set_error("scale dtype %d is not a float dtype", d.scale_dtype); return CT_E_DTYPE; }
+    if (quantizing && (!is_float_dt(d.x_dtype) || !is_float_dt(d.compute_dtype))) {
+        set_error("x / compute dtype must be float (got %d / %d)", d.x_dtype, d.compute_dtype);
+        return CT_E_DTYPE;
+    }
+    if (has_zp && dt_size(d.zp_dtype) == 0) { set_error("bad zero-point dtype %d", d.zp_dtype); return CT_E_DTYPE; }
+    if ((op == CT_OP_DEQUANTIZE || op == CT_OP_UNPACK_DEQUANTIZE || op == CT_OP_FAKE_QUANTIZE) && !is_float_dt(d.out_dtype)) {
+        set_error("output dtype %d is not a float dtype", d.out_dtype);
+        return CT_E_DTYPE;
+    }
+    if (op == CT_OP_QUANTIZE && dt_size(d.q_dtype) == 0) { set_error("bad q dtype"); return CT_E_DTYPE; }
+    if (op == CT_OP_DEQUANTIZE && dt_size(d.q_dtype) == 0) { set_error("bad q dtype"); return CT_E_DTYPE; }
+    return CT_OK;
+}
+
+int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in, const void* const* scale,
+                const void* const* zp, const int32_t* const* g_idx, void* const* out, int device, cudaStream_t stream) {
+    if (n < 0 || (n > 0 && (!descs || !in || !scale || !out))) { set_error("null table"); return CT_E_ARG; }
+    int rc = check_device(device);
+    if (rc) return rc;
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+
+    std::vector<Plan> plans((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        rc = validate_desc(&descs[i]);
+        if (rc) return rc;
+        const void* z = zp ? zp[i] : nullptr;
+        rc = check_dtypes(op, descs[i], z != nullptr);
+        if (rc) return rc;
+        if (descs[i].rows * descs[i].cols > 0 && (!in[i] || !scale[i] || !out[i])) { set_error("null tensor pointer (tensor %d)", i); return CT_E_ARG; }
+        plans[i] = plan_one(op, descs[i], in[i], scale[i], z, g_idx ? g_idx[i] : nullptr, out[i]);
+    }
+    // group fast jobs by kernel signature (and clamp constants), one launch per group
+    std::vector<char> done((size_t)n, 0);
+    for (int i = 0; i < n; ++i) {
+        if (done[i]) continue;
+        if (!plans[i].fast) {
+            rc = run_generic(op, descs[i], in[i], scale[i], zp ? zp[i] : nullptr, g_idx ? g_idx[i] : nullptr, out[i], stream);
+            if (rc) return rc;
+            done[i] = 1;
+            continue;
+        }
+        std::vector<Job> jobs;
+        uint32_t tiles = 0;
+        for (int k = i; k < n; ++k) {
+            if (done[k] || !plans[k].fast || !(plans[k].sig == plans[i].sig) || plans[k].cm.bits != plans[i].cm.bits) continue;
+            const uint32_t nt = (plans[k].job.n_chunks + TILE_CHUNKS - 1) / TILE_CHUNKS;
+            if ((uint64_t)tiles + nt >= 0xffffffffull) break;
+            Job j = plans[k].job;
+            j.tile_begin = tiles;
+            j.tile_end = tiles + nt;
+            tiles += nt;
+            jobs.push_back(j);
+            done[k] = 1;
+        }
+        LaunchPlan lp;
+        lp.cm = plans[i].cm;
+        lp.total_tiles = tiles;
+        lp.tbl.n = (int)jobs.size();
+        lp.tbl.jobs = nullptr;
+        lp.tbl.one = jobs[0];
+        Job* dev_jobs = nullptr;
+        if (jobs.size() > 1) {
+            CT_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&dev_jobs), jobs.size() * sizeof(Job), stream));
+            CT_CUDA_TRY(cudaMemcpyAsync(dev_jobs, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, stream));
+            lp.tbl.jobs = dev_jobs;
+        }
+        rc = launch_sig(plans[i].sig, lp, device, stream);
+        if (dev_jobs) cudaFreeAsync(dev_jobs, stream);
+        if (rc) return rc;
+    }
+    return CT_OK;
+}
+
+static int run_one(int op, const ct_quant_desc* d, const void* in, const void* scale, const void* zp,
+                   const int32_t* g_idx, void* out, int device, void* stream) {
+    if (!d) { set_error("null descriptor"); return CT_E_ARG; }
+    const void* ins[1] = {in};
+    const void* scales[1] = {scale};
+    const void* zps[1] = {zp};
+    const int32_t* gis[1] = {g_idx};
+    void* outs[1] = {out};
+    return run_batched(op, 1, d, ins, scales, zps, gis, outs, device, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// standalone pack / unpack
+static int run_bits(bool pack, const void* in, void* out, int64_t rows, int64_t cols, int bits, int packed_dim,
+                    int device, cudaStream_t stream) {
+    if (bits < 1 || bits > 8) { set_error("num_bits %d outside [1, 8]", bits); return CT_E_BITS; }
+    if (packed_dim != 0 && packed_dim != 1) { set_error("packed_dim must be 0 or 1"); return CT_E_ARG; }
+    if (rows < 0 || cols < 0) { set_error("negative shape"); return CT_E_SHAPE; }
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (rows * cols == 0) return CT_OK;
+    if (!in || !out) { set_error("null tensor pointer"); return CT_E_ARG; }
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    const int64_t n = rows * cols;
+    const int in_bytes = pack ? 8 : bits;
+    if (packed_dim == 1 && (bits == 4 || bits == 8) && (cols * bits) % 32 == 0 && n % 8 == 0 && (n / 8) < 0x7fffffffLL &&
+        aligned16(in) && aligned16(out) && ((n / 8) * in_bytes) % 16 == 0) {
+        LaunchPlan lp;
+        memset(&lp, 0, sizeof(lp));
+        lp.tbl.n = 1;
+        lp.tbl.one.in = reinterpret_cast<const uint8_t*>(in);
+        lp.tbl.one.out = reinterpret_cast<uint8_t*>(out);
+        lp.tbl.one.n_chunks = (uint32_t)(n / 8);
+        lp.tbl.one.tile_begin = 0;
+        lp.tbl.one.tile_end = (lp.tbl.one.n_chunks + TILE_CHUNKS - 1) / TILE_CHUNKS;
+        lp.tbl.one.dc = make_fastdiv(0x7FFFFFFFull);
+        lp.total_tiles = lp.tbl.one.tile_end;
+        lp.cm = make_common(CT_F32, CT_Q_INT, bits);
+        FastSig s{pack ? F_PACK : F_UNPACK, CT_I8, bits, 0};
+        return launch_fast_bits(s, lp, device, stream);
+    }
+    if (pack) return launch_generic_pack(reinterpret_cast<const int8_t*>(in), reinterpret_cast<int32_t*>(out), rows, cols, bits, packed_dim, stream);
+    return launch_generic_unpack(reinterpret_cast<const int32_t*>(in), reinterpret_cast<int8_t*>(out), rows, cols, bits, packed_dim, stream);
+}
+
+}  // namespace ctb
+
+using namespace ctb;
+
+extern "C" {
+
+int ct_pack_int32(const int8_t* in, int32_t* out, int64_t rows, int64_t cols, int bits, int packed_dim, int device, void* stream) {
+    return run_bits(true, in, out, rows, cols, bits, packed_dim, device, reinterpret_cast<cudaStream_t>(stream));
+}
+int ct_unpack_int32(const int32_t* in, int8_t* out, int64_t rows, int64_t cols, int bits, int packed_dim, int device, void* stream) {
+    return run_bits(false, in, out, rows, cols, bits, packed_dim, device, reinterpret_cast<cudaStream_t>(stream));
+}
+int ct_quantize(const ct_quant_desc* d, const void* x, const void* scale, const void* zp, const int32_t* g_idx, void* q_out, int device, void* stream) {
+    return run_one(CT_OP_QUANTIZE, d, x, scale, zp, g_idx, q_out, device, stream);
+}
+int ct_dequantize(const ct_quant_desc* d, const void* q, const void* scale, const void* zp, const int32_t* g_idx, void* out, int device, void* stream) {
+    return run_one(CT_OP_DEQUANTIZE, d, q, scale, zp, g_idx, out, device, stream);
+}
+int ct_fake_quantize(const ct_quant_desc* d, const void* x, const void* scale, const void* zp, const int32_t* g_idx, void* out, int device, void* stream) {
+    return run_one(CT_OP_FAKE_QUANTIZE, d, x, scale, zp, g_idx, out, device, stream);
+}
+int ct_quantize_pack_int32(const ct_quant_desc* d, const void* x, const void* scale, const void* zp, const int32_t* g_idx, int32_t* packed, int device, void* stream) {
+    return run_one(CT_OP_QUANTIZE_PACK, d, x, scale, zp, g_idx, packed, device, stream);
+}
+int ct_unpack_dequantize_int32(const ct_quant_desc* d, const int32_t* packed, const void* scale, const void* zp, const int32_t* g_idx, void* out, int device, void* stream) {
+    return run_one(CT_OP_UNPACK_DEQUANTIZE, d, packed, scale, zp, g_idx, out, device, stream);
+}
+int ct_batched(int op, int n, const ct_quant_desc* descs, const void* const* in, const void* const* scale,
+               const void* const* zp, void* const* out, int device, void* stream) {
+    return run_batched(op, n, descs, in, scale, zp, nullptr, out, device, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+// engine.h -- internal interfaces between the translation units of libct_b200.so
+#pragma once
+
+#include "common.cuh"
+#include "stream.cuh"
+
+namespace ctb {
+
+// ---- fast (flat, streaming) path -------------------------------------------------------
+enum FastOp { F_QUANTPACK = 0, F_UNPACKDEQ = 1, F_QUANT = 2, F_DEQUANT = 3, F_FAKE = 4, F_PACK = 5, F_UNPACK = 6 };
+
+struct FastSig {
+    int op;      // FastOp
+    int p_dt;    // CT_BF16 / CT_F16 / CT_F32 (unused for F_PACK / F_UNPACK)
+    int sel;     // QUANTPACK/UNPACKDEQ/PACK/UNPACK: bits (4 | 8); QUANT/DEQUANT/FAKE: QKind
+    int zp;      // 0 none, 1 int8
+    bool operator==(const FastSig& o) const { return op == o.op && p_dt == o.p_dt && sel == o.sel && zp == o.zp; }
+};
+
+// defined in fast_pack.cu / fast_quant.cu / fast_fake.cu
+int launch_fast_quantpack(const FastSig&, const LaunchPlan&, int device, cudaStream_t);
+int launch_fast_unpackdeq(const FastSig&, const LaunchPlan&, int device, cudaStream_t);
+int launch_fast_quant(const FastSig&, const LaunchPlan&, int device, cudaStream_t);
+int launch_fast_dequant(const FastSig&, const LaunchPlan&, int device, cudaStream_t);
+int launch_fast_fake(const FastSig&, const LaunchPlan&, int device, cudaStream_t);
+int launch_fast_bits(const FastSig&, const LaunchPlan&, int device, cudaStream_t);
+
+// ---- generic path (any strategy, g_idx, ragged shapes, mixed dtypes) -----------------------
+enum GenericMode { G_QUANTIZE = 0, G_DEQUANTIZE = 1, G_FAKE = 2 };
+int launch_generic_quant(int mode, const ct_quant_desc& d, const void* in, const void* scale, const void* zp,
+                         const int32_t* g_idx, void* out, cudaStream_t stream);
+int launch_generic_quantpack(const ct_quant_desc& d, const void* x, const void* scale, const void* zp,
+                             const int32_t* g_idx, int32_t* packed, cudaStream_t stream);
+int launch_generic_unpackdeq(const ct_quant_desc& d, const int32_t* packed, const void* scale, const void* zp,
+                             const int32_t* g_idx, void* out, cudaStream_t stream);
+int launch_generic_pack(const int8_t* in, int32_t* out, int64_t rows, int64_t cols, int bits, int packed_dim, cudaStream_t stream);
+int launch_generic_unpack(const int32_t* in, int8_t* out, int64_t rows, int64_t cols, int bits, int packed_dim, cudaStream_t stream);
+
+// ---- dispatch (dispatch.cu): one tensor or a table of tensors ---------------------------------
+int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in, const void* const* scale,
+                const void* const* zp, const int32_t* const* g_idx, void* const* out, int device, cudaStream_t stream);
+
+int check_device(int device);
+
+}  // namespace ctb

@@ -1,0 +1,315 @@
+// generic.cu -- shape- and dtype-generic kernels: every strategy (tensor / channel / token /
+// group incl. g_idx and one-row scales / block with implicit padding), ragged row lengths, all
+// bit widths 1..8, packed_dim 0 and 1, mixed x / scale / zero-point dtypes.  These are the
+// catch-all behind the streaming fast path (dispatch.cu decides); they are coalesced and
+// bit-exact but not tuned for the roofline.
+#include "engine.h"
+#include "quant_core.cuh"
+
+namespace ctb {
+
+struct GParams {
+    int64_t rows, cols, rdiv, cdiv, srs;
+    int x_dt, s_dt, zp_dt, cd, q_dt, out_dt, qtype, bits;
+    const void* in;
+    const void* scale;
+    const void* zp;
+    const int32_t* gidx;
+    void* out;
+    float qmin, qmax;
+};
+
+__device__ __forceinline__ int64_t scale_index(const GParams& p, int64_t r, int64_t c) {
+    int64_t rb = (p.rdiv == 1) ? r : (p.rdiv == CT_DIV_INF ? 0 : r / p.rdiv);
+    int64_t cb;
+    if (p.gidx) cb = p.gidx[c];
+    else cb = (p.cdiv == CT_DIV_INF) ? 0 : c / p.cdiv;
+    return rb * p.srs + cb;
+}
+
+// quantized value (in compute dtype, as fp32) of x[r, c]
+__device__ __forceinline__ float quant_at(const GParams& p, int64_t r, int64_t c) {
+    const int64_t si = scale_index(p, r, c);
+    const float x = load_as_f32(p.in, r * p.cols + c, p.x_dt);
+    const float s = load_as_f32(p.scale, si, p.s_dt);
+    float z = 0.f;
+    if (p.zp) z = rnd_dt(load_as_f32(p.zp, si, p.zp_dt), p.x_dt);   // zero_point.to(x.dtype)
+    return quant_scalar(x, s, p.zp != nullptr, z, p.cd, p.qtype, p.qmin, p.qmax);
+}
+
+// dequantized value of code q (already widened to fp32) at [r, c], rounded per op to scale dtype
+__device__ __forceinline__ float dequant_at(const GParams& p, float q, int64_t r, int64_t c) {
+    const int64_t si = scale_index(p, r, c);
+    float v = rnd_dt(q, p.s_dt);
+    const float s = load_as_f32(p.scale, si, p.s_dt);
+    if (p.zp) v = rnd_dt(__fsub_rn(v, rnd_dt(load_as_f32(p.zp, si, p.zp_dt), p.s_dt)), p.s_dt);
+    return rnd_dt(__fmul_rn(v, s), p.s_dt);
+}
+
+__global__ void __launch_bounds__(256) generic_quant_kernel(const __grid_constant__ GParams p, int mode) {
+    const int64_t n = p.rows * p.cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / p.cols, c = i - r * p.cols;
+        if (mode == G_QUANTIZE) {
+            store_from_f32(p.out, i, p.q_dt, quant_at(p, r, c));
+        } else if (mode == G_DEQUANTIZE) {
+            store_from_f32(p.out, i, p.out_dt, dequant_at(p, load_as_f32(p.in, i, p.q_dt), r, c));
+        } else {
+            store_from_f32(p.out, i, p.out_dt, dequant_at(p, quant_at(p, r, c), r, c));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bit packing: one thread owns a group of 32 consecutive elements along the packed dimension,
+// which maps to exactly BITS int32 words (helpers.py:62-96).  Words are sums of
+// (code + offset) << pos in wrapping int32 arithmetic, like the reference's scatter_add_.
+// ---------------------------------------------------------------------------------------------
+template <int BITS, class LoadFn>
+__device__ __forceinline__ void pack_group(uint32_t (&words)[BITS], int nvalid, LoadFn load) {
+#pragma unroll
+    for (int k = 0; k < BITS; ++k) words[k] = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (j < nvalid) {
+            const int32_t u = load(j) + (1 << (BITS - 1));
+            const int bitpos = j * BITS;
+            const int w = bitpos >> 5, sh = bitpos & 31;
+            words[w] += (uint32_t)u << sh;
+            const int ov = sh + BITS - 32;
+            if (ov > 0) words[w + 1] += (uint32_t)(u >> (BITS - ov));
+        }
+    }
+}
+
+template <int BITS, class StoreFn>
+__device__ __forceinline__ void unpack_group(const uint32_t (&words)[BITS], int nvalid, StoreFn store) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (j < nvalid) {
+            const int bitpos = j * BITS;
+            const int w = bitpos >> 5, sh = bitpos & 31;
+            uint32_t v = words[w] >> sh;
+            if (sh + BITS > 32) v |= words[w + 1] << (32 - sh);
+            v &= (1u << BITS) - 1u;
+            store(j, (int)v - (1 << (BITS - 1)));
+        }
+    }
+}
+
+// packed_dim == 1: in [rows, cols] -> out [rows, nw]; thread = (row, group)
+template <int BITS>
+__global__ void __launch_bounds__(256) pack_dim1_kernel(const int8_t* __restrict__ in, int32_t* __restrict__ out,
+                                                        int64_t rows, int64_t cols, int64_t nw) {
+    const int64_t groups = (cols + 31) / 32;
+    const int64_t total = rows * groups;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / groups, g = t - r * groups;
+        const int64_t c0 = g * 32;
+        const int nvalid = (int)min((int64_t)32, cols - c0);
+        const int8_t* src = in + r * cols + c0;
+        uint32_t words[BITS];
+        pack_group<BITS>(words, nvalid, [&](int j) { return (int32_t)src[j]; });
+#pragma unroll
+        for (int k = 0; k < BITS; ++k)
+            if (g * BITS + k < nw) out[r * nw + g * BITS + k] = (int32_t)words[k];
+    }
+}
+
+// packed_dim == 0: in [rows, cols] packs down the rows -> out [nw, cols]; thread = (group, col)
+template <int BITS>
+__global__ void __launch_bounds__(256) pack_dim0_kernel(const int8_t* __restrict__ in, int32_t* __restrict__ out,
+                                                        int64_t rows, int64_t cols, int64_t nw) {
+    const int64_t groups = (rows + 31) / 32;
+    const int64_t total = groups * cols;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = t / cols, c = t - g * cols;
+        const int64_t r0 = g * 32;
+        const int nvalid = (int)min((int64_t)32, rows - r0);
+        uint32_t words[BITS];
+        pack_group<BITS>(words, nvalid, [&](int j) { return (int32_t)in[(r0 + j) * cols + c]; });
+#pragma unroll
+        for (int k = 0; k < BITS; ++k)
+            if (g * BITS + k < nw) out[(g * BITS + k) * cols + c] = (int32_t)words[k];
+    }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256) unpack_dim1_kernel(const int32_t* __restrict__ in, int8_t* __restrict__ out,
+                                                          int64_t rows, int64_t cols, int64_t nw) {
+    const int64_t groups = (cols + 31) / 32;
+    const int64_t total = rows * groups;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / groups, g = t - r * groups;
+        const int64_t c0 = g * 32;
+        const int nvalid = (int)min((int64_t)32, cols - c0);
+        uint32_t words[BITS];
+#pragma unroll
+        for (int k = 0; k < BITS; ++k) words[k] = (g * BITS + k < nw) ? (uint32_t)in[r * nw + g * BITS + k] : 0u;
+        int8_t* dst = out + r * cols + c0;
+        unpack_group<BITS>(words, nvalid, [&](int j, int v) { dst[j] = (int8_t)v; });
+    }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256) unpack_dim0_kernel(const int32_t* __restrict__ in, int8_t* __restrict__ out,
+                                                          int64_t rows, int64_t cols, int64_t nw) {
+    const int64_t groups = (rows + 31) / 32;
+    const int64_t total = groups * cols;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = t / cols, c = t - g * cols;
+        const int64_t r0 = g * 32;
+        const int nvalid = (int)min((int64_t)32, rows - r0);
+        uint32_t words[BITS];
+#pragma unroll
+        for (int k = 0; k < BITS; ++k) words[k] = (g * BITS + k < nw) ? (uint32_t)in[(g * BITS + k) * cols + c] : 0u;
+        unpack_group<BITS>(words, nvalid, [&](int j, int v) { out[(r0 + j) * cols + c] = (int8_t)v; });
+    }
+}
+
+// fused generic quantize -> pack (packed_dim 1) and unpack -> dequantize
+template <int BITS>
+__global__ void __launch_bounds__(256) quantpack_generic_kernel(const __grid_constant__ GParams p, int64_t nw) {
+    const int64_t groups = (p.cols + 31) / 32;
+    const int64_t total = p.rows * groups;
+    int32_t* out = reinterpret_cast<int32_t*>(p.out);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / groups, g = t - r * groups;
+        const int64_t c0 = g * 32;
+        const int nvalid = (int)min((int64_t)32, p.cols - c0);
+        uint32_t words[BITS];
+        pack_group<BITS>(words, nvalid, [&](int j) {
+            const float q = quant_at(p, r, c0 + j);
+            return (q != q) ? 0 : (int32_t)q;   // .to(int8)
+        });
+#pragma unroll
+        for (int k = 0; k < BITS; ++k)
+            if (g * BITS + k < nw) out[r * nw + g * BITS + k] = (int32_t)words[k];
+    }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256) unpackdeq_generic_kernel(const __grid_constant__ GParams p, int64_t nw) {
+    const int64_t groups = (p.cols + 31) / 32;
+    const int64_t total = p.rows * groups;
+    const int32_t* in = reinterpret_cast<const int32_t*>(p.in);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / groups, g = t - r * groups;
+        const int64_t c0 = g * 32;
+        const int nvalid = (int)min((int64_t)32, p.cols - c0);
+        uint32_t words[BITS];
+#pragma unroll
+        for (int k = 0; k < BITS; ++k) words[k] = (g * BITS + k < nw) ? (uint32_t)in[r * nw + g * BITS + k] : 0u;
+        unpack_group<BITS>(words, nvalid, [&](int j, int v) {
+            store_from_f32(p.out, r * p.cols + c0 + j, p.out_dt, dequant_at(p, (float)v, r, c0 + j));
+        });
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+static GParams make_params(const ct_quant_desc& d, const void* in, const void* scale, const void* zp,
+                           const int32_t* gidx, void* out) {
+    GParams p;
+    p.rows = d.rows; p.cols = d.cols; p.rdiv = d.rdiv; p.cdiv = d.cdiv; p.srs = d.s_row_stride;
+    p.x_dt = d.x_dtype; p.s_dt = d.scale_dtype; p.zp_dt = d.zp_dtype; p.cd = d.compute_dtype;
+    p.q_dt = d.q_dtype; p.out_dt = d.out_dtype; p.qtype = d.qtype; p.bits = d.num_bits;
+    p.in = in; p.scale = scale; p.zp = zp; p.gidx = gidx; p.out = out;
+    if (d.qtype == CT_Q_INT) {
+        const float r = (float)(1 << d.num_bits);
+        p.qmax = r / 2 - 1; p.qmin = -r / 2;
+    } else {
+        p.qmax = 448.f; p.qmin = -448.f;
+    }
+    return p;
+}
+
+static unsigned grid_for(int64_t work_items) {
+    int64_t b = (work_items + 255) / 256;
+    if (b < 1) b = 1;
+    if (b > 148 * 32) b = 148 * 32;
+    return (unsigned)b;
+}
+
+int launch_generic_quant(int mode, const ct_quant_desc& d, const void* in, const void* scale, const void* zp,
+                         const int32_t* g_idx, void* out, cudaStream_t stream) {
+    const int64_t n = d.rows * d.cols;
+    if (n == 0) return CT_OK;
+    GParams p = make_params(d, in, scale, zp, g_idx, out);
+    generic_quant_kernel<<<grid_for(n), 256, 0, stream>>>(p, mode);
+    count_launch();
+    CT_CUDA_TRY(cudaGetLastError());
+    return CT_OK;
+}
+
+#define BITS_SWITCH(bits, EXPR)                 \
+    switch (bits) {                             \
+    case 1: { constexpr int B = 1; EXPR; } break; \
+    case 2: { constexpr int B = 2; EXPR; } break; \
+    case 3: { constexpr int B = 3; EXPR; } break; \
+    case 4: { constexpr int B = 4; EXPR; } break; \
+    case 5: { constexpr int B = 5; EXPR; } break; \
+    case 6: { constexpr int B = 6; EXPR; } break; \
+    case 7: { constexpr int B = 7; EXPR; } break; \
+    case 8: { constexpr int B = 8; EXPR; } break; \
+    default: set_error("num_bits %d outside [1, 8]", bits); return CT_E_BITS; \
+    }
+
+int launch_generic_quantpack(const ct_quant_desc& d, const void* x, const void* scale, const void* zp,
+                             const int32_t* g_idx, int32_t* packed, cudaStream_t stream) {
+    if (d.rows * d.cols == 0) return CT_OK;
+    GParams p = make_params(d, x, scale, zp, g_idx, packed);
+    const int64_t nw = (d.cols * d.num_bits + 31) / 32;
+    const int64_t items = d.rows * ((d.cols + 31) / 32);
+    BITS_SWITCH(d.num_bits, (quantpack_generic_kernel<B><<<grid_for(items), 256, 0, stream>>>(p, nw)));
+    count_launch();
+    CT_CUDA_TRY(cudaGetLastError());
+    return CT_OK;
+}
+
+int launch_generic_unpackdeq(const ct_quant_desc& d, const int32_t* packed, const void* scale, const void* zp,
+                             const int32_t* g_idx, void* out, cudaStream_t stream) {
+    if (d.rows * d.cols == 0) return CT_OK;
+    GParams p = make_params(d, packed, scale, zp, g_idx, out);
+    const int64_t nw = (d.cols * d.num_bits + 31) / 32;
+    const int64_t items = d.rows * ((d.cols + 31) / 32);
+    BITS_SWITCH(d.num_bits, (unpackdeq_generic_kernel<B><<<grid_for(items), 256, 0, stream>>>(p, nw)));
+    count_launch();
+    CT_CUDA_TRY(cudaGetLastError());
+    return CT_OK;
+}
+
+int launch_generic_pack(const int8_t* in, int32_t* out, int64_t rows, int64_t cols, int bits, int packed_dim, cudaStream_t stream) {
+    if (rows * cols == 0) return CT_OK;
+    if (packed_dim == 1) {
+        const int64_t nw = (cols * bits + 31) / 32;
+        const int64_t items = rows * ((cols + 31) / 32);
+        BITS_SWITCH(bits, (pack_dim1_kernel<B><<<grid_for(items), 256, 0, stream>>>(in, out, rows, cols, nw)));
+    } else {
+        const int64_t nw = (rows * bits + 31) / 32;
+        const int64_t items = ((rows + 31) / 32) * cols;
+        BITS_SWITCH(bits, (pack_dim0_kernel<B><<<grid_for(items), 256, 0, stream>>>(in, out, rows, cols, nw)));
+    }
+    count_launch();
+    CT_CUDA_TRY(cudaGetLastError());
+    return CT_OK;
+}
+
+int launch_generic_unpack(const int32_t* in, int8_t* out, int64_t rows, int64_t cols, int bits, int packed_dim, cudaStream_t stream) {
+    if (rows * cols == 0) return CT_OK;
+    if (packed_dim == 1) {
+        const int64_t nw = (cols * bits + 31) / 32;
+        const int64_t items = rows * ((cols + 31) / 32);
+        BITS_SWITCH(bits, (unpack_dim1_kernel<B><<<grid_for(items), 256, 0, stream>>>(in, out, rows, cols, nw)));
+    } else {
+        const int64_t nw = (rows * bits + 31) / 32;
+        const int64_t items = ((rows + 31) / 32) * cols;
+        BITS_SWITCH(bits, (unpack_dim0_kernel<B><<<grid_for(items), 256, 0, stream>>>(in, out, rows, cols, nw)));
+    }
+    count_launch();
+    CT_CUDA_TRY(cudaGetLastError());
+    return CT_OK;
+}
+
+}  // namespace ctb

@@ -1,0 +1,402 @@
+// sparse.cu -- bitmask packing and the two bitmask-sparse storage formats.
+//
+//   pack_bitmasks / unpack_bitmasks : utils/helpers.py:306-343 (numpy.packbits, bitorder little):
+//       bit k of byte b of row r  <->  column 8*b + k
+//   sparse24  (CompressionFormat.sparse_24_bitmask, config/base.py:18): per 4 consecutive elements
+//       keep the 2 of largest |x| (ties: lower column first); values [R, C/2] + bitmask [R, C/8]
+//   bitmask   (CompressionFormat.sparse_bitmask, config/base.py:17): values = x[x != 0] row-major,
+//       bitmask = pack_bitmasks(x != 0), row_offsets = exclusive prefix of per-row counts
+// The two compressors themselves are absent from the reference snapshot; the formats follow the
+// restatement in oracle/ct_oracle.c ("parity unpinned"), only the mask bit order is pinned.
+//
+// Thread mapping: one lane owns 8 consecutive columns = one bitmask byte; the byte is formed with
+// compare + shift inside the lane, and lanes exchange bytes with warp shuffles so that every
+// fourth lane issues one aligned 32-bit store of four mask bytes.
+#include <cub/device/device_scan.cuh>
+
+#include "engine.h"
+#include "quant_core.cuh"
+
+namespace ctb {
+
+// ---------------------------------------------------------------------------------------------
+// element access by byte width
+// ---------------------------------------------------------------------------------------------
+template <int ES> struct Raw;
+template <> struct Raw<1> { using T = uint8_t; };
+template <> struct Raw<2> { using T = uint16_t; };
+template <> struct Raw<4> { using T = uint32_t; };
+
+// magnitude key: larger key <=> larger |x| (for non-NaN floats, and for int8)
+template <int DT> __device__ __forceinline__ uint32_t abs_key(uint32_t raw) {
+    if (DT == CT_I8) { int v = (int)(int8_t)raw; return (uint32_t)(v < 0 ? -v : v); }
+    if (DT == CT_F8E4M3) return raw & 0x7fu;
+    if (DT == CT_F32 || DT == CT_I32) {
+        if (DT == CT_I32) { int v = (int)raw; return (uint32_t)(v < 0 ? -(int64_t)v : v); }
+        return raw & 0x7fffffffu;
+    }
+    return raw & 0x7fffu;  // bf16 / f16
+}
+template <int DT> __device__ __forceinline__ bool is_nonzero(uint32_t raw) {
+    if (DT == CT_I8 || DT == CT_I32 || DT == CT_U8) return raw != 0;
+    if (DT == CT_F8E4M3) return (raw & 0x7fu) != 0;
+    if (DT == CT_F32) return (raw & 0x7fffffffu) != 0;
+    return (raw & 0x7fffu) != 0;   // -0.0 == 0
+}
+
+__device__ __forceinline__ void store_mask_byte(uint8_t* bitmask_row_base, int64_t byte_idx, uint32_t byte, bool valid, bool can_vec) {
+    // combine 4 neighbouring lanes' bytes; lane%4==0 stores a word when the 4 bytes are in range & aligned
+    uint32_t v = valid ? byte : 0u;
+    v |= __shfl_down_sync(0xffffffffu, v, 1) << 8;
+    v |= __shfl_down_sync(0xffffffffu, v, 2) << 16;
+    if (can_vec) {
+        if ((threadIdx.x & 3) == 0 && valid) *reinterpret_cast<uint32_t*>(bitmask_row_base + byte_idx) = v;
+    } else if (valid) {
+        bitmask_row_base[byte_idx] = (uint8_t)byte;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack / unpack bitmasks
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_bitmasks_kernel(const uint8_t* __restrict__ bm, uint8_t* __restrict__ out,
+                                                            int64_t rows, int64_t cols, int64_t nb) {
+    const int64_t total = rows * nb;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / nb, b = t - r * nb;
+        const uint8_t* src = bm + r * cols + b * 8;
+        const int nvalid = (int)min((int64_t)8, cols - b * 8);
+        uint32_t byte = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < nvalid && src[k]) byte |= 1u << k;
+        out[t] = (uint8_t)byte;
+    }
+}
+__global__ void __launch_bounds__(256) unpack_bitmasks_kernel(const uint8_t* __restrict__ packed, uint8_t* __restrict__ bm,
+                                                              int64_t rows, int64_t cols, int64_t nb) {
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols, c = i - r * cols;
+        bm[i] = (packed[r * nb + (c >> 3)] >> (c & 7)) & 1u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sparse24: lane = 8 columns = 2 quads.  cols % 8 == 0 fast layout; cols % 4 == 0 handled via nvalid.
+// ---------------------------------------------------------------------------------------------
+template <int DT, int ES>
+__global__ void __launch_bounds__(256) sparse24_compress_kernel(const void* __restrict__ xin, void* __restrict__ vout,
+                                                                uint8_t* __restrict__ bitmask, int64_t rows, int64_t cols, int64_t nb) {
+    using T = typename Raw<ES>::T;
+    const T* x = reinterpret_cast<const T*>(xin);
+    T* values = reinterpret_cast<T*>(vout);
+    const int64_t nb_pad = (nb + 3) & ~(int64_t)3;   // whole groups of 4 lanes stay on one row
+    const int64_t total = rows * nb_pad;
+    const bool vec_ok = (nb % 4 == 0) && ((reinterpret_cast<uintptr_t>(bitmask) & 3) == 0);
+    const int64_t span = ((total + 31) / 32) * 32;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < span; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / nb_pad, b = t - r * nb_pad;
+        const bool valid = (t < total) && (b < nb);
+        uint32_t byte = 0;
+        if (valid) {
+            const int64_t c0 = b * 8;
+            const int nq = (cols - c0 >= 8) ? 2 : 1;
+            uint32_t raw[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) raw[k] = (k < nq * 4) ? (uint32_t)x[r * cols + c0 + k] : 0u;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (q < nq) {
+                    uint32_t key[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) key[j] = abs_key<DT>(raw[q * 4 + j]);
+                    uint32_t keep = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        int beat = 0;
+#pragma unroll
+                        for (int m = 0; m < 4; ++m)
+                            if (m != j && (key[m] > key[j] || (key[m] == key[j] && m < j))) ++beat;
+                        if (beat < 2) keep |= 1u << j;
+                    }
+                    byte |= keep << (4 * q);
+                    // the two kept elements in column order
+                    const int i0 = __ffs(keep) - 1;
+                    const int i1 = 31 - __clz(keep);
+                    T* dst = values + r * (cols / 2) + (c0 / 2) + q * 2;
+                    dst[0] = (T)raw[q * 4 + i0];
+                    dst[1] = (T)raw[q * 4 + i1];
+                }
+            }
+        }
+        store_mask_byte(bitmask + r * nb, b, byte, valid, vec_ok);
+    }
+}
+
+template <int ES>
+__global__ void __launch_bounds__(256) sparse24_decompress_kernel(const void* __restrict__ vin, const uint8_t* __restrict__ bitmask,
+                                                                  void* __restrict__ out, int64_t rows, int64_t cols, int64_t nb) {
+    using T = typename Raw<ES>::T;
+    const T* values = reinterpret_cast<const T*>(vin);
+    T* o = reinterpret_cast<T*>(out);
+    const int64_t total = rows * nb;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / nb, b = t - r * nb;
+        const uint32_t byte = bitmask[t];
+        const int64_t c0 = b * 8;
+        const int nvalid = (int)min((int64_t)8, cols - c0);
+        // values consumed before this byte in the row: 2 per full quad (valid 2:4 masks)
+        int64_t vi = r * (cols / 2) + c0 / 2;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k < nvalid) {
+                T v = 0;
+                if ((byte >> k) & 1u) v = values[vi++];
+                o[r * cols + c0 + k] = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// unstructured bitmask: count -> scan -> scatter
+// ---------------------------------------------------------------------------------------------
+template <int DT, int ES>
+__global__ void __launch_bounds__(256) bitmask_count_kernel(const void* __restrict__ xin, uint8_t* __restrict__ bitmask,
+                                                            int64_t* __restrict__ counts, int64_t rows, int64_t cols, int64_t nb) {
+    using T = typename Raw<ES>::T;
+    const T* x = reinterpret_cast<const T*>(xin);
+    __shared__ int warp_sums[8];
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        int local = 0;
+        for (int64_t b = threadIdx.x; b < nb; b += blockDim.x) {
+            const int64_t c0 = b * 8;
+            const int nvalid = (int)min((int64_t)8, cols - c0);
+            uint32_t byte = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < nvalid && is_nonzero<DT>((uint32_t)x[r * cols + c0 + k])) byte |= 1u << k;
+            bitmask[r * nb + b] = (uint8_t)byte;
+            local += __popc(byte);
+        }
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = local;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int s = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += warp_sums[w];
+            counts[r] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// one block per row: per-thread popcounts over the row's mask bytes -> block exclusive scan -> scatter
+template <int ES, bool COMPRESS>
+__global__ void __launch_bounds__(256) bitmask_move_kernel(const void* __restrict__ src, const uint8_t* __restrict__ bitmask,
+                                                           const int64_t* __restrict__ row_offsets, void* __restrict__ dst,
+                                                           int64_t rows, int64_t cols, int64_t nb) {
+    using T = typename Raw<ES>::T;
+    __shared__ int warp_tot[8];
+    __shared__ int carry_s;
+    const T* s = reinterpret_cast<const T*>(src);
+    T* d = reinterpret_cast<T*>(dst);
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        if (threadIdx.x == 0) carry_s = 0;
+        __syncthreads();
+        const int64_t base = row_offsets[r];
+        for (int64_t b0 = 0; b0 < nb; b0 += blockDim.x) {
+            const int64_t b = b0 + threadIdx.x;
+            const uint32_t byte = (b < nb) ? bitmask[r * nb + b] : 0u;
+            const int cnt = __popc(byte);
+            // block exclusive scan of cnt
+            int incl = cnt;
+            for (int o = 1; o < 32; o <<= 1) {
+                int n = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((threadIdx.x & 31) >= o) incl += n;
+            }
+            if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+            __syncthreads();
+            int woff = 0;
+            for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += warp_tot[w];
+            int64_t pos = base + carry_s + woff + incl - cnt;
+            if (b < nb) {
+                const int64_t c0 = b * 8;
+                const int nvalid = (int)min((int64_t)8, cols - c0);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k < nvalid) {
+                        const bool on = (byte >> k) & 1u;
+                        if (COMPRESS) {
+                            if (on) d[pos++] = s[r * cols + c0 + k];
+                        } else {
+                            T v = 0;
+                            if (on) v = s[pos++];
+                            d[r * cols + c0 + k] = v;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == blockDim.x - 1) carry_s += woff + incl;
+            __syncthreads();
+        }
+    }
+}
+
+static unsigned grid_for(int64_t items) {
+    int64_t b = (items + 255) / 256;
+    if (b < 1) b = 1;
+    if (b > 148 * 16) b = 148 * 16;
+    return (unsigned)b;
+}
+static int esize_of(int dt) { return dt_size(dt); }
+
+}  // namespace ctb
+
+using namespace ctb;
+
+#define PRECHECK(device)                                  \
+    int rc = check_device(device);                        \
+    if (rc) return rc;                                    \
+    DeviceGuard guard(device);                            \
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice"); \
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+int ct_pack_bitmasks(const uint8_t* bytemask, uint8_t* packed, int64_t rows, int64_t cols, int device, void* stream) {
+    PRECHECK(device);
+    if (rows * cols == 0) return CT_OK;
+    if (!bytemask || !packed) { set_error("null pointer"); return CT_E_ARG; }
+    const int64_t nb = (cols + 7) / 8;
+    pack_bitmasks_kernel<<<grid_for(rows * nb), 256, 0, st>>>(bytemask, packed, rows, cols, nb);
+    count_launch();
+    CT_CUDA_TRY(cudaGetLastError());
+    return CT_OK;
+}
+int ct_unpack_bitmasks(const uint8_t* packed, uint8_t* bytemask, int64_t rows, int64_t cols, int device, void* stream) {
+    PRECHECK(device);
+    if (rows * cols == 0) return CT_OK;
+    if (!bytemask || !packed) { set_error("null pointer"); return CT_E_ARG; }
+    const int64_t nb = (cols + 7) / 8;
+    unpack_bitmasks_kernel<<<grid_for(rows * cols), 256, 0, st>>>(packed, bytemask, rows, cols, nb);
+    count_launch();
+    CT_CUDA_TRY(cudaGetLastError());
+    return CT_OK;
+}
+
+int ct_sparse24_compress(const void* x, int dtype, void* values, uint8_t* bitmask, int64_t rows, int64_t cols, int device, void* stream) {
+    PRECHECK(device);
+    if (cols % 4 != 0) { set_error("2:4 compression needs cols %% 4 == 0 (got %lld)", (long long)cols); return CT_E_SHAPE; }
+    if (rows * cols == 0) return CT_OK;
+    if (!x || !values || !bitmask) { set_error("null pointer"); return CT_E_ARG; }
+    const int64_t nb = (cols + 7) / 8;
+    const unsigned g = grid_for(rows * ((nb + 3) & ~(int64_t)3));
+    switch (dtype) {
+    case CT_BF16: sparse24_compress_kernel<CT_BF16, 2><<<g, 256, 0, st>>>(x, values, bitmask, rows, cols, nb); break;
+    case CT_F16: sparse24_compress_kernel<CT_F16, 2><<<g, 256, 0, st>>>(x, values, bitmask, rows, cols, nb); break;
+    case CT_F32: sparse24_compress_kernel<CT_F32, 4><<<g, 256, 0, st>>>(x, values, bitmask, rows, cols, nb); break;
+    case CT_I8: sparse24_compress_kernel<CT_I8, 1><<<g, 256, 0, st>>>(x, values, bitmask, rows, cols, nb); break;
+    case CT_F8E4M3: sparse24_compress_kernel<CT_F8E4M3, 1><<<g, 256, 0, st>>>(x, values, bitmask, rows, cols, nb); break;
+    default: set_error("unsupported dtype %d", dtype); return CT_E_DTYPE;
+    }
+    count_launch();
+    CT_CUDA_TRY(cudaGetLastError());
+    return CT_OK;
+}
+
+int ct_sparse24_decompress(const void* values, int dtype, const uint8_t* bitmask, void* out, int64_t rows, int64_t cols, int device, void* stream) {
+    PRECHECK(device);
+    if (cols % 4 != 0) { set_error("2:4 decompression needs cols %% 4 == 0"); return CT_E_SHAPE; }
+    if (rows * cols == 0) return CT_OK;
+    if (!out || !values || !bitmask) { set_error("null pointer"); return CT_E_ARG; }
+    const int64_t nb = (cols + 7) / 8;
+    const unsigned g = grid_for(rows * nb);
+    switch (esize_of(dtype)) {
+    case 1: sparse24_decompress_kernel<1><<<g, 256, 0, st>>>(values, bitmask, out, rows, cols, nb); break;
+    case 2: sparse24_decompress_kernel<2><<<g, 256, 0, st>>>(values, bitmask, out, rows, cols, nb); break;
+    case 4: sparse24_decompress_kernel<4><<<g, 256, 0, st>>>(values, bitmask, out, rows, cols, nb); break;
+    default: set_error("unsupported dtype %d", dtype); return CT_E_DTYPE;
+    }
+    count_launch();
+    CT_CUDA_TRY(cudaGetLastError());
+    return CT_OK;
+}
+
+int64_t ct_bitmask_workspace_bytes(int64_t rows, int64_t cols) {
+    (void)cols;
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const int64_t*)nullptr, (int64_t*)nullptr, (int)(rows + 1));
+    return (int64_t)((rows + 1) * sizeof(int64_t) + ((tmp + 255) & ~(size_t)255) + 256);
+}
+
+int ct_bitmask_count(const void* x, int dtype, uint8_t* bitmask, int64_t* row_offsets, int64_t* nnz_out, void* workspace,
+                     int64_t rows, int64_t cols, int device, void* stream) {
+    PRECHECK(device);
+    if (!row_offsets || !nnz_out || !workspace) { set_error("null pointer"); return CT_E_ARG; }
+    if (rows == 0) { CT_CUDA_TRY(cudaMemsetAsync(nnz_out, 0, sizeof(int64_t), st)); return CT_OK; }
+    if (!x || !bitmask) { set_error("null pointer"); return CT_E_ARG; }
+    const int64_t nb = (cols + 7) / 8;
+    int64_t* counts = reinterpret_cast<int64_t*>(workspace);               // rows + 1 entries, last = 0
+    void* tmp = reinterpret_cast<uint8_t*>(workspace) + (((rows + 1) * sizeof(int64_t) + 255) & ~(size_t)255);
+    CT_CUDA_TRY(cudaMemsetAsync(counts + rows, 0, sizeof(int64_t), st));
+    const unsigned g = (unsigned)(rows < 148 * 8 ? rows : 148 * 8);
+    switch (dtype) {
+    case CT_BF16: bitmask_count_kernel<CT_BF16, 2><<<g, 256, 0, st>>>(x, bitmask, counts, rows, cols, nb); break;
+    case CT_F16: bitmask_count_kernel<CT_F16, 2><<<g, 256, 0, st>>>(x, bitmask, counts, rows, cols, nb); break;
+    case CT_F32: bitmask_count_kernel<CT_F32, 4><<<g, 256, 0, st>>>(x, bitmask, counts, rows, cols, nb); break;
+    case CT_I8: bitmask_count_kernel<CT_I8, 1><<<g, 256, 0, st>>>(x, bitmask, counts, rows, cols, nb); break;
+    case CT_F8E4M3: bitmask_count_kernel<CT_F8E4M3, 1><<<g, 256, 0, st>>>(x, bitmask, counts, rows, cols, nb); break;
+    default: set_error("unsupported dtype %d", dtype); return CT_E_DTYPE;
+    }
+    count_launch();
+    CT_CUDA_TRY(cudaGetLastError());
+    // exclusive scan over rows+1 counts into a (rows+1)-long temp, then split: first `rows` -> row_offsets, last -> nnz
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, counts, (int)(rows + 1));
+    CT_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, counts, (int)(rows + 1), st));
+    count_launch();
+    CT_CUDA_TRY(cudaMemcpyAsync(row_offsets, counts, rows * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    CT_CUDA_TRY(cudaMemcpyAsync(nnz_out, counts + rows, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    return CT_OK;
+}
+
+int ct_bitmask_compress(const void* x, int dtype, const uint8_t* bitmask, const int64_t* row_offsets, void* values,
+                        int64_t rows, int64_t cols, int device, void* stream) {
+    PRECHECK(device);
+    if (rows * cols == 0) return CT_OK;
+    if (!x || !bitmask || !row_offsets) { set_error("null pointer"); return CT_E_ARG; }
+    const int64_t nb = (cols + 7) / 8;
+    const unsigned g = (unsigned)(rows < 148 * 8 ? rows : 148 * 8);
+    switch (esize_of(dtype)) {
+    case 1: bitmask_move_kernel<1, true><<<g, 256, 0, st>>>(x, bitmask, row_offsets, values, rows, cols, nb); break;
+    case 2: bitmask_move_kernel<2, true><<<g, 256, 0, st>>>(x, bitmask, row_offsets, values, rows, cols, nb); break;
+    case 4: bitmask_move_kernel<4, true><<<g, 256, 0, st>>>(x, bitmask, row_offsets, values, rows, cols, nb); break;
+    default: set_error("unsupported dtype %d", dtype); return CT_E_DTYPE;
+    }
+    count_launch();
+    CT_CUDA_TRY(cudaGetLastError());
+    return CT_OK;
+}
+
+int ct_bitmask_decompress(const void* values, int dtype, const uint8_t* bitmask, const int64_t* row_offsets, void* out,
+                          int64_t rows, int64_t cols, int device, void* stream) {
+    PRECHECK(device);
+    if (rows * cols == 0) return CT_OK;
+    if (!out || !bitmask || !row_offsets) { set_error("null pointer"); return CT_E_ARG; }
+    const int64_t nb = (cols + 7) / 8;
+    const unsigned g = (unsigned)(rows < 148 * 8 ? rows : 148 * 8);
+    switch (esize_of(dtype)) {
+    case 1: bitmask_move_kernel<1, false><<<g, 256, 0, st>>>(values, bitmask, row_offsets, out, rows, cols, nb); break;
+    case 2: bitmask_move_kernel<2, false><<<g, 256, 0, st>>>(values, bitmask, row_offsets, out, rows, cols, nb); break;
+    case 4: bitmask_move_kernel<4, false><<<g, 256, 0, st>>>(values, bitmask, row_offsets, out, rows, cols, nb); break;
+    default: set_error("unsupported dtype %d", dtype); return CT_E_DTYPE;
+    }
+    count_launch();
+    CT_CUDA_TRY(cudaGetLastError());
+    return CT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,570 @@
+"""
+Tensor-level front end of the C ABI: torch tensors in, torch tensors out, same argument meaning
+and error behaviour as the reference's per-tensor functions
+
+    compressors/pack_quantized/helpers.py : pack_to_int32 (:20-101), unpack_from_int32 (:104-180)
+    quantization/lifecycle/forward.py     : quantize (:36-73), dequantize (:76-145),
+                                            fake_quantize (:148-181), _process_quantization (:184-241)
+    utils/helpers.py                      : pack_bitmasks (:306-317), unpack_bitmasks (:320-343)
+
+(paths under src/compressed_tensors of the reference).  Host logic only: shape / dtype / strategy
+resolution and output allocation.  All arithmetic happens in libct_b200.so on a B200.
+
+Device policy: CUDA tensors run on their device and the current stream.  CPU tensors are staged
+through the current CUDA device (large 2-D tensors via the pipelined ct_host_run) and the result
+is returned on the CPU, as the reference would.  With no CUDA device the call raises; there is
+no eager / CPU fallback.  Meta tensors only get their output shape and dtype computed.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+
+__all__ = [
+    "pack_to_int32",
+    "unpack_from_int32",
+    "quantize",
+    "dequantize",
+    "fake_quantize",
+    "quantize_pack",
+    "unpack_dequantize",
+    "pack_bitmasks",
+    "unpack_bitmasks",
+    "sparse24_compress",
+    "sparse24_decompress",
+    "bitmask_compress",
+    "bitmask_decompress",
+    "batched",
+]
+
+_FLOAT_DTYPES = (torch.float32, torch.float16, torch.bfloat16)
+# tensors at least this large take the pipelined host path when they live on the CPU
+_HOST_PIPELINE_MIN_BYTES = 8 << 20
+
+
+# --------------------------------------------------------------------------------------------
+# device staging
+# --------------------------------------------------------------------------------------------
+def _dev_index(*tensors: Optional[torch.Tensor]) -> int:
+    for t in tensors:
+        if t is not None and t.is_cuda:
+            return N.require_device(t.device)
+    return N.require_device(None)
+
+
+def _to_dev(t: Optional[torch.Tensor], idx: int) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.is_cuda:
+        if t.device.index != idx:
+            raise ValueError(f"tensors live on different CUDA devices ({t.device} vs cuda:{idx})")
+        return t if t.is_contiguous() else t.contiguous()
+    return t.contiguous().to(f"cuda:{idx}", non_blocking=True)
+
+
+def _back(out: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    return out if like.is_cuda else out.cpu()
+
+
+# --------------------------------------------------------------------------------------------
+# pack / unpack
+# --------------------------------------------------------------------------------------------
+def pack_to_int32(value: torch.Tensor, num_bits: int, packed_dim: int = 1) -> torch.Tensor:
+    """reference: compressors/pack_quantized/helpers.py:20-101 (same checks, same messages)"""
+    if value.dtype is not torch.int8:
+        raise ValueError("Tensor must be quantized to torch.int8 before packing")
+    if not 1 <= num_bits <= 8:
+        raise ValueError(f"Packing is only supported for num_bits in [1, 8], got {num_bits}")
+    if value.ndim > 2:
+        return torch.stack([pack_to_int32(value[i], num_bits, packed_dim) for i in range(value.shape[0])])
+    if value.ndim != 2:
+        raise ValueError(f"expected a 2-D (or stacked 3-D) tensor, got shape {tuple(value.shape)}")
+    rows, cols = value.shape
+    if packed_dim == 1:
+        out_shape = (rows, math.ceil(cols * num_bits / 32))
+    elif packed_dim == 0:
+        out_shape = (math.ceil(rows * num_bits / 32), cols)
+    else:
+        raise ValueError(f"packed_dim must be 0 or 1, got {packed_dim}")
+    if value.device.type == "meta":
+        out = torch.empty(out_shape, dtype=torch.int32, device="meta")
+        return out
+    idx = _dev_index(value)
+    v = _to_dev(value, idx)
+    out = torch.empty(out_shape, dtype=torch.int32, device=v.device)
+    rc = N.lib().ct_pack_int32(N.ptr(v), N.ptr(out), rows, cols, int(num_bits), int(packed_dim), idx, N.stream_ptr(idx))
+    N.check(rc, "pack_to_int32")
+    out = _back(out, value)
+    if packed_dim == 0:
+        # the reference returns the transpose of a [cols, words] buffer (helpers.py:98-99); keep
+        # that (non-contiguous) memory format so `.contiguous()` callers behave identically
+        out = out.t().contiguous().t()
+    return out
+
+
+def unpack_from_int32(value: torch.Tensor, num_bits: int, shape: Sequence[int], packed_dim: int = 1) -> torch.Tensor:
+    """reference: compressors/pack_quantized/helpers.py:104-180"""
+    if value.dtype is not torch.int32:
+        raise ValueError(f"Expected {torch.int32} but got {value.dtype}, Aborting unpack.")
+    if not 1 <= num_bits <= 8:
+        raise ValueError(f"Unpacking is only supported for num_bits in [1, 8], got {num_bits}")
+    shape = tuple(int(s) for s in shape)
+    if value.ndim > 2:
+        return torch.stack([unpack_from_int32(value[i], num_bits, shape[1:], packed_dim) for i in range(value.shape[0])])
+    if packed_dim not in (0, 1):
+        raise ValueError(f"packed_dim must be 0 or 1, got {packed_dim}")
+    if packed_dim == 1:
+        rows, cols = value.shape[0], shape[1]
+        need = math.ceil(cols * num_bits / 32)
+        if value.shape[1] < need:
+            raise ValueError(f"packed tensor has {value.shape[1]} words per row, {need} needed for {cols} columns")
+        if value.shape[1] != need:
+            value = value[:, :need]
+    else:
+        rows, cols = shape[0], value.shape[1]
+        need = math.ceil(rows * num_bits / 32)
+        if value.shape[0] < need:
+            raise ValueError(f"packed tensor has {value.shape[0]} word rows, {need} needed for {rows} rows")
+        if value.shape[0] != need:
+            value = value[:need]
+    if value.device.type == "meta":
+        return torch.empty((rows, cols), dtype=torch.int8, device="meta")
+    idx = _dev_index(value)
+    v = _to_dev(value, idx)
+    out = torch.empty((rows, cols), dtype=torch.int8, device=v.device)
+    rc = N.lib().ct_unpack_int32(N.ptr(v), N.ptr(out), rows, cols, int(num_bits), int(packed_dim), idx, N.stream_ptr(idx))
+    N.check(rc, "unpack_from_int32")
+    return _back(out, value)
+
+
+# --------------------------------------------------------------------------------------------
+# strategy resolution (host logic of forward.py:184-241 and forward_helpers.py:62-177)
+# --------------------------------------------------------------------------------------------
+def _strategy_name(args) -> str:
+    s = getattr(args, "strategy", None)
+    return getattr(s, "value", s)
+
+
+def _type_name(args) -> str:
+    t = getattr(args, "type", "int")
+    return getattr(t, "value", t)
+
+
+class _Problem:
+    """resolved 2-D view of one quantization call"""
+
+    __slots__ = ("rows", "cols", "rdiv", "cdiv", "srs", "scale", "zp", "g_idx", "strategy")
+
+
+def _resolve(x: torch.Tensor, scale: torch.Tensor, zero_point: Optional[torch.Tensor], args, g_idx) -> _Problem:
+    strategy = _strategy_name(args)
+    p = _Problem()
+    p.strategy = strategy
+    p.g_idx = None
+    cols = x.shape[-1] if x.ndim >= 1 else 1
+    rows = x.numel() // max(cols, 1) if x.numel() else 0
+    p.rows, p.cols = rows, cols
+
+    if zero_point is not None and zero_point.shape != scale.shape:
+        scale, zero_point = torch.broadcast_tensors(scale, zero_point)
+
+    if strategy == "block":
+        bs = getattr(args, "block_structure", None)
+        if bs is None or x.ndim != 2:
+            raise ValueError("block quantization needs a 2-D tensor and a block_structure")
+        bh, bw = int(bs[0]), int(bs[1])
+        nrb, ncb = math.ceil(rows / bh), math.ceil(cols / bw)
+        if scale.numel() != nrb * ncb:
+            raise ValueError(f"block scale has {scale.numel()} elements, expected {nrb}x{ncb}")
+        p.rdiv, p.cdiv, p.srs = bh, bw, ncb
+        p.scale, p.zp = scale.reshape(nrb, ncb), (zero_point.reshape(nrb, ncb) if zero_point is not None else None)
+        return p
+
+    if strategy in ("group", "tensor_group"):
+        group_size = int(getattr(args, "group_size"))
+        while scale.ndim < 2:  # forward_helpers.py:137-139
+            scale = scale.unsqueeze(1)
+            zero_point = zero_point.unsqueeze(1) if zero_point is not None else None
+        if cols >= group_size and cols % group_size != 0:
+            raise ValueError(
+                "tensor column shape must be divisble " f"by the given group_size {group_size} but got {cols}"
+            )
+        ngroups = math.ceil(cols / group_size)
+        if g_idx is not None and g_idx.device.type != "meta" and not bool((g_idx == -1).any()):
+            p.g_idx = g_idx
+        last = scale.shape[-1]
+        if last not in (1, ngroups):
+            raise ValueError(f"group scale has {last} columns, expected {ngroups}")
+        cdiv = group_size if last == ngroups else N.INF
+        p.g_idx = p.g_idx if last == ngroups else None
+    else:
+        # tensor / channel / token / attn_head: plain broadcasting of x / scale
+        last = scale.shape[-1] if scale.ndim >= 1 else 1
+        if last == 1:
+            cdiv = N.INF
+        elif last == cols:
+            cdiv = 1
+        else:
+            raise ValueError(f"scale of shape {tuple(scale.shape)} does not broadcast against {tuple(x.shape)}")
+
+    lead = scale.shape[:-1] if scale.ndim >= 1 else ()
+    if all(int(d) == 1 for d in lead):
+        # one row of scales shared by every row of x
+        p.rdiv, p.cdiv, p.srs = (1 if cdiv != N.INF or last != 1 else N.INF), cdiv, 0
+        if last == 1:
+            p.rdiv, p.cdiv, p.srs = N.INF, N.INF, 0
+        p.scale = scale.reshape(-1)
+        p.zp = zero_point.reshape(-1) if zero_point is not None else None
+    else:
+        target = tuple(x.shape[:-1]) + (last,)
+        try:
+            sc = scale.expand(target)
+            zp = zero_point.expand(target) if zero_point is not None else None
+        except RuntimeError as e:
+            raise ValueError(f"scale of shape {tuple(scale.shape)} does not broadcast against {tuple(x.shape)}") from e
+        p.rdiv, p.cdiv, p.srs = 1, cdiv, last
+        p.scale = sc.reshape(rows, last)
+        p.zp = zp.reshape(rows, last) if zp is not None else None
+    return p
+
+
+def _qparams(args) -> Tuple[int, int]:
+    qtype = N.Q_FLOAT if _type_name(args) == "float" else N.Q_INT
+    bits = int(getattr(args, "num_bits", 8))
+    if qtype == N.Q_FLOAT and bits != 8:
+        raise NotImplementedError("Only num_bits in (8) are supported for float quantization on this path")
+    if qtype == N.Q_INT and not 1 <= bits <= 8:
+        raise NotImplementedError(f"integer quantization on this path supports 1..8 bits, got {bits}")
+    return qtype, bits
+
+
+def _check_float(t: torch.Tensor, what: str):
+    if t.dtype not in _FLOAT_DTYPES:
+        raise NotImplementedError(f"{what} dtype {t.dtype} is not supported by compressed_tensors_b200 (fp32/fp16/bf16 only)")
+
+
+def _desc(p: _Problem, x_dt, s_dt, zp_dt, cd, q_dt, out_dt, qtype, bits) -> N.QuantDesc:
+    d = N.QuantDesc()
+    d.rows, d.cols, d.rdiv, d.cdiv, d.s_row_stride = p.rows, p.cols, p.rdiv, p.cdiv, p.srs
+    d.x_dtype = N.DT.get(x_dt, N.DT_NONE)
+    d.scale_dtype = N.DT[s_dt]
+    d.zp_dtype = N.DT[zp_dt] if zp_dt is not None else N.DT_NONE
+    d.compute_dtype = N.DT.get(cd, N.DT_NONE)
+    d.q_dtype = N.DT.get(q_dt, N.DT_NONE)
+    d.out_dtype = N.DT.get(out_dt, N.DT_NONE)
+    d.qtype, d.num_bits = qtype, bits
+    return d
+
+
+def _run(fn_name: str, op: int, d: N.QuantDesc, p: _Problem, src: torch.Tensor, out_shape, out_dtype) -> torch.Tensor:
+    """src: the streamed input tensor (x, q or packed words), already 2-D"""
+    lib = N.lib()
+    on_cpu = not src.is_cuda
+    idx = _dev_index(src, p.scale)
+    if (
+        on_cpu
+        and p.g_idx is None
+        and src.numel() * src.element_size() >= _HOST_PIPELINE_MIN_BYTES
+        and not p.scale.is_cuda
+    ):
+        # pipelined H2D / kernel / D2H on host buffers
+        srcc = src.contiguous()
+        sc = p.scale.contiguous()
+        zp = p.zp.contiguous() if p.zp is not None else None
+        out = torch.empty(out_shape, dtype=out_dtype, pin_memory=srcc.is_pinned())
+        rc = lib.ct_host_run(op, ctypes.byref(d), N.ptr(srcc), N.ptr(sc), N.ptr(zp), N.ptr(out), idx)
+        N.check(rc, fn_name)
+        return out
+    s_dev = _to_dev(src, idx)
+    sc = _to_dev(p.scale, idx)
+    zp = _to_dev(p.zp, idx)
+    gi = _to_dev(p.g_idx.to(torch.int32) if p.g_idx is not None else None, idx)
+    out = torch.empty(out_shape, dtype=out_dtype, device=s_dev.device)
+    rc = getattr(lib, fn_name)(ctypes.byref(d), N.ptr(s_dev), N.ptr(sc), N.ptr(zp), N.ptr(gi), N.ptr(out), idx, N.stream_ptr(idx))
+    N.check(rc, fn_name)
+    return out.cpu() if on_cpu else out
+
+
+def _apply_global_scale(scale, global_scale):
+    return scale if global_scale is None else scale / global_scale
+
+
+# --------------------------------------------------------------------------------------------
+# quantize / dequantize / fake_quantize
+# --------------------------------------------------------------------------------------------
+@torch.no_grad()
+def quantize(x, scale, zero_point, args, dtype: Optional[torch.dtype] = None, g_idx=None, global_scale=None) -> torch.Tensor:
+    """reference: quantization/lifecycle/forward.py:36-73"""
+    scale = _apply_global_scale(scale, global_scale)
+    _check_float(x, "input")
+    _check_float(scale, "scale")
+    qtype, bits = _qparams(args)
+    cd = torch.result_type(x, scale)
+    strategy = _strategy_name(args)
+    if strategy in ("group", "tensor_group"):
+        out_dtype = dtype if dtype is not None else x.dtype  # forward_helpers.py:134,171
+    else:
+        out_dtype = dtype if dtype is not None else cd
+    p = _resolve(x, scale, zero_point, args, g_idx)
+    if x.device.type == "meta":
+        return torch.empty(x.shape, dtype=out_dtype, device="meta")
+    if x.numel() == 0:
+        return torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    if out_dtype not in N.DT:
+        raise NotImplementedError(f"quantize(dtype={out_dtype}) is not supported")
+    d = _desc(p, x.dtype, p.scale.dtype, p.zp.dtype if p.zp is not None else None, cd, out_dtype, out_dtype, qtype, bits)
+    x2 = x.reshape(p.rows, p.cols)
+    out = _run("ct_quantize", N.OP_QUANTIZE, d, p, x2, (p.rows, p.cols), out_dtype)
+    return out.reshape(x.shape)
+
+
+def _infer_dequant_args(x_q: torch.Tensor, scale: torch.Tensor):
+    """strategy inference of forward.py:99-130 when args is None"""
+    from types import SimpleNamespace
+
+    if scale.ndim in (0, 1):
+        return SimpleNamespace(strategy="tensor", group_size=None, block_structure=None)
+    if scale.ndim == 2:
+        if scale.shape[1] == 1:
+            return SimpleNamespace(strategy="channel", group_size=None, block_structure=None)
+        if scale.shape[0] == 1 or scale.shape[0] == x_q.shape[0]:
+            return SimpleNamespace(strategy="group", group_size=int(x_q.shape[1] / scale.shape[1]), block_structure=None)
+        rows, cols = x_q.shape[-2], x_q.shape[-1]
+        return SimpleNamespace(strategy="block", group_size=None,
+                               block_structure=[rows // scale.shape[0], cols // scale.shape[1]])
+    raise ValueError(
+        f"Could not infer a quantization strategy from scale with {scale.ndim} "
+        "dimmensions. Expected 0 or 2 dimmensions."
+    )
+
+
+@torch.no_grad()
+def dequantize(x_q, scale, zero_point=None, args=None, dtype: Optional[torch.dtype] = None, g_idx=None, global_scale=None) -> torch.Tensor:
+    """reference: quantization/lifecycle/forward.py:76-145"""
+    if args is None:
+        args = _infer_dequant_args(x_q, scale)
+    if dtype is None:
+        dtype = scale.dtype
+    scale = _apply_global_scale(scale, global_scale)
+    _check_float(scale, "scale")
+    strategy = _strategy_name(args)
+    # the dtype argument is honoured only on the group path
+    out_dtype = dtype if strategy in ("group", "tensor_group") else scale.dtype
+    p = _resolve(x_q, scale, zero_point, args, g_idx)
+    if strategy == "block":
+        # inferred block sizes may not cover the tensor (forward.py:118-126); the reference pads
+        # x to the block multiple, so the scale grid must be exactly ceil-div sized (checked above)
+        pass
+    if x_q.device.type == "meta":
+        return torch.empty(x_q.shape, dtype=out_dtype, device="meta")
+    if x_q.numel() == 0:
+        return torch.empty(x_q.shape, dtype=out_dtype, device=x_q.device)
+    if x_q.dtype not in N.DT or out_dtype not in _FLOAT_DTYPES:
+        raise NotImplementedError(f"dequantize from {x_q.dtype} to {out_dtype} is not supported")
+    d = _desc(p, None, p.scale.dtype, p.zp.dtype if p.zp is not None else None, None, x_q.dtype, out_dtype, N.Q_INT, 8)
+    q2 = x_q.reshape(p.rows, p.cols)
+    out = _run("ct_dequantize", N.OP_DEQUANTIZE, d, p, q2, (p.rows, p.cols), out_dtype)
+    return out.reshape(x_q.shape)
+
+
+@torch.no_grad()
+def fake_quantize(x, scale, zero_point, args, g_idx=None, global_scale=None) -> torch.Tensor:
+    """reference: quantization/lifecycle/forward.py:148-181"""
+    scale = _apply_global_scale(scale, global_scale)
+    _check_float(x, "input")
+    _check_float(scale, "scale")
+    qtype, bits = _qparams(args)
+    cd = torch.result_type(x, scale)
+    strategy = _strategy_name(args)
+    out_dtype = x.dtype if strategy in ("group", "tensor_group") else scale.dtype
+    p = _resolve(x, scale, zero_point, args, g_idx)
+    if x.device.type == "meta":
+        return torch.empty(x.shape, dtype=out_dtype, device="meta")
+    if x.numel() == 0:
+        return torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    d = _desc(p, x.dtype, p.scale.dtype, p.zp.dtype if p.zp is not None else None, cd, None, out_dtype, qtype, bits)
+    x2 = x.reshape(p.rows, p.cols)
+    out = _run("ct_fake_quantize", N.OP_FAKE_QUANTIZE, d, p, x2, (p.rows, p.cols), out_dtype)
+    return out.reshape(x.shape)
+
+
+# --------------------------------------------------------------------------------------------
+# fused compressor bodies
+# --------------------------------------------------------------------------------------------
+@torch.no_grad()
+def quantize_pack(x, scale, zero_point, args, g_idx=None, global_scale=None) -> torch.Tensor:
+    """quantize(dtype=int8) -> pack_to_int32 in one pass (pack_quantized/base.py:96-104).
+    x: [..., R, C] float; returns int32 [..., R, ceil(C*bits/32)]"""
+    if x.ndim > 2:
+        # N-D weights (MoE experts) pack slice by slice (helpers.py:44-51); scales follow the leading dim
+        outs = []
+        for i in range(x.shape[0]):
+            sc = scale[i] if scale.ndim == x.ndim else scale
+            zp = zero_point[i] if (zero_point is not None and zero_point.ndim == x.ndim) else zero_point
+            outs.append(quantize_pack(x[i], sc, zp, args, g_idx, global_scale))
+        return torch.stack(outs)
+    scale = _apply_global_scale(scale, global_scale)
+    _check_float(x, "input")
+    _check_float(scale, "scale")
+    qtype, bits = _qparams(args)
+    if qtype != N.Q_INT:
+        raise ValueError("pack-quantized compression needs integer quantization")
+    cd = torch.result_type(x, scale)
+    p = _resolve(x, scale, zero_point, args, g_idx)
+    out_shape = (p.rows, math.ceil(p.cols * bits / 32))
+    if x.device.type == "meta":
+        return torch.empty(out_shape, dtype=torch.int32, device="meta")
+    d = _desc(p, x.dtype, p.scale.dtype, p.zp.dtype if p.zp is not None else None, cd, torch.int8, None, qtype, bits)
+    return _run("ct_quantize_pack_int32", N.OP_QUANTIZE_PACK, d, p, x.reshape(p.rows, p.cols), out_shape, torch.int32)
+
+
+@torch.no_grad()
+def unpack_dequantize(packed, scale, zero_point, num_bits: int, shape: Sequence[int], g_idx=None,
+                      dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """unpack_from_int32 -> dequantize(args=None) in one pass (pack_quantized/base.py:159-166);
+    the strategy is inferred from the scale shape exactly like forward.py:99-130."""
+    shape = tuple(int(s) for s in shape)
+    if packed.dtype is not torch.int32:
+        raise ValueError(f"Expected {torch.int32} but got {packed.dtype}, Aborting unpack.")
+    if not 1 <= num_bits <= 8:
+        raise ValueError(f"Unpacking is only supported for num_bits in [1, 8], got {num_bits}")
+    if packed.ndim > 2:
+        outs = []
+        for i in range(packed.shape[0]):
+            sc = scale[i] if scale.ndim == packed.ndim else scale
+            zp = zero_point[i] if (zero_point is not None and zero_point.ndim == packed.ndim) else zero_point
+            outs.append(unpack_dequantize(packed[i], sc, zp, num_bits, shape[1:], g_idx, dtype))
+        return torch.stack(outs)
+    _check_float(scale, "scale")
+    like = torch.empty(shape, dtype=torch.int8, device="meta")
+    args = _infer_dequant_args(like, scale)
+    if dtype is None:
+        dtype = scale.dtype
+    strategy = _strategy_name(args)
+    out_dtype = dtype if strategy in ("group", "tensor_group") else scale.dtype
+    p = _resolve(like, scale, zero_point, args, g_idx)
+    need = math.ceil(p.cols * num_bits / 32)
+    if packed.shape[-1] < need:
+        raise ValueError(f"packed tensor has {packed.shape[-1]} words per row, {need} needed")
+    if packed.shape[-1] != need:
+        packed = packed[:, :need]
+    if packed.device.type == "meta":
+        return torch.empty(shape, dtype=out_dtype, device="meta")
+    d = _desc(p, None, p.scale.dtype, p.zp.dtype if p.zp is not None else None, None, torch.int8, out_dtype, N.Q_INT, int(num_bits))
+    return _run("ct_unpack_dequantize_int32", N.OP_UNPACK_DEQUANTIZE, d, p, packed, shape, out_dtype)
+
+
+# --------------------------------------------------------------------------------------------
+# multi-tensor launch (the module loop of ModelCompressor.compress_model in one kernel)
+# --------------------------------------------------------------------------------------------
+@torch.no_grad()
+def batched(op: int, problems: Sequence[Tuple[N.QuantDesc, torch.Tensor, torch.Tensor, Optional[torch.Tensor], torch.Tensor]],
+            device_index: Optional[int] = None) -> None:
+    """problems: (desc, in, scale, zp, out) with every tensor already on the same CUDA device."""
+    n = len(problems)
+    if n == 0:
+        return
+    idx = device_index if device_index is not None else _dev_index(problems[0][1])
+    descs = (N.QuantDesc * n)(*[p[0] for p in problems])
+    vp = ctypes.c_void_p * n
+    ins = vp(*[p[1].data_ptr() for p in problems])
+    scs = vp(*[p[2].data_ptr() for p in problems])
+    zps = vp(*[(p[3].data_ptr() if p[3] is not None else 0) for p in problems])
+    outs = vp(*[p[4].data_ptr() for p in problems])
+    rc = N.lib().ct_batched(int(op), n, descs, ctypes.cast(ins, ctypes.c_void_p), ctypes.cast(scs, ctypes.c_void_p),
+                            ctypes.cast(zps, ctypes.c_void_p), ctypes.cast(outs, ctypes.c_void_p), idx, N.stream_ptr(idx))
+    N.check(rc, "ct_batched")
+
+
+# --------------------------------------------------------------------------------------------
+# bitmasks and sparse formats
+# --------------------------------------------------------------------------------------------
+def pack_bitmasks(bytemasks: torch.Tensor) -> torch.Tensor:
+    """reference: utils/helpers.py:306-317 (numpy.packbits, axis=-1, bitorder='little')"""
+    cols = bytemasks.shape[-1]
+    nb = (cols + 7) // 8
+    out_shape = tuple(bytemasks.shape[:-1]) + (nb,)
+    if bytemasks.numel() == 0:
+        return torch.empty(out_shape, dtype=torch.uint8, device=bytemasks.device)
+    idx = _dev_index(bytemasks)
+    bm = _to_dev(bytemasks.to(torch.uint8) if bytemasks.dtype != torch.bool else bytemasks.view(torch.uint8), idx)
+    rows = bm.numel() // cols
+    out = torch.empty(out_shape, dtype=torch.uint8, device=bm.device)
+    N.check(N.lib().ct_pack_bitmasks(N.ptr(bm), N.ptr(out), rows, cols, idx, N.stream_ptr(idx)), "pack_bitmasks")
+    return _back(out, bytemasks)
+
+
+def unpack_bitmasks(packed_bitmasks: torch.Tensor, original_shape: Sequence[int]) -> torch.Tensor:
+    """reference: utils/helpers.py:320-343"""
+    original_shape = tuple(int(s) for s in original_shape)
+    cols = original_shape[-1]
+    rows = math.prod(original_shape[:-1]) if len(original_shape) > 1 else 1
+    if rows * cols == 0:
+        return torch.empty(original_shape, dtype=torch.bool, device=packed_bitmasks.device)
+    idx = _dev_index(packed_bitmasks)
+    pk = _to_dev(packed_bitmasks, idx)
+    out = torch.empty(original_shape, dtype=torch.uint8, device=pk.device)
+    N.check(N.lib().ct_unpack_bitmasks(N.ptr(pk), N.ptr(out), rows, cols, idx, N.stream_ptr(idx)), "unpack_bitmasks")
+    return _back(out.view(torch.bool), packed_bitmasks)
+
+
+def sparse24_compress(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """2:4 bitmask compression of a 2-D tensor -> (values [R, C/2], bitmask uint8 [R, ceil(C/8)])"""
+    if x.ndim != 2:
+        raise ValueError("sparse24 compression expects a 2-D tensor")
+    rows, cols = x.shape
+    if cols % 4 != 0:
+        raise ValueError(f"2:4 compression needs the column count to be a multiple of 4, got {cols}")
+    idx = _dev_index(x)
+    xd = _to_dev(x, idx)
+    values = torch.empty((rows, cols // 2), dtype=x.dtype, device=xd.device)
+    bitmask = torch.empty((rows, (cols + 7) // 8), dtype=torch.uint8, device=xd.device)
+    rc = N.lib().ct_sparse24_compress(N.ptr(xd), N.DT[x.dtype], N.ptr(values), N.ptr(bitmask), rows, cols, idx, N.stream_ptr(idx))
+    N.check(rc, "sparse24_compress")
+    return _back(values, x), _back(bitmask, x)
+
+
+def sparse24_decompress(values: torch.Tensor, bitmask: torch.Tensor, shape: Sequence[int]) -> torch.Tensor:
+    rows, cols = int(shape[0]), int(shape[1])
+    idx = _dev_index(values)
+    v, b = _to_dev(values, idx), _to_dev(bitmask, idx)
+    out = torch.empty((rows, cols), dtype=values.dtype, device=v.device)
+    rc = N.lib().ct_sparse24_decompress(N.ptr(v), N.DT[values.dtype], N.ptr(b), N.ptr(out), rows, cols, idx, N.stream_ptr(idx))
+    N.check(rc, "sparse24_decompress")
+    return _back(out, values)
+
+
+def bitmask_compress(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """unstructured bitmask compression -> (values [nnz], bitmask uint8 [R, ceil(C/8)], row_offsets int64 [R])"""
+    if x.ndim != 2:
+        raise ValueError("bitmask compression expects a 2-D tensor")
+    rows, cols = x.shape
+    idx = _dev_index(x)
+    xd = _to_dev(x, idx)
+    lib = N.lib()
+    bitmask = torch.empty((rows, (cols + 7) // 8), dtype=torch.uint8, device=xd.device)
+    row_offsets = torch.empty((rows,), dtype=torch.int64, device=xd.device)
+    nnz = torch.zeros((1,), dtype=torch.int64, device=xd.device)
+    ws = torch.empty((max(int(lib.ct_bitmask_workspace_bytes(rows, cols)), 256),), dtype=torch.uint8, device=xd.device)
+    N.check(lib.ct_bitmask_count(N.ptr(xd), N.DT[x.dtype], N.ptr(bitmask), N.ptr(row_offsets), N.ptr(nnz), N.ptr(ws),
+                                 rows, cols, idx, N.stream_ptr(idx)), "bitmask_count")
+    total = int(nnz.item())
+    values = torch.empty((total,), dtype=x.dtype, device=xd.device)
+    N.check(lib.ct_bitmask_compress(N.ptr(xd), N.DT[x.dtype], N.ptr(bitmask), N.ptr(row_offsets), N.ptr(values),
+                                    rows, cols, idx, N.stream_ptr(idx)), "bitmask_compress")
+    return _back(values, x), _back(bitmask, x), _back(row_offsets, x)
+
+
+def bitmask_decompress(values: torch.Tensor, bitmask: torch.Tensor, row_offsets: torch.Tensor, shape: Sequence[int]) -> torch.Tensor:
+    rows, cols = int(shape[0]), int(shape[1])
+    idx = _dev_index(values, bitmask)
+    v, b, ro = _to_dev(values, idx), _to_dev(bitmask, idx), _to_dev(row_offsets, idx)
+    out = torch.empty((rows, cols), dtype=values.dtype, device=b.device)
+    N.check(N.lib().ct_bitmask_decompress(N.ptr(v), N.DT[values.dtype], N.ptr(b), N.ptr(ro), N.ptr(out), rows, cols,
+                                          idx, N.stream_ptr(idx)), "bitmask_decompress")
+    return _back(out, bitmask)

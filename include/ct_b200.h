@@ -1,0 +1,183 @@
+/*
+ * ct_b200.h -- C ABI of the B200-native compress/decompress + quantize/dequantize engine.
+ *
+ * This is the drop-in boundary for the per-tensor hot path of
+ * vllm-project/compressed-tensors.  The reference has no native layer (it is
+ * 100% Python/torch eager), so each entry point names the reference Python
+ * function whose body it replaces (paths under src/compressed_tensors of the
+ * reference).  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add to bind them.
+ *
+ * Conventions
+ *   - plain C types only; every function returns a ct_status_t (0 = ok, <0 = error);
+ *     ct_last_error() gives a thread-local message.  Nothing throws across the boundary.
+ *   - the caller owns every buffer.  `device` >= 0: all pointers are device pointers on
+ *     that CUDA device and the work is ENQUEUED on `stream` (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream); no synchronisation happens inside.
+ *     Functions named ct_host_* take HOST pointers, stage through the device in
+ *     pipelined chunks and return when the outputs are complete in host memory.
+ *   - reentrant, no global mutable state besides per-device lazily created scratch
+ *     guarded by a mutex (the reference's convert_checkpoint calls decompress from a
+ *     thread pool: entrypoints/convert/convert_checkpoint.py:110-134).
+ *   - there is NO CPU implementation behind this ABI: with no usable CUDA device every
+ *     compute entry point fails with CT_E_NODEV.
+ */
+#ifndef CT_B200_H
+#define CT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ct_status_t {
+    CT_OK = 0,
+    CT_E_DTYPE = -1,       /* unsupported / inconsistent dtype */
+    CT_E_BITS = -2,        /* num_bits outside [1, 8] */
+    CT_E_SHAPE = -3,       /* inconsistent shapes (e.g. cols % group_size != 0) */
+    CT_E_ALIGN = -4,       /* pointer alignment not supported */
+    CT_E_CUDA = -5,        /* CUDA runtime error (message in ct_last_error) */
+    CT_E_ARG = -6,         /* NULL pointer / bad enum */
+    CT_E_NODEV = -7,       /* no usable CUDA device: this library has no CPU path */
+    CT_E_UNSUPPORTED = -8
+} ct_status_t;
+
+typedef enum ct_dtype_t {
+    CT_NONE = -1,
+    CT_F32 = 0,
+    CT_F16 = 1,
+    CT_BF16 = 2,
+    CT_I8 = 3,
+    CT_F8E4M3 = 4,         /* torch.float8_e4m3fn */
+    CT_I32 = 5,
+    CT_U8 = 6,             /* also torch.bool */
+    CT_I64 = 7
+} ct_dtype_t;
+
+typedef enum ct_qtype_t { CT_Q_INT = 0, CT_Q_FLOAT = 1 } ct_qtype_t;
+
+#define CT_DIV_INF INT64_MAX
+
+/*
+ * One 2-D quantization problem: x is [rows, cols] row-major contiguous.
+ * Scale / zero-point element used for x[r, c]:
+ *     sidx = (r / rdiv) * s_row_stride + (g_idx ? g_idx[c] : c / cdiv)
+ * which covers every strategy of quantization/lifecycle/forward.py:184-241:
+ *     TENSOR  rdiv = cdiv = CT_DIV_INF, s_row_stride = 0
+ *     CHANNEL/TOKEN  rdiv = 1, s_row_stride = 1, cdiv = CT_DIV_INF
+ *     GROUP   rdiv = 1, s_row_stride = n_groups (0 for a one-row scale), cdiv = group_size
+ *     BLOCK   rdiv = block_h, s_row_stride = ceil(cols / block_w), cdiv = block_w
+ * compute_dtype is the torch promotion of `x / scale` (forward_helpers.py:538): every
+ * reference op rounds to it, and the kernels reproduce those roundings bit for bit.
+ */
+typedef struct ct_quant_desc {
+    int64_t rows, cols;
+    int64_t rdiv, cdiv, s_row_stride;
+    int32_t x_dtype;        /* float tensor: input of quantize / fake_quantize */
+    int32_t scale_dtype;
+    int32_t zp_dtype;       /* CT_NONE when there is no zero point */
+    int32_t compute_dtype;
+    int32_t q_dtype;        /* quantized tensor: CT_I8 / CT_F8E4M3, or a float dtype ("dtype=None") */
+    int32_t out_dtype;      /* float output of dequantize / fake_quantize */
+    int32_t qtype;          /* ct_qtype_t */
+    int32_t num_bits;
+} ct_quant_desc;
+
+/* ---- library / device ---------------------------------------------------- */
+const char* ct_version(void);
+const char* ct_last_error(void);
+int ct_device_count(void);                 /* 0 when no CUDA device / driver */
+int ct_device_ok(int device);              /* 1 if `device` is sm_100 (B200) */
+/* tuning knobs (also read from env CT_B200_PIPE / CT_B200_STAGES / CT_B200_CTAS_PER_SM):
+ * pipe 0 = direct 128-bit global loads, 1 = TMA bulk-copy shared-memory ring */
+int ct_set_tuning(int pipe, int stages, int ctas_per_sm);
+/* number of kernels this library has launched in the calling process */
+int64_t ct_launch_count(void);
+
+/* ---- int32 bit packing ---------------------------------------------------
+ * replaces compressors/pack_quantized/helpers.py:20-101 (pack_to_int32) and
+ * :104-180 (unpack_from_int32) for one 2-D slice.
+ *   in  int8 [rows, cols]
+ *   packed_dim = 1: out int32 [rows, ceil(cols*bits/32)]
+ *   packed_dim = 0: out int32 [ceil(rows*bits/32), cols]  (the .contiguous() of the
+ *                   transposed view the reference returns, pack_quantized/base.py:109-110) */
+int ct_pack_int32(const int8_t* in, int32_t* out, int64_t rows, int64_t cols, int bits, int packed_dim,
+                  int device, void* stream);
+int ct_unpack_int32(const int32_t* in, int8_t* out, int64_t rows, int64_t cols, int bits, int packed_dim,
+                    int device, void* stream);
+
+/* ---- quantize / dequantize / fake_quantize ---------------------------------
+ * replace quantization/lifecycle/forward_helpers.py:523-546 (_quantize), :549-572
+ * (_dequantize), :180-215 (_quantize_dequantize) together with the strategy reshapes of
+ * :62-177 (_process_block, _process_group) and quant_args.py:460-496. */
+int ct_quantize(const ct_quant_desc* d, const void* x, const void* scale, const void* zp, const int32_t* g_idx,
+                void* q_out, int device, void* stream);
+int ct_dequantize(const ct_quant_desc* d, const void* q, const void* scale, const void* zp, const int32_t* g_idx,
+                  void* out, int device, void* stream);
+int ct_fake_quantize(const ct_quant_desc* d, const void* x, const void* scale, const void* zp, const int32_t* g_idx,
+                     void* out, int device, void* stream);
+
+/* ---- fused compressor bodies ------------------------------------------------
+ * quantize(dtype=int8) -> pack_to_int32 in one pass (pack_quantized/base.py:96-104) and
+ * unpack_from_int32 -> dequantize (pack_quantized/base.py:159-166); the int8
+ * intermediate never touches HBM.  packed is int32 [rows, ceil(cols*bits/32)]. */
+int ct_quantize_pack_int32(const ct_quant_desc* d, const void* x, const void* scale, const void* zp,
+                           const int32_t* g_idx, int32_t* packed, int device, void* stream);
+int ct_unpack_dequantize_int32(const ct_quant_desc* d, const int32_t* packed, const void* scale, const void* zp,
+                               const int32_t* g_idx, void* out, int device, void* stream);
+
+/* ---- multi-tensor (whole-model) launches -------------------------------------
+ * One persistent launch over `n` independent tensors: the body of the module loop of
+ * ModelCompressor.compress_model / decompress_model
+ * (compressors/model_compressors/model_compressor.py:153-172, :183-207).
+ * descs / pointer tables are HOST arrays of length n; tensor i uses descs[i], x[i], ... */
+typedef enum ct_batch_op_t {
+    CT_OP_QUANTIZE_PACK = 0,      /* in x        -> out packed int32 */
+    CT_OP_UNPACK_DEQUANTIZE = 1,  /* in packed   -> out float */
+    CT_OP_QUANTIZE = 2,           /* in x        -> out q (int8 / fp8) */
+    CT_OP_DEQUANTIZE = 3,         /* in q        -> out float */
+    CT_OP_FAKE_QUANTIZE = 4       /* in x        -> out float */
+} ct_batch_op_t;
+int ct_batched(int op, int n, const ct_quant_desc* descs, const void* const* in, const void* const* scale,
+               const void* const* zp, void* const* out, int device, void* stream);
+
+/* ---- bitmasks and sparse formats ----------------------------------------------
+ * pack_bitmasks / unpack_bitmasks: utils/helpers.py:306-343 (numpy.packbits little).
+ * sparse24 / bitmask compress+decompress: the Sparse24BitMask / Bitmask compressors named
+ * by CompressionFormat.sparse_24_bitmask / sparse_bitmask (config/base.py:17-18); they are
+ * absent from the reference snapshot, so these follow the restated format of
+ * oracle/ct_oracle.c ("parity unpinned"). */
+int ct_pack_bitmasks(const uint8_t* bytemask, uint8_t* packed, int64_t rows, int64_t cols, int device, void* stream);
+int ct_unpack_bitmasks(const uint8_t* packed, uint8_t* bytemask, int64_t rows, int64_t cols, int device, void* stream);
+int ct_sparse24_compress(const void* x, int dtype, void* values, uint8_t* bitmask, int64_t rows, int64_t cols,
+                         int device, void* stream);
+int ct_sparse24_decompress(const void* values, int dtype, const uint8_t* bitmask, void* out, int64_t rows,
+                           int64_t cols, int device, void* stream);
+/* unstructured: two-phase.  count writes row_offsets[rows] (exclusive scan of per-row nnz) and
+ * *nnz_out (device int64); compress then scatters values.  workspace from ct_bitmask_workspace_bytes. */
+int64_t ct_bitmask_workspace_bytes(int64_t rows, int64_t cols);
+int ct_bitmask_count(const void* x, int dtype, uint8_t* bitmask, int64_t* row_offsets, int64_t* nnz_out,
+                     void* workspace, int64_t rows, int64_t cols, int device, void* stream);
+int ct_bitmask_compress(const void* x, int dtype, const uint8_t* bitmask, const int64_t* row_offsets, void* values,
+                        int64_t rows, int64_t cols, int device, void* stream);
+int ct_bitmask_decompress(const void* values, int dtype, const uint8_t* bitmask, const int64_t* row_offsets,
+                          void* out, int64_t rows, int64_t cols, int device, void* stream);
+
+/* ---- host-buffer entry points (what a CPU-resident caller of the reference API hits) ----
+ * Same semantics as ct_batched with n == 1, but every pointer is a HOST pointer (pinned memory
+ * gives full PCIe rate; pageable works).  Rows are streamed through the device in chunks with
+ * H2D copy / kernel / D2H copy overlapped on three streams.  Blocking. */
+int ct_host_run(int op, const ct_quant_desc* d, const void* in, const void* scale, const void* zp, void* out,
+                int device);
+
+/* ---- self tests (device-side exhaustive checks used by tests/) ----------------- */
+/* compares the fast reciprocal-based quotient rounding used by the kernels with IEEE
+ * division for every (x, s) pair of 16-bit patterns of `dtype` (CT_BF16 or CT_F16) with
+ * s restricted to the fast-path range; writes the mismatch count to *mismatches (host). */
+int ct_selftest_division(int dtype, uint64_t* mismatches, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CT_B200_H */

@@ -1,0 +1,390 @@
+"""
+GPU parity tests: the sm_100a kernels (through compressed_tensors_b200.ops -> C ABI) against
+  (1) the golden vectors produced by running the reference (tests/golden),
+  (2) the oracle on larger seeded inputs,
+  (3) size-independent properties at BASELINE.json's full tensor sizes.
+Bit-exact everywhere (integer codes, packed words, fp8 bytes AND dequantized floats: the
+north star allows 1 ulp on floats, these tests demand 0).
+"""
+import ctypes
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+import oracle
+from compressed_tensors_b200 import _native as N
+from compressed_tensors_b200 import ops
+from tests.golden import load
+from tests.util import bits_equal, diff_report
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def ns(**kw):
+    d = dict(strategy="tensor", group_size=None, block_structure=None, num_bits=8, type="int", symmetric=True)
+    d.update(kw)
+    return SimpleNamespace(**d)
+
+
+def cuda(t):
+    return None if t is None else t.to(DEV)
+
+
+@pytest.fixture(params=["tma", "direct"])
+def pipe(request):
+    N.set_tuning(1 if request.param == "tma" else 0, 4, 0)
+    yield request.param
+    N.set_tuning(1, 4, 0)
+
+
+# --------------------------------------------------------------------------------------------
+# 0. the arithmetic proof the fast path rests on
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [N.DT[torch.bfloat16], N.DT[torch.float16]])
+def test_division_selftest_exhaustive(dt):
+    mism = ctypes.c_uint64(123)
+    N.check(N.lib().ct_selftest_division(dt, ctypes.byref(mism), 0))
+    assert mism.value == 0
+
+
+# --------------------------------------------------------------------------------------------
+# 1. golden vectors
+# --------------------------------------------------------------------------------------------
+def test_pack_golden_gpu():
+    for c in load("pack"):
+        v = c["value"].to(DEV)
+        got = ops.pack_to_int32(v, c["bits"], c["packed_dim"])
+        assert got.is_cuda and got.dtype == torch.int32
+        assert torch.equal(got.contiguous().cpu(), c["packed"]), (c["bits"], c["packed_dim"], tuple(v.shape))
+        if c["packed_dim"] == 0:
+            assert list(got.shape) == c["view_shape"]
+        if not c.get("out_of_range"):
+            back = ops.unpack_from_int32(c["packed"].to(DEV), c["bits"], c["value"].shape, c["packed_dim"])
+            assert torch.equal(back.cpu(), c["value"])
+
+
+_Q = load("quant")
+
+
+def _cid(c):
+    a = c["args"]
+    x = c["x"] if isinstance(c["x"], str) else "act"
+    return f"{x}-{a['strategy']}-g{a.get('group_size')}-b{a['num_bits']}{a['type']}-{'sym' if a['symmetric'] else 'asym'}-{c['tag']}"
+
+
+@pytest.mark.parametrize("c", _Q["cases"], ids=_cid)
+def test_quant_golden_gpu(c):
+    x = _Q["x"][c["x"]] if isinstance(c["x"], str) else c["x"]
+    a = SimpleNamespace(**c["args"])
+    xd, sd, zd, gd = cuda(x), cuda(c["scale"]), cuda(c["zp"]), cuda(c["g_idx"])
+    q = ops.quantize(xd, sd, zd, a, dtype=c["q"].dtype, g_idx=gd)
+    assert bits_equal(q.cpu(), c["q"]), "quantize: " + diff_report(q.cpu(), c["q"])
+    qf = ops.quantize(xd, sd, zd, a, dtype=None, g_idx=gd)
+    assert bits_equal(qf.cpu(), c["qf"]), "quantize(dtype=None): " + diff_report(qf.cpu(), c["qf"])
+    dq = ops.dequantize(cuda(c["q"]), sd, zd, args=a, g_idx=gd)
+    assert bits_equal(dq.cpu(), c["dq"]), "dequantize: " + diff_report(dq.cpu(), c["dq"])
+    if c["dq_inferred"] is not None:
+        dqi = ops.dequantize(cuda(c["q"]), sd, zd, g_idx=gd)
+        assert bits_equal(dqi.cpu(), c["dq_inferred"]), "dequantize(inferred): " + diff_report(dqi.cpu(), c["dq_inferred"])
+    fq = ops.fake_quantize(xd, sd, zd, a, g_idx=gd)
+    assert bits_equal(fq.cpu(), c["fq"]), "fake_quantize: " + diff_report(fq.cpu(), c["fq"])
+
+
+def test_sweep_golden_gpu(pipe):
+    """every bf16 / fp16 bit pattern x 4 scales, int4 / int8+zp / fp8 / fake-quant; every int8 and fp8 code"""
+    sw = load("sweep")
+    pat = torch.arange(65536, dtype=torch.int32).to(torch.uint16)
+    n = 0
+    for name, dt in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+        x = pat.view(dt).reshape(256, 256).clone()
+        x[x.isnan()] = 0
+        xd = x.to(DEV)
+        for sval in (2.0 ** -7, 0.01, 1.0, 37.5):
+            s = torch.tensor([sval]).to(dt).to(DEV)
+            key = f"{name}/s{sval}"
+            got = ops.quantize(xd, s, None, ns(num_bits=4), dtype=torch.int8)
+            assert torch.equal(got.cpu(), sw[key + "/int4"]), key + diff_report(got.cpu(), sw[key + "/int4"])
+            zp = torch.tensor([3], dtype=torch.int8, device=DEV)
+            got = ops.quantize(xd, s, zp, ns(num_bits=8, symmetric=False), dtype=torch.int8)
+            assert torch.equal(got.cpu(), sw[key + "/int8zp3"]), key + diff_report(got.cpu(), sw[key + "/int8zp3"])
+            got = ops.quantize(xd, s, None, ns(type="float"), dtype=torch.float8_e4m3fn)
+            assert torch.equal(got.cpu().view(torch.uint8), sw[key + "/fp8"]), key + diff_report(got.cpu().view(torch.uint8), sw[key + "/fp8"])
+            got = ops.fake_quantize(xd, s, None, ns(num_bits=4))
+            assert torch.equal(got.cpu().view(torch.int16), sw[key + "/fq_int4"]), key + " fq_int4 " + diff_report(got.cpu(), sw[key + "/fq_int4"].view(dt))
+            got = ops.fake_quantize(xd, s, None, ns(type="float"))
+            assert torch.equal(got.cpu().view(torch.int16), sw[key + "/fq_fp8"]), key + " fq_fp8 " + diff_report(got.cpu(), sw[key + "/fq_fp8"].view(dt))
+            n += 5
+    codes = torch.arange(-128, 128, dtype=torch.int8).reshape(1, 256).to(DEV)
+    f8 = torch.arange(256, dtype=torch.int32).to(torch.uint8).view(torch.float8_e4m3fn).reshape(1, 256).to(DEV)
+    for name, dt in (("bf16", torch.bfloat16), ("fp16", torch.float16), ("fp32", torch.float32)):
+        for sval in (0.00731, 0.02, 1.0, 1.7):
+            s = torch.tensor([sval]).to(dt).to(DEV)
+            zp = torch.tensor([-5], dtype=torch.int8, device=DEV)
+            assert bits_equal(ops.dequantize(codes, s, None).cpu(), sw[f"dq/{name}/s{sval}/int8"])
+            assert bits_equal(ops.dequantize(codes, s, zp).cpu(), sw[f"dq/{name}/s{sval}/int8zp"])
+            d = ops.dequantize(f8, s, None).cpu()
+            d[d.isnan()] = 0
+            assert bits_equal(d, sw[f"dq/{name}/s{sval}/fp8"])
+            n += 3
+    assert n == len(sw)
+
+
+def test_bitmask_golden_gpu():
+    sp = load("sparse")
+    for c in sp["bitmask"]:
+        got = ops.pack_bitmasks(c["mask"].to(DEV))
+        assert torch.equal(got.cpu(), c["packed"])
+        assert torch.equal(ops.unpack_bitmasks(c["packed"].to(DEV), list(c["mask"].shape)).cpu(), c["mask"])
+
+
+# --------------------------------------------------------------------------------------------
+# 2. seeded inputs vs the oracle, fast (streaming) path, both pipelines
+# --------------------------------------------------------------------------------------------
+def _weights(shape, dtype, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * 0.02).to(dtype)
+
+
+def _group_qparams(w, bits, group, sym, dtype):
+    wf = w.float().unflatten(-1, (-1, group))
+    mn, mx = wf.amin(-1).clamp(max=0), wf.amax(-1).clamp(min=0)
+    qmax, qmin = 2 ** (bits - 1) - 1, -(2 ** (bits - 1))
+    if sym:
+        scale = torch.maximum(mn.abs(), mx.abs()) / ((qmax - qmin) / 2)
+        zp = None
+    else:
+        scale = (mx - mn) / float(qmax - qmin)
+        zp = (qmin - mn / scale).clamp(qmin, qmax).round().to(torch.int8)
+    scale = scale.to(dtype)
+    scale[scale == 0] = torch.finfo(dtype).eps
+    return scale, zp
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("bits,sym", [(4, True), (4, False), (8, True), (8, False)])
+def test_quantize_pack_vs_oracle(pipe, dtype, bits, sym):
+    w = _weights((1024, 4096), dtype, 1000 + bits)
+    scale, zp = _group_qparams(w, bits, 128, sym, dtype)
+    a = ns(strategy="group", group_size=128, num_bits=bits, symmetric=sym)
+    want_q = oracle.quantize(w, scale, zp, strategy="group", group_size=128, num_bits=bits, dtype=torch.int8)
+    want = oracle.pack_to_int32(want_q, bits)
+    launches = N.launch_count()
+    got = ops.quantize_pack(w.to(DEV), scale.to(DEV), cuda(zp), a)
+    assert N.launch_count() == launches + 1, "fused path must be a single kernel"
+    assert torch.equal(got.cpu(), want), diff_report(got.cpu(), want)
+    # decompress side: unpack + dequantize == oracle dequantize == oracle fake_quantize
+    want_dq = oracle.dequantize(want_q, scale, zp)
+    got_dq = ops.unpack_dequantize(got, scale.to(DEV), cuda(zp), bits, w.shape)
+    assert bits_equal(got_dq.cpu(), want_dq), diff_report(got_dq.cpu(), want_dq)
+    want_fq = oracle.fake_quantize(w, scale, zp, strategy="group", group_size=128, num_bits=bits)
+    assert bits_equal(want_dq, want_fq)
+    got_fq = ops.fake_quantize(w.to(DEV), scale.to(DEV), cuda(zp), a)
+    assert bits_equal(got_fq.cpu(), want_fq), diff_report(got_fq.cpu(), want_fq)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("strategy", ["tensor", "channel", "group"])
+def test_fp8_quantize_dequantize_vs_oracle(pipe, dtype, strategy):
+    w = _weights((1024, 4096), dtype, 77)
+    if strategy == "tensor":
+        scale = (w.float().abs().max() / 448).to(dtype).reshape(1)
+        kw = dict(strategy="tensor")
+    elif strategy == "channel":
+        scale = (w.float().abs().amax(-1, keepdim=True) / 448).to(dtype)
+        kw = dict(strategy="channel")
+    else:
+        scale = (w.float().unflatten(-1, (-1, 128)).abs().amax(-1) / 448).to(dtype)
+        kw = dict(strategy="group", group_size=128)
+    a = ns(type="float", **kw)
+    want = oracle.quantize(w, scale, None, qtype="float", dtype=torch.float8_e4m3fn, **kw)
+    got = ops.quantize(w.to(DEV), scale.to(DEV), None, a, dtype=torch.float8_e4m3fn)
+    assert torch.equal(got.cpu().view(torch.uint8), want.view(torch.uint8)), diff_report(got.cpu().view(torch.uint8), want.view(torch.uint8))
+    want_dq = oracle.dequantize(want, scale, None)
+    got_dq = ops.dequantize(got, scale.to(DEV), None)
+    assert bits_equal(got_dq.cpu(), want_dq), diff_report(got_dq.cpu(), want_dq)
+    want_fq = oracle.fake_quantize(w, scale, None, qtype="float", **kw)
+    got_fq = ops.fake_quantize(w.to(DEV), scale.to(DEV), None, a)
+    assert bits_equal(got_fq.cpu(), want_fq), diff_report(got_fq.cpu(), want_fq)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("sym", [True, False])
+def test_int8_channel_quantize_vs_oracle(pipe, dtype, sym):
+    w = _weights((512, 4096), dtype, 5)
+    wf = w.float()
+    mn, mx = wf.amin(-1, keepdim=True).clamp(max=0), wf.amax(-1, keepdim=True).clamp(min=0)
+    if sym:
+        scale, zp = (torch.maximum(mn.abs(), mx.abs()) / 127.5).to(dtype), None
+    else:
+        scale = ((mx - mn) / 255.0).to(dtype)
+        zp = (-128 - mn / scale.float()).clamp(-128, 127).round().to(torch.int8)
+    a = ns(strategy="channel", num_bits=8, symmetric=sym)
+    want = oracle.quantize(w, scale, zp, strategy="channel", num_bits=8, dtype=torch.int8)
+    got = ops.quantize(w.to(DEV), scale.to(DEV), cuda(zp), a, dtype=torch.int8)
+    assert torch.equal(got.cpu(), want), diff_report(got.cpu(), want)
+    want_dq = oracle.dequantize(want, scale, zp)
+    got_dq = ops.dequantize(got, scale.to(DEV), cuda(zp))
+    assert bits_equal(got_dq.cpu(), want_dq), diff_report(got_dq.cpu(), want_dq)
+    want_fq = oracle.fake_quantize(w, scale, zp, strategy="channel", num_bits=8)
+    got_fq = ops.fake_quantize(w.to(DEV), scale.to(DEV), cuda(zp), a)
+    assert bits_equal(got_fq.cpu(), want_fq), diff_report(got_fq.cpu(), want_fq)
+
+
+def test_extreme_scales_take_the_ieee_division_path():
+    """scales outside [2^-100, 2^100], zero, subnormal: the per-chunk slow path must still match"""
+    g = torch.Generator().manual_seed(9)
+    x = (torch.randn(64, 1024, generator=g)).bfloat16()
+    x[0, :16] = torch.tensor([0.0, -0.0, 1e-38, -1e-38, 3e38, -3e38, 1e-30, 1.0] * 2).bfloat16()
+    scales = torch.tensor([1e-38, 9e-41, 3e38, 2.0 ** -101, 2.0 ** 101, 2.0 ** -100, 2.0 ** 100, 1e-45] * 8).bfloat16().reshape(64, 1)
+    scales[scales == 0] = 1e-40
+    for a, kw in ((ns(strategy="channel", num_bits=4), dict(num_bits=4)), (ns(strategy="channel", type="float"), dict(qtype="float"))):
+        dt = torch.int8 if a.type == "int" else torch.float8_e4m3fn
+        want = oracle.quantize(x, scales, None, strategy="channel", dtype=dt, **kw)
+        got = ops.quantize(x.to(DEV), scales.to(DEV), None, a, dtype=dt)
+        assert torch.equal(got.cpu().view(torch.uint8), want.view(torch.uint8)), diff_report(got.cpu().view(torch.uint8), want.view(torch.uint8))
+
+
+@pytest.mark.parametrize("bits", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("shape", [(64, 4096), (33, 100), (7, 1), (128, 33)])
+def test_pack_unpack_vs_oracle(pipe, bits, shape):
+    g = torch.Generator().manual_seed(bits * 7 + shape[1])
+    q = torch.randint(-(1 << (bits - 1)), 1 << (bits - 1), shape, dtype=torch.int8, generator=g)
+    for pd in (1, 0):
+        want = oracle.pack_to_int32(q, bits, pd)
+        got = ops.pack_to_int32(q.to(DEV), bits, pd)
+        assert torch.equal(got.contiguous().cpu(), want)
+        back = ops.unpack_from_int32(got, bits, q.shape, pd)
+        assert torch.equal(back.cpu(), q)
+
+
+def test_ragged_and_odd_bits_fused_vs_oracle():
+    """generic kernels: rows not a multiple of 32 elements, 3/5/6/7-bit codes, g_idx, one-row scales"""
+    w = _weights((50, 200), torch.bfloat16, 3)
+    for bits in (2, 3, 5, 6, 7):
+        scale = (w.float().abs().amax(-1, keepdim=True) / (2 ** (bits - 1) - 0.5)).bfloat16()
+        a = ns(strategy="channel", num_bits=bits)
+        want = oracle.pack_to_int32(oracle.quantize(w, scale, None, strategy="channel", num_bits=bits, dtype=torch.int8), bits)
+        got = ops.quantize_pack(w.to(DEV), scale.to(DEV), None, a)
+        assert torch.equal(got.cpu(), want), bits
+        dq = ops.unpack_dequantize(got, scale.to(DEV), None, bits, w.shape)
+        want_dq = oracle.fake_quantize(w, scale, None, strategy="channel", num_bits=bits)
+        assert bits_equal(dq.cpu(), want_dq), bits
+
+
+# --------------------------------------------------------------------------------------------
+# 3. BASELINE.json full sizes: properties that need no oracle pass over the whole tensor
+# --------------------------------------------------------------------------------------------
+LLAMA8B = [(4096, 4096), (1024, 4096), (14336, 4096), (4096, 14336)]
+
+
+@pytest.mark.parametrize("shape", LLAMA8B)
+def test_full_size_w4a16_properties(shape):
+    R, C = shape
+    g = torch.Generator(device=DEV).manual_seed(1000)
+    w = (torch.randn(R, C, device=DEV, generator=g) * 0.02).bfloat16()
+    scale = (w.float().unflatten(-1, (-1, 128)).abs().amax(-1) / 7.5).bfloat16()
+    a = ns(strategy="group", group_size=128, num_bits=4)
+    packed = ops.quantize_pack(w, scale, None, a)
+    assert packed.shape == (R, C // 8) and packed.dtype == torch.int32
+    # (a) fused == unfused composition, (b) pack/unpack round trip, (c) decompress == fake_quantize
+    q = ops.quantize(w, scale, None, a, dtype=torch.int8)
+    assert int(q.min()) >= -8 and int(q.max()) <= 7
+    assert torch.equal(ops.pack_to_int32(q, 4), packed)
+    assert torch.equal(ops.unpack_from_int32(packed, 4, w.shape), q)
+    dq = ops.unpack_dequantize(packed, scale, None, 4, w.shape)
+    assert bits_equal(dq, ops.fake_quantize(w, scale, None, a))
+    assert bits_equal(dq, ops.dequantize(q, scale, None))
+    # (d) idempotence: quantizing the dequantized tensor reproduces the codes
+    assert torch.equal(ops.quantize_pack(dq, scale, None, a), packed)
+    # (e) spot rows against the oracle
+    rows = torch.tensor([0, 1, R // 2, R - 1])
+    want = oracle.pack_to_int32(oracle.quantize(w[rows].cpu(), scale[rows].cpu(), None, strategy="group", group_size=128, num_bits=4, dtype=torch.int8), 4)
+    assert torch.equal(packed[rows].cpu(), want)
+
+
+@pytest.mark.parametrize("shape", LLAMA8B)
+def test_full_size_fp8_properties(shape):
+    R, C = shape
+    g = torch.Generator(device=DEV).manual_seed(1001)
+    w = (torch.randn(R, C, device=DEV, generator=g) * 0.02).bfloat16()
+    scale = (w.float().abs().max() / 448).bfloat16().reshape(1)
+    a = ns(type="float")
+    q = ops.quantize(w, scale, None, a, dtype=torch.float8_e4m3fn)
+    dq = ops.dequantize(q, scale, None)
+    assert bits_equal(dq, ops.fake_quantize(w, scale, None, a))
+    assert torch.equal(ops.quantize(dq, scale, None, a, dtype=torch.float8_e4m3fn).view(torch.uint8), q.view(torch.uint8))
+    rows = torch.tensor([0, R // 3, R - 1])
+    want = oracle.quantize(w[rows].cpu(), scale.cpu(), None, qtype="float", dtype=torch.float8_e4m3fn)
+    assert torch.equal(q[rows].cpu().view(torch.uint8), want.view(torch.uint8))
+
+
+def test_batched_launch_equals_per_tensor():
+    """one persistent launch over a table of tensors == per-tensor launches"""
+    shapes = [(1024, 4096), (512, 1024), (4096, 512), (64, 128), (2048, 14336)]
+    a = ns(strategy="group", group_size=128, num_bits=4)
+    ws, scs, singles, outs, probs = [], [], [], [], []
+    for i, (R, C) in enumerate(shapes):
+        w = _weights((R, C), torch.bfloat16, 50 + i).to(DEV)
+        sc = (w.float().unflatten(-1, (-1, 128)).abs().amax(-1) / 7.5).bfloat16()
+        singles.append(ops.quantize_pack(w, sc, None, a))
+        out = torch.zeros(R, C // 8, dtype=torch.int32, device=DEV)
+        p = ops._resolve(w, sc, None, a, None)
+        d = ops._desc(p, w.dtype, sc.dtype, None, torch.bfloat16, torch.int8, None, N.Q_INT, 4)
+        probs.append((d, w, sc, None, out))
+        ws.append(w); scs.append(sc); outs.append(out)
+    launches = N.launch_count()
+    ops.batched(N.OP_QUANTIZE_PACK, probs)
+    assert N.launch_count() == launches + 1
+    for s, o in zip(singles, outs):
+        assert torch.equal(s, o)
+
+
+def test_host_buffers_pipeline_equals_device_path():
+    """CPU tensors go through ct_host_run (chunked H2D / kernel / D2H) and must give identical bytes"""
+    w = _weights((12288, 4096), torch.bfloat16, 31)   # 96 MiB -> 3 chunks
+    scale = (w.float().unflatten(-1, (-1, 128)).abs().amax(-1) / 7.5).bfloat16()
+    a = ns(strategy="group", group_size=128, num_bits=4)
+    dev = ops.quantize_pack(w.to(DEV), scale.to(DEV), None, a).cpu()
+    host = ops.quantize_pack(w, scale, None, a)
+    assert not host.is_cuda and torch.equal(host, dev)
+    back_dev = ops.unpack_dequantize(dev.to(DEV), scale.to(DEV), None, 4, w.shape).cpu()
+    back_host = ops.unpack_dequantize(host, scale, None, 4, w.shape)
+    assert not back_host.is_cuda and bits_equal(back_host, back_dev)
+    s8 = (w.float().abs().max() / 448).bfloat16().reshape(1)
+    q_host = ops.quantize(w, s8, None, ns(type="float"), dtype=torch.float8_e4m3fn)
+    q_dev = ops.quantize(w.to(DEV), s8.to(DEV), None, ns(type="float"), dtype=torch.float8_e4m3fn).cpu()
+    assert torch.equal(q_host.view(torch.uint8), q_dev.view(torch.uint8))
+
+
+# --------------------------------------------------------------------------------------------
+# 4. sparse formats vs the restated oracle (parity unpinned, see oracle header)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32, torch.int8])
+@pytest.mark.parametrize("shape", [(128, 4096), (17, 40), (5, 12)])
+def test_sparse24_vs_oracle(dtype, shape):
+    g = torch.Generator().manual_seed(shape[1])
+    x = torch.randn(shape, generator=g) * 10
+    x = x.round().to(dtype) if dtype == torch.int8 else x.to(dtype)
+    vals, bm = oracle.sparse24_compress(x)
+    gv, gb = ops.sparse24_compress(x.to(DEV))
+    assert torch.equal(gb.cpu(), bm)
+    assert bits_equal(gv.cpu(), vals)
+    dense = ops.sparse24_decompress(gv, gb, x.shape)
+    assert bits_equal(dense.cpu(), oracle.sparse24_decompress(vals, bm, x.shape))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32, torch.int8])
+@pytest.mark.parametrize("shape", [(64, 4096), (9, 37), (300, 1000)])
+def test_bitmask_compress_vs_oracle(dtype, shape):
+    g = torch.Generator().manual_seed(shape[0])
+    x = torch.randn(shape, generator=g) * 5
+    x[torch.rand(shape, generator=g) < 0.7] = 0
+    x = x.round().to(dtype) if dtype == torch.int8 else x.to(dtype)
+    vals, bm, offs = oracle.bitmask_compress(x)
+    gv, gb, go = ops.bitmask_compress(x.to(DEV))
+    assert torch.equal(gb.cpu(), bm) and torch.equal(go.cpu(), offs)
+    assert bits_equal(gv.cpu(), vals)
+    dense = ops.bitmask_decompress(gv, gb, go, x.shape)
+    assert bits_equal(dense.cpu(), x.where(x != 0, torch.zeros_like(x)))

@@ -1,0 +1,119 @@
+"""
+CPU-only checks of the product's host logic (no kernel runs here):
+  * libct_b200.so loads and exports every symbol include/ct_b200.h declares
+  * the strategy -> scale-addressing resolution of compressed_tensors_b200.ops feeds the
+    ORACLE arithmetic and must then reproduce the reference's golden outputs
+  * error behaviour mirrors the reference
+"""
+import ctypes
+import os
+import re
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+import oracle
+from compressed_tensors_b200 import _native as N
+from compressed_tensors_b200 import ops
+from tests.golden import load
+from tests.util import bits_equal, diff_report
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "ct_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ct_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 24
+    lib = ctypes.CDLL(N.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in ct_b200.h but not exported"
+    assert declared == set(N.EXPORTED_SYMBOLS), declared ^ set(N.EXPORTED_SYMBOLS)
+    assert b"sm_100a" in N.lib().ct_version()
+
+
+def test_no_cpu_path():
+    """without a GPU every compute entry point must refuse (never fall back)"""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert N.lib().ct_device_count() == 0
+    q = torch.zeros(4, 32, dtype=torch.int8)
+    with pytest.raises(N.NativeLibraryError):
+        ops.pack_to_int32(q, 4)
+    out = torch.zeros(4, 4, dtype=torch.int32)
+    rc = N.lib().ct_pack_int32(N.ptr(q), N.ptr(out), 4, 32, 4, 1, 0, None)
+    assert rc == N.CT_E_NODEV
+    assert "no CPU path" in N.last_error() or "CUDA" in N.last_error()
+
+
+def test_error_messages_match_reference():
+    with pytest.raises(ValueError, match="Tensor must be quantized to torch.int8 before packing"):
+        ops.pack_to_int32(torch.zeros(2, 2, dtype=torch.int32), 4)
+    with pytest.raises(ValueError, match=r"Packing is only supported for num_bits in \[1, 8\], got 9"):
+        ops.pack_to_int32(torch.zeros(2, 2, dtype=torch.int8), 9)
+    with pytest.raises(ValueError, match="Aborting unpack"):
+        ops.unpack_from_int32(torch.zeros(2, 2, dtype=torch.int8), 4, (2, 2))
+    with pytest.raises(ValueError, match=r"Unpacking is only supported for num_bits in \[1, 8\], got 0"):
+        ops.unpack_from_int32(torch.zeros(2, 2, dtype=torch.int32), 0, (2, 2))
+    a = SimpleNamespace(strategy="group", group_size=128, num_bits=4, type="int", block_structure=None)
+    with pytest.raises(ValueError, match="tensor column shape must be divisble"):
+        ops.quantize(torch.zeros(4, 200), torch.ones(4, 2), None, a)
+
+
+def test_meta_tensors_only_compute_shapes():
+    a = SimpleNamespace(strategy="group", group_size=128, num_bits=4, type="int", block_structure=None)
+    x = torch.empty(64, 512, dtype=torch.bfloat16, device="meta")
+    s = torch.empty(64, 4, dtype=torch.bfloat16, device="meta")
+    q = ops.quantize(x, s, None, a, dtype=torch.int8)
+    assert q.device.type == "meta" and q.dtype == torch.int8 and q.shape == x.shape
+    p = ops.quantize_pack(x, s, None, a)
+    assert p.device.type == "meta" and p.dtype == torch.int32 and p.shape == (64, 64)
+    assert ops.pack_to_int32(torch.empty(8, 100, dtype=torch.int8, device="meta"), 3).shape == (8, 10)
+    assert ops.fake_quantize(x, s, None, a).dtype == torch.bfloat16
+
+
+_Q = load("quant")
+
+
+def _oracle_with_product_addressing(c, x):
+    """run the oracle's C arithmetic with the addressing computed by the PRODUCT's host logic"""
+    a = SimpleNamespace(**c["args"])
+    p = ops._resolve(x, c["scale"], c["zp"], a, c["g_idx"])
+    cd = torch.result_type(x, c["scale"])
+    x2 = x.reshape(p.rows, p.cols).contiguous()
+    out = torch.empty(p.rows, p.cols, dtype=c["q"].dtype)
+    L = oracle.lib()
+    sc = p.scale.contiguous()
+    zp = p.zp.contiguous() if p.zp is not None else None
+    gi = p.g_idx.to(torch.int32).contiguous() if p.g_idx is not None else None
+    rc = L.orc_quantize(oracle._p(x2), oracle.DT[x2.dtype], oracle._p(sc), oracle.DT[sc.dtype], oracle._p(zp),
+                        oracle.DT[zp.dtype] if zp is not None else -1, oracle._p(gi), oracle._p(out), oracle.DT[out.dtype],
+                        ctypes.c_int64(p.rows), ctypes.c_int64(p.cols), ctypes.c_int64(p.rdiv), ctypes.c_int64(p.cdiv),
+                        ctypes.c_int64(p.srs), oracle.DT[cd], 0 if a.type == "int" else 1, a.num_bits)
+    assert rc == 0
+    return out.reshape(x.shape)
+
+
+@pytest.mark.parametrize("i", range(len(_Q["cases"])))
+def test_product_addressing_reproduces_golden(i):
+    c = _Q["cases"][i]
+    x = _Q["x"][c["x"]] if isinstance(c["x"], str) else c["x"]
+    got = _oracle_with_product_addressing(c, x)
+    assert bits_equal(got, c["q"]), diff_report(got, c["q"])
+
+
+def test_dequant_strategy_inference():
+    x = torch.empty(8, 64, dtype=torch.int8)
+    assert ops._infer_dequant_args(x, torch.ones(1)).strategy == "tensor"
+    assert ops._infer_dequant_args(x, torch.ones(())).strategy == "tensor"
+    assert ops._infer_dequant_args(x, torch.ones(8, 1)).strategy == "channel"
+    g = ops._infer_dequant_args(x, torch.ones(8, 4))
+    assert g.strategy == "group" and g.group_size == 16
+    g = ops._infer_dequant_args(x, torch.ones(1, 2))
+    assert g.strategy == "group" and g.group_size == 32
+    b = ops._infer_dequant_args(x, torch.ones(2, 2))
+    assert b.strategy == "block" and b.block_structure == [4, 32]
+    with pytest.raises(ValueError, match="Could not infer"):
+        ops._infer_dequant_args(x, torch.ones(2, 2, 2))
