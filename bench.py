@@ -62,48 +62,66 @@ def profile_traffic(kernel: str):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
-
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled through NVML every few ms during the timed region
+    (nvidia-smi itself takes ~100 ms per query, too coarse for a sub-second region)"""
 
     def __init__(self, index: int):
         self.index = index
-        self.samples = []
+        self.sm, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._t = None
+        self._h = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v for v in vis.split(",") if v.strip() != ""]
+                if index < len(ids) and ids[index].strip().isdigit():
+                    phys = int(ids[index])
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._h = None
 
     def _loop(self):
+        nv = self._nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([f.strip() for f in out.split(",")])
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.002)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._loop, daemon=True)
-        self._t.start()
+        if self._h is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._t is not None:
+            self._t.join(timeout=2)
 
     def summary(self):
-        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
-        mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            for k, nm in enumerate(names):
-                if len(s) > 3 + k and s[3 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -131,7 +149,7 @@ def args_w4():
     return SimpleNamespace(strategy="group", group_size=GROUP, block_structure=None, num_bits=BITS, type="int", symmetric=True)
 
 
-def time_steps(fn, steps: int, warmup: int, dist_on: bool):
+def time_steps(fn, steps: int, warmup: int, dist_on: bool, sampler=None):
     """W untimed steps, then exactly K steps bracketed by barrier + synchronize; CUDA events on the launching stream"""
     import torch.distributed as dist
 
@@ -142,11 +160,15 @@ def time_steps(fn, steps: int, warmup: int, dist_on: bool):
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler is not None:
+        sampler.__enter__()
     e0.record()
     for _ in range(steps):
         fn()
     e1.record()
     torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.__exit__()
     if dist_on:
         dist.barrier()
     ms = e0.elapsed_time(e1)
@@ -195,8 +217,8 @@ def run_b200(a):
         ops.batched(N.OP_QUANTIZE_PACK, probs, local)
 
     l0 = N.launch_count()
-    with ClockSampler(local) as cs:
-        ms = time_steps(step, a.steps, a.warmup, dist_on)
+    cs = ClockSampler(local)
+    ms = time_steps(step, a.steps, a.warmup, dist_on, sampler=cs)
     launches = (N.launch_count() - l0) - a.warmup  # one launch per step
     clocks = cs.summary()
     ms_per_step = ms / a.steps

@@ -108,8 +108,12 @@ __device__ __forceinline__ float quot(float x, const ScaleCtx& c) {
     if (SLOW) return __fdiv_rn(x, c.s);
     float q = __fmul_rn(x, c.r);
     if (P::DT == CT_F16) {
+        // one residual step -> correctly rounded fp32 quotient.  Skipped when the first product is
+        // +-0 (the FMA chain would turn -0 into +0) or +-inf / NaN (inf - inf).
         float rem = __fmaf_rn(-q, c.s, x);
-        q = __fmaf_rn(rem, c.r, q);
+        float q1 = __fmaf_rn(rem, c.r, q);
+        const float a = fabsf(q);
+        q = (a > 0.f && a < __int_as_float(0x7f800000)) ? q1 : q;
     }
     return q;
 }

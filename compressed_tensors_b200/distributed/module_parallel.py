@@ -1,0 +1,55 @@
+"""
+replace_module_parallel: apply `apply_fn` (compress_module) to a list of modules across ranks
+(mirror of distributed/module_parallel.py:23-90).
+
+  1. modules are dealt to ranks by greedy_bin_packing on their byte size
+  2. non-owner ranks run apply_fn on a META copy of the module (shape-only compressor path) so every
+     rank ends up with the same parameter names / shapes / dtypes
+  3. the owner runs apply_fn for real (one GPU, no collective inside)
+  4. recouple: for every resulting tensor the owner broadcasts the data (dist.broadcast, NCCL over
+     NVLink on GPUs; float8 viewed as uint8); the reference pickles state dicts through the CPU
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+from ..utils.module import get_direct_state_dict, replace_direct_state_dict
+from .assign import greedy_bin_packing
+from .utils import as_broadcastable, module_size
+
+__all__ = ["replace_module_parallel"]
+
+
+def _to_meta(module: torch.nn.Module):
+    sd = get_direct_state_dict(module)
+    replace_direct_state_dict(module, {k: torch.empty_like(v, device="meta") for k, v in sd.items()})
+
+
+def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callable = module_size, desc: Optional[str] = None):
+    rank, world = dist.get_rank(), dist.get_world_size()
+    devices = {id(m): next(iter(get_direct_state_dict(m).values())).device for m in modules if len(get_direct_state_dict(m))}
+    _, _, owner = greedy_bin_packing(modules, world, weight_fn)
+
+    for m in modules:
+        if owner[m] != rank:
+            _to_meta(m)
+            apply_fn(m)
+    for m in modules:
+        if owner[m] == rank:
+            apply_fn(m)
+
+    for m in modules:  # same (sorted) order on every rank
+        sd = get_direct_state_dict(m)
+        dev = devices.get(id(m), torch.device("cpu"))
+        new = {}
+        for name in sd:  # identical key order on all ranks (same compressor code path)
+            t = sd[name]
+            if owner[m] != rank:
+                t = torch.empty(t.shape, dtype=t.dtype, device=dev)
+            buf = as_broadcastable(t.contiguous())
+            dist.broadcast(buf, src=owner[m])
+            new[name] = buf.view(t.dtype) if buf.dtype != t.dtype else buf
+        replace_direct_state_dict(m, new)

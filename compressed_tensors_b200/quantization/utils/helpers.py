@@ -1,0 +1,126 @@
+"""
+Quantization helpers on the host side of the path: ranges, the min/max -> (scale, zero point)
+rule, dynamic qparams, block padding.  Mirror of quantization/utils/helpers.py:50-249, :374-428.
+
+These operate on QPARAM-sized tensors (one value per tensor / channel / group / block): they are
+host plumbing around the hot path, written with torch ops on whatever device the data lives on.
+The min/max reduction over the full tensor and its fusion in front of quantize+pack is the
+"next" row (f)1 of SURVEY.md section 8.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import Tensor
+from torch.nn import Module
+
+from ..quant_args import FP4_E2M1_DATA, FP8_E4M3_DATA, QuantizationArgs, QuantizationStrategy, QuantizationType, round_to_quantized_type_dtype
+
+__all__ = [
+    "calculate_range",
+    "calculate_qparams",
+    "compute_dynamic_scales_and_zp",
+    "is_module_quantized",
+    "strategy_cdiv",
+    "maybe_pad_tensor_for_block_quant",
+]
+
+
+def calculate_range(quantization_args: QuantizationArgs, device) -> tuple[Tensor, Tensor]:
+    """(q_min, q_max) as 0-dim fp32 tensors (helpers.py:198-226)"""
+    if quantization_args.type == QuantizationType.INT:
+        span = 2.0 ** quantization_args.num_bits
+        lo, hi = -span / 2, span / 2 - 1
+    elif quantization_args.type == QuantizationType.FLOAT:
+        if quantization_args.num_bits == 8:
+            lo, hi = FP8_E4M3_DATA.min, FP8_E4M3_DATA.max
+        elif quantization_args.num_bits == 4:
+            lo, hi = FP4_E2M1_DATA.min, FP4_E2M1_DATA.max
+        else:
+            raise NotImplementedError("Range calculation only supported for 4 and 8 bits")
+    else:
+        raise ValueError(f"Invalid quantization type {quantization_args.type}")
+    return torch.tensor(lo, device=device), torch.tensor(hi, device=device)
+
+
+def calculate_qparams(min_vals: Tensor, max_vals: Tensor, quantization_args: QuantizationArgs,
+                      global_scale: Tensor | None = None) -> tuple[Tensor, Tensor]:
+    """observer rule of the reference (helpers.py:50-137), same op order so the scales agree bit for bit"""
+    if quantization_args.type == QuantizationType.FLOAT and quantization_args.num_bits == 4:
+        raise NotImplementedError("FP4 / MX scale generation is outside this engine's path (SURVEY 8(f) rank 2)")
+    min_vals = torch.min(min_vals, torch.zeros_like(min_vals))
+    max_vals = torch.max(max_vals, torch.zeros_like(max_vals))
+    device = min_vals.device
+    bit_min, bit_max = calculate_range(quantization_args, device)
+    bit_range = bit_max - bit_min
+    if quantization_args.symmetric:
+        max_val_pos = torch.max(torch.abs(min_vals), torch.abs(max_vals))
+        scales = max_val_pos / (float(bit_range) / 2)
+        zero_points = torch.zeros(scales.shape, device=device, dtype=min_vals.dtype)
+    else:
+        scales = (max_vals - min_vals) / float(bit_range)
+        zero_points = bit_min - (min_vals / scales)
+        zero_points = torch.clamp(zero_points, bit_min, bit_max)
+    if global_scale is not None:
+        scales = global_scale * scales
+    if quantization_args.scale_dtype is not None:
+        scales = round_to_quantized_type_dtype(scales, dtype=quantization_args.scale_dtype)
+    eps_dtype = quantization_args.scale_dtype if quantization_args.scale_dtype is not None else scales.dtype
+    if eps_dtype == FP8_E4M3_DATA.dtype:
+        eps = 0.125
+    else:
+        eps = torch.finfo(eps_dtype).eps if eps_dtype.is_floating_point else 1
+    scales = torch.where(scales == 0, torch.tensor(eps, dtype=scales.dtype, device=device), scales)
+    zero_points = round_to_quantized_type_dtype(zero_points, dtype=quantization_args.zp_dtype, cast_to_original_dtype=False)
+    if scales.ndim == 0:
+        scales, zero_points = scales.reshape(1), zero_points.reshape(1)
+    return scales, zero_points
+
+
+def compute_dynamic_scales_and_zp(value: Tensor, args: QuantizationArgs, module: Module = None, global_scale: Tensor | None = None):
+    """min/max over the strategy's reduction dims, then calculate_qparams (helpers.py:140-195)"""
+    keep = True
+    if args.strategy == QuantizationStrategy.TOKEN:
+        dims = tuple(i for i in range(value.ndim) if i not in (0, 1))
+    elif args.strategy == QuantizationStrategy.TENSOR:
+        dims = None
+    elif args.strategy in (QuantizationStrategy.TENSOR_GROUP, QuantizationStrategy.GROUP):
+        dims, keep = -1, False
+        value = value.unflatten(-1, (math.ceil(value.shape[-1] / args.group_size), args.group_size))
+    else:
+        ok = (QuantizationStrategy.TOKEN, QuantizationStrategy.TENSOR, QuantizationStrategy.TENSOR_GROUP, QuantizationStrategy.GROUP)
+        raise ValueError(f"Dynamic quantization is only supported for {ok}")
+    if not dims:
+        mn, mx = torch.aminmax(value)
+    else:
+        mn = torch.amin(value, dim=dims, keepdims=keep)
+        mx = torch.amax(value, dim=dims, keepdims=keep)
+    return calculate_qparams(mn, mx, args, global_scale=global_scale)
+
+
+def is_module_quantized(module: Module) -> bool:
+    """a module is quantized when its scheme has any of weights / input / output args (helpers.py:229-249)"""
+    scheme = getattr(module, "quantization_scheme", None)
+    if scheme is None:
+        return False
+    return any(getattr(scheme, k, None) is not None for k in ("weights", "input_activations", "output_activations"))
+
+
+def strategy_cdiv(value: int, divisor: int, strategy=None, strict: bool = False) -> int:
+    """ceil-division used for scale shapes; complains (or raises when strict) on a ragged last group"""
+    out = math.ceil(value / divisor)
+    if out * divisor != value and strict:
+        raise ValueError(f"{strategy} quantization strategy requires strict division of weight/activation size {value} "
+                         f"and group/block size {divisor}.")
+    return out
+
+
+def maybe_pad_tensor_for_block_quant(tensor: Tensor, block_structure: tuple[int, int]) -> Tensor:
+    """zero-pad the last two dims up to multiples of the block (helpers.py:374-428)"""
+    bh, bw = block_structure
+    rows, cols = tensor.shape[-2], tensor.shape[-1]
+    pr, pc = (-rows) % bh, (-cols) % bw
+    if pr == 0 and pc == 0:
+        return tensor
+    return torch.nn.functional.pad(tensor, (0, pc, 0, pr), mode="constant", value=0)

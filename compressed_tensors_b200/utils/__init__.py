@@ -1,0 +1,3 @@
+from .helpers import *  # noqa: F401,F403
+from .module import *  # noqa: F401,F403
+from .impl_backend import ImplBackend  # noqa: F401

@@ -1,0 +1,61 @@
+"""
+Small host utilities of the path (mirror of the pieces of utils/helpers.py the compressors use):
+getattr_chain (:…), patch_attr, tensor_follows_mask_structure (:87-109) and the bitmask pair
+pack_bitmasks / unpack_bitmasks (:306-343) -- the latter run as CUDA kernels, not numpy.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Any
+
+import torch
+
+from ..ops import pack_bitmasks, unpack_bitmasks
+
+__all__ = ["getattr_chain", "patch_attr", "tensor_follows_mask_structure", "pack_bitmasks", "unpack_bitmasks", "TensorStateDict"]
+
+TensorStateDict = dict[str, torch.Tensor]
+_MISSING = object()
+
+
+def getattr_chain(obj: Any, chain_str: str, *args, **kwargs) -> Any:
+    """getattr along a dotted path with an optional default (positional or default=...)"""
+    if len(args) >= 1:
+        default, has_default = args[0], True
+    elif "default" in kwargs:
+        default, has_default = kwargs["default"], True
+    else:
+        default, has_default = _MISSING, False
+    cur = obj
+    for name in chain_str.split("."):
+        nxt = getattr(cur, name, _MISSING)
+        if nxt is _MISSING or (cur is None):
+            if has_default:
+                return default
+            raise AttributeError(f"{chain_str} not found on {obj}")
+        cur = nxt
+    return cur
+
+
+@contextlib.contextmanager
+def patch_attr(base: object, attr: str, value: Any):
+    """temporarily set base.attr = value"""
+    sentinel = object()
+    original = getattr(base, attr, sentinel)
+    setattr(base, attr, value)
+    try:
+        yield
+    finally:
+        if original is sentinel:
+            delattr(base, attr)
+        else:
+            setattr(base, attr, original)
+
+
+def tensor_follows_mask_structure(tensor: torch.Tensor, mask: str = "2:4") -> bool:
+    """at least n zeros in every chunk of m elements; raises ValueError otherwise (helpers.py:87-109)"""
+    n, m = (int(v) for v in mask.split(":"))
+    zeros = (tensor.reshape(-1, m) == 0).sum(dim=1)
+    if not bool(torch.all(zeros >= n)):
+        raise ValueError()
+    return True

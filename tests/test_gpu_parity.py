@@ -16,7 +16,7 @@ import oracle
 from compressed_tensors_b200 import _native as N
 from compressed_tensors_b200 import ops
 from tests.golden import load
-from tests.util import bits_equal, diff_report
+from tests.util import bits_equal, diff_report, same, same_values
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -57,12 +57,12 @@ def test_pack_golden_gpu():
         v = c["value"].to(DEV)
         got = ops.pack_to_int32(v, c["bits"], c["packed_dim"])
         assert got.is_cuda and got.dtype == torch.int32
-        assert torch.equal(got.contiguous().cpu(), c["packed"]), (c["bits"], c["packed_dim"], tuple(v.shape))
+        same_values(got.contiguous().cpu(), c["packed"], str((c["bits"], c["packed_dim"], tuple(v.shape))))
         if c["packed_dim"] == 0:
             assert list(got.shape) == c["view_shape"]
         if not c.get("out_of_range"):
             back = ops.unpack_from_int32(c["packed"].to(DEV), c["bits"], c["value"].shape, c["packed_dim"])
-            assert torch.equal(back.cpu(), c["value"])
+            same_values(back.cpu(), c["value"], "")
 
 
 _Q = load("quant")
@@ -80,16 +80,16 @@ def test_quant_golden_gpu(c):
     a = SimpleNamespace(**c["args"])
     xd, sd, zd, gd = cuda(x), cuda(c["scale"]), cuda(c["zp"]), cuda(c["g_idx"])
     q = ops.quantize(xd, sd, zd, a, dtype=c["q"].dtype, g_idx=gd)
-    assert bits_equal(q.cpu(), c["q"]), "quantize: " + diff_report(q.cpu(), c["q"])
+    same(q.cpu(), c["q"], "quantize: ")
     qf = ops.quantize(xd, sd, zd, a, dtype=None, g_idx=gd)
-    assert bits_equal(qf.cpu(), c["qf"]), "quantize(dtype=None): " + diff_report(qf.cpu(), c["qf"])
+    same(qf.cpu(), c["qf"], "quantize(dtype=None): ")
     dq = ops.dequantize(cuda(c["q"]), sd, zd, args=a, g_idx=gd)
-    assert bits_equal(dq.cpu(), c["dq"]), "dequantize: " + diff_report(dq.cpu(), c["dq"])
+    same(dq.cpu(), c["dq"], "dequantize: ")
     if c["dq_inferred"] is not None:
         dqi = ops.dequantize(cuda(c["q"]), sd, zd, g_idx=gd)
-        assert bits_equal(dqi.cpu(), c["dq_inferred"]), "dequantize(inferred): " + diff_report(dqi.cpu(), c["dq_inferred"])
+        same(dqi.cpu(), c["dq_inferred"], "dequantize(inferred): ")
     fq = ops.fake_quantize(xd, sd, zd, a, g_idx=gd)
-    assert bits_equal(fq.cpu(), c["fq"]), "fake_quantize: " + diff_report(fq.cpu(), c["fq"])
+    same(fq.cpu(), c["fq"], "fake_quantize: ")
 
 
 def test_sweep_golden_gpu(pipe):
@@ -105,16 +105,16 @@ def test_sweep_golden_gpu(pipe):
             s = torch.tensor([sval]).to(dt).to(DEV)
             key = f"{name}/s{sval}"
             got = ops.quantize(xd, s, None, ns(num_bits=4), dtype=torch.int8)
-            assert torch.equal(got.cpu(), sw[key + "/int4"]), key + diff_report(got.cpu(), sw[key + "/int4"])
+            same_values(got.cpu(), sw[key + "/int4"], str(key))
             zp = torch.tensor([3], dtype=torch.int8, device=DEV)
             got = ops.quantize(xd, s, zp, ns(num_bits=8, symmetric=False), dtype=torch.int8)
-            assert torch.equal(got.cpu(), sw[key + "/int8zp3"]), key + diff_report(got.cpu(), sw[key + "/int8zp3"])
+            same_values(got.cpu(), sw[key + "/int8zp3"], str(key))
             got = ops.quantize(xd, s, None, ns(type="float"), dtype=torch.float8_e4m3fn)
-            assert torch.equal(got.cpu().view(torch.uint8), sw[key + "/fp8"]), key + diff_report(got.cpu().view(torch.uint8), sw[key + "/fp8"])
+            same_values(got.cpu().view(torch.uint8), sw[key + "/fp8"], str(key))
             got = ops.fake_quantize(xd, s, None, ns(num_bits=4))
-            assert torch.equal(got.cpu().view(torch.int16), sw[key + "/fq_int4"]), key + " fq_int4 " + diff_report(got.cpu(), sw[key + "/fq_int4"].view(dt))
+            same_values(got.cpu().view(torch.int16), sw[key + "/fq_int4"], str(key + " fq_int4 "))
             got = ops.fake_quantize(xd, s, None, ns(type="float"))
-            assert torch.equal(got.cpu().view(torch.int16), sw[key + "/fq_fp8"]), key + " fq_fp8 " + diff_report(got.cpu(), sw[key + "/fq_fp8"].view(dt))
+            same_values(got.cpu().view(torch.int16), sw[key + "/fq_fp8"], str(key + " fq_fp8 "))
             n += 5
     codes = torch.arange(-128, 128, dtype=torch.int8).reshape(1, 256).to(DEV)
     f8 = torch.arange(256, dtype=torch.int32).to(torch.uint8).view(torch.float8_e4m3fn).reshape(1, 256).to(DEV)
@@ -122,11 +122,11 @@ def test_sweep_golden_gpu(pipe):
         for sval in (0.00731, 0.02, 1.0, 1.7):
             s = torch.tensor([sval]).to(dt).to(DEV)
             zp = torch.tensor([-5], dtype=torch.int8, device=DEV)
-            assert bits_equal(ops.dequantize(codes, s, None).cpu(), sw[f"dq/{name}/s{sval}/int8"])
-            assert bits_equal(ops.dequantize(codes, s, zp).cpu(), sw[f"dq/{name}/s{sval}/int8zp"])
+            same(ops.dequantize(codes, s, None).cpu(), sw[f"dq/{name}/s{sval}/int8"], "")
+            same(ops.dequantize(codes, s, zp).cpu(), sw[f"dq/{name}/s{sval}/int8zp"], "")
             d = ops.dequantize(f8, s, None).cpu()
             d[d.isnan()] = 0
-            assert bits_equal(d, sw[f"dq/{name}/s{sval}/fp8"])
+            same(d, sw[f"dq/{name}/s{sval}/fp8"], "")
             n += 3
     assert n == len(sw)
 
@@ -135,8 +135,8 @@ def test_bitmask_golden_gpu():
     sp = load("sparse")
     for c in sp["bitmask"]:
         got = ops.pack_bitmasks(c["mask"].to(DEV))
-        assert torch.equal(got.cpu(), c["packed"])
-        assert torch.equal(ops.unpack_bitmasks(c["packed"].to(DEV), list(c["mask"].shape)).cpu(), c["mask"])
+        same_values(got.cpu(), c["packed"], "")
+        same_values(ops.unpack_bitmasks(c["packed"].to(DEV), list(c["mask"].shape)).cpu(), c["mask"], "")
 
 
 # --------------------------------------------------------------------------------------------
@@ -173,15 +173,15 @@ def test_quantize_pack_vs_oracle(pipe, dtype, bits, sym):
     launches = N.launch_count()
     got = ops.quantize_pack(w.to(DEV), scale.to(DEV), cuda(zp), a)
     assert N.launch_count() == launches + 1, "fused path must be a single kernel"
-    assert torch.equal(got.cpu(), want), diff_report(got.cpu(), want)
+    same_values(got.cpu(), want, "")
     # decompress side: unpack + dequantize == oracle dequantize == oracle fake_quantize
     want_dq = oracle.dequantize(want_q, scale, zp)
     got_dq = ops.unpack_dequantize(got, scale.to(DEV), cuda(zp), bits, w.shape)
-    assert bits_equal(got_dq.cpu(), want_dq), diff_report(got_dq.cpu(), want_dq)
+    same(got_dq.cpu(), want_dq, "")
     want_fq = oracle.fake_quantize(w, scale, zp, strategy="group", group_size=128, num_bits=bits)
-    assert bits_equal(want_dq, want_fq)
+    same_values(want_dq, want_fq, "oracle dq vs fq")
     got_fq = ops.fake_quantize(w.to(DEV), scale.to(DEV), cuda(zp), a)
-    assert bits_equal(got_fq.cpu(), want_fq), diff_report(got_fq.cpu(), want_fq)
+    same(got_fq.cpu(), want_fq, "")
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
@@ -200,13 +200,13 @@ def test_fp8_quantize_dequantize_vs_oracle(pipe, dtype, strategy):
     a = ns(type="float", **kw)
     want = oracle.quantize(w, scale, None, qtype="float", dtype=torch.float8_e4m3fn, **kw)
     got = ops.quantize(w.to(DEV), scale.to(DEV), None, a, dtype=torch.float8_e4m3fn)
-    assert torch.equal(got.cpu().view(torch.uint8), want.view(torch.uint8)), diff_report(got.cpu().view(torch.uint8), want.view(torch.uint8))
+    same_values(got.cpu().view(torch.uint8), want.view(torch.uint8), "")
     want_dq = oracle.dequantize(want, scale, None)
     got_dq = ops.dequantize(got, scale.to(DEV), None)
-    assert bits_equal(got_dq.cpu(), want_dq), diff_report(got_dq.cpu(), want_dq)
+    same(got_dq.cpu(), want_dq, "")
     want_fq = oracle.fake_quantize(w, scale, None, qtype="float", **kw)
     got_fq = ops.fake_quantize(w.to(DEV), scale.to(DEV), None, a)
-    assert bits_equal(got_fq.cpu(), want_fq), diff_report(got_fq.cpu(), want_fq)
+    same(got_fq.cpu(), want_fq, "")
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
@@ -223,13 +223,13 @@ def test_int8_channel_quantize_vs_oracle(pipe, dtype, sym):
     a = ns(strategy="channel", num_bits=8, symmetric=sym)
     want = oracle.quantize(w, scale, zp, strategy="channel", num_bits=8, dtype=torch.int8)
     got = ops.quantize(w.to(DEV), scale.to(DEV), cuda(zp), a, dtype=torch.int8)
-    assert torch.equal(got.cpu(), want), diff_report(got.cpu(), want)
+    same_values(got.cpu(), want, "")
     want_dq = oracle.dequantize(want, scale, zp)
     got_dq = ops.dequantize(got, scale.to(DEV), cuda(zp))
-    assert bits_equal(got_dq.cpu(), want_dq), diff_report(got_dq.cpu(), want_dq)
+    same(got_dq.cpu(), want_dq, "")
     want_fq = oracle.fake_quantize(w, scale, zp, strategy="channel", num_bits=8)
     got_fq = ops.fake_quantize(w.to(DEV), scale.to(DEV), cuda(zp), a)
-    assert bits_equal(got_fq.cpu(), want_fq), diff_report(got_fq.cpu(), want_fq)
+    same(got_fq.cpu(), want_fq, "")
 
 
 def test_extreme_scales_take_the_ieee_division_path():
@@ -243,7 +243,7 @@ def test_extreme_scales_take_the_ieee_division_path():
         dt = torch.int8 if a.type == "int" else torch.float8_e4m3fn
         want = oracle.quantize(x, scales, None, strategy="channel", dtype=dt, **kw)
         got = ops.quantize(x.to(DEV), scales.to(DEV), None, a, dtype=dt)
-        assert torch.equal(got.cpu().view(torch.uint8), want.view(torch.uint8)), diff_report(got.cpu().view(torch.uint8), want.view(torch.uint8))
+        same_values(got.cpu().view(torch.uint8), want.view(torch.uint8), "")
 
 
 @pytest.mark.parametrize("bits", [1, 2, 3, 4, 5, 6, 7, 8])
@@ -254,9 +254,9 @@ def test_pack_unpack_vs_oracle(pipe, bits, shape):
     for pd in (1, 0):
         want = oracle.pack_to_int32(q, bits, pd)
         got = ops.pack_to_int32(q.to(DEV), bits, pd)
-        assert torch.equal(got.contiguous().cpu(), want)
+        same_values(got.contiguous().cpu(), want, "")
         back = ops.unpack_from_int32(got, bits, q.shape, pd)
-        assert torch.equal(back.cpu(), q)
+        same_values(back.cpu(), q, "")
 
 
 def test_ragged_and_odd_bits_fused_vs_oracle():
@@ -267,10 +267,10 @@ def test_ragged_and_odd_bits_fused_vs_oracle():
         a = ns(strategy="channel", num_bits=bits)
         want = oracle.pack_to_int32(oracle.quantize(w, scale, None, strategy="channel", num_bits=bits, dtype=torch.int8), bits)
         got = ops.quantize_pack(w.to(DEV), scale.to(DEV), None, a)
-        assert torch.equal(got.cpu(), want), bits
+        same_values(got.cpu(), want, str(bits))
         dq = ops.unpack_dequantize(got, scale.to(DEV), None, bits, w.shape)
         want_dq = oracle.fake_quantize(w, scale, None, strategy="channel", num_bits=bits)
-        assert bits_equal(dq.cpu(), want_dq), bits
+        same_values(dq.cpu(), want_dq, f"ragged dq bits={bits}")
 
 
 # --------------------------------------------------------------------------------------------
@@ -291,17 +291,17 @@ def test_full_size_w4a16_properties(shape):
     # (a) fused == unfused composition, (b) pack/unpack round trip, (c) decompress == fake_quantize
     q = ops.quantize(w, scale, None, a, dtype=torch.int8)
     assert int(q.min()) >= -8 and int(q.max()) <= 7
-    assert torch.equal(ops.pack_to_int32(q, 4), packed)
-    assert torch.equal(ops.unpack_from_int32(packed, 4, w.shape), q)
+    same_values(ops.pack_to_int32(q, 4), packed, "")
+    same_values(ops.unpack_from_int32(packed, 4, w.shape), q, "")
     dq = ops.unpack_dequantize(packed, scale, None, 4, w.shape)
-    assert bits_equal(dq, ops.fake_quantize(w, scale, None, a))
-    assert bits_equal(dq, ops.dequantize(q, scale, None))
+    same_values(dq, ops.fake_quantize(w, scale, None, a), "decompress == fake_quantize")
+    same(dq, ops.dequantize(q, scale, None), "")
     # (d) idempotence: quantizing the dequantized tensor reproduces the codes
-    assert torch.equal(ops.quantize_pack(dq, scale, None, a), packed)
+    same_values(ops.quantize_pack(dq, scale, None, a), packed, "")
     # (e) spot rows against the oracle
     rows = torch.tensor([0, 1, R // 2, R - 1])
     want = oracle.pack_to_int32(oracle.quantize(w[rows].cpu(), scale[rows].cpu(), None, strategy="group", group_size=128, num_bits=4, dtype=torch.int8), 4)
-    assert torch.equal(packed[rows].cpu(), want)
+    same_values(packed[rows].cpu(), want, "")
 
 
 @pytest.mark.parametrize("shape", LLAMA8B)
@@ -313,11 +313,11 @@ def test_full_size_fp8_properties(shape):
     a = ns(type="float")
     q = ops.quantize(w, scale, None, a, dtype=torch.float8_e4m3fn)
     dq = ops.dequantize(q, scale, None)
-    assert bits_equal(dq, ops.fake_quantize(w, scale, None, a))
-    assert torch.equal(ops.quantize(dq, scale, None, a, dtype=torch.float8_e4m3fn).view(torch.uint8), q.view(torch.uint8))
+    same_values(dq, ops.fake_quantize(w, scale, None, a), "decompress == fake_quantize")
+    same_values(ops.quantize(dq, scale, None, a, dtype=torch.float8_e4m3fn).view(torch.uint8), q.view(torch.uint8), "")
     rows = torch.tensor([0, R // 3, R - 1])
     want = oracle.quantize(w[rows].cpu(), scale.cpu(), None, qtype="float", dtype=torch.float8_e4m3fn)
-    assert torch.equal(q[rows].cpu().view(torch.uint8), want.view(torch.uint8))
+    same_values(q[rows].cpu().view(torch.uint8), want.view(torch.uint8), "")
 
 
 def test_batched_launch_equals_per_tensor():
@@ -338,7 +338,7 @@ def test_batched_launch_equals_per_tensor():
     ops.batched(N.OP_QUANTIZE_PACK, probs)
     assert N.launch_count() == launches + 1
     for s, o in zip(singles, outs):
-        assert torch.equal(s, o)
+        same_values(s, o, "")
 
 
 def test_host_buffers_pipeline_equals_device_path():
@@ -355,7 +355,7 @@ def test_host_buffers_pipeline_equals_device_path():
     s8 = (w.float().abs().max() / 448).bfloat16().reshape(1)
     q_host = ops.quantize(w, s8, None, ns(type="float"), dtype=torch.float8_e4m3fn)
     q_dev = ops.quantize(w.to(DEV), s8.to(DEV), None, ns(type="float"), dtype=torch.float8_e4m3fn).cpu()
-    assert torch.equal(q_host.view(torch.uint8), q_dev.view(torch.uint8))
+    same_values(q_host.view(torch.uint8), q_dev.view(torch.uint8), "")
 
 
 # --------------------------------------------------------------------------------------------
@@ -369,10 +369,10 @@ def test_sparse24_vs_oracle(dtype, shape):
     x = x.round().to(dtype) if dtype == torch.int8 else x.to(dtype)
     vals, bm = oracle.sparse24_compress(x)
     gv, gb = ops.sparse24_compress(x.to(DEV))
-    assert torch.equal(gb.cpu(), bm)
-    assert bits_equal(gv.cpu(), vals)
+    same_values(gb.cpu(), bm, "")
+    same(gv.cpu(), vals, "")
     dense = ops.sparse24_decompress(gv, gb, x.shape)
-    assert bits_equal(dense.cpu(), oracle.sparse24_decompress(vals, bm, x.shape))
+    same(dense.cpu(), oracle.sparse24_decompress(vals, bm, x.shape), "")
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32, torch.int8])
@@ -384,7 +384,7 @@ def test_bitmask_compress_vs_oracle(dtype, shape):
     x = x.round().to(dtype) if dtype == torch.int8 else x.to(dtype)
     vals, bm, offs = oracle.bitmask_compress(x)
     gv, gb, go = ops.bitmask_compress(x.to(DEV))
-    assert torch.equal(gb.cpu(), bm) and torch.equal(go.cpu(), offs)
-    assert bits_equal(gv.cpu(), vals)
+    same_values(gb.cpu(), bm, "")
+    same(gv.cpu(), vals, "")
     dense = ops.bitmask_decompress(gv, gb, go, x.shape)
-    assert bits_equal(dense.cpu(), x.where(x != 0, torch.zeros_like(x)))
+    same(dense.cpu(), x.where(x != 0, torch.zeros_like(x)), "")

@@ -33,3 +33,19 @@ def diff_report(a: torch.Tensor, b: torch.Tensor) -> str:
     n = int(bad.sum())
     idx = bad.nonzero().flatten()[:5].tolist()
     return f"{n}/{af.numel()} differ; first {[(i, af[i].item(), bf[i].item()) for i in idx]}"
+
+
+def same(a: torch.Tensor, b: torch.Tensor, what: str = "") -> None:
+    """bit-exact comparison with a compact failure message (no tensor dumps)"""
+    import pytest
+
+    if not bits_equal(a, b):
+        pytest.fail(f"{what}: {diff_report(a, b)}", pytrace=False)
+
+
+def same_values(a: torch.Tensor, b: torch.Tensor, what: str = "") -> None:
+    """torch.equal semantics (the reference's own assertion: -0.0 == +0.0)"""
+    import pytest
+
+    if a.dtype != b.dtype or a.shape != b.shape or not torch.equal(a, b):
+        pytest.fail(f"{what}: {diff_report(a, b)}", pytrace=False)

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""
+Tuning sweep on one B200: times the headline multi-tensor ops for a list of
+(pipe, stages, ctas_per_sm) settings on `--layers` Llama-3-8B layers (>> L2) and prints one JSON
+line per setting.  Run under gpurun; results go to gpurun_out/sweep.jsonl.
+"""
+import argparse
+import json
+import os
+import sys
+from types import SimpleNamespace
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import bench  # noqa: E402
+from compressed_tensors_b200 import _native as N  # noqa: E402
+from compressed_tensors_b200 import ops  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--layers", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--configs", default="tma:4:3,tma:3:4,tma:2:5,tma:2:6,tma:6:2,tma:8:2,direct:0:4,direct:0:6,direct:0:8")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    ws, scs = bench.make_weights(dev, a.layers, 1000)
+    n = sum(w.numel() for w in ws)
+    peak, _ = bench.peaks()
+    qa = bench.args_w4()
+    outs = [torch.empty(w.shape[0], w.shape[1] // 8, dtype=torch.int32, device=dev) for w in ws]
+    back = [torch.empty_like(w) for w in ws]
+    f8 = SimpleNamespace(strategy="tensor", group_size=None, block_structure=None, num_bits=8, type="float", symmetric=True)
+    s8 = [(w.abs().max().float() / 448).bfloat16().reshape(1) for w in ws]
+    q8 = [torch.empty(w.shape, dtype=torch.float8_e4m3fn, device=dev) for w in ws]
+    P = {"quantpack": [], "unpackdeq": [], "fp8_q": [], "fp8_dq": [], "fake_w4": []}
+    for w, sc, o, b, s, q in zip(ws, scs, outs, back, s8, q8):
+        p = ops._resolve(w, sc, None, qa, None)
+        P["quantpack"].append((ops._desc(p, w.dtype, sc.dtype, None, torch.bfloat16, torch.int8, None, N.Q_INT, 4), w, sc, None, o))
+        P["unpackdeq"].append((ops._desc(p, None, sc.dtype, None, None, torch.int8, torch.bfloat16, N.Q_INT, 4), o, sc, None, b))
+        P["fake_w4"].append((ops._desc(p, w.dtype, sc.dtype, None, torch.bfloat16, None, torch.bfloat16, N.Q_INT, 4), w, sc, None, b))
+        p8 = ops._resolve(w, s, None, f8, None)
+        P["fp8_q"].append((ops._desc(p8, w.dtype, s.dtype, None, torch.bfloat16, torch.float8_e4m3fn, None, N.Q_FLOAT, 8), w, s, None, q))
+        P["fp8_dq"].append((ops._desc(p8, None, s.dtype, None, None, torch.float8_e4m3fn, torch.bfloat16, N.Q_INT, 8), q, s, None, b))
+    OPS = {"quantpack": (N.OP_QUANTIZE_PACK, 2.515625), "unpackdeq": (N.OP_UNPACK_DEQUANTIZE, 2.515625),
+           "fp8_q": (N.OP_QUANTIZE, 3.0), "fp8_dq": (N.OP_DEQUANTIZE, 3.0), "fake_w4": (N.OP_FAKE_QUANTIZE, 4.0 + 2 / 128)}
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    with open(a.out, "a") as f:
+        for cfg in a.configs.split(","):
+            pipe, stages, ctas = cfg.split(":")
+            N.set_tuning(1 if pipe == "tma" else 0, int(stages) or 4, int(ctas))
+            rec = {"pipe": pipe, "stages": int(stages), "ctas_per_sm": int(ctas)}
+            for name, (op, bpe) in OPS.items():
+                ms = bench.time_steps(lambda: ops.batched(op, P[name], 0), a.steps, 3, False) / a.steps
+                rec[name] = round(n * bpe / (ms * 1e-3) / 1e9, 1)
+                rec[name + "_frac"] = round(rec[name] / peak, 3)
+            line = json.dumps(rec)
+            print(line, flush=True)
+            f.write(line + "\n")
+
+
+if __name__ == "__main__":
+    main()
