@@ -25,8 +25,10 @@ COMPRESSION_FORMAT_PRIORITY: List[CompressionFormat] = [
 def infer_module_format(module_type: type, scheme: QuantizationScheme) -> CompressionFormat:
     from .base import BaseCompressor
 
-    if scheme.weights is not None and scheme.weights.type == "float" and scheme.weights.num_bits == 4:
-        raise NotImplementedError("FP4 (nvfp4 / mxfp4) compression is outside this engine's path")
+    w = scheme.weights
+    if w is not None and w.type == "float" and (w.num_bits == 4 or w.scale_dtype == torch.uint8):
+        # nvfp4-pack-quantized / mxfp4-pack-quantized / mxfp8-quantized of the reference's priority list
+        raise NotImplementedError("FP4 / MX (nvfp4, mxfp4, mxfp8) compression is outside this engine's path (SURVEY 8(f) rank 2)")
     for fmt in COMPRESSION_FORMAT_PRIORITY:
         if BaseCompressor.get_value_from_registry(fmt.value).can_compress(module_type, scheme):
             return fmt

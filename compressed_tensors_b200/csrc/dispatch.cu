@@ -80,7 +80,7 @@ static Plan plan_one(int op, const ct_quant_desc& d, const void* in, const void*
     p.fast = false;
     memset(&p.job, 0, sizeof(p.job));
     memset(&p.cm, 0, sizeof(p.cm));
-    p.sig = FastSig{0, 0, 0, 0};
+    p.sig = FastSig{0, 0, 0, 0, 1};
     const int64_t n = d.rows * d.cols;
     if (g_idx || n == 0 || n % 8 != 0 || (n / 8) >= 0x7fffffffLL) return p;
     if (!aligned16(in) || !aligned16(out)) return p;
@@ -93,12 +93,14 @@ static Plan plan_one(int op, const ct_quant_desc& d, const void* in, const void*
     int p_dt, in_bytes_per_chunk;
     FastSig sig;
     sig.zp = zpk;
+    sig.group = 1;
     switch (op) {
     case CT_OP_QUANTIZE_PACK:
         if (d.qtype != CT_Q_INT || (d.num_bits != 4 && d.num_bits != 8)) return p;
         if ((d.cols * d.num_bits) % 32 != 0) return p;
         if (d.x_dtype != d.scale_dtype || d.x_dtype != d.compute_dtype || !is_float_dt(d.x_dtype)) return p;
         p_dt = d.x_dtype; sig.op = F_QUANTPACK; sig.sel = d.num_bits; in_bytes_per_chunk = 8 * dt_size(p_dt);
+        sig.group = fast_group_quantpack(p_dt, d.num_bits);
         break;
     case CT_OP_UNPACK_DEQUANTIZE:
         if (d.num_bits != 4 && d.num_bits != 8) return p;
@@ -111,6 +113,7 @@ static Plan plan_one(int op, const ct_quant_desc& d, const void* in, const void*
         if (d.qtype == CT_Q_INT && d.q_dtype != CT_I8) return p;
         if (d.qtype == CT_Q_FLOAT && d.q_dtype != CT_F8E4M3) return p;
         p_dt = d.x_dtype; sig.op = F_QUANT; sig.sel = (d.qtype == CT_Q_FLOAT) ? 2 : 1; in_bytes_per_chunk = 8 * dt_size(p_dt);
+        sig.group = fast_group_quant(p_dt);
         break;
     case CT_OP_DEQUANTIZE:
         if (d.out_dtype != d.scale_dtype || !is_float_dt(d.out_dtype)) return p;
@@ -128,6 +131,11 @@ static Plan plan_one(int op, const ct_quant_desc& d, const void* in, const void*
         return p;
     }
     sig.p_dt = p_dt;
+    // a thread unit (group of chunks) must see one scale and must not straddle the end of the tensor
+    if (sig.group > 1) {
+        const bool scale_ok = is_inf(D) || ((D / 8) % sig.group == 0);
+        if (!scale_ok || (n / 8) % sig.group != 0) sig.group = 1;
+    }
     // a partial last tile must still be a multiple of 16 bytes for the bulk copy
     if (((n / 8) * in_bytes_per_chunk) % 16 != 0) return p;
 
@@ -271,21 +279,23 @@ static int run_bits(bool pack, const void* in, void* out, int64_t rows, int64_t 
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
     const int64_t n = rows * cols;
-    const int in_bytes = pack ? 8 : bits;
-    if (packed_dim == 1 && (bits == 4 || bits == 8) && (cols * bits) % 32 == 0 && n % 8 == 0 && (n / 8) < 0x7fffffffLL &&
-        aligned16(in) && aligned16(out) && ((n / 8) * in_bytes) % 16 == 0) {
+    // for these two ops a chunk is 16 codes; 4-bit packing works on units of 2 chunks
+    const int in_bytes = pack ? 16 : 2 * bits;
+    const int unit = (pack && bits == 4) ? 32 : 16;
+    if (packed_dim == 1 && (bits == 4 || bits == 8) && (cols * bits) % 32 == 0 && n % unit == 0 && (n / 16) < 0x7fffffffLL &&
+        aligned16(in) && aligned16(out) && ((n / 16) * in_bytes) % 16 == 0) {
         LaunchPlan lp;
         memset(&lp, 0, sizeof(lp));
         lp.tbl.n = 1;
         lp.tbl.one.in = reinterpret_cast<const uint8_t*>(in);
         lp.tbl.one.out = reinterpret_cast<uint8_t*>(out);
-        lp.tbl.one.n_chunks = (uint32_t)(n / 8);
+        lp.tbl.one.n_chunks = (uint32_t)(n / 16);
         lp.tbl.one.tile_begin = 0;
         lp.tbl.one.tile_end = (lp.tbl.one.n_chunks + TILE_CHUNKS - 1) / TILE_CHUNKS;
         lp.tbl.one.dc = make_fastdiv(0x7FFFFFFFull);
         lp.total_tiles = lp.tbl.one.tile_end;
         lp.cm = make_common(CT_F32, CT_Q_INT, bits);
-        FastSig s{pack ? F_PACK : F_UNPACK, CT_I8, bits, 0};
+        FastSig s{pack ? F_PACK : F_UNPACK, CT_I8, bits, 0, 1};
         return launch_fast_bits(s, lp, device, stream);
     }
     if (pack) return launch_generic_pack(reinterpret_cast<const int8_t*>(in), reinterpret_cast<int32_t*>(out), rows, cols, bits, packed_dim, stream);

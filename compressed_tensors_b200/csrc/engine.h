@@ -14,7 +14,8 @@ struct FastSig {
     int p_dt;    // CT_BF16 / CT_F16 / CT_F32 (unused for F_PACK / F_UNPACK)
     int sel;     // QUANTPACK/UNPACKDEQ/PACK/UNPACK: bits (4 | 8); QUANT/DEQUANT/FAKE: QKind
     int zp;      // 0 none, 1 int8
-    bool operator==(const FastSig& o) const { return op == o.op && p_dt == o.p_dt && sel == o.sel && zp == o.zp; }
+    int group;   // chunks per thread unit (1, 2 or 4): stream.cuh
+    bool operator==(const FastSig& o) const { return op == o.op && p_dt == o.p_dt && sel == o.sel && zp == o.zp && group == o.group; }
 };
 
 // defined in fast_pack.cu / fast_quant.cu / fast_fake.cu
@@ -24,6 +25,8 @@ int launch_fast_quant(const FastSig&, const LaunchPlan&, int device, cudaStream_
 int launch_fast_dequant(const FastSig&, const LaunchPlan&, int device, cudaStream_t);
 int launch_fast_fake(const FastSig&, const LaunchPlan&, int device, cudaStream_t);
 int launch_fast_bits(const FastSig&, const LaunchPlan&, int device, cudaStream_t);
+int fast_group_quantpack(int p_dt, int bits);   // preferred unit size of the instantiated kernels
+int fast_group_quant(int p_dt);
 
 // ---- generic path (any strategy, g_idx, ragged shapes, mixed dtypes) -----------------------
 enum GenericMode { G_QUANTIZE = 0, G_DEQUANTIZE = 1, G_FAKE = 2 };

@@ -6,7 +6,7 @@ namespace ctb {
 
 #define SIG_FAIL(sig)                                                                              \
     do {                                                                                           \
-        set_error("no fast kernel for op=%d dtype=%d sel=%d zp=%d", sig.op, sig.p_dt, sig.sel, sig.zp); \
+        set_error("no fast kernel for op=%d dtype=%d sel=%d zp=%d group=%d", sig.op, sig.p_dt, sig.sel, sig.zp, sig.group); \
         return CT_E_UNSUPPORTED;                                                                   \
     } while (0)
 

@@ -1,20 +1,23 @@
 // stream.cuh -- the two persistent streaming pipelines every hot-path op is instantiated on.
 //
 // Work decomposition (all hot-path ops are elementwise over a flat, contiguous tensor):
-//   chunk = 8 consecutive elements            (one thread's unit of work)
-//   tile  = TILE_CHUNKS chunks = 8192 elems   (one CTA's unit of work; 16 KB of bf16)
-//   job   = one tensor; a launch covers a table of jobs (whole-model batches), tiles are
-//           numbered globally and dealt round-robin to a persistent grid of
-//           n_SM * ctas_per_sm CTAs.
+//   chunk = 8 consecutive elements
+//   unit  = Op::GROUP consecutive chunks = one thread's piece of work.  GROUP is chosen per op so
+//           that the thread's OUTPUT is one 16-byte store (4-bit packing: 32 elements -> 4 words;
+//           1-byte codes: 16 elements) and the scale / reciprocal is fetched once per unit.
+//   tile  = TILE_CHUNKS chunks = 8192 elements (16 KB of bf16) = one CTA's unit of work
+//   job   = one tensor; a launch covers a table of jobs (whole-model batches); tiles are numbered
+//           globally and dealt round-robin to a persistent grid of n_SM * ctas_per_sm CTAs.
 //
 // Pipeline 1 ("tma"): warp-specialised.  One producer lane issues 1-D bulk async copies
 // (cp.async.bulk, the TMA engine without a tensor map) of whole input tiles into a ring of
-// shared-memory stages, each guarded by a full/empty mbarrier pair; NCW consumer warps wait on
-// the full barrier, read their chunks from shared memory with conflict-free vector LDS, do the
-// arithmetic in registers and store results with coalesced streaming stores.  Bytes in flight
-// per SM = stages * tile_bytes * ctas_per_sm, independent of register pressure.
-// Pipeline 0 ("direct"): every thread issues its tile's 128-bit ld.global.nc loads up front
-// (UNROLL = chunks per thread per tile) and relies on occupancy for memory-level parallelism.
+// shared-memory stages, each guarded by a full/empty mbarrier pair (waits use the hardware
+// suspend hint, so the idle producer does not burn issue slots).  NCW consumer warps wait on the
+// full barrier, read their units from shared memory with bank-conflict-free swizzled LDS.128, do
+// the arithmetic in registers and write with coalesced 16-byte streaming stores.  The scale loads
+// of a tile are issued BEFORE the barrier wait and consumed after it.
+// Pipeline 0 ("direct"): every thread issues its tile's 128-bit global loads up front and relies on
+// occupancy for memory-level parallelism (kept as the comparison point and for profiling).
 #pragma once
 
 #include "common.cuh"
@@ -53,7 +56,7 @@ struct Common {
 };
 
 __device__ __forceinline__ uint32_t job_tile_end(const JobTable& t, int j) { return t.n == 1 ? t.one.tile_end : t.jobs[j].tile_end; }
-// by-value copy: the job lives in registers for the duration of a tile
+// by-value copy: the job lives in registers until a tile of another tensor comes up
 __device__ __forceinline__ Job job_at(const JobTable& t, int j) {
     if (t.n == 1) return t.one;
     return t.jobs[j];
@@ -61,46 +64,80 @@ __device__ __forceinline__ Job job_at(const JobTable& t, int j) {
 
 // ------------------------------------------------------------------------------------
 // Op concept:
-//   static constexpr int IN_BYTES;            streamed input bytes per chunk (4, 8, 16 or 32)
-//   struct Ctx;                               per-chunk scale / zero-point context
-//   static Ctx prefetch(J, cm, gc);           issued BEFORE the data arrives
-//   static void run(J, cm, ctx, gc, in[]);    in[] = IN_BYTES/4 words of this chunk
+//   static constexpr int IN_BYTES;     streamed input bytes per chunk (4, 8, 16 or 32)
+//   static constexpr int GROUP;        chunks per unit (1, 2 or 4)
+//   struct Raw;                        raw scale / zero-point bits of a unit (plain loads only)
+//   static Raw prefetch(J, gc0);       issued BEFORE the data arrives; no dependent arithmetic
+//   static void run(J, cm, raw, gc0, w[GROUP][IN_BYTES/4], off);   gc0 = first chunk of the unit;
+//                                      w[k] holds chunk (k + off) mod GROUP (see swz_off)
 // ------------------------------------------------------------------------------------
 
-template <int BYTES> struct InWords { uint32_t w[BYTES / 4]; };
-
 template <int BYTES>
-__device__ __forceinline__ void lds_chunk(const uint8_t* p, uint32_t (&w)[BYTES / 4]) {
+__device__ __forceinline__ void lds_chunk(uint32_t saddr, uint32_t (&w)[BYTES / 4]) {
     if constexpr (BYTES == 4) {
-        w[0] = *reinterpret_cast<const uint32_t*>(p);
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[0]) : "r"(saddr));
     } else if constexpr (BYTES == 8) {
-        uint2 v = *reinterpret_cast<const uint2*>(p);
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(saddr));
+    } else if constexpr (BYTES == 16) {
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(saddr));
+    } else {
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(saddr));
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(saddr + 16));
+    }
+}
+// CACHED = true keeps the line in L1 (several loads of one thread share 128-byte lines)
+template <int BYTES, bool CACHED>
+__device__ __forceinline__ void ldg_chunk(const uint8_t* p, uint32_t (&w)[BYTES / 4]) {
+    if constexpr (BYTES == 4) {
+        w[0] = CACHED ? __ldg(reinterpret_cast<const uint32_t*>(p)) : ldg_stream4(p);
+    } else if constexpr (BYTES == 8) {
+        uint2 v = CACHED ? __ldg(reinterpret_cast<const uint2*>(p)) : ldg_stream8(p);
         w[0] = v.x; w[1] = v.y;
     } else if constexpr (BYTES == 16) {
-        uint4 v = *reinterpret_cast<const uint4*>(p);
+        uint4 v = CACHED ? __ldg(reinterpret_cast<const uint4*>(p)) : ldg_stream16(p);
         w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
     } else {
-        uint4 v = *reinterpret_cast<const uint4*>(p);
-        uint4 u = *reinterpret_cast<const uint4*>(p + 16);
+        uint4 v = CACHED ? __ldg(reinterpret_cast<const uint4*>(p)) : ldg_stream16(p);
+        uint4 u = CACHED ? __ldg(reinterpret_cast<const uint4*>(p + 16)) : ldg_stream16(p + 16);
         w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
         w[4] = u.x; w[5] = u.y; w[6] = u.z; w[7] = u.w;
     }
 }
-template <int BYTES>
-__device__ __forceinline__ void ldg_chunk(const uint8_t* p, uint32_t (&w)[BYTES / 4]) {
-    if constexpr (BYTES == 4) {
-        w[0] = ldg_stream4(p);
-    } else if constexpr (BYTES == 8) {
-        uint2 v = ldg_stream8(p);
-        w[0] = v.x; w[1] = v.y;
-    } else if constexpr (BYTES == 16) {
-        uint4 v = ldg_stream16(p);
-        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-    } else {
-        uint4 v = ldg_stream16(p);
-        uint4 u = ldg_stream16(p + 16);
-        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-        w[4] = u.x; w[5] = u.y; w[6] = u.z; w[7] = u.w;
+
+// Bank-conflict-free reads of a unit from shared memory: lane l reads chunk (k + swz_off(l)) mod GROUP
+// in its k-th LDS.128, so the 8 lanes of a quarter warp always cover 8 different 16-byte bank groups
+// (unit stride = GROUP * 16 bytes).  Register k of the thread therefore holds chunk (k + off) mod GROUP;
+// the op rotates its per-chunk outputs back before the store (rotate_out below).
+template <int GROUP>
+__device__ __forceinline__ int swz_off(int lane) {
+    if constexpr (GROUP == 4) return (lane >> 1) & 3;
+    else if constexpr (GROUP == 2) return (lane >> 2) & 1;
+    else return 0;
+}
+// o holds GROUP blocks of WPC words, block k belonging to chunk (k + off) mod GROUP: put them in chunk order
+template <int GROUP, int WPC>
+__device__ __forceinline__ void rotate_out(uint32_t (&o)[GROUP * WPC], int off) {
+    if constexpr (GROUP == 2) {
+        const bool sw = off & 1;
+#pragma unroll
+        for (int i = 0; i < WPC; ++i) {
+            const uint32_t a = o[i], b = o[WPC + i];
+            o[i] = sw ? b : a;
+            o[WPC + i] = sw ? a : b;
+        }
+    } else if constexpr (GROUP == 4) {
+        const bool r1 = off & 1, r2 = off & 2;
+#pragma unroll
+        for (int i = 0; i < WPC; ++i) {
+            uint32_t a0 = o[i], a1 = o[WPC + i], a2 = o[2 * WPC + i], a3 = o[3 * WPC + i];
+            // block k -> position k+1
+            uint32_t b0 = r1 ? a3 : a0, b1 = r1 ? a0 : a1, b2 = r1 ? a1 : a2, b3 = r1 ? a2 : a3;
+            // block k -> position k+2
+            o[i] = r2 ? b2 : b0;
+            o[WPC + i] = r2 ? b3 : b1;
+            o[2 * WPC + i] = r2 ? b0 : b2;
+            o[3 * WPC + i] = r2 ? b1 : b3;
+        }
     }
 }
 
@@ -113,18 +150,22 @@ __global__ void __launch_bounds__(32 * (NCW + 1)) stream_tma_kernel(const __grid
                                                                    uint32_t total_tiles, int stages) {
     constexpr int TILE_BYTES = TILE_CHUNKS * Op::IN_BYTES;
     constexpr int CTHREADS = NCW * 32;
-    constexpr int ITERS = TILE_CHUNKS / CTHREADS;
+    constexpr int G = Op::GROUP;
+    constexpr int UNITS = TILE_CHUNKS / G;
+    constexpr int ITERS = UNITS / CTHREADS;
+    static_assert(UNITS % CTHREADS == 0, "tile must split evenly over the consumer threads");
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-    uint64_t* empty = full + MAX_STAGES;
-    uint8_t* data = smem_raw + 256;
+    const uint32_t sbase = smem_u32(smem_raw);
+    const uint32_t full0 = sbase;                    // full[s]  at sbase + 8 s
+    const uint32_t empty0 = sbase + 8 * MAX_STAGES;  // empty[s] at sbase + 96 + 8 s
+    const uint32_t data0 = sbase + 256;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], NCW);
+            mbar_init_a(full0 + 8 * s, 1);
+            mbar_init_a(empty0 + 8 * s, NCW);
         }
         mbar_fence_init();
     }
@@ -136,16 +177,19 @@ __global__ void __launch_bounds__(32 * (NCW + 1)) stream_tma_kernel(const __grid
             const uint64_t policy = l2_evict_first_policy();
             int s = 0, j = 0;
             uint32_t ph = 0;
+            Job J = job_at(tbl, 0);
             for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                while (tile >= job_tile_end(tbl, j)) ++j;
-                const Job J = job_at(tbl, j);
+                if (tile >= J.tile_end) {
+                    while (tile >= job_tile_end(tbl, j)) ++j;
+                    J = job_at(tbl, j);
+                }
                 const uint32_t lt = tile - J.tile_begin;
                 const uint32_t base = lt * TILE_CHUNKS;
                 const uint32_t chunks = min((uint32_t)TILE_CHUNKS, J.n_chunks - base);
                 const uint32_t bytes = chunks * Op::IN_BYTES;
-                mbar_wait(&empty[s], ph ^ 1u);
-                mbar_expect_tx(&full[s], bytes);
-                bulk_g2s(data + (size_t)s * TILE_BYTES, J.in + (size_t)lt * TILE_BYTES, bytes, &full[s], policy);
+                mbar_wait_a(empty0 + 8 * s, ph ^ 1u);
+                mbar_expect_tx_a(full0 + 8 * s, bytes);
+                bulk_g2s_a(data0 + (uint32_t)s * TILE_BYTES, J.in + (size_t)lt * TILE_BYTES, bytes, full0 + 8 * s, policy);
                 if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
@@ -154,30 +198,58 @@ __global__ void __launch_bounds__(32 * (NCW + 1)) stream_tma_kernel(const __grid
         const int ctid = threadIdx.x;  // 0 .. CTHREADS-1
         int s = 0, j = 0;
         uint32_t ph = 0;
-        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int off = (Op::IN_BYTES == 16) ? swz_off<G>(lane) : 0;
+        // The scale / zero-point loads run ONE TILE AHEAD of the arithmetic: they miss L2 (each is
+        // used once) and would otherwise expose a full DRAM round trip per tile.
+        Job Jn = job_at(tbl, 0);
+        typename Op::Raw raw_next[ITERS];
+        uint32_t tile = blockIdx.x;
+        if (tile < total_tiles) {
             while (tile >= job_tile_end(tbl, j)) ++j;
-            const Job J = job_at(tbl, j);
+            Jn = job_at(tbl, j);
+            const uint32_t base = (tile - Jn.tile_begin) * TILE_CHUNKS;
+            const uint32_t chunks = min((uint32_t)TILE_CHUNKS, Jn.n_chunks - base);
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                const uint32_t c0 = (uint32_t)(it * CTHREADS + ctid) * G;
+                if (c0 < chunks) raw_next[it] = Op::prefetch(Jn, base + c0);
+            }
+        }
+        for (; tile < total_tiles; tile += gridDim.x) {
+            const Job J = Jn;
             const uint32_t base = (tile - J.tile_begin) * TILE_CHUNKS;
             const uint32_t chunks = min((uint32_t)TILE_CHUNKS, J.n_chunks - base);
-            typename Op::Ctx ctx[ITERS];
+            typename Op::Raw raw[ITERS];
 #pragma unroll
-            for (int it = 0; it < ITERS; ++it) {
-                const uint32_t c = it * CTHREADS + ctid;
-                if (c < chunks) ctx[it] = Op::prefetch(J, cm, base + c);
+            for (int it = 0; it < ITERS; ++it) raw[it] = raw_next[it];
+            const uint32_t tn = tile + gridDim.x;
+            if (tn < total_tiles) {
+                if (tn >= Jn.tile_end) {
+                    while (tn >= job_tile_end(tbl, j)) ++j;
+                    Jn = job_at(tbl, j);
+                }
+                const uint32_t nbase = (tn - Jn.tile_begin) * TILE_CHUNKS;
+                const uint32_t nchunks = min((uint32_t)TILE_CHUNKS, Jn.n_chunks - nbase);
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it) {
+                    const uint32_t c0 = (uint32_t)(it * CTHREADS + ctid) * G;
+                    if (c0 < nchunks) raw_next[it] = Op::prefetch(Jn, nbase + c0);
+                }
             }
-            mbar_wait(&full[s], ph);
-            const uint8_t* sp = data + (size_t)s * TILE_BYTES;
+            mbar_wait_a(full0 + 8 * s, ph);
+            const uint32_t sp = data0 + (uint32_t)s * TILE_BYTES;
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
-                const uint32_t c = it * CTHREADS + ctid;
-                if (c < chunks) {
-                    uint32_t w[Op::IN_BYTES / 4];
-                    lds_chunk<Op::IN_BYTES>(sp + (size_t)c * Op::IN_BYTES, w);
-                    Op::run(J, cm, ctx[it], base + c, w);
+                const uint32_t c0 = (uint32_t)(it * CTHREADS + ctid) * G;
+                if (c0 < chunks) {
+                    uint32_t w[G][Op::IN_BYTES / 4];
+#pragma unroll
+                    for (int k = 0; k < G; ++k) lds_chunk<Op::IN_BYTES>(sp + (c0 + ((k + off) & (G - 1))) * Op::IN_BYTES, w[k]);
+                    Op::run(J, cm, raw[it], base + c0, w, off);
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            if (lane == 0) mbar_arrive_a(empty0 + 8 * s);
             if (++s == stages) { s = 0; ph ^= 1u; }
         }
     }
@@ -190,27 +262,33 @@ template <class Op>
 __global__ void __launch_bounds__(DIRECT_THREADS) stream_direct_kernel(const __grid_constant__ JobTable tbl,
                                                                        const __grid_constant__ Common cm,
                                                                        uint32_t total_tiles) {
-    constexpr int ITERS = TILE_CHUNKS / DIRECT_THREADS;
+    constexpr int G = Op::GROUP;
+    constexpr int UNITS = TILE_CHUNKS / G;
+    constexpr int ITERS = UNITS / DIRECT_THREADS;
     int j = 0;
+    Job J = job_at(tbl, 0);
     for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        while (tile >= job_tile_end(tbl, j)) ++j;
-        const Job J = job_at(tbl, j);
+        if (tile >= J.tile_end) {
+            while (tile >= job_tile_end(tbl, j)) ++j;
+            J = job_at(tbl, j);
+        }
         const uint32_t base = (tile - J.tile_begin) * TILE_CHUNKS;
         const uint32_t chunks = min((uint32_t)TILE_CHUNKS, J.n_chunks - base);
-        uint32_t w[ITERS][Op::IN_BYTES / 4];
-        typename Op::Ctx ctx[ITERS];
+        uint32_t w[ITERS][G][Op::IN_BYTES / 4];
+        typename Op::Raw raw[ITERS];
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
-            const uint32_t c = it * DIRECT_THREADS + threadIdx.x;
-            if (c < chunks) {
-                ldg_chunk<Op::IN_BYTES>(J.in + (size_t)(base + c) * Op::IN_BYTES, w[it]);
-                ctx[it] = Op::prefetch(J, cm, base + c);
+            const uint32_t c0 = (uint32_t)(it * DIRECT_THREADS + threadIdx.x) * G;
+            if (c0 < chunks) {
+#pragma unroll
+                for (int k = 0; k < G; ++k) ldg_chunk<Op::IN_BYTES, (G > 1)>(J.in + (size_t)(base + c0 + k) * Op::IN_BYTES, w[it][k]);
+                raw[it] = Op::prefetch(J, base + c0);
             }
         }
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
-            const uint32_t c = it * DIRECT_THREADS + threadIdx.x;
-            if (c < chunks) Op::run(J, cm, ctx[it], base + c, w[it]);
+            const uint32_t c0 = (uint32_t)(it * DIRECT_THREADS + threadIdx.x) * G;
+            if (c0 < chunks) Op::run(J, cm, raw[it], base + c0, w[it], 0);
         }
     }
 }

@@ -25,12 +25,16 @@ __all__ = ["replace_module_parallel"]
 
 def _to_meta(module: torch.nn.Module):
     sd = get_direct_state_dict(module)
-    replace_direct_state_dict(module, {k: torch.empty_like(v, device="meta") for k, v in sd.items()})
+    replace_direct_state_dict(module, {k: torch.empty_like(v, device="meta") for k, v in sd.items() if v is not None})
 
 
 def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callable = module_size, desc: Optional[str] = None):
     rank, world = dist.get_rank(), dist.get_world_size()
-    devices = {id(m): next(iter(get_direct_state_dict(m).values())).device for m in modules if len(get_direct_state_dict(m))}
+    devices = {}
+    for m in modules:
+        tensors = [t for t in get_direct_state_dict(m).values() if t is not None]
+        if tensors:
+            devices[id(m)] = tensors[0].device
     _, _, owner = greedy_bin_packing(modules, world, weight_fn)
 
     for m in modules:
@@ -47,6 +51,8 @@ def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callab
         new = {}
         for name in sd:  # identical key order on all ranks (same compressor code path)
             t = sd[name]
+            if t is None:
+                continue
             if owner[m] != rank:
                 t = torch.empty(t.shape, dtype=t.dtype, device=dev)
             buf = as_broadcastable(t.contiguous())
