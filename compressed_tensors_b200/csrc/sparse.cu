@@ -400,3 +400,138 @@ int ct_bitmask_decompress(const void* values, int dtype, const uint8_t* bitmask,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// 2:4 "semi-structured" values + metadata in the CUTLASS / marlin-24 layout
+// (utils/semi_structured_conversions.py:33-60 reorder offsets, :66-197 from dense, :204-298 to dense).
+// One thread per metadata element: QPE (4 for int16 meta, 8 for int32 meta) groups of KS dense
+// elements (4, or 2 for fp32) each contribute a 4-bit code idx0 | idx1 << 2 and 2 (1) kept values.
+// ---------------------------------------------------------------------------------------------
+namespace ctb {
+
+__device__ __forceinline__ int64_t meta_offset(int64_t r, int64_t c, int64_t m, int meta_bytes) {
+    const int64_t gy = (meta_bytes == 2) ? 32 : 16;
+    int64_t rr = r / 64 * 64 + (r % 2) * 2 + (r % 8) / 4 + ((r % gy) % 4) / 2 * 32 + ((r % 64) / 8) * 4;
+    const int tr = (rr % 2 == 0) && (c % 2 == 1);
+    const int bl = (rr % 2 == 1) && (c % 2 == 0);
+    rr += tr - bl;
+    const int64_t cc = c - (tr - bl);
+    return (cc / 2) * m * 2 + rr * 2 + (cc % 2);
+}
+
+// ES = element bytes of the dense data (1, 2, 4); KS = dense elements per code (4, or 2 for fp32)
+template <int DT, int ES, int KS, int MB>
+__global__ void __launch_bounds__(256) semi_from_dense_kernel(const void* __restrict__ din, void* __restrict__ sout, void* __restrict__ mout,
+                                                              int64_t m, int64_t k, int64_t ncols) {
+    using T = typename Raw<ES>::T;
+    constexpr int QPE = MB * 2;
+    const T* dense = reinterpret_cast<const T*>(din);
+    T* sparse = reinterpret_cast<T*>(sout);
+    const int64_t total = m * ncols;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / ncols, c = t - r * ncols;
+        uint32_t word = 0;
+#pragma unroll
+        for (int q = 0; q < QPE; ++q) {
+            const int64_t base = r * k + (c * QPE + q) * KS;
+            T v[KS];
+#pragma unroll
+            for (int i = 0; i < KS; ++i) v[i] = dense[base + i];
+            int m0, m1, m3;
+            if (KS == 4) { m0 = is_nonzero<DT>((uint32_t)v[0]); m1 = is_nonzero<DT>((uint32_t)v[1]); m3 = is_nonzero<DT>((uint32_t)v[KS - 1]); }
+            else { m0 = m1 = is_nonzero<DT>((uint32_t)v[0]); m3 = is_nonzero<DT>((uint32_t)v[KS - 1]); }
+            const int e0 = m0 & m1, e1 = (!m0) & m1, e2 = (!m0) & (!m1);
+            const int idx0 = e1 | (e2 << 1);
+            const int idx1 = (e0 | e2 | m3) | ((e1 | (!m1)) << 1);
+            word |= (uint32_t)(idx0 | (idx1 << 2)) << (4 * q);
+            const int64_t so = r * (k / 2) + (c * QPE + q) * (KS / 2);
+            if (KS == 4) {
+                T a = v[0], b = v[1];
+                // select by index without dynamic register indexing
+                a = (idx0 == 1) ? v[1] : ((idx0 == 2) ? v[2] : v[0]);
+                b = (idx1 == 1) ? v[1] : ((idx1 == 2) ? v[2] : v[KS - 1]);
+                sparse[so] = a;
+                sparse[so + 1] = b;
+            } else {
+                sparse[so] = (idx0 / 2 == 0) ? v[0] : v[KS - 1];
+            }
+        }
+        const int64_t off = meta_offset(r, c, m, MB);
+        if (MB == 2) reinterpret_cast<int16_t*>(mout)[off] = (int16_t)word;
+        else reinterpret_cast<int32_t*>(mout)[off] = (int32_t)word;
+    }
+}
+
+// sparse [m, kh] in ES-byte units (fp32 data is moved as pairs of 16-bit halves) -> dense [m, 2 kh]
+template <int ES, int MB>
+__global__ void __launch_bounds__(256) semi_to_dense_kernel(const void* __restrict__ sin, const void* __restrict__ min_, void* __restrict__ dout,
+                                                            int64_t m, int64_t kh, int64_t ncols) {
+    using T = typename Raw<ES>::T;
+    constexpr int QPE = MB * 2;
+    const T* sparse = reinterpret_cast<const T*>(sin);
+    T* dense = reinterpret_cast<T*>(dout);
+    const int64_t total = m * ncols;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / ncols, c = t - r * ncols;
+        const int64_t off = meta_offset(r, c, m, MB);
+        const uint32_t word = (MB == 2) ? (uint32_t)(uint16_t)reinterpret_cast<const int16_t*>(min_)[off] : (uint32_t)reinterpret_cast<const int32_t*>(min_)[off];
+#pragma unroll
+        for (int q = 0; q < QPE; ++q) {
+            const int idx0 = (word >> (4 * q)) & 3, idx1 = (word >> (4 * q + 2)) & 3;
+            const int64_t quad = c * QPE + q;
+            const T a = sparse[r * kh + quad * 2], b = sparse[r * kh + quad * 2 + 1];
+            T* d = dense + r * 2 * kh + quad * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = (i == idx1) ? b : ((i == idx0) ? a : (T)0);   // idx1 written last, like scatter_
+        }
+    }
+}
+
+}  // namespace ctb
+
+extern "C" {
+
+int ct_semi_structured_from_dense(const void* dense, int dtype, void* sparse, void* meta, int64_t m, int64_t k, int device, void* stream) {
+    PRECHECK(device);
+    const int mb = (dtype == CT_I8) ? 4 : 2;
+    const int ks = (dtype == CT_F32) ? 2 : 4;
+    if (m % 64 != 0) { set_error("semi-structured layout needs rows %% 64 == 0 (got %lld)", (long long)m); return CT_E_SHAPE; }
+    if (k % (ks * mb * 2) != 0) { set_error("Number of columns of dense matrix %lld must be divisible by %d", (long long)k, ks * mb * 2); return CT_E_SHAPE; }
+    if (m * k == 0) return CT_OK;
+    if (!dense || !sparse || !meta) { set_error("null pointer"); return CT_E_ARG; }
+    const int64_t ncols = k / (ks * mb * 2);
+    const unsigned g = grid_for(m * ncols);
+    switch (dtype) {
+    case CT_I8: semi_from_dense_kernel<CT_I8, 1, 4, 4><<<g, 256, 0, st>>>(dense, sparse, meta, m, k, ncols); break;
+    case CT_F16: semi_from_dense_kernel<CT_F16, 2, 4, 2><<<g, 256, 0, st>>>(dense, sparse, meta, m, k, ncols); break;
+    case CT_BF16: semi_from_dense_kernel<CT_BF16, 2, 4, 2><<<g, 256, 0, st>>>(dense, sparse, meta, m, k, ncols); break;
+    case CT_F32: semi_from_dense_kernel<CT_F32, 4, 2, 2><<<g, 256, 0, st>>>(dense, sparse, meta, m, k, ncols); break;
+    default: set_error("Invalid datatype %d of dense matrix", dtype); return CT_E_DTYPE;
+    }
+    count_launch();
+    CT_CUDA_TRY(cudaGetLastError());
+    return CT_OK;
+}
+
+/* k = number of sparse columns; dense is [m, 2k] */
+int ct_semi_structured_to_dense(const void* sparse, int dtype, const void* meta, void* dense, int64_t m, int64_t k, int device, void* stream) {
+    PRECHECK(device);
+    const int mb = (dtype == CT_I8) ? 4 : 2;
+    const int64_t kh = (dtype == CT_F32) ? 2 * k : k;
+    if (m % 64 != 0) { set_error("semi-structured layout needs rows %% 64 == 0 (got %lld)", (long long)m); return CT_E_SHAPE; }
+    if ((2 * kh) % (4 * mb * 2) != 0) { set_error("sparse column count %lld inconsistent with the metadata layout", (long long)k); return CT_E_SHAPE; }
+    if (m * k == 0) return CT_OK;
+    if (!dense || !sparse || !meta) { set_error("null pointer"); return CT_E_ARG; }
+    const int64_t ncols = 2 * kh / (4 * mb * 2);
+    const unsigned g = grid_for(m * ncols);
+    switch (dtype) {
+    case CT_I8: semi_to_dense_kernel<1, 4><<<g, 256, 0, st>>>(sparse, meta, dense, m, kh, ncols); break;
+    case CT_F16: case CT_BF16: case CT_F32: semi_to_dense_kernel<2, 2><<<g, 256, 0, st>>>(sparse, meta, dense, m, kh, ncols); break;
+    default: set_error("Invalid datatype %d of sparse matrix", dtype); return CT_E_DTYPE;
+    }
+    count_launch();
+    CT_CUDA_TRY(cudaGetLastError());
+    return CT_OK;
+}
+
+}  // extern "C"

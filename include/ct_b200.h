@@ -164,6 +164,17 @@ int ct_bitmask_compress(const void* x, int dtype, const uint8_t* bitmask, const 
 int ct_bitmask_decompress(const void* values, int dtype, const uint8_t* bitmask, const int64_t* row_offsets,
                           void* out, int64_t rows, int64_t cols, int device, void* stream);
 
+/* 2:4 "semi-structured" values + metadata in the CUTLASS / marlin-24 layout: replaces
+ * utils/semi_structured_conversions.py:66-197 (sparse_semi_structured_from_dense_cutlass) and
+ * :204-298 (sparse_semi_structured_to_dense_cutlass).  dense [m, k] -> sparse [m, k/2] + meta
+ * (int16 [m, k/16] for 2-byte data, int32 [m, k/32] for int8 data, int16 [m, k/8] for fp32 1:2),
+ * meta reordered for ColumnMajorInterleaved<2> (:33-60).  m % 64 == 0.  to_dense takes the number
+ * of SPARSE columns k and writes dense [m, 2k]. */
+int ct_semi_structured_from_dense(const void* dense, int dtype, void* sparse, void* meta, int64_t m, int64_t k,
+                                  int device, void* stream);
+int ct_semi_structured_to_dense(const void* sparse, int dtype, const void* meta, void* dense, int64_t m, int64_t k,
+                                int device, void* stream);
+
 /* ---- host-buffer entry points (what a CPU-resident caller of the reference API hits) ----
  * Same semantics as ct_batched with n == 1, but every pointer is a HOST pointer (pinned memory
  * gives full PCIe rate; pageable works).  Rows are streamed through the device in chunks with

@@ -68,6 +68,7 @@ def lib() -> ctypes.CDLL:
             "orc_pack_int32 orc_unpack_int32 orc_quantize orc_dequantize orc_fake_quantize "
             "orc_pack_bitmasks orc_unpack_bitmasks orc_sparse24_compress orc_sparse24_decompress "
             "orc_bitmask_compress orc_bitmask_decompress orc_quantize_pack orc_unpack_dequantize "
+            "orc_semi_structured_from_dense orc_semi_structured_to_dense "
             "orc_num_threads"
         ).split():
             getattr(_lib, name).restype = ctypes.c_int
@@ -301,3 +302,26 @@ def bitmask_decompress(values: torch.Tensor, bitmask: torch.Tensor, shape) -> to
     out = torch.empty(rows, cols, dtype=values.dtype)
     _check(lib().orc_bitmask_decompress(_p(values.contiguous()), DT[values.dtype], _p(bitmask.contiguous()), _p(out), _i64(rows), _i64(cols)), "bmd")
     return out
+
+
+# --------------------------------------------------------------------------- #
+# 2:4 semi-structured (CUTLASS / marlin-24 metadata) -- utils/semi_structured_conversions.py:66-298
+# --------------------------------------------------------------------------- #
+def semi_structured_from_dense(dense: torch.Tensor):
+    dense = dense.contiguous()
+    m, k = dense.shape
+    meta_dtype = torch.int32 if dense.dtype == torch.int8 else torch.int16
+    qpe = 8 if meta_dtype == torch.int32 else 4
+    ks = 2 if dense.dtype == torch.float32 else 4
+    sparse = torch.empty(m, k // 2, dtype=dense.dtype)
+    meta = torch.empty(m, k // (ks * qpe), dtype=meta_dtype)
+    _check(lib().orc_semi_structured_from_dense(_p(dense), DT[dense.dtype], _p(sparse), _p(meta), _i64(m), _i64(k)), "semi_from_dense")
+    return sparse, meta
+
+
+def semi_structured_to_dense(sparse: torch.Tensor, meta: torch.Tensor) -> torch.Tensor:
+    sparse, meta = sparse.contiguous(), meta.contiguous()
+    m, k = sparse.shape
+    dense = torch.empty(m, 2 * k, dtype=sparse.dtype)
+    _check(lib().orc_semi_structured_to_dense(_p(sparse), DT[sparse.dtype], _p(meta), _p(dense), _i64(m), _i64(k)), "semi_to_dense")
+    return dense

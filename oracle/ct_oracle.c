@@ -555,3 +555,98 @@ int orc_num_threads(void) {
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------- */
+/* 2:4 "semi-structured" (CUTLASS / marlin-24) value + metadata layout        */
+/* utils/semi_structured_conversions.py:33-60 (meta reordering offsets),      */
+/* :66-197 (from dense), :204-298 (to dense).  Pinned by golden vectors.      */
+/*   dense [m, k]; non-fp32: quads of 4 elements, keep 2 -> sparse [m, k/2];  */
+/*   fp32: pairs of 2, keep 1 -> sparse [m, k/2].  One 4-bit code per quad    */
+/*   (idx0 | idx1 << 2); meta element = 4 (int16) or 8 (int32, int8 data)     */
+/*   codes; meta stored reordered for ColumnMajorInterleaved<2>.              */
+/* ------------------------------------------------------------------------- */
+static int64_t meta_offset(int64_t r, int64_t c, int64_t m, int meta_bytes) {
+    const int64_t gy = (meta_bytes == 2) ? 32 : 16;
+    int64_t rr = r / 64 * 64 + (r % 2) * 2 + (r % 8) / 4 + ((r % gy) % 4) / 2 * 32 + ((r % 64) / 8) * 4;
+    int tr = (rr % 2 == 0) && (c % 2 == 1);
+    int bl = (rr % 2 == 1) && (c % 2 == 0);
+    rr += tr - bl;
+    int64_t cc = c - (tr - bl);
+    return (cc / 2) * m * 2 + rr * 2 + (cc % 2);
+}
+
+static inline int elem_nonzero(const void* p, int64_t i, int dt) {
+    switch (dt) {
+    case DT_I8: return ((const int8_t*)p)[i] != 0;
+    case DT_F16: case DT_BF16: return (((const uint16_t*)p)[i] & 0x7fffu) != 0;
+    case DT_F32: return (((const uint32_t*)p)[i] & 0x7fffffffu) != 0;
+    case DT_I32: return ((const int32_t*)p)[i] != 0;
+    default: return 0;
+    }
+}
+
+/* meta: int32 [m, k/32] for int8 data, else int16 [m, k/16] (fp32: [m, k/8]) */
+int orc_semi_structured_from_dense(const void* dense, int dt, void* sparse, void* meta, int64_t m, int64_t k) {
+    const int es = (dt == DT_F32 || dt == DT_I32) ? 4 : ((dt == DT_I8) ? 1 : 2);
+    const int meta_bytes = (dt == DT_I8) ? 4 : 2;
+    const int qpe = meta_bytes * 2;                 /* 4-bit codes per meta element */
+    const int ks = (dt == DT_F32) ? 2 : 4;          /* dense elements per code */
+    if (k % (ks * qpe) != 0) return ORC_E_SHAPE;
+    const int64_t ncols = k / (ks * qpe);
+    for (int64_t r = 0; r < m; ++r)
+        for (int64_t c = 0; c < ncols; ++c) {
+            uint32_t word = 0;
+            for (int q = 0; q < qpe; ++q) {
+                const int64_t base = r * k + (c * qpe + q) * ks;
+                int m0, m1, m2, m3;
+                if (ks == 4) {
+                    m0 = elem_nonzero(dense, base, dt); m1 = elem_nonzero(dense, base + 1, dt);
+                    m2 = elem_nonzero(dense, base + 2, dt); m3 = elem_nonzero(dense, base + 3, dt);
+                } else {
+                    m0 = m1 = elem_nonzero(dense, base, dt);
+                    m2 = m3 = elem_nonzero(dense, base + 1, dt);
+                }
+                (void)m2;
+                const int e0 = m0 & m1, e1 = (!m0) & m1, e2 = (!m0) & (!m1);
+                const int bit0 = e1, bit1 = e2, bit2 = e0 | e2 | m3, bit3 = e1 | (!m1);
+                const int idx0 = bit0 | (bit1 << 1), idx1 = bit2 | (bit3 << 1);
+                word |= (uint32_t)(idx0 | (idx1 << 2)) << (4 * q);
+                const int64_t so = r * (k / 2) + (c * qpe + q) * (ks / 2);
+                if (ks == 4) {
+                    memcpy((char*)sparse + so * es, (const char*)dense + (base + idx0) * es, es);
+                    memcpy((char*)sparse + (so + 1) * es, (const char*)dense + (base + idx1) * es, es);
+                } else {
+                    memcpy((char*)sparse + so * es, (const char*)dense + (base + idx0 / 2) * es, es);
+                }
+            }
+            const int64_t off = meta_offset(r, c, m, meta_bytes);
+            if (meta_bytes == 2) ((int16_t*)meta)[off] = (int16_t)word;
+            else ((int32_t*)meta)[off] = (int32_t)word;
+        }
+    return ORC_OK;
+}
+
+/* sparse [m, k] (k = sparse columns) -> dense [m, 2k] */
+int orc_semi_structured_to_dense(const void* sparse, int dt, const void* meta, void* dense, int64_t m, int64_t k) {
+    const int meta_bytes = (dt == DT_I8) ? 4 : 2;
+    const int qpe = meta_bytes * 2;
+    /* fp32 is processed as pairs of 16-bit halves (semi_structured_conversions.py:289-293) */
+    const int es = (dt == DT_I8) ? 1 : 2;
+    const int64_t kh = (dt == DT_F32 || dt == DT_I32) ? 2 * k : k;      /* sparse columns in es-sized units */
+    if ((2 * kh) % (4 * qpe) != 0) return ORC_E_SHAPE;
+    const int64_t ncols = 2 * kh / (4 * qpe);
+    memset(dense, 0, (size_t)(m * 2 * kh * es));
+    for (int64_t r = 0; r < m; ++r)
+        for (int64_t c = 0; c < ncols; ++c) {
+            const int64_t off = meta_offset(r, c, m, meta_bytes);
+            const uint32_t word = (meta_bytes == 2) ? (uint32_t)(uint16_t)((const int16_t*)meta)[off] : (uint32_t)((const int32_t*)meta)[off];
+            for (int q = 0; q < qpe; ++q) {
+                const int idx0 = (word >> (4 * q)) & 3, idx1 = (word >> (4 * q + 2)) & 3;
+                const int64_t quad = c * qpe + q;
+                const int64_t dbase = r * 2 * kh + quad * 4, sbase = r * kh + quad * 2;
+                memcpy((char*)dense + (dbase + idx0) * es, (const char*)sparse + sbase * es, es);
+                memcpy((char*)dense + (dbase + idx1) * es, (const char*)sparse + (sbase + 1) * es, es);
+            }
+        }
+    return ORC_OK;
+}

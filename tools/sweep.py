@@ -20,18 +20,10 @@ from compressed_tensors_b200 import _native as N  # noqa: E402
 from compressed_tensors_b200 import ops  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--layers", type=int, default=8)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--configs", default="tma:4:3,tma:3:4,tma:2:5,tma:2:6,tma:6:2,tma:8:2,direct:0:4,direct:0:6,direct:0:8")
-    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
-    a = ap.parse_args()
+def build_problems(layers: int):
     dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
-    ws, scs = bench.make_weights(dev, a.layers, 1000)
+    ws, scs = bench.make_weights(dev, layers, 1000)
     n = sum(w.numel() for w in ws)
-    peak, _ = bench.peaks()
     qa = bench.args_w4()
     outs = [torch.empty(w.shape[0], w.shape[1] // 8, dtype=torch.int32, device=dev) for w in ws]
     back = [torch.empty_like(w) for w in ws]
@@ -49,6 +41,19 @@ def main():
         P["fp8_dq"].append((ops._desc(p8, None, s.dtype, None, None, torch.float8_e4m3fn, torch.bfloat16, N.Q_INT, 8), q, s, None, b))
     OPS = {"quantpack": (N.OP_QUANTIZE_PACK, 2.515625), "unpackdeq": (N.OP_UNPACK_DEQUANTIZE, 2.515625),
            "fp8_q": (N.OP_QUANTIZE, 3.0), "fp8_dq": (N.OP_DEQUANTIZE, 3.0), "fake_w4": (N.OP_FAKE_QUANTIZE, 4.0 + 2 / 128)}
+    return P, OPS, n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--layers", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--configs", default="tma:4:3,tma:3:4,tma:2:5,tma:2:6,tma:6:2,tma:8:2,direct:0:4,direct:0:6,direct:0:8")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
+    a = ap.parse_args()
+    torch.cuda.set_device(0)
+    P, OPS, n = build_problems(a.layers)
+    peak, _ = bench.peaks()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     with open(a.out, "a") as f:
         for cfg in a.configs.split(","):
