@@ -61,6 +61,15 @@ def profile_traffic(kernel: str):
         return None
 
 
+def traffic_per_launch(kernel: str, n_elems: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full` capture
+    (profiles/ncu_ops_r1.md, taken on 4 layers), scaled by element count to this launch's size"""
+    t = profile_traffic(kernel)
+    if not t:
+        return None
+    return int(t["dram_bytes_per_launch"] / t["elements_per_launch"] * n_elems)
+
+
 class ClockSampler:
     """SM clock / throttle reasons sampled through NVML every few ms during the timed region
     (nvidia-smi itself takes ~100 ms per query, too coarse for a sub-second region)"""
@@ -261,18 +270,15 @@ def run_b200(a):
         codes = [torch.randint(-8, 8, (14336, 4096), dtype=torch.int8, device=dev) for _ in range(8)]
         nel = sum(c.numel() for c in codes)
         pk = [torch.empty(c.shape[0], c.shape[1] // 8, dtype=torch.int32, device=dev) for c in codes]
-        lib = N.lib()
-
-        def pack_all():
-            for c, o in zip(codes, pk):
-                lib.ct_pack_int32(N.ptr(c), N.ptr(o), c.shape[0], c.shape[1], 4, 1, local, N.stream_ptr(local))
-
-        def unpack_all():
-            for c, o in zip(codes, pk):
-                lib.ct_unpack_int32(N.ptr(o), N.ptr(c), c.shape[0], c.shape[1], 4, 1, local, N.stream_ptr(local))
-
-        extra["int4_pack"] = rate(pack_all, nel * 1.5, nel)
-        extra["int4_unpack"] = rate(unpack_all, nel * 1.5, nel)
+        pdesc = []
+        for c in codes:
+            d = N.QuantDesc()
+            d.rows, d.cols, d.num_bits = c.shape[0], c.shape[1], 4
+            pdesc.append(d)
+        pack_probs = [(d, c, None, None, o) for d, c, o in zip(pdesc, codes, pk)]
+        unpack_probs = [(d, o, None, None, c) for d, c, o in zip(pdesc, codes, pk)]
+        extra["int4_pack"] = rate(lambda: ops.batched(N.OP_PACK_INT32, pack_probs, local), nel * 1.5, nel)
+        extra["int4_unpack"] = rate(lambda: ops.batched(N.OP_UNPACK_INT32, unpack_probs, local), nel * 1.5, nel)
         del codes, pk
 
     # end to end through the plugin API on host (pinned) state dicts
@@ -296,7 +302,7 @@ def run_b200(a):
                        "l2": "inputs (%.1f GB per step) >> 126 MB L2, no flush needed" % (weight_bytes / 1e9),
                        "launch": "one multi-tensor persistent launch per step", "pipe": os.environ.get("CT_B200_PIPE", "tma")},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": profile_traffic("quantize_pack"), "peak_source": peak_src,
+                         "traffic": traffic_per_launch("quantize_pack", n_elems), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "frac_of_8TBps_nominal": round(achieved / 8000.0, 4)},
             "gpu_launches": int(launches), "clocks": clocks,
         }

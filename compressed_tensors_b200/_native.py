@@ -37,7 +37,7 @@ DT = {
 }
 
 # ct_batch_op_t
-OP_QUANTIZE_PACK, OP_UNPACK_DEQUANTIZE, OP_QUANTIZE, OP_DEQUANTIZE, OP_FAKE_QUANTIZE = range(5)
+OP_QUANTIZE_PACK, OP_UNPACK_DEQUANTIZE, OP_QUANTIZE, OP_DEQUANTIZE, OP_FAKE_QUANTIZE, OP_PACK_INT32, OP_UNPACK_INT32 = range(7)
 
 Q_INT, Q_FLOAT = 0, 1
 

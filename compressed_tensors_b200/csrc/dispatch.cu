@@ -151,6 +151,26 @@ static Plan plan_one(int op, const ct_quant_desc& d, const void* in, const void*
     return p;
 }
 
+// standalone pack / unpack (packed_dim 1) as a streaming job; for these ops a chunk is 16 codes
+static Plan plan_bits(bool pack, int64_t rows, int64_t cols, int bits, const void* in, void* out) {
+    Plan p;
+    p.fast = false;
+    memset(&p.job, 0, sizeof(p.job));
+    p.cm = make_common(CT_F32, CT_Q_INT, bits);
+    p.sig = FastSig{pack ? F_PACK : F_UNPACK, CT_I8, bits, 0, 1};
+    const int64_t n = rows * cols;
+    const int in_bytes = pack ? 16 : 2 * bits;
+    const int unit = (pack && bits == 4) ? 32 : 16;   // 4-bit packing works on units of 2 chunks
+    if (!(bits == 4 || bits == 8) || (cols * bits) % 32 != 0 || n == 0 || n % unit != 0 || (n / 16) >= 0x7fffffffLL) return p;
+    if (!aligned16(in) || !aligned16(out) || ((n / 16) * in_bytes) % 16 != 0) return p;
+    p.fast = true;
+    p.job.in = reinterpret_cast<const uint8_t*>(in);
+    p.job.out = reinterpret_cast<uint8_t*>(out);
+    p.job.n_chunks = (uint32_t)(n / 16);
+    p.job.dc = make_fastdiv(0x7FFFFFFFull);
+    return p;
+}
+
 static int launch_sig(const FastSig& s, const LaunchPlan& lp, int device, cudaStream_t st) {
     switch (s.op) {
     case F_QUANTPACK: return launch_fast_quantpack(s, lp, device, st);
@@ -197,7 +217,8 @@ static int check_dtypes(int op, const ct_quant_desc& d, bool has_zp) {
 
 int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in, const void* const* scale,
                 const void* const* zp, const int32_t* const* g_idx, void* const* out, int device, cudaStream_t stream) {
-    if (n < 0 || (n > 0 && (!descs || !in || !scale || !out))) { set_error("null table"); return CT_E_ARG; }
+    const bool bits_op = (op == CT_OP_PACK_INT32 || op == CT_OP_UNPACK_INT32);
+    if (n < 0 || (n > 0 && (!descs || !in || (!scale && !bits_op) || !out))) { set_error("null table"); return CT_E_ARG; }
     int rc = check_device(device);
     if (rc) return rc;
     DeviceGuard guard(device);
@@ -205,6 +226,14 @@ int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in
 
     std::vector<Plan> plans((size_t)n);
     for (int i = 0; i < n; ++i) {
+        if (bits_op) {
+            const ct_quant_desc& d = descs[i];
+            if (d.num_bits < 1 || d.num_bits > 8) { set_error("num_bits %d outside [1, 8]", d.num_bits); return CT_E_BITS; }
+            if (d.rows < 0 || d.cols < 0) { set_error("negative shape"); return CT_E_SHAPE; }
+            if (d.rows * d.cols > 0 && (!in[i] || !out[i])) { set_error("null tensor pointer (tensor %d)", i); return CT_E_ARG; }
+            plans[i] = plan_bits(op == CT_OP_PACK_INT32, d.rows, d.cols, d.num_bits, in[i], out[i]);
+            continue;
+        }
         rc = validate_desc(&descs[i]);
         if (rc) return rc;
         const void* z = zp ? zp[i] : nullptr;
@@ -218,7 +247,16 @@ int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in
     for (int i = 0; i < n; ++i) {
         if (done[i]) continue;
         if (!plans[i].fast) {
-            rc = run_generic(op, descs[i], in[i], scale[i], zp ? zp[i] : nullptr, g_idx ? g_idx[i] : nullptr, out[i], stream);
+            if (bits_op) {
+                if (descs[i].rows * descs[i].cols == 0) { done[i] = 1; continue; }
+                rc = (op == CT_OP_PACK_INT32)
+                         ? launch_generic_pack(reinterpret_cast<const int8_t*>(in[i]), reinterpret_cast<int32_t*>(out[i]), descs[i].rows, descs[i].cols, descs[i].num_bits, 1, stream)
+                         : launch_generic_unpack(reinterpret_cast<const int32_t*>(in[i]), reinterpret_cast<int8_t*>(out[i]), descs[i].rows, descs[i].cols, descs[i].num_bits, 1, stream);
+                if (rc) return rc;
+                done[i] = 1;
+                continue;
+            }
+            rc = run_generic(op, descs[i], in[i], scale ? scale[i] : nullptr, zp ? zp[i] : nullptr, g_idx ? g_idx[i] : nullptr, out[i], stream);
             if (rc) return rc;
             done[i] = 1;
             continue;

@@ -473,7 +473,7 @@ def batched(op: int, problems: Sequence[Tuple[N.QuantDesc, torch.Tensor, torch.T
     descs = (N.QuantDesc * n)(*[p[0] for p in problems])
     vp = ctypes.c_void_p * n
     ins = vp(*[p[1].data_ptr() for p in problems])
-    scs = vp(*[p[2].data_ptr() for p in problems])
+    scs = vp(*[(p[2].data_ptr() if p[2] is not None else 0) for p in problems])
     zps = vp(*[(p[3].data_ptr() if p[3] is not None else 0) for p in problems])
     outs = vp(*[p[4].data_ptr() for p in problems])
     rc = N.lib().ct_batched(int(op), n, descs, ctypes.cast(ins, ctypes.c_void_p), ctypes.cast(scs, ctypes.c_void_p),

@@ -137,7 +137,9 @@ typedef enum ct_batch_op_t {
     CT_OP_UNPACK_DEQUANTIZE = 1,  /* in packed   -> out float */
     CT_OP_QUANTIZE = 2,           /* in x        -> out q (int8 / fp8) */
     CT_OP_DEQUANTIZE = 3,         /* in q        -> out float */
-    CT_OP_FAKE_QUANTIZE = 4       /* in x        -> out float */
+    CT_OP_FAKE_QUANTIZE = 4,      /* in x        -> out float */
+    CT_OP_PACK_INT32 = 5,         /* in int8 codes -> out packed int32 (packed_dim 1; desc: rows, cols, num_bits; no scale) */
+    CT_OP_UNPACK_INT32 = 6        /* in packed   -> out int8 codes */
 } ct_batch_op_t;
 int ct_batched(int op, int n, const ct_quant_desc* descs, const void* const* in, const void* const* scale,
                const void* const* zp, void* const* out, int device, void* stream);

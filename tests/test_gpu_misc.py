@@ -1,0 +1,91 @@
+"""GPU tests: multi-tensor pack/unpack launches, 2:4 semi-structured (marlin-24 remnant) kernels."""
+import pytest
+import torch
+
+import oracle
+from compressed_tensors_b200 import _native as N
+from compressed_tensors_b200 import ops
+from compressed_tensors_b200.utils.permutations_24 import get_permutations_24
+from compressed_tensors_b200.utils.semi_structured_conversions import (
+    mask_creator,
+    sparse_semi_structured_from_dense_cutlass,
+    sparse_semi_structured_to_dense_cutlass,
+)
+from tests.golden import load
+from tests.util import same, same_values
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_batched_pack_unpack_equals_per_tensor():
+    g = torch.Generator().manual_seed(3)
+    shapes = [(1024, 4096), (64, 128), (512, 14336), (33, 100), (7, 64)]   # the last two take the generic kernel
+    codes = [torch.randint(-8, 8, s, dtype=torch.int8, generator=g).to(DEV) for s in shapes]
+    want = [ops.pack_to_int32(c, 4) for c in codes]
+    outs = [torch.zeros_like(w) for w in want]
+    descs = []
+    for c in codes:
+        d = N.QuantDesc()
+        d.rows, d.cols, d.num_bits = c.shape[0], c.shape[1], 4
+        descs.append(d)
+    launches = N.launch_count()
+    ops.batched(N.OP_PACK_INT32, [(d, c, None, None, o) for d, c, o in zip(descs, codes, outs)])
+    assert N.launch_count() - launches == 3, "3 flat tensors in one launch + 2 generic launches"
+    for o, w, c in zip(outs, want, codes):
+        same_values(o, w, "batched pack")
+        same_values(o.cpu(), oracle.pack_to_int32(c.cpu(), 4), "batched pack vs oracle")
+    back = [torch.zeros_like(c) for c in codes]
+    ops.batched(N.OP_UNPACK_INT32, [(d, o, None, None, b) for d, o, b in zip(descs, outs, back)])
+    for b, c in zip(back, codes):
+        same_values(b, c, "batched unpack")
+
+
+def test_semi_structured_golden_gpu():
+    sp = load("sparse")
+    for c in sp["semi"]:
+        sparse, meta = sparse_semi_structured_from_dense_cutlass(c["dense"].to(DEV))
+        assert sparse.is_cuda and meta.dtype == c["meta"].dtype and meta.shape == c["meta"].shape
+        same(sparse.cpu(), c["sparse"], f"semi sparse {c['dense'].dtype}")
+        same_values(meta.cpu(), c["meta"], f"semi meta {c['dense'].dtype}")
+        back = sparse_semi_structured_to_dense_cutlass(c["sparse"].to(DEV), c["meta"].to(DEV)).cpu()
+        same(back, oracle.semi_structured_to_dense(c["sparse"], c["meta"]), "semi to_dense vs oracle")
+        if back.dtype != torch.float32:   # fp32: the reference quiets fp16-sNaN-looking halves (see oracle test)
+            same(back, c["back"], "semi to_dense vs reference")
+
+
+@pytest.mark.parametrize("dtype,shape", [(torch.bfloat16, (256, 4096)), (torch.float16, (128, 512)), (torch.int8, (64, 1024)), (torch.float32, (64, 64))])
+def test_semi_structured_vs_oracle(dtype, shape):
+    g = torch.Generator().manual_seed(shape[1])
+    x = torch.randn(shape, generator=g) * 10
+    x = x.round().clamp(-127, 127).to(dtype) if dtype == torch.int8 else x.to(dtype)
+    pruned = (x.float() * mask_creator(x.to(DEV)).cpu()).to(dtype)
+    sparse, meta = sparse_semi_structured_from_dense_cutlass(pruned.to(DEV))
+    ws, wm = oracle.semi_structured_from_dense(pruned)
+    same(sparse.cpu(), ws, "sparse")
+    same_values(meta.cpu(), wm, "meta")
+    dense = sparse_semi_structured_to_dense_cutlass(sparse, meta).cpu()
+    same(dense, oracle.semi_structured_to_dense(ws, wm), "dense")
+    if dtype != torch.float32:
+        same_values(dense, pruned, "round trip of a 2:4 matrix")
+
+
+def test_mask_creator_golden_gpu():
+    for c in load("sparse")["mask_creator"]:
+        m = mask_creator(c["x"].float().to(DEV))
+        assert m.dtype == torch.float32 and m.shape == c["x"].shape
+        same_values(m.cpu().bool(), c["mask"], f"mask_creator {c['x'].dtype}")
+    with pytest.raises(ValueError, match="can't be evenly divided"):
+        mask_creator(torch.zeros(3, 3, device=DEV))
+
+
+def test_semi_structured_errors():
+    with pytest.raises(RuntimeError, match="2-dimensional"):
+        sparse_semi_structured_from_dense_cutlass(torch.zeros(4, device=DEV))
+    with pytest.raises(RuntimeError, match="divisible by 32"):
+        sparse_semi_structured_from_dense_cutlass(torch.zeros(48, 64, dtype=torch.half, device=DEV))
+    with pytest.raises(RuntimeError, match="divisible by 16"):
+        sparse_semi_structured_from_dense_cutlass(torch.zeros(64, 24, dtype=torch.half, device=DEV))
+    with pytest.raises(RuntimeError, match="Invalid datatype"):
+        sparse_semi_structured_from_dense_cutlass(torch.zeros(64, 64, dtype=torch.float64, device=DEV))
+    assert get_permutations_24(4)[0].numel() == 1024
