@@ -82,10 +82,12 @@ def sparse_semi_structured_to_dense_cutlass(sparse: torch.Tensor, meta_reordered
 
 def mask_creator(tensor: torch.Tensor) -> torch.Tensor:
     """2:4 mask (float32 ones / zeros, tensor's shape): the 2 largest |x| of every 4 consecutive
-    elements are kept (semi_structured_conversions.py:301-330; tie order is unspecified there)."""
+    elements are kept (semi_structured_conversions.py:301-330).  The reference drops the first two
+    entries of an ascending argsort, which on ties drops the LOWER columns; the select kernel keeps
+    the lower column on ties, so it is run on the column-reversed quads."""
     if tensor.numel() % 4 != 0:
         raise ValueError(f"Tensor of size {tensor.shape} can't be evenly divided into 4 groups")
-    flat = tensor.detach().reshape(-1, 4)
+    flat = tensor.detach().reshape(-1, 4).flip(-1)
     _, bitmask = ops.sparse24_compress(flat.contiguous())
-    mask = ops.unpack_bitmasks(bitmask, flat.shape)
+    mask = ops.unpack_bitmasks(bitmask, flat.shape).flip(-1)
     return mask.to(torch.float32).reshape(tensor.shape)
