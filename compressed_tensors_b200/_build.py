@@ -29,6 +29,7 @@ SOURCES = [
     "selftest.cu",
     "host_pipeline.cu",
     "sparse.cu",
+    "fast_observe.cu",
 ]
 HEADERS = ["common.cuh", "quant_core.cuh", "stream.cuh", "ops.cuh", "engine.h", "../../include/ct_b200.h"]
 

@@ -37,7 +37,7 @@ DT = {
 }
 
 # ct_batch_op_t
-OP_QUANTIZE_PACK, OP_UNPACK_DEQUANTIZE, OP_QUANTIZE, OP_DEQUANTIZE, OP_FAKE_QUANTIZE, OP_PACK_INT32, OP_UNPACK_INT32 = range(7)
+OP_QUANTIZE_PACK, OP_UNPACK_DEQUANTIZE, OP_QUANTIZE, OP_DEQUANTIZE, OP_FAKE_QUANTIZE, OP_PACK_INT32, OP_UNPACK_INT32, OP_OBSERVE_QUANTIZE_PACK = range(8)
 
 Q_INT, Q_FLOAT = 0, 1
 
@@ -85,6 +85,7 @@ _PROTOS = {
     "ct_fake_quantize": (_int, [_descp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "ct_quantize_pack_int32": (_int, [_descp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "ct_unpack_dequantize_int32": (_int, [_descp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "ct_observe_quantize_pack_int32": (_int, [_descp, _vp, _vp, _vp, _vp, _int, _vp]),
     "ct_batched": (_int, [_int, _int, _descp, _vp, _vp, _vp, _vp, _int, _vp]),
     "ct_pack_bitmasks": (_int, [_vp, _vp, _i64, _i64, _int, _vp]),
     "ct_unpack_bitmasks": (_int, [_vp, _vp, _i64, _i64, _int, _vp]),

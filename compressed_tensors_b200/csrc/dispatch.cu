@@ -102,6 +102,28 @@ static Plan plan_one(int op, const ct_quant_desc& d, const void* in, const void*
         p_dt = d.x_dtype; sig.op = F_QUANTPACK; sig.sel = d.num_bits; in_bytes_per_chunk = 8 * dt_size(p_dt);
         sig.group = fast_group_quantpack(p_dt, d.num_bits);
         break;
+    case CT_OP_OBSERVE_QUANTIZE_PACK: {
+        // fused observer: `scale` / `zp` are OUTPUTS; group strategy only, a group = 32 * {1,2,4,8} elements
+        if (d.qtype != CT_Q_INT || (d.num_bits != 4 && d.num_bits != 8)) return p;
+        if ((d.cols * d.num_bits) % 32 != 0 || n % 32 != 0) return p;
+        if (d.x_dtype != d.scale_dtype || d.x_dtype != d.compute_dtype || (d.x_dtype != CT_BF16 && d.x_dtype != CT_F16)) return p;
+        if (is_inf(D) || D != d.cdiv || D % 32 != 0) return p;
+        const int64_t lpg = D / 32;
+        if (lpg != 1 && lpg != 2 && lpg != 4 && lpg != 8) return p;
+        p_dt = d.x_dtype; sig.op = F_OBSERVE_QP; sig.sel = d.num_bits; in_bytes_per_chunk = 16;
+        sig.group = (int)lpg;
+        p.fast = true;
+        p.sig = sig;
+        p.sig.p_dt = p_dt;
+        p.job.in = reinterpret_cast<const uint8_t*>(in);
+        p.job.scale = scale;
+        p.job.zp = zp;
+        p.job.out = reinterpret_cast<uint8_t*>(out);
+        p.job.n_chunks = (uint32_t)(n / 8);
+        p.job.dc = make_fastdiv((uint64_t)(D / 8));
+        p.cm = make_common(p_dt, d.qtype, d.num_bits);
+        return p;
+    }
     case CT_OP_UNPACK_DEQUANTIZE:
         if (d.num_bits != 4 && d.num_bits != 8) return p;
         if ((d.cols * d.num_bits) % 32 != 0) return p;
@@ -178,6 +200,7 @@ static int launch_sig(const FastSig& s, const LaunchPlan& lp, int device, cudaSt
     case F_QUANT: return launch_fast_quant(s, lp, device, st);
     case F_DEQUANT: return launch_fast_dequant(s, lp, device, st);
     case F_FAKE: return launch_fast_fake(s, lp, device, st);
+    case F_OBSERVE_QP: return launch_fast_observe(s, lp, device, st);
     default: return launch_fast_bits(s, lp, device, st);
     }
 }
@@ -193,13 +216,17 @@ static int run_generic(int op, const ct_quant_desc& d, const void* in, const voi
     case CT_OP_QUANTIZE: return launch_generic_quant(G_QUANTIZE, d, in, scale, zp, g_idx, out, st);
     case CT_OP_DEQUANTIZE: return launch_generic_quant(G_DEQUANTIZE, d, in, scale, zp, g_idx, out, st);
     case CT_OP_FAKE_QUANTIZE: return launch_generic_quant(G_FAKE, d, in, scale, zp, g_idx, out, st);
+    case CT_OP_OBSERVE_QUANTIZE_PACK:
+        set_error("fused observe+quantize+pack supports bf16/fp16 group quantization with group_size in {32,64,128,256}, "
+                  "4- or 8-bit codes, 16-byte aligned contiguous tensors; run the observer and quantize_pack separately otherwise");
+        return CT_E_UNSUPPORTED;
     }
     set_error("unknown op %d", op);
     return CT_E_ARG;
 }
 
 static int check_dtypes(int op, const ct_quant_desc& d, bool has_zp) {
-    const bool quantizing = (op == CT_OP_QUANTIZE_PACK || op == CT_OP_QUANTIZE || op == CT_OP_FAKE_QUANTIZE);
+    const bool quantizing = (op == CT_OP_QUANTIZE_PACK || op == CT_OP_QUANTIZE || op == CT_OP_FAKE_QUANTIZE || op == CT_OP_OBSERVE_QUANTIZE_PACK);
     if (!is_float_dt(d.scale_dtype)) { set_error("scale dtype %d is not a float dtype", d.scale_dtype); return CT_E_DTYPE; }
     if (quantizing && (!is_float_dt(d.x_dtype) || !is_float_dt(d.compute_dtype))) {
         set_error("x / compute dtype must be float (got %d / %d)", d.x_dtype, d.compute_dtype);
@@ -366,6 +393,9 @@ int ct_quantize_pack_int32(const ct_quant_desc* d, const void* x, const void* sc
 }
 int ct_unpack_dequantize_int32(const ct_quant_desc* d, const int32_t* packed, const void* scale, const void* zp, const int32_t* g_idx, void* out, int device, void* stream) {
     return run_one(CT_OP_UNPACK_DEQUANTIZE, d, packed, scale, zp, g_idx, out, device, stream);
+}
+int ct_observe_quantize_pack_int32(const ct_quant_desc* d, const void* x, void* scale_out, void* zp_out, int32_t* packed, int device, void* stream) {
+    return run_one(CT_OP_OBSERVE_QUANTIZE_PACK, d, x, scale_out, zp_out, nullptr, packed, device, stream);
 }
 int ct_batched(int op, int n, const ct_quant_desc* descs, const void* const* in, const void* const* scale,
                const void* const* zp, void* const* out, int device, void* stream) {

@@ -25,7 +25,7 @@ __all__ = ["replace_module_parallel"]
 
 def _to_meta(module: torch.nn.Module):
     sd = get_direct_state_dict(module)
-    replace_direct_state_dict(module, {k: torch.empty_like(v, device="meta") for k, v in sd.items() if v is not None})
+    replace_direct_state_dict(module, {k: (torch.empty_like(v, device="meta") if v is not None else None) for k, v in sd.items()})
 
 
 def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callable = module_size, desc: Optional[str] = None):
@@ -52,10 +52,16 @@ def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callab
         for name in sd:  # identical key order on all ranks (same compressor code path)
             t = sd[name]
             if t is None:
+                new[name] = None
                 continue
-            if owner[m] != rank:
-                t = torch.empty(t.shape, dtype=t.dtype, device=dev)
-            buf = as_broadcastable(t.contiguous())
-            dist.broadcast(buf, src=owner[m])
-            new[name] = buf.view(t.dtype) if buf.dtype != t.dtype else buf
+            if owner[m] == rank:
+                buf = as_broadcastable(t.contiguous().to(dev))
+                dist.broadcast(buf, src=owner[m])
+                new[name] = t                                   # the owner keeps its own tensors
+            else:
+                buf = as_broadcastable(torch.empty(t.shape, dtype=t.dtype, device=dev))
+                dist.broadcast(buf, src=owner[m])
+                got = buf.view(t.dtype) if buf.dtype != t.dtype else buf
+                # tensors the shape-only path already produced for real (e.g. weight_shape, on the CPU) stay where they were
+                new[name] = got if t.device.type == "meta" else got.to(t.device)
         replace_direct_state_dict(m, new)

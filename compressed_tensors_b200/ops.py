@@ -459,6 +459,58 @@ def unpack_dequantize(packed, scale, zero_point, num_bits: int, shape: Sequence[
     return _run("ct_unpack_dequantize_int32", N.OP_UNPACK_DEQUANTIZE, d, p, packed, shape, out_dtype)
 
 
+@torch.no_grad()
+def observe_quantize_pack(x: torch.Tensor, args) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """Memoryless min-max observer + quantize + pack in ONE pass over the weight:
+    returns (weight_packed int32, weight_scale in x.dtype [R, C/G], weight_zero_point int8 [R, C/G] or None).
+
+    Equivalent to the reference flow  min/max per group -> calculate_qparams (utils/helpers.py:50-137)
+    -> quantize(dtype=int8) -> pack_to_int32, bit for bit.  The fused kernel covers group quantization of
+    bf16 / fp16 weights with group_size in {32, 64, 128, 256} and 4- or 8-bit codes; every other case runs
+    the same three steps as separate GPU ops."""
+    from .quantization.utils.helpers import calculate_qparams  # host-side qparam rule (tiny tensors)
+
+    qtype, bits = _qparams(args)
+    strategy = _strategy_name(args)
+    symmetric = bool(getattr(args, "symmetric", True))
+    if x.ndim != 2:
+        raise ValueError("observe_quantize_pack expects a 2-D weight")
+    rows, cols = x.shape
+    idx = _dev_index(x)
+    xd = _to_dev(x, idx)
+    group = int(getattr(args, "group_size", 0) or 0)
+    fused_ok = (qtype == N.Q_INT and strategy == "group" and group in (32, 64, 128, 256) and cols % group == 0
+                and x.dtype in (torch.bfloat16, torch.float16) and bits in (4, 8) and (cols * bits) % 32 == 0
+                and (rows * cols) % 32 == 0)
+    if fused_ok:
+        ng = cols // group
+        scale = torch.empty((rows, ng), dtype=x.dtype, device=xd.device)
+        zp = None if symmetric else torch.empty((rows, ng), dtype=torch.int8, device=xd.device)
+        packed = torch.empty((rows, cols * bits // 32), dtype=torch.int32, device=xd.device)
+        d = N.QuantDesc()
+        d.rows, d.cols, d.rdiv, d.cdiv, d.s_row_stride = rows, cols, 1, group, ng
+        d.x_dtype = d.scale_dtype = d.compute_dtype = N.DT[x.dtype]
+        d.zp_dtype = N.DT_NONE if symmetric else N.DT[torch.int8]
+        d.q_dtype, d.out_dtype, d.qtype, d.num_bits = N.DT[torch.int8], N.DT_NONE, qtype, bits
+        rc = N.lib().ct_observe_quantize_pack_int32(ctypes.byref(d), N.ptr(xd), N.ptr(scale), N.ptr(zp), N.ptr(packed), idx, N.stream_ptr(idx))
+        N.check(rc, "observe_quantize_pack")
+        return _back(packed, x), _back(scale, x), (_back(zp, x) if zp is not None else None)
+    # unfused: observer with torch reductions on the device, then the fused quantize+pack kernel
+    if strategy == "group":
+        xr = xd.unflatten(-1, (-1, group))
+        mn, mx = xr.amin(-1), xr.amax(-1)
+    elif strategy == "channel":
+        mn, mx = xd.amin(-1, keepdim=True), xd.amax(-1, keepdim=True)
+    elif strategy == "tensor":
+        mn, mx = (t.reshape(1) for t in torch.aminmax(xd))
+    else:
+        raise NotImplementedError(f"observe_quantize_pack does not support strategy {strategy}")
+    scale, zp = calculate_qparams(mn, mx, args)
+    zp = None if symmetric else zp
+    packed = quantize_pack(xd, scale, zp, args)
+    return _back(packed, x), _back(scale, x), (_back(zp, x) if zp is not None else None)
+
+
 # --------------------------------------------------------------------------------------------
 # multi-tensor launch (the module loop of ModelCompressor.compress_model in one kernel)
 # --------------------------------------------------------------------------------------------

@@ -127,6 +127,15 @@ int ct_quantize_pack_int32(const ct_quant_desc* d, const void* x, const void* sc
 int ct_unpack_dequantize_int32(const ct_quant_desc* d, const int32_t* packed, const void* scale, const void* zp,
                                const int32_t* g_idx, void* out, int device, void* stream);
 
+/* one-pass min-max observer + quantize + pack for GROUP-quantized integer weights (bf16 / fp16, 4- or 8-bit,
+ * group_size in {32, 64, 128, 256}): computes scale (x dtype, [rows, cols/group]) and, when zp_out != NULL
+ * (asymmetric, d->zp_dtype = CT_I8), the int8 zero point with the reference's observer rule calculate_qparams
+ * (quantization/utils/helpers.py:50-137) on the per-group min / max, then quantizes and packs with them in the same
+ * pass.  Replaces observer + quantize + pack_to_int32.  Returns CT_E_UNSUPPORTED for
+ * anything else: run the observer and ct_quantize_pack_int32 separately. */
+int ct_observe_quantize_pack_int32(const ct_quant_desc* d, const void* x, void* scale_out, void* zp_out, int32_t* packed,
+                                   int device, void* stream);
+
 /* ---- multi-tensor (whole-model) launches -------------------------------------
  * One persistent launch over `n` independent tensors: the body of the module loop of
  * ModelCompressor.compress_model / decompress_model
@@ -139,7 +148,8 @@ typedef enum ct_batch_op_t {
     CT_OP_DEQUANTIZE = 3,         /* in q        -> out float */
     CT_OP_FAKE_QUANTIZE = 4,      /* in x        -> out float */
     CT_OP_PACK_INT32 = 5,         /* in int8 codes -> out packed int32 (packed_dim 1; desc: rows, cols, num_bits; no scale) */
-    CT_OP_UNPACK_INT32 = 6        /* in packed   -> out int8 codes */
+    CT_OP_UNPACK_INT32 = 6,       /* in packed   -> out int8 codes */
+    CT_OP_OBSERVE_QUANTIZE_PACK = 7 /* in x      -> out packed int32; scale[i] / zp[i] are OUTPUTS (see ct_observe_quantize_pack_int32) */
 } ct_batch_op_t;
 int ct_batched(int op, int n, const ct_quant_desc* descs, const void* const* in, const void* const* scale,
                const void* const* zp, void* const* out, int device, void* stream);

@@ -26,7 +26,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libct_oracle.so")
-_SRC = os.path.join(_HERE, "ct_oracle.c")
+_SRC = os.path.join(_HERE, "ct_oracle_all.c")  # includes ct_oracle.c and ct_oracle_qparams.c
+_PARTS = [os.path.join(_HERE, f) for f in ("ct_oracle_all.c", "ct_oracle.c", "ct_oracle_qparams.c")]
 
 INT64_MAX = (1 << 63) - 1
 
@@ -48,7 +49,7 @@ def build(force: bool = False) -> str:
     if (
         not force
         and os.path.exists(_SO)
-        and os.path.getmtime(_SO) >= os.path.getmtime(_SRC)
+        and os.path.getmtime(_SO) >= max(os.path.getmtime(p) for p in _PARTS)
     ):
         return _SO
     cmd = ["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-fno-fast-math", "-o", _SO, _SRC, "-lm"]

@@ -1,0 +1,3 @@
+/* translation unit of libct_oracle.so (TEST INFRASTRUCTURE ONLY) */
+#include "ct_oracle.c"
+#include "ct_oracle_qparams.c"
