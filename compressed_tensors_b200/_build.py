@@ -30,6 +30,7 @@ SOURCES = [
     "host_pipeline.cu",
     "sparse.cu",
     "fast_observe.cu",
+    "host_many.cu",
 ]
 HEADERS = ["common.cuh", "quant_core.cuh", "stream.cuh", "ops.cuh", "engine.h", "../../include/ct_b200.h"]
 

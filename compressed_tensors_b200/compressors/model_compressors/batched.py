@@ -1,8 +1,14 @@
 """
-Whole-model launches: every pack-quantized / naive-quantized module whose tensors are resident on
-one CUDA device is compressed (or decompressed) by a single multi-tensor kernel launch per
-(format, dtype, bit-width) signature.  Results are bit-identical to the per-module plugin path
-(tests/test_gpu_model.py); modules that do not qualify go through that path unchanged.
+Whole-model launches: every pack-quantized / naive-quantized module is compressed (or decompressed)
+together with all other modules of the same (format, placement) group
+
+  * tensors resident on one CUDA device  -> ONE multi-tensor kernel launch per kernel signature (ct_batched)
+  * tensors resident in host memory      -> ONE pipelined H2D -> kernel -> D2H queue across all of them
+                                            (ct_host_run_many); outputs land in host memory (pinned when
+                                            the inputs are)
+
+Results are bit-identical to the per-module plugin path (tests/test_gpu_compressors.py); modules that do
+not qualify (other formats, activation ordering, N-D weights, meta tensors) take that path unchanged.
 """
 from __future__ import annotations
 
@@ -24,18 +30,36 @@ _BATCHABLE = (CompressionFormat.pack_quantized, CompressionFormat.naive_quantize
               CompressionFormat.float_quantized)
 
 
-def _eligible(module, fmt) -> bool:
-    if fmt not in _BATCHABLE:
-        return False
-    w = getattr(module, "weight", None) if fmt is not None else None
+def _placement(module, key: str):
+    """('cuda', index) / ('cpu', None) when the module's streamed tensor and qparams share a placement, else None"""
     sd = module._parameters
-    t = sd.get("weight", None) if "weight" in sd else sd.get("weight_packed", None)
-    sc = sd.get("weight_scale", None)
-    if t is None or sc is None or not t.is_cuda or not sc.is_cuda or t.ndim != 2:
-        return False
-    if sd.get("weight_g_idx", None) is not None and bool((sd["weight_g_idx"] != -1).all()):
-        return False  # activation ordering: per-module path
-    return True
+    t, sc = sd.get(key, None), sd.get("weight_scale", None)
+    if t is None or sc is None or t.ndim != 2 or t.device != sc.device or t.device.type not in ("cuda", "cpu"):
+        return None
+    zp = sd.get("weight_zero_point", None)
+    if zp is not None and zp.device != t.device:
+        return None
+    g = sd.get("weight_g_idx", None)
+    if g is not None and bool((g != -1).all()):
+        return None  # activation ordering: per-module path
+    if t.device.type == "cpu" and not torch.cuda.is_available():
+        return None  # the per-module path raises the loud "no CUDA device" error
+    return (t.device.type, t.device.index)
+
+
+def _run(op: int, probs, place):
+    if not probs:
+        return
+    if place[0] == "cuda":
+        ops.batched(op, probs, place[1])
+    else:
+        ops.host_batched(op, probs)
+
+
+def _empty(shape, dtype, like: torch.Tensor):
+    if like.is_cuda:
+        return torch.empty(shape, dtype=dtype, device=like.device)
+    return torch.empty(shape, dtype=dtype, pin_memory=like.is_pinned())
 
 
 def compress_modules_batched(modules, force_format: Optional[CompressionFormat] = None) -> None:
@@ -45,12 +69,13 @@ def compress_modules_batched(modules, force_format: Optional[CompressionFormat] 
         if not isinstance(scheme, QuantizationScheme):
             continue
         fmt = _resolve_format(m, scheme, force_format)
-        if _eligible(m, fmt) and scheme.weights is not None and "weight" in m._parameters:
-            groups[(fmt, m.weight.device.index)].append(m)
+        place = _placement(m, "weight") if (fmt in _BATCHABLE and scheme.weights is not None) else None
+        if place is not None:
+            groups[(fmt, place)].append(m)
         else:
             compress_module(m, force_format)
 
-    for (fmt, dev), mods in groups.items():
+    for (fmt, place), mods in groups.items():
         comp = BaseCompressor.get_value_from_registry(fmt.value)
         pack = fmt == CompressionFormat.pack_quantized
         probs, staged = [], []
@@ -66,19 +91,18 @@ def compress_modules_batched(modules, force_format: Optional[CompressionFormat] 
                 qtype, bits = ops._qparams(args)
                 cd = torch.result_type(w, sc)
                 if pack:
-                    out = torch.empty((p.rows, -(-p.cols * bits // 32)), dtype=torch.int32, device=w.device)
+                    out = _empty((p.rows, -(-p.cols * bits // 32)), torch.int32, w)
                     d = ops._desc(p, w.dtype, p.scale.dtype, p.zp.dtype if p.zp is not None else None, cd, torch.int8, None, qtype, bits)
                 else:
                     qd = args.pytorch_dtype()
-                    out = torch.empty(w.shape, dtype=qd, device=w.device)
+                    out = _empty(w.shape, qd, w)
                     d = ops._desc(p, w.dtype, p.scale.dtype, p.zp.dtype if p.zp is not None else None, cd, qd, qd, qtype, bits)
             except (ValueError, NotImplementedError):
                 compress_module(m, force_format)
                 continue
             probs.append((d, w.contiguous(), p.scale.contiguous(), p.zp.contiguous() if p.zp is not None else None, out))
             staged.append((m, sd, out))
-        if probs:
-            ops.batched(N.OP_QUANTIZE_PACK if pack else N.OP_QUANTIZE, probs, dev)
+        _run(N.OP_QUANTIZE_PACK if pack else N.OP_QUANTIZE, probs, place)
         for m, sd, out in staged:
             scheme = m.quantization_scheme
             args = scheme.weights
@@ -104,12 +128,13 @@ def decompress_modules_batched(modules, force_format: Optional[CompressionFormat
             continue
         fmt = _resolve_format(m, scheme, force_format)
         key_t = "weight_packed" if fmt == CompressionFormat.pack_quantized else "weight"
-        if _eligible(m, fmt) and key_t in m._parameters and scheme.weights is not None:
-            groups[(fmt, m._parameters[key_t].device.index)].append(m)
+        place = _placement(m, key_t) if (fmt in _BATCHABLE and scheme.weights is not None) else None
+        if place is not None:
+            groups[(fmt, place)].append(m)
         else:
             decompress_module(m, force_format)
 
-    for (fmt, dev), mods in groups.items():
+    for (fmt, place), mods in groups.items():
         pack = fmt == CompressionFormat.pack_quantized
         probs, staged = [], []
         for m in mods:
@@ -130,18 +155,16 @@ def decompress_modules_batched(modules, force_format: Optional[CompressionFormat
                     like = torch.empty(shape, dtype=torch.int8, device="meta")
                     iargs = ops._infer_dequant_args(like, sc)
                     p = ops._resolve(like, sc, zp, iargs, None)
-                    out_dtype = sc.dtype
-                    out = torch.empty(shape, dtype=out_dtype, device=packed.device)
-                    d = ops._desc(p, None, p.scale.dtype, p.zp.dtype if p.zp is not None else None, None, torch.int8, out_dtype, N.Q_INT, args.num_bits)
+                    out = _empty(shape, sc.dtype, packed)
+                    d = ops._desc(p, None, p.scale.dtype, p.zp.dtype if p.zp is not None else None, None, torch.int8, sc.dtype, N.Q_INT, args.num_bits)
                     src = packed.contiguous()
                     new.pop("weight_packed")
                 else:
                     q = sd["weight"]
                     iargs = ops._infer_dequant_args(q, sc)
                     p = ops._resolve(q, sc, zp, iargs, None)
-                    out_dtype = sc.dtype
-                    out = torch.empty(q.shape, dtype=out_dtype, device=q.device)
-                    d = ops._desc(p, None, p.scale.dtype, p.zp.dtype if p.zp is not None else None, None, q.dtype, out_dtype, N.Q_INT, 8)
+                    out = _empty(q.shape, sc.dtype, q)
+                    d = ops._desc(p, None, p.scale.dtype, p.zp.dtype if p.zp is not None else None, None, q.dtype, sc.dtype, N.Q_INT, 8)
                     src = q.contiguous()
             except (ValueError, NotImplementedError):
                 decompress_module(m, force_format)
@@ -149,8 +172,7 @@ def decompress_modules_batched(modules, force_format: Optional[CompressionFormat
             probs.append((d, src, p.scale.contiguous(), p.zp.contiguous() if p.zp is not None else None, out))
             new["weight"] = out
             staged.append((m, new))
-        if probs:
-            ops.batched(N.OP_UNPACK_DEQUANTIZE if pack else N.OP_DEQUANTIZE, probs, dev)
+        _run(N.OP_UNPACK_DEQUANTIZE if pack else N.OP_DEQUANTIZE, probs, place)
         for m, new in staged:
             replace_direct_state_dict(m, new)
             m.quantization_status = QuantizationStatus.DECOMPRESSED

@@ -533,6 +533,30 @@ def batched(op: int, problems: Sequence[Tuple[N.QuantDesc, torch.Tensor, torch.T
     N.check(rc, "ct_batched")
 
 
+@torch.no_grad()
+def host_batched(op: int, problems: Sequence[Tuple[N.QuantDesc, torch.Tensor, torch.Tensor, Optional[torch.Tensor], torch.Tensor]],
+                 device_index: Optional[int] = None) -> None:
+    """like `batched` but every tensor lives in HOST memory (pinned for full PCIe rate): one pipelined
+    H2D -> kernel -> D2H queue across all tensors (ct_host_run_many).  Blocking."""
+    n = len(problems)
+    if n == 0:
+        return
+    for p in problems:
+        for t in (p[1], p[2], p[3], p[4]):
+            if t is not None and (t.is_cuda or not t.is_contiguous()):
+                raise ValueError("host_batched expects contiguous CPU tensors")
+    idx = device_index if device_index is not None else N.require_device(None)
+    descs = (N.QuantDesc * n)(*[p[0] for p in problems])
+    vp = ctypes.c_void_p * n
+    ins = vp(*[p[1].data_ptr() for p in problems])
+    scs = vp(*[p[2].data_ptr() for p in problems])
+    zps = vp(*[(p[3].data_ptr() if p[3] is not None else 0) for p in problems])
+    outs = vp(*[p[4].data_ptr() for p in problems])
+    rc = N.lib().ct_host_run_many(int(op), n, descs, ctypes.cast(ins, ctypes.c_void_p), ctypes.cast(scs, ctypes.c_void_p),
+                                  ctypes.cast(zps, ctypes.c_void_p), ctypes.cast(outs, ctypes.c_void_p), idx)
+    N.check(rc, "ct_host_run_many")
+
+
 # --------------------------------------------------------------------------------------------
 # bitmasks and sparse formats
 # --------------------------------------------------------------------------------------------

@@ -194,6 +194,12 @@ int ct_semi_structured_to_dense(const void* sparse, int dtype, const void* meta,
 int ct_host_run(int op, const ct_quant_desc* d, const void* in, const void* scale, const void* zp, void* out,
                 int device);
 
+/* The same op over n host-resident tensors (a CPU-resident model: the body of ModelCompressor.compress_model /
+ * decompress_model for state dicts that live in host memory), pipelined ACROSS tensors: all row chunks form one
+ * queue through 4 staging slots, so the PCIe copy engines do not drain between tensors.  Blocking. */
+int ct_host_run_many(int op, int n, const ct_quant_desc* descs, const void* const* in, const void* const* scale,
+                     const void* const* zp, void* const* out, int device);
+
 /* ---- self tests (device-side exhaustive checks used by tests/) ----------------- */
 /* compares the fast reciprocal-based quotient rounding used by the kernels with IEEE
  * division for every (x, s) pair of 16-bit patterns of `dtype` (CT_BF16 or CT_F16) with

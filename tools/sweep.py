@@ -30,9 +30,11 @@ def build_problems(layers: int):
     f8 = SimpleNamespace(strategy="tensor", group_size=None, block_structure=None, num_bits=8, type="float", symmetric=True)
     s8 = [(w.abs().max().float() / 448).bfloat16().reshape(1) for w in ws]
     q8 = [torch.empty(w.shape, dtype=torch.float8_e4m3fn, device=dev) for w in ws]
-    P = {"quantpack": [], "unpackdeq": [], "fp8_q": [], "fp8_dq": [], "fake_w4": []}
-    for w, sc, o, b, s, q in zip(ws, scs, outs, back, s8, q8):
+    P = {"quantpack": [], "unpackdeq": [], "fp8_q": [], "fp8_dq": [], "fake_w4": [], "observe_qp": []}
+    sc_out = [torch.empty_like(s) for s in scs]
+    for w, sc, o, b, s, q, so in zip(ws, scs, outs, back, s8, q8, sc_out):
         p = ops._resolve(w, sc, None, qa, None)
+        P["observe_qp"].append((ops._desc(p, w.dtype, sc.dtype, None, torch.bfloat16, torch.int8, None, N.Q_INT, 4), w, so, None, o))
         P["quantpack"].append((ops._desc(p, w.dtype, sc.dtype, None, torch.bfloat16, torch.int8, None, N.Q_INT, 4), w, sc, None, o))
         P["unpackdeq"].append((ops._desc(p, None, sc.dtype, None, None, torch.int8, torch.bfloat16, N.Q_INT, 4), o, sc, None, b))
         P["fake_w4"].append((ops._desc(p, w.dtype, sc.dtype, None, torch.bfloat16, None, torch.bfloat16, N.Q_INT, 4), w, sc, None, b))
@@ -40,7 +42,7 @@ def build_problems(layers: int):
         P["fp8_q"].append((ops._desc(p8, w.dtype, s.dtype, None, torch.bfloat16, torch.float8_e4m3fn, None, N.Q_FLOAT, 8), w, s, None, q))
         P["fp8_dq"].append((ops._desc(p8, None, s.dtype, None, None, torch.float8_e4m3fn, torch.bfloat16, N.Q_INT, 8), q, s, None, b))
     OPS = {"quantpack": (N.OP_QUANTIZE_PACK, 2.515625), "unpackdeq": (N.OP_UNPACK_DEQUANTIZE, 2.515625),
-           "fp8_q": (N.OP_QUANTIZE, 3.0), "fp8_dq": (N.OP_DEQUANTIZE, 3.0), "fake_w4": (N.OP_FAKE_QUANTIZE, 4.0 + 2 / 128)}
+           "observe_qp": (N.OP_OBSERVE_QUANTIZE_PACK, 2.515625), "fp8_q": (N.OP_QUANTIZE, 3.0), "fp8_dq": (N.OP_DEQUANTIZE, 3.0), "fake_w4": (N.OP_FAKE_QUANTIZE, 4.0 + 2 / 128)}
     return P, OPS, n
 
 
