@@ -267,7 +267,7 @@ def run_b200(a):
         extra["fp8_dequantize"] = rate(lambda: ops.batched(N.OP_DEQUANTIZE, dqprobs, local), n_elems * 3.0, weight_bytes)
         del q8, back, qprobs, dqprobs
         # standalone int4 pack / unpack on int8 codes (one big tensor set: largest shape x 8)
-        codes = [torch.randint(-8, 8, (14336, 4096), dtype=torch.int8, device=dev) for _ in range(8)]
+        codes = [torch.randint(-8, 8, (14336, 4096), dtype=torch.int8, device=dev) for _ in range(32)]  # 1.88 G codes: 2.8 GB of traffic per launch
         nel = sum(c.numel() for c in codes)
         pk = [torch.empty(c.shape[0], c.shape[1] // 8, dtype=torch.int32, device=dev) for c in codes]
         pdesc = []

@@ -57,7 +57,7 @@ _WORKER = textwrap.dedent(
                 a = v.view(torch.uint8) if v.dtype == torch.float8_e4m3fn else v
                 b = s2[k].view(torch.uint8) if s2[k].dtype == torch.float8_e4m3fn else s2[k]
                 assert torch.equal(a, b), f"{preset} {n1}.{k} differs from the single-process result"
-                sums.append(a.double().sum())
+                sums.append(a.double().sum().to(dev))
         t = torch.stack(sums)
         other = t.clone()
         dist.broadcast(other, src=0)
