@@ -79,19 +79,26 @@ class ModelCompressor:
                    force_compression_format=quantization_format)
 
     # ---- compression ------------------------------------------------------------------------
-    def compress_model(self, model: torch.nn.Module, skip_compressed: bool = False) -> None:
+    def compress_model(self, model: torch.nn.Module, skip_compressed: bool = False, distributed: Optional[bool] = None) -> None:
+        """
+        `distributed` (extension; default None = the reference's behaviour, follow `is_distributed()`): pass False
+        when every rank holds its OWN model (independent replicas / shards), so that no module is dealt to another rank.
+        """
         modules = [
             m for _, m in model.named_modules(remove_duplicate=True)
             if is_module_quantized(m) and (not skip_compressed or getattr(m, "quantization_status", None) != QuantizationStatus.COMPRESSED)
         ]
         from ...distributed import is_distributed, replace_module_parallel
 
-        if not is_distributed():
-            from .batched import compress_modules_batched
+        from .batched import compress_modules_batched
 
+        if distributed is None:
+            distributed = is_distributed()
+        if not distributed:
             compress_modules_batched(modules, self.force_compression_format)
         else:
-            replace_module_parallel(modules, partial(compress_module, format=self.force_compression_format), desc=None)
+            replace_module_parallel(modules, partial(compress_module, format=self.force_compression_format), desc=None,
+                                    apply_many_fn=partial(compress_modules_batched, force_format=self.force_compression_format))
         if self.quantization_config is not None:
             self.quantization_config.quantization_status = QuantizationStatus.COMPRESSED
         self.add_decompress_hook(model)

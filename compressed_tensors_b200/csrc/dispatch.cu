@@ -85,7 +85,15 @@ static Plan plan_one(int op, const ct_quant_desc& d, const void* in, const void*
     if (g_idx || n == 0 || n % 8 != 0 || (n / 8) >= 0x7fffffffLL) return p;
     if (!aligned16(in) || !aligned16(out)) return p;
     int64_t D;
-    if (!flat_divisor(d, D)) return p;
+    bool two_d = false;
+    if (!flat_divisor(d, D)) {
+        // 2-D scale addressing (BLOCK strategy, one-row group scales): chunks must not straddle rows or column blocks
+        if (op == CT_OP_OBSERVE_QUANTIZE_PACK || d.cols % 8 != 0 || (d.cols / 8) >= 0x7fffffffLL) return p;
+        if (!is_inf(d.cdiv) && d.cdiv % 8 != 0) return p;
+        if (d.s_row_stride < 0 || d.s_row_stride >= 0x7fffffffLL) return p;
+        two_d = true;
+        D = d.cdiv;
+    }
     if (!is_inf(D) && D % 8 != 0) return p;
     if (zp && d.zp_dtype != CT_I8) return p;
     const int zpk = zp ? 1 : 0;
@@ -156,7 +164,8 @@ static Plan plan_one(int op, const ct_quant_desc& d, const void* in, const void*
     // a thread unit (group of chunks) must see one scale and must not straddle the end of the tensor
     if (sig.group > 1) {
         const bool scale_ok = is_inf(D) || ((D / 8) % sig.group == 0);
-        if (!scale_ok || (n / 8) % sig.group != 0) sig.group = 1;
+        const bool row_ok = !two_d || ((d.cols / 8) % sig.group == 0);
+        if (!scale_ok || !row_ok || (n / 8) % sig.group != 0) sig.group = 1;
     }
     // a partial last tile must still be a multiple of 16 bytes for the bulk copy
     if (((n / 8) * in_bytes_per_chunk) % 16 != 0) return p;
@@ -169,6 +178,11 @@ static Plan plan_one(int op, const ct_quant_desc& d, const void* in, const void*
     p.job.out = reinterpret_cast<uint8_t*>(out);
     p.job.n_chunks = (uint32_t)(n / 8);
     p.job.dc = make_fastdiv(is_inf(D) ? (uint64_t)0x7FFFFFFFull : (uint64_t)(D / 8));
+    if (two_d) {
+        p.job.cpr = make_fastdiv((uint64_t)(d.cols / 8));
+        p.job.rd = make_fastdiv(is_inf(d.rdiv) ? (uint64_t)0x7FFFFFFFull : (uint64_t)d.rdiv);
+        p.job.srs = (uint32_t)d.s_row_stride;
+    }
     p.cm = make_common(p_dt, d.qtype, d.num_bits);
     return p;
 }

@@ -29,10 +29,18 @@ struct RawQP {
 };
 struct NoRaw {};
 
+// index of the scale / zero point of chunk gc (the whole unit shares it)
+__device__ __forceinline__ uint32_t scale_index(const Job& J, uint32_t gc) {
+    if (J.cpr.d == 0) return fd_div(gc, J.dc);                       // flat: TENSOR / CHANNEL / GROUP
+    const uint32_t r = fd_div(gc, J.cpr);                             // 2-D: BLOCK, one-row group scales
+    const uint32_t cc = gc - r * J.cpr.d;
+    return fd_div(r, J.rd) * J.srs + fd_div(cc, J.dc);
+}
+
 template <class P, int ZP>
 __device__ __forceinline__ RawQP fetch_qp(const Job& J, uint32_t gc) {
     RawQP r;
-    const uint32_t si = fd_div(gc, J.dc);
+    const uint32_t si = scale_index(J, gc);
     if constexpr (P::DT == CT_F32) r.s = __float_as_uint(__ldg(reinterpret_cast<const float*>(J.scale) + si));
     else r.s = __ldg(reinterpret_cast<const unsigned short*>(J.scale) + si);
     r.z = 0;

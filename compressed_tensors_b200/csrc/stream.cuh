@@ -39,7 +39,12 @@ struct Job {
     uint32_t tile_begin;   // global id of this job's first tile
     uint32_t tile_end;
     uint32_t _pad;
-    FastDiv dc;            // chunks per scale element (scale index = chunk / dc)
+    FastDiv dc;            // flat mode: chunks per scale element (scale index = chunk / dc); 2-D mode: chunks per column block
+    // 2-D mode (BLOCK strategy, one-row group scales): sidx = (row / rd) * srs + (chunk_in_row / dc)
+    FastDiv cpr;           // chunks per row (d == 0: flat mode)
+    FastDiv rd;            // rows per scale row (block height; "infinite" for a one-row scale)
+    uint32_t srs;          // scale row stride
+    uint32_t _pad2;
 };
 
 struct JobTable {

@@ -28,7 +28,16 @@ def _to_meta(module: torch.nn.Module):
     replace_direct_state_dict(module, {k: (torch.empty_like(v, device="meta") if v is not None else None) for k, v in sd.items()})
 
 
-def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callable = module_size, desc: Optional[str] = None):
+def _wire_device(dev: torch.device) -> torch.device:
+    """where a tensor has to live to be broadcast: NCCL only moves device memory, so a host-resident module goes through this rank's GPU"""
+    if dev.type != "cuda" and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callable = module_size, desc: Optional[str] = None,
+                            apply_many_fn: Optional[Callable] = None):
+    """`apply_many_fn(list_of_modules)` (extension): when given, the owner's modules are processed in one batched call"""
     rank, world = dist.get_rank(), dist.get_world_size()
     devices = {}
     for m in modules:
@@ -41,13 +50,17 @@ def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callab
         if owner[m] != rank:
             _to_meta(m)
             apply_fn(m)
-    for m in modules:
-        if owner[m] == rank:
+    mine = [m for m in modules if owner[m] == rank]
+    if apply_many_fn is not None:
+        apply_many_fn(mine)
+    else:
+        for m in mine:
             apply_fn(m)
 
     for m in modules:  # same (sorted) order on every rank
         sd = get_direct_state_dict(m)
-        dev = devices.get(id(m), torch.device("cpu"))
+        home = devices.get(id(m), torch.device("cpu"))
+        dev = _wire_device(home)
         new = {}
         for name in sd:  # identical key order on all ranks (same compressor code path)
             t = sd[name]
@@ -63,5 +76,5 @@ def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callab
                 dist.broadcast(buf, src=owner[m])
                 got = buf.view(t.dtype) if buf.dtype != t.dtype else buf
                 # tensors the shape-only path already produced for real (e.g. weight_shape, on the CPU) stay where they were
-                new[name] = got if t.device.type == "meta" else got.to(t.device)
+                new[name] = got.to(home) if t.device.type == "meta" else got.to(t.device)
         replace_direct_state_dict(m, new)

@@ -34,7 +34,8 @@ _WORKER = textwrap.dedent(
     dev = f"cuda:{rank}"
     T.DEV = dev
     torch.cuda.set_device(rank)
-    for preset in ("W4A16", "FP8_DYNAMIC"):
+    for preset, where in (("W4A16", dev), ("FP8_DYNAMIC", dev), ("W4A16", "cpu")):   # the last one: host-resident model over NCCL
+        T.DEV = where
         model = _model()
         apply_quantization_config(model, QuantizationConfig(config_groups={preset: ["Linear"]}, ignore=["lm_head"]))
         _calibrate(model)
@@ -45,7 +46,7 @@ _WORKER = textwrap.dedent(
         launches = N.launch_count()
         ModelCompressor.from_pretrained_model(model).compress_model(model)   # distributed path
         mine = N.launch_count() - launches
-        assert 0 < mine < 9, f"rank {rank} launched {mine} kernels: work was not split"
+        assert 0 < mine < 9 or where == "cpu", f"rank {rank} launched {mine} kernels: work was not split"
         sums = []
         for (n1, m1), (n2, m2) in zip(model.named_modules(), single.named_modules()):
             s1, s2 = get_direct_state_dict(m1), get_direct_state_dict(m2)
@@ -53,7 +54,7 @@ _WORKER = textwrap.dedent(
             for k, v in s1.items():
                 if v is None:
                     continue
-                assert v.device == torch.device(dev) or k == "weight_shape", (n1, k, v.device)
+                assert v.device == torch.device(where) or k == "weight_shape", (n1, k, v.device)
                 a = v.view(torch.uint8) if v.dtype == torch.float8_e4m3fn else v
                 b = s2[k].view(torch.uint8) if s2[k].dtype == torch.float8_e4m3fn else s2[k]
                 assert torch.equal(a, b), f"{preset} {n1}.{k} differs from the single-process result"

@@ -89,3 +89,47 @@ def test_semi_structured_errors():
     with pytest.raises(RuntimeError, match="Invalid datatype"):
         sparse_semi_structured_from_dense_cutlass(torch.zeros(64, 64, dtype=torch.float64, device=DEV))
     assert get_permutations_24(4)[0].numel() == 1024
+
+
+# --------------------------------------------------------------------------------------------
+# BLOCK strategy / one-row group scales on the streaming fast path (2-D scale addressing)
+# --------------------------------------------------------------------------------------------
+from types import SimpleNamespace  # noqa: E402
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("shape,block", [((1000, 4096), (128, 128)), ((256, 1024), (64, 256)), ((130, 520), (32, 8))])
+def test_block_quant_fast_path_vs_oracle(dtype, shape, block):
+    g = torch.Generator().manual_seed(shape[0])
+    w = (torch.randn(shape, generator=g) * 0.02).to(dtype)
+    bh, bw = block
+    nr, nc = -(-shape[0] // bh), -(-shape[1] // bw)
+    wp = torch.zeros(nr * bh, nc * bw)
+    wp[: shape[0], : shape[1]] = w.float()
+    scale = (wp.reshape(nr, bh, nc, bw).abs().amax((1, 3)) / 448).to(dtype)
+    scale[scale == 0] = 1.0
+    a = SimpleNamespace(strategy="block", group_size=None, block_structure=[bh, bw], num_bits=8, type="float", symmetric=True)
+    kw = dict(strategy="block", block_structure=[bh, bw], qtype="float", num_bits=8)
+    want = oracle.quantize(w, scale, None, dtype=torch.float8_e4m3fn, **kw)
+    before = N.launch_count()
+    got = ops.quantize(w.to(DEV), scale.to(DEV), None, a, dtype=torch.float8_e4m3fn)
+    assert N.launch_count() == before + 1
+    same_values(got.cpu().view(torch.uint8), want.view(torch.uint8), "block fp8 quantize")
+    same(ops.dequantize(got, scale.to(DEV), None, args=a).cpu(), oracle.dequantize(want, scale, None, strategy="block", block_structure=[bh, bw]), "block dequantize")
+    same(ops.fake_quantize(w.to(DEV), scale.to(DEV), None, a).cpu(), oracle.fake_quantize(w, scale, None, **kw), "block fake_quantize")
+    # int4 + pack with block scales
+    a4 = SimpleNamespace(strategy="block", group_size=None, block_structure=[bh, bw], num_bits=4, type="int", symmetric=True)
+    s4 = (wp.reshape(nr, bh, nc, bw).abs().amax((1, 3)) / 7.5).to(dtype)
+    s4[s4 == 0] = 1.0
+    want4 = oracle.pack_to_int32(oracle.quantize(w, s4, None, strategy="block", block_structure=[bh, bw], num_bits=4, dtype=torch.int8), 4)
+    same_values(ops.quantize_pack(w.to(DEV), s4.to(DEV), None, a4).cpu(), want4, "block int4 quantize_pack")
+
+
+def test_one_row_group_scale_fast_path():
+    g = torch.Generator().manual_seed(1)
+    w = (torch.randn(512, 1024, generator=g) * 0.02).bfloat16()
+    scale = (w.float().unflatten(-1, (-1, 64)).abs().amax((0, 2)) / 7.5).bfloat16().reshape(1, -1)
+    a = SimpleNamespace(strategy="group", group_size=64, block_structure=None, num_bits=4, type="int", symmetric=True)
+    want = oracle.quantize(w, scale, None, strategy="group", group_size=64, num_bits=4, dtype=torch.int8)
+    same_values(ops.quantize(w.to(DEV), scale.to(DEV), None, a, dtype=torch.int8).cpu(), want, "one-row group scale")
+    same_values(ops.quantize_pack(w.to(DEV), scale.to(DEV), None, a).cpu(), oracle.pack_to_int32(want, 4), "one-row group scale, packed")
