@@ -103,11 +103,23 @@ class ModelCompressor:
             self.quantization_config.quantization_status = QuantizationStatus.COMPRESSED
         self.add_decompress_hook(model)
 
-    def decompress_model(self, model: torch.nn.Module) -> None:
+    def decompress_model(self, model: torch.nn.Module, distributed: Optional[bool] = None) -> None:
+        """
+        The reference decompresses every module on every rank (model_compressor.py:196 leaves the distributed
+        version as a TODO).  Here, with `torch.distributed` initialised (or `distributed=True`), modules are dealt
+        to ranks exactly like in compress_model and the dense weights come back by NCCL broadcast.
+        """
         modules = [m for _, m in model.named_modules(remove_duplicate=True) if is_module_quantized(m)]
+        from ...distributed import is_distributed, replace_module_parallel
         from .batched import decompress_modules_batched
 
-        decompress_modules_batched(modules, self.force_compression_format)
+        if distributed is None:
+            distributed = is_distributed()
+        if not distributed:
+            decompress_modules_batched(modules, self.force_compression_format)
+        else:
+            replace_module_parallel(modules, partial(decompress_module, format=self.force_compression_format), desc=None,
+                                    apply_many_fn=partial(decompress_modules_batched, force_format=self.force_compression_format))
         if self.quantization_config is not None:
             self.quantization_config.quantization_status = QuantizationStatus.DECOMPRESSED
         self.remove_decompression_hook(model)

@@ -51,6 +51,10 @@ class PackedQuantizationCompressor(BaseCompressor):
             words = math.ceil(weight.shape[-1] * args.num_bits / 32)
             state_dict["weight_packed"] = torch.empty((*weight.shape[:-1], words), dtype=torch.int32, device="meta")
             state_dict["weight_shape"] = torch.tensor(weight.shape)
+            # the reference's shape-only path leaves the zero point unpacked; here it takes the owner's (packed) shape
+            # so that module-parallel ranks can receive the owner's tensors by plain broadcast
+            if not args.symmetric and args.strategy in PACK_ZP_STRATS and zero_point is not None:
+                state_dict["weight_zero_point"] = ops.pack_to_int32(zero_point, args.num_bits, packed_dim=0).contiguous()
             return cls._remove_symmetric_zp(state_dict, scheme)
 
         state_dict["weight_packed"] = ops.quantize_pack(weight, scale, zero_point, args, g_idx=g_idx)
@@ -71,15 +75,15 @@ class PackedQuantizationCompressor(BaseCompressor):
         args = scheme.weights
         shape = tuple(int(v) for v in original_shape.tolist())
 
-        if packed.device.type == "meta":
-            state_dict["weight"] = torch.empty(shape, dtype=scale.dtype, device="meta")
-            return state_dict
-
         if not args.symmetric and args.strategy in PACK_ZP_STRATS:
             assert zero_point is not None, "Asymmetric quant requires zero-point values"
             zp_shape = (*shape[:-1], scale.shape[-1])
-            zero_point = ops.unpack_from_int32(zero_point, args.num_bits, zp_shape, packed_dim=0)
+            zero_point = ops.unpack_from_int32(zero_point, args.num_bits, zp_shape, packed_dim=0)   # shape-only on meta
             state_dict["weight_zero_point"] = zero_point
+
+        if packed.device.type == "meta":
+            state_dict["weight"] = torch.empty(shape, dtype=scale.dtype, device="meta")
+            return state_dict
 
         state_dict["weight"] = ops.unpack_dequantize(packed, scale, zero_point, args.num_bits, shape, g_idx=g_idx)
         return state_dict

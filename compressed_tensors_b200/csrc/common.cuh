@@ -28,7 +28,9 @@ struct Tuning {
     int pipe;         // 0 direct loads, 1 TMA bulk ring
     int stages;       // ring depth for the TMA variant
     int ctas_per_sm;  // persistent CTAs per SM
+    int dynamic;      // TMA variant: 1 = tiles claimed from a device counter (default), 0 = static round-robin deal
 };
+constexpr int DYNAMIC_MIN_TILES_PER_SM = 24;   // below this many tiles per SM a launch keeps the static deal (no scratch, no memset)
 Tuning tuning();
 int sm_count(int device);
 

@@ -321,14 +321,27 @@ int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in
         lp.tbl.n = (int)jobs.size();
         lp.tbl.jobs = nullptr;
         lp.tbl.one = jobs[0];
-        Job* dev_jobs = nullptr;
-        if (jobs.size() > 1) {
-            CT_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&dev_jobs), jobs.size() * sizeof(Job), stream));
-            CT_CUDA_TRY(cudaMemcpyAsync(dev_jobs, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, stream));
-            lp.tbl.jobs = dev_jobs;
+        // Device scratch of the launch (stream-ordered allocation, so concurrent callers never share it):
+        // [16 bytes: tile counter of the dynamic schedule, zero] [job table when there is more than one job].
+        // Launches with few tiles per CTA keep the static deal and need no scratch at all.
+        uint8_t* scratch = nullptr;
+        const bool many = jobs.size() > 1;
+        const bool dynamic = tuning().dynamic && tiles >= (uint32_t)(DYNAMIC_MIN_TILES_PER_SM * sm_count(device));
+        if (many || dynamic) {
+            const size_t tbl_bytes = many ? jobs.size() * sizeof(Job) : 0;
+            CT_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), 16 + tbl_bytes, stream));
+            if (many) {
+                std::vector<uint8_t> img(16 + tbl_bytes, 0);
+                memcpy(img.data() + 16, jobs.data(), tbl_bytes);
+                CT_CUDA_TRY(cudaMemcpyAsync(scratch, img.data(), img.size(), cudaMemcpyHostToDevice, stream));
+                lp.tbl.jobs = reinterpret_cast<const Job*>(scratch + 16);
+            } else {
+                CT_CUDA_TRY(cudaMemsetAsync(scratch, 0, 16, stream));
+            }
+            if (dynamic) lp.sched = reinterpret_cast<uint32_t*>(scratch);
         }
         rc = launch_sig(plans[i].sig, lp, device, stream);
-        if (dev_jobs) cudaFreeAsync(dev_jobs, stream);
+        if (scratch) cudaFreeAsync(scratch, stream);
         if (rc) return rc;
     }
     return CT_OK;

@@ -30,12 +30,13 @@ int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 // ---- tuning ---------------------------------------------------------------------------------
 static std::mutex g_tune_mu;
-static Tuning g_tune = {-1, 0, 0};
+static Tuning g_tune = {-1, 0, 0, 1};
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     if (!v || !*v) return dflt;
     if (!strcmp(v, "tma")) return 1;
+    if (!strcmp(v, "tma-static")) return 2;
     if (!strcmp(v, "direct")) return 0;
     return atoi(v);
 }
@@ -43,7 +44,9 @@ static int env_int(const char* name, int dflt) {
 Tuning tuning() {
     std::lock_guard<std::mutex> lk(g_tune_mu);
     if (g_tune.pipe < 0) {
-        g_tune.pipe = env_int("CT_B200_PIPE", 1);
+        const int p = env_int("CT_B200_PIPE", 1);
+        g_tune.pipe = p ? 1 : 0;
+        g_tune.dynamic = p == 2 ? 0 : 1;
         g_tune.stages = env_int("CT_B200_STAGES", 4);
         g_tune.ctas_per_sm = env_int("CT_B200_CTAS_PER_SM", 0);
     }
@@ -54,6 +57,7 @@ Tuning tuning() {
 void set_tuning(int pipe, int stages, int ctas) {
     std::lock_guard<std::mutex> lk(g_tune_mu);
     g_tune.pipe = pipe ? 1 : 0;
+    g_tune.dynamic = pipe == 2 ? 0 : 1;
     g_tune.stages = stages > 0 ? stages : 4;
     g_tune.ctas_per_sm = ctas;
 }

@@ -149,10 +149,27 @@ __device__ __forceinline__ void rotate_out(uint32_t (&o)[GROUP * WPC], int off) 
 // ------------------------------------------------------------------------------------
 // pipeline 1: TMA bulk-copy ring
 // ------------------------------------------------------------------------------------
+// Tile schedule.  `sched` != nullptr: DYNAMIC -- the producer lane of every CTA claims tile ids from a
+// zero-initialised device counter with atomicAdd, one claim in flight ahead of its use.  A static
+// round-robin deal leaves bandwidth on the table on B200: SMs do not all see the same HBM bandwidth
+// (two dies, eight stacks), so equal shares finish at different times and the launch waits for the
+// slowest SM (measured with tools/ubench/mix_ceiling.cu: 6.4-6.8 TB/s static vs 7.2 TB/s dynamic
+// for a 2:1 / 4:1 read:write stream).  `sched` == nullptr: static deal (small launches, <= 1 tile a CTA).
+// Either way the producer publishes {tile, next tile} of a stage in shared memory before it arms the
+// stage's full barrier; consumers pick both up after the wait (release/acquire through the mbarrier).
+constexpr uint32_t SMEM_HDR = 384;   // full[12] | empty[12] | ids[12] (8 bytes each), then the data ring
+
+__device__ __forceinline__ void sts_v2(uint32_t saddr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void lds_v2(uint32_t saddr, uint32_t& a, uint32_t& b) {
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(saddr) : "memory");
+}
+
 template <class Op>
 __global__ void __launch_bounds__(32 * (NCW + 1)) stream_tma_kernel(const __grid_constant__ JobTable tbl,
                                                                    const __grid_constant__ Common cm,
-                                                                   uint32_t total_tiles, int stages) {
+                                                                   uint32_t total_tiles, int stages, uint32_t* sched) {
     constexpr int TILE_BYTES = TILE_CHUNKS * Op::IN_BYTES;
     constexpr int CTHREADS = NCW * 32;
     constexpr int G = Op::GROUP;
@@ -161,9 +178,10 @@ __global__ void __launch_bounds__(32 * (NCW + 1)) stream_tma_kernel(const __grid
     static_assert(UNITS % CTHREADS == 0, "tile must split evenly over the consumer threads");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t sbase = smem_u32(smem_raw);
-    const uint32_t full0 = sbase;                    // full[s]  at sbase + 8 s
-    const uint32_t empty0 = sbase + 8 * MAX_STAGES;  // empty[s] at sbase + 96 + 8 s
-    const uint32_t data0 = sbase + 256;
+    const uint32_t full0 = sbase;                        // full[s]  at sbase + 8 s
+    const uint32_t empty0 = sbase + 8 * MAX_STAGES;      // empty[s] at sbase + 96 + 8 s
+    const uint32_t ids0 = sbase + 16 * MAX_STAGES;       // ids[s]   at sbase + 192 + 8 s
+    const uint32_t data0 = sbase + SMEM_HDR;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -182,20 +200,39 @@ __global__ void __launch_bounds__(32 * (NCW + 1)) stream_tma_kernel(const __grid
             const uint64_t policy = l2_evict_first_policy();
             int s = 0, j = 0;
             uint32_t ph = 0;
-            Job J = job_at(tbl, 0);
-            for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                if (tile >= J.tile_end) {
-                    while (tile >= job_tile_end(tbl, j)) ++j;
-                    J = job_at(tbl, j);
+            // cur / nxt are known, nn is the claim in flight
+            uint32_t cur, nxt, nn;
+            if (sched) {
+                cur = atomicAdd(sched, 2u);
+                nxt = cur + 1;                    // the first claim takes two tiles: both ids are needed at once
+            } else {
+                cur = blockIdx.x;
+                nxt = cur + gridDim.x;
+            }
+            if (cur >= total_tiles) {             // nothing left for this CTA: tell the consumers
+                sts_v2(ids0, cur, cur);
+                mbar_arrive_a(full0);
+            } else {
+                Job J = job_at(tbl, 0);
+                while (cur < total_tiles) {
+                    if (sched) nn = (nxt < total_tiles) ? atomicAdd(sched, 1u) : nxt;
+                    else nn = nxt + gridDim.x;
+                    if (cur >= J.tile_end) {
+                        while (cur >= job_tile_end(tbl, j)) ++j;
+                        J = job_at(tbl, j);
+                    }
+                    const uint32_t lt = cur - J.tile_begin;
+                    const uint32_t base = lt * TILE_CHUNKS;
+                    const uint32_t chunks = min((uint32_t)TILE_CHUNKS, J.n_chunks - base);
+                    const uint32_t bytes = chunks * Op::IN_BYTES;
+                    mbar_wait_a(empty0 + 8 * s, ph ^ 1u);
+                    sts_v2(ids0 + 8 * s, cur, nxt);
+                    mbar_expect_tx_a(full0 + 8 * s, bytes);
+                    bulk_g2s_a(data0 + (uint32_t)s * TILE_BYTES, J.in + (size_t)lt * TILE_BYTES, bytes, full0 + 8 * s, policy);
+                    if (++s == stages) { s = 0; ph ^= 1u; }
+                    cur = nxt;
+                    nxt = nn;
                 }
-                const uint32_t lt = tile - J.tile_begin;
-                const uint32_t base = lt * TILE_CHUNKS;
-                const uint32_t chunks = min((uint32_t)TILE_CHUNKS, J.n_chunks - base);
-                const uint32_t bytes = chunks * Op::IN_BYTES;
-                mbar_wait_a(empty0 + 8 * s, ph ^ 1u);
-                mbar_expect_tx_a(full0 + 8 * s, bytes);
-                bulk_g2s_a(data0 + (uint32_t)s * TILE_BYTES, J.in + (size_t)lt * TILE_BYTES, bytes, full0 + 8 * s, policy);
-                if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
     } else {
@@ -208,7 +245,9 @@ __global__ void __launch_bounds__(32 * (NCW + 1)) stream_tma_kernel(const __grid
         // used once) and would otherwise expose a full DRAM round trip per tile.
         Job Jn = job_at(tbl, 0);
         typename Op::Raw raw_next[ITERS];
-        uint32_t tile = blockIdx.x;
+        uint32_t tile, nxt;
+        mbar_wait_a(full0, 0);
+        lds_v2(ids0, tile, nxt);
         if (tile < total_tiles) {
             while (tile >= job_tile_end(tbl, j)) ++j;
             Jn = job_at(tbl, j);
@@ -220,20 +259,20 @@ __global__ void __launch_bounds__(32 * (NCW + 1)) stream_tma_kernel(const __grid
                 if (c0 < chunks) raw_next[it] = Op::prefetch(Jn, base + c0);
             }
         }
-        for (; tile < total_tiles; tile += gridDim.x) {
+        while (tile < total_tiles) {
+            // invariant: full[s] of `tile` has been waited for, `nxt` is the tile after it
             const Job J = Jn;
             const uint32_t base = (tile - J.tile_begin) * TILE_CHUNKS;
             const uint32_t chunks = min((uint32_t)TILE_CHUNKS, J.n_chunks - base);
             typename Op::Raw raw[ITERS];
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) raw[it] = raw_next[it];
-            const uint32_t tn = tile + gridDim.x;
-            if (tn < total_tiles) {
-                if (tn >= Jn.tile_end) {
-                    while (tn >= job_tile_end(tbl, j)) ++j;
+            if (nxt < total_tiles) {
+                if (nxt >= Jn.tile_end) {
+                    while (nxt >= job_tile_end(tbl, j)) ++j;
                     Jn = job_at(tbl, j);
                 }
-                const uint32_t nbase = (tn - Jn.tile_begin) * TILE_CHUNKS;
+                const uint32_t nbase = (nxt - Jn.tile_begin) * TILE_CHUNKS;
                 const uint32_t nchunks = min((uint32_t)TILE_CHUNKS, Jn.n_chunks - nbase);
 #pragma unroll
                 for (int it = 0; it < ITERS; ++it) {
@@ -241,7 +280,6 @@ __global__ void __launch_bounds__(32 * (NCW + 1)) stream_tma_kernel(const __grid
                     if (c0 < nchunks) raw_next[it] = Op::prefetch(Jn, nbase + c0);
                 }
             }
-            mbar_wait_a(full0 + 8 * s, ph);
             const uint32_t sp = data0 + (uint32_t)s * TILE_BYTES;
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
@@ -256,6 +294,11 @@ __global__ void __launch_bounds__(32 * (NCW + 1)) stream_tma_kernel(const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive_a(empty0 + 8 * s);
             if (++s == stages) { s = 0; ph ^= 1u; }
+            tile = nxt;
+            if (tile >= total_tiles) break;
+            mbar_wait_a(full0 + 8 * s, ph);
+            uint32_t t2;
+            lds_v2(ids0 + 8 * s, t2, nxt);
         }
     }
 }
@@ -305,6 +348,7 @@ struct LaunchPlan {
     JobTable tbl;
     Common cm;
     uint32_t total_tiles;
+    uint32_t* sched = nullptr;   // zeroed device counter for the dynamic tile schedule (nullptr = static deal); owned by dispatch.cu
 };
 
 template <class Op>
@@ -321,12 +365,12 @@ int launch_stream(const LaunchPlan& lp, int device, cudaStream_t stream) {
         // keep stages * tile * ctas within ~200 KB of shared memory per SM
         while ((size_t)stages * TILE_BYTES * ctas + 1024 * ctas > 200 * 1024 && stages > 2) --stages;
         while ((size_t)stages * TILE_BYTES * ctas + 1024 * ctas > 200 * 1024 && ctas > 1) --ctas;
-        const size_t smem = 256 + (size_t)stages * TILE_BYTES;
+        const size_t smem = SMEM_HDR + (size_t)stages * TILE_BYTES;
         auto kfn = stream_tma_kernel<Op>;
         CT_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         uint32_t grid = (uint32_t)(sms * ctas);
         if (grid > lp.total_tiles) grid = lp.total_tiles;
-        kfn<<<grid, 32 * (NCW + 1), smem, stream>>>(lp.tbl, lp.cm, lp.total_tiles, stages);
+        kfn<<<grid, 32 * (NCW + 1), smem, stream>>>(lp.tbl, lp.cm, lp.total_tiles, stages, grid < lp.total_tiles ? lp.sched : nullptr);
     } else {
         int ctas = tn.ctas_per_sm > 0 ? tn.ctas_per_sm : 8;
         uint32_t grid = (uint32_t)(sms * ctas);

@@ -24,8 +24,9 @@ __all__ = ["replace_module_parallel"]
 
 
 def _to_meta(module: torch.nn.Module):
+    """data -> meta; `*_shape` bookkeeping tensors hold VALUES the shape-only path reads (decompress), they stay real"""
     sd = get_direct_state_dict(module)
-    replace_direct_state_dict(module, {k: (torch.empty_like(v, device="meta") if v is not None else None) for k, v in sd.items()})
+    replace_direct_state_dict(module, {k: (v if v is None or k.endswith("shape") else torch.empty_like(v, device="meta")) for k, v in sd.items()})
 
 
 def _wire_device(dev: torch.device) -> torch.device:

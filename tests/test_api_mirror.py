@@ -261,7 +261,9 @@ def test_pack_compressor_meta_path():
     assert set(out) == {"weight_packed", "weight_shape", "weight_scale", "weight_zero_point"}
     assert out["weight_packed"].shape == (64, 64) and out["weight_packed"].dtype == torch.int32
     assert out["weight_shape"].tolist() == [64, 512]
+    assert out["weight_zero_point"].shape == (8, 4) and out["weight_zero_point"].dtype == torch.int32
     back = PackedQuantizationCompressor.decompress(out, scheme)
+    assert back["weight_zero_point"].shape == (64, 4) and back["weight_zero_point"].dtype == torch.int8
     assert back["weight"].shape == (64, 512) and back["weight"].dtype == torch.bfloat16 and back["weight"].device.type == "meta"
     sym = PackedQuantizationCompressor.compress(sd, preset_name_to_scheme("W4A16", ["Linear"]))
     assert "weight_zero_point" not in sym

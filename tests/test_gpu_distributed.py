@@ -21,7 +21,7 @@ _WORKER = textwrap.dedent(
     sys.path.insert(0, sys.argv[1])
     from compressed_tensors_b200.distributed import init_dist, is_distributed
     from compressed_tensors_b200.compressors import ModelCompressor
-    from compressed_tensors_b200.compressors.model_compressors.batched import compress_modules_batched
+    from compressed_tensors_b200.compressors.model_compressors.batched import compress_modules_batched, decompress_modules_batched
     from compressed_tensors_b200.quantization import QuantizationConfig, apply_quantization_config
     from compressed_tensors_b200.utils import get_direct_state_dict
     from compressed_tensors_b200 import _native as N
@@ -34,7 +34,7 @@ _WORKER = textwrap.dedent(
     dev = f"cuda:{rank}"
     T.DEV = dev
     torch.cuda.set_device(rank)
-    for preset, where in (("W4A16", dev), ("FP8_DYNAMIC", dev), ("W4A16", "cpu")):   # the last one: host-resident model over NCCL
+    for preset, where in (("W4A16", dev), ("W4A16_ASYM", dev), ("FP8_DYNAMIC", dev), ("W4A16", "cpu")):   # the last one: host-resident model over NCCL
         T.DEV = where
         model = _model()
         apply_quantization_config(model, QuantizationConfig(config_groups={preset: ["Linear"]}, ignore=["lm_head"]))
@@ -44,7 +44,8 @@ _WORKER = textwrap.dedent(
         mods = [m for m in single.modules() if getattr(m, "quantization_scheme", None) is not None]
         compress_modules_batched(mods, None)                     # single-process result on this GPU
         launches = N.launch_count()
-        ModelCompressor.from_pretrained_model(model).compress_model(model)   # distributed path
+        mc = ModelCompressor.from_pretrained_model(model)
+        mc.compress_model(model)   # distributed path
         mine = N.launch_count() - launches
         assert 0 < mine < 9 or where == "cpu", f"rank {rank} launched {mine} kernels: work was not split"
         sums = []
@@ -63,6 +64,16 @@ _WORKER = textwrap.dedent(
         other = t.clone()
         dist.broadcast(other, src=0)
         assert torch.equal(t, other), "ranks disagree"
+        # and back: distributed decompress_model == single-process decompress, on every rank
+        decompress_modules_batched(mods, None)
+        mc.decompress_model(model)
+        for (n1, m1), (n2, m2) in zip(model.named_modules(), single.named_modules()):
+            s1, s2 = get_direct_state_dict(m1), get_direct_state_dict(m2)
+            assert set(s1) == set(s2), (n1, sorted(s1), sorted(s2))
+            for k, v in s1.items():
+                if v is not None:
+                    assert v.dtype == s2[k].dtype and torch.equal(v, s2[k]), f"{preset} {n1}.{k}: distributed decompress differs"
+                    assert v.device == torch.device(where) or k == "weight_shape", (n1, k, v.device)
     dist.barrier()
     dist.destroy_process_group()
     print("OK", rank)

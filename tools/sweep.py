@@ -60,7 +60,7 @@ def main():
     with open(a.out, "a") as f:
         for cfg in a.configs.split(","):
             pipe, stages, ctas = cfg.split(":")
-            N.set_tuning(1 if pipe == "tma" else 0, int(stages) or 4, int(ctas))
+            N.set_tuning({"tma": 1, "tmas": 2}.get(pipe, 0), int(stages) or 4, int(ctas))   # tmas = TMA ring, static deal
             rec = {"pipe": pipe, "stages": int(stages), "ctas_per_sm": int(ctas)}
             for name, (op, bpe) in OPS.items():
                 ts = sorted(bench.time_steps(lambda: ops.batched(op, P[name], 0), a.steps, 3, False) / a.steps for _ in range(5))
