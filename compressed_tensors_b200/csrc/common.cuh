@@ -33,6 +33,7 @@ struct Tuning {
 constexpr int DYNAMIC_MIN_TILES_PER_SM = 24;   // below this many tiles per SM a launch keeps the static deal (no scratch, no memset)
 Tuning tuning();
 int sm_count(int device);
+int scratch_alloc(void** p, size_t bytes, int device, cudaStream_t stream);   // stream-ordered, free with cudaFreeAsync
 
 // RAII device guard
 struct DeviceGuard {

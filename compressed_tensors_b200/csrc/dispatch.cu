@@ -329,7 +329,8 @@ int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in
         const bool dynamic = tuning().dynamic && tiles >= (uint32_t)(DYNAMIC_MIN_TILES_PER_SM * sm_count(device));
         if (many || dynamic) {
             const size_t tbl_bytes = many ? jobs.size() * sizeof(Job) : 0;
-            CT_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), 16 + tbl_bytes, stream));
+            rc = scratch_alloc(reinterpret_cast<void**>(&scratch), 16 + tbl_bytes, device, stream);
+            if (rc) return rc;
             if (many) {
                 std::vector<uint8_t> img(16 + tbl_bytes, 0);
                 memcpy(img.data() + 16, jobs.data(), tbl_bytes);

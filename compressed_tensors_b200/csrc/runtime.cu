@@ -86,6 +86,35 @@ static int dev_info(int device) {
 }
 int sm_count(int device) { return dev_info(device) == 0 ? g_sms[device] : 148; }
 
+// ---- launch scratch ---------------------------------------------------------------------------
+// Job tables and tile counters come from a library-owned stream-ordered pool per device whose release
+// threshold is "never": the default pool hands its memory back at every synchronisation, which made the
+// first launch after a sync pay for a fresh physical allocation.
+static cudaMemPool_t g_pool[64];
+static bool g_pool_init[64];
+
+int scratch_alloc(void** p, size_t bytes, int device, cudaStream_t stream) {
+    if (device < 0 || device >= 64) { set_error("bad device %d", device); return CT_E_ARG; }
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        if (!g_pool_init[device]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = device;
+            CT_CUDA_TRY(cudaMemPoolCreate(&g_pool[device], &props));
+            uint64_t keep = ~0ull;
+            CT_CUDA_TRY(cudaMemPoolSetAttribute(g_pool[device], cudaMemPoolAttrReleaseThreshold, &keep));
+            g_pool_init[device] = true;
+        }
+        pool = g_pool[device];
+    }
+    CT_CUDA_TRY(cudaMallocFromPoolAsync(p, bytes, pool, stream));
+    return CT_OK;
+}
+
 int check_device(int device) {
     if (dev_info(device) != 0) {
         set_error("no usable CUDA device %d: libct_b200 has no CPU path", device);

@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""
+Per-launch timing distribution of the multi-tensor ops on one B200 (one CUDA-event pair per launch):
+tells a systematic slowdown from sporadic stalls.  Prints one JSON line per (op, pipe).
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+import sweep  # noqa: E402
+from compressed_tensors_b200 import _native as N  # noqa: E402
+from compressed_tensors_b200 import ops  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--layers", type=int, default=8)
+    ap.add_argument("--launches", type=int, default=40)
+    ap.add_argument("--pipes", default="1,2")
+    a = ap.parse_args()
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    P, OPS, n = sweep.build_problems(a.layers)
+    codes = [torch.randint(-8, 8, (14336, 4096), dtype=torch.int8, device=dev) for _ in range(16)]
+    pk = [torch.empty(c.shape[0], c.shape[1] // 8, dtype=torch.int32, device=dev) for c in codes]
+    descs = []
+    for c in codes:
+        d = N.QuantDesc()
+        d.rows, d.cols, d.num_bits = c.shape[0], c.shape[1], 4
+        descs.append(d)
+    nel = sum(c.numel() for c in codes)
+    jobs = {k: (op, P[k], n * bpe) for k, (op, bpe) in OPS.items()}
+    jobs["int4_pack"] = (N.OP_PACK_INT32, [(d, c, None, None, o) for d, c, o in zip(descs, codes, pk)], nel * 1.5)
+    jobs["int4_unpack"] = (N.OP_UNPACK_INT32, [(d, o, None, None, c) for d, c, o in zip(descs, codes, pk)], nel * 1.5)
+    for pipe in [int(p) for p in a.pipes.split(",")]:
+        N.set_tuning(pipe, 4, 3)
+        for name, (op, probs, nbytes) in jobs.items():
+            for _ in range(3):
+                ops.batched(op, probs, 0)
+            torch.cuda.synchronize()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.launches)]
+            for e0, e1 in ev:
+                e0.record()
+                ops.batched(op, probs, 0)
+                e1.record()
+            torch.cuda.synchronize()
+            ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+            s = sorted(ms)
+            print(json.dumps({"op": name, "pipe": {1: "tma-dynamic", 2: "tma-static"}[pipe], "GBps_best": round(nbytes / s[0] / 1e6, 1),
+                              "GBps_median": round(nbytes / s[len(s) // 2] / 1e6, 1), "GBps_worst": round(nbytes / s[-1] / 1e6, 1),
+                              "ms": [round(v, 3) for v in ms]}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
