@@ -27,7 +27,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libct_oracle.so")
 _SRC = os.path.join(_HERE, "ct_oracle_all.c")  # includes ct_oracle.c and ct_oracle_qparams.c
-_PARTS = [os.path.join(_HERE, f) for f in ("ct_oracle_all.c", "ct_oracle.c", "ct_oracle_qparams.c")]
+_PARTS = [os.path.join(_HERE, f) for f in ("ct_oracle_all.c", "ct_oracle.c", "ct_oracle_qparams.c", "ct_oracle_fp4.c")]
 
 INT64_MAX = (1 << 63) - 1
 
@@ -70,6 +70,8 @@ def lib() -> ctypes.CDLL:
             "orc_pack_bitmasks orc_unpack_bitmasks orc_sparse24_compress orc_sparse24_decompress "
             "orc_bitmask_compress orc_bitmask_decompress orc_quantize_pack orc_unpack_dequantize "
             "orc_semi_structured_from_dense orc_semi_structured_to_dense "
+            "orc_quantize_gs orc_dequantize_gs orc_fake_quantize_gs "
+            "orc_cast_to_fp4 orc_pack_fp4 orc_unpack_fp4 orc_mx_scale_compress orc_mx_scale_decompress "
             "orc_num_threads"
         ).split():
             getattr(_lib, name).restype = ctypes.c_int
@@ -171,12 +173,32 @@ def _prep(x, scale, zero_point, g_idx, strategy):
     return x2, s, z, gi
 
 
+def _qtype(qtype: str, num_bits: int) -> int:
+    """0 int, 1 fp8 e4m3, 2 fp4 e2m1 (quant_args.py:482-487: FLOAT with num_bits 8 / 4)"""
+    if qtype == "int":
+        return 0
+    if int(num_bits) == 8:
+        return 1
+    if int(num_bits) == 4:
+        return 2
+    raise NotImplementedError("Only num_bits in (4, 8) are supported")
+
+
+def _global_scale(scale, global_scale):
+    """`scale = scale / global_scale` (forward_helpers.py:535-536) is evaluated inside the C code in
+    se = result_type(scale, global_scale); supported: one float32 value held in a 1-D (or higher) tensor"""
+    if global_scale is None:
+        return None, scale.dtype
+    if global_scale.dtype != torch.float32 or global_scale.numel() != 1 or global_scale.ndim == 0:
+        raise NotImplementedError("oracle: global_scale must be a float32 tensor of shape [1]")
+    return global_scale.contiguous(), torch.result_type(scale, global_scale)
+
+
 def quantize(x, scale, zero_point=None, *, strategy="tensor", group_size=None, block_structure=None,
              num_bits=8, qtype="int", dtype=None, g_idx=None, global_scale=None) -> torch.Tensor:
     """forward.py:36-73 -> _process_quantization(do_quantize=True, do_dequantize=False)."""
-    if global_scale is not None:
-        scale = scale / global_scale
-    cd = torch.result_type(x, scale)
+    gs, se = _global_scale(scale, global_scale)
+    cd = torch.result_type(x, torch.empty_like(scale, dtype=se))
     x2, s, z, gi = _prep(x, scale, zero_point, g_idx, strategy)
     rdiv, cdiv, srs = _addressing(x2.shape, s, strategy, group_size, block_structure)
     if strategy in ("group", "tensor_group"):
@@ -187,9 +209,9 @@ def quantize(x, scale, zero_point=None, *, strategy="tensor", group_size=None, b
     # when the group path casts compute-dtype values to x.dtype no extra rounding occurs
     # for integers / fp8 grid values, so storing straight to out_dtype is exact.
     out = torch.empty(x2.shape, dtype=out_dtype)
-    rc = lib().orc_quantize(_p(x2), DT[x2.dtype], _p(s), DT[s.dtype], _p(z), DT[z.dtype] if z is not None else -1,
-                            _p(gi), _p(out), DT[out_dtype], _i64(x2.shape[0]), _i64(x2.shape[1]),
-                            _i64(rdiv), _i64(cdiv), _i64(srs), DT[cd], 0 if qtype == "int" else 1, int(num_bits))
+    rc = lib().orc_quantize_gs(_p(x2), DT[x2.dtype], _p(s), DT[s.dtype], _p(z), DT[z.dtype] if z is not None else -1,
+                               _p(gi), _p(out), DT[out_dtype], _i64(x2.shape[0]), _i64(x2.shape[1]),
+                               _i64(rdiv), _i64(cdiv), _i64(srs), DT[cd], _qtype(qtype, num_bits), int(num_bits), _p(gs), DT[se])
     _check(rc, "quantize")
     return out.reshape(x.shape)
 
@@ -216,16 +238,15 @@ def dequantize(x_q, scale, zero_point=None, *, strategy=None, group_size=None, b
             )
     if dtype is None:
         dtype = scale.dtype
-    if global_scale is not None:
-        scale = scale / global_scale
+    gs, se = _global_scale(scale, global_scale)
     x2, s, z, gi = _prep(x_q, scale, zero_point, g_idx, strategy)
     rdiv, cdiv, srs = _addressing(x2.shape, s, strategy, group_size, block_structure)
     # dtype= is honoured only on the group path
-    out_dtype = dtype if strategy in ("group", "tensor_group") else s.dtype
+    out_dtype = dtype if strategy in ("group", "tensor_group") else se
     out = torch.empty(x2.shape, dtype=out_dtype)
-    rc = lib().orc_dequantize(_p(x2), DT[x2.dtype], _p(s), DT[s.dtype], _p(z), DT[z.dtype] if z is not None else -1,
-                              _p(gi), _p(out), DT[out_dtype], _i64(x2.shape[0]), _i64(x2.shape[1]),
-                              _i64(rdiv), _i64(cdiv), _i64(srs))
+    rc = lib().orc_dequantize_gs(_p(x2), DT[x2.dtype], _p(s), DT[s.dtype], _p(z), DT[z.dtype] if z is not None else -1,
+                                 _p(gi), _p(out), DT[out_dtype], _i64(x2.shape[0]), _i64(x2.shape[1]),
+                                 _i64(rdiv), _i64(cdiv), _i64(srs), _p(gs), DT[se])
     _check(rc, "dequantize")
     return out.reshape(x_q.shape)
 
@@ -233,16 +254,15 @@ def dequantize(x_q, scale, zero_point=None, *, strategy=None, group_size=None, b
 def fake_quantize(x, scale, zero_point=None, *, strategy="tensor", group_size=None, block_structure=None,
                   num_bits=8, qtype="int", g_idx=None, global_scale=None) -> torch.Tensor:
     """forward.py:148-181 -> _quantize_dequantize (forward_helpers.py:180-215)."""
-    if global_scale is not None:
-        scale = scale / global_scale
-    cd = torch.result_type(x, scale)
+    gs, se = _global_scale(scale, global_scale)
+    cd = torch.result_type(x, torch.empty_like(scale, dtype=se))
     x2, s, z, gi = _prep(x, scale, zero_point, g_idx, strategy)
     rdiv, cdiv, srs = _addressing(x2.shape, s, strategy, group_size, block_structure)
-    out_dtype = x.dtype if strategy in ("group", "tensor_group") else s.dtype
+    out_dtype = x.dtype if strategy in ("group", "tensor_group") else se
     out = torch.empty(x2.shape, dtype=out_dtype)
-    rc = lib().orc_fake_quantize(_p(x2), DT[x2.dtype], _p(s), DT[s.dtype], _p(z), DT[z.dtype] if z is not None else -1,
-                                 _p(gi), _p(out), DT[out_dtype], _i64(x2.shape[0]), _i64(x2.shape[1]),
-                                 _i64(rdiv), _i64(cdiv), _i64(srs), DT[cd], 0 if qtype == "int" else 1, int(num_bits))
+    rc = lib().orc_fake_quantize_gs(_p(x2), DT[x2.dtype], _p(s), DT[s.dtype], _p(z), DT[z.dtype] if z is not None else -1,
+                                    _p(gi), _p(out), DT[out_dtype], _i64(x2.shape[0]), _i64(x2.shape[1]),
+                                    _i64(rdiv), _i64(cdiv), _i64(srs), DT[cd], _qtype(qtype, num_bits), int(num_bits), _p(gs), DT[se])
     _check(rc, "fake_quantize")
     return out.reshape(x.shape)
 
@@ -326,3 +346,50 @@ def semi_structured_to_dense(sparse: torch.Tensor, meta: torch.Tensor) -> torch.
     dense = torch.empty(m, 2 * k, dtype=sparse.dtype)
     _check(lib().orc_semi_structured_to_dense(_p(sparse), DT[sparse.dtype], _p(meta), _p(dense), _i64(m), _i64(k)), "semi_to_dense")
     return dense
+
+
+# --------------------------------------------------------------------------- #
+# FP4 (E2M1) and MX (E8M0 scale) pieces -- ct_oracle_fp4.c
+# --------------------------------------------------------------------------- #
+def cast_to_fp4(x: torch.Tensor) -> torch.Tensor:
+    """quantization/utils/fp4_utils.py:77-98"""
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _check(lib().orc_cast_to_fp4(_p(x), DT[x.dtype], _p(out), _i64(x.numel())), "cast_to_fp4")
+    return out
+
+
+def pack_fp4_to_uint8(x: torch.Tensor) -> torch.Tensor:
+    """compressors/nvfp4/helpers.py:108-158"""
+    m, n = x.shape
+    if n % 2 != 0:
+        raise ValueError("tensor must have an even number of columns for nvfp4 compression")
+    x = x.contiguous()
+    out = torch.empty((m, n // 2), dtype=torch.uint8)
+    _check(lib().orc_pack_fp4(_p(x), DT[x.dtype], _p(out), _i64(m), _i64(n)), "pack_fp4_to_uint8")
+    return out
+
+
+def unpack_fp4_from_uint8(a: torch.Tensor, m: int, n: int, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """compressors/nvfp4/helpers.py:162-193"""
+    assert a.dtype == torch.uint8
+    a = a.contiguous()
+    out = torch.empty((m, n), dtype=dtype)
+    _check(lib().orc_unpack_fp4(_p(a), _p(out), DT[dtype], _i64(m), _i64(n)), "unpack_fp4_from_uint8")
+    return out
+
+
+def compress_mx_scale(scale: torch.Tensor, scale_dtype: torch.dtype = torch.uint8) -> torch.Tensor:
+    """compressors/mx_utils.py:18-31"""
+    scale = scale.contiguous()
+    out = torch.empty(scale.shape, dtype=torch.uint8)
+    _check(lib().orc_mx_scale_compress(_p(scale), DT[scale.dtype], _p(out), _i64(scale.numel())), "compress_mx_scale")
+    return out.to(scale_dtype)
+
+
+def decompress_mx_scale(scale: torch.Tensor) -> torch.Tensor:
+    """compressors/mx_utils.py:34-44"""
+    scale = scale.contiguous()
+    out = torch.empty(scale.shape, dtype=torch.bfloat16)
+    _check(lib().orc_mx_scale_decompress(_p(scale), _p(out), _i64(scale.numel())), "decompress_mx_scale")
+    return out

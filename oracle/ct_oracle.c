@@ -33,7 +33,7 @@
 
 /* dtype codes shared with oracle/__init__.py */
 enum { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2, DT_I8 = 3, DT_F8E4M3 = 4, DT_I32 = 5, DT_U8 = 6, DT_I64 = 7 };
-enum { Q_INT = 0, Q_FLOAT = 1 };
+enum { Q_INT = 0, Q_FLOAT = 1, Q_FP4 = 2 };   /* Q_FLOAT = fp8 e4m3, Q_FP4 = fp4 e2m1 (ct_oracle_fp4.c) */
 
 #define ORC_OK 0
 #define ORC_E_DTYPE (-1)
@@ -296,11 +296,16 @@ static inline void q_range(int qtype, int bits, float* qmin, float* qmax) {
         float r = ldexpf(1.0f, bits);
         *qmax = r / 2 - 1;
         *qmin = -r / 2;
+    } else if (qtype == Q_FP4) { /* FP4 e2m1, quant_args.py FP4_E2M1_DATA */
+        *qmax = 6.0f;
+        *qmin = -6.0f;
     } else { /* FP8 e4m3 */
         *qmax = 448.0f;
         *qmin = -448.0f;
     }
 }
+
+float orc_fp4_round(float v);   /* cast_to_fp4, ct_oracle_fp4.c */
 
 /* torch.clamp(t, min, max): NaN propagates */
 static inline float clampf(float v, float lo, float hi) {
@@ -314,15 +319,22 @@ static inline float quant_core(float x, float s, int has_zp, float zp_in_xdt, in
     if (has_zp) t = rnd(t + zp_in_xdt, cd);           /* :539-540, in-place add in cd */
     t = clampf(t, qmin, qmax);                        /* quant_args.py:481 */
     if (qtype == Q_INT) t = nearbyintf(t);            /* torch.round = half-to-even, :490 */
+    else if (qtype == Q_FP4) t = orc_fp4_round(t);    /* FP4_E2M1_DATA.cast_to_fp4, :485 */
     else t = f8e4m3_to_f32(f32_to_f8e4m3(t));         /* .to(float8_e4m3fn) then back, :483,:495 */
     return t;
 }
 
-int orc_quantize(const void* x, int x_dt, const void* scale, int s_dt, const void* zp, int zp_dt,
+/* global scale (forward_helpers.py:535-536, 559-560, 196-197): `scale = scale / global_scale` first, in  */
+/* se_dt = result_type(scale, global_scale); every later "scale.dtype" is se_dt.  gs == NULL: se_dt = s_dt */
+static inline float eff_scale(float sv, const float* gs, int se_dt) { return gs ? rnd(sv / gs[0], se_dt) : sv; }
+
+int orc_quantize_gs(const void* x, int x_dt, const void* scale, int s_dt, const void* zp, int zp_dt,
                  const int32_t* g_idx, void* out, int out_dt, int64_t rows, int64_t cols,
-                 int64_t rdiv, int64_t cdiv, int64_t s_row_stride, int cd, int qtype, int bits) {
+                 int64_t rdiv, int64_t cdiv, int64_t s_row_stride, int cd, int qtype, int bits,
+                 const float* gs, int se_dt) {
     if (!is_float_dt(x_dt) || !is_float_dt(s_dt) || !is_float_dt(cd)) return ORC_E_DTYPE;
     if (qtype == Q_INT && (bits < 1 || bits > 8)) return ORC_E_BITS;
+    if (!gs) se_dt = s_dt;
     float qmin, qmax;
     q_range(qtype, bits, &qmin, &qmax);
 #pragma omp parallel for schedule(static)
@@ -331,7 +343,7 @@ int orc_quantize(const void* x, int x_dt, const void* scale, int s_dt, const voi
         for (int64_t c = 0; c < cols; ++c) {
             int64_t si = sbase + (g_idx ? (int64_t)g_idx[c] : c / cdiv);
             float xv = load_as_f32(x, r * cols + c, x_dt);
-            float sv = load_as_f32(scale, si, s_dt);
+            float sv = eff_scale(load_as_f32(scale, si, s_dt), gs, se_dt);
             float zv = 0.0f;
             if (zp) zv = rnd(load_as_f32(zp, si, zp_dt), x_dt); /* zero_point.to(x.dtype) */
             float q = quant_core(xv, sv, zp != NULL, zv, cd, qtype, qmin, qmax);
@@ -341,29 +353,44 @@ int orc_quantize(const void* x, int x_dt, const void* scale, int s_dt, const voi
     return ORC_OK;
 }
 
-int orc_dequantize(const void* q, int q_dt, const void* scale, int s_dt, const void* zp, int zp_dt,
+int orc_quantize(const void* x, int x_dt, const void* scale, int s_dt, const void* zp, int zp_dt,
+                 const int32_t* g_idx, void* out, int out_dt, int64_t rows, int64_t cols,
+                 int64_t rdiv, int64_t cdiv, int64_t s_row_stride, int cd, int qtype, int bits) {
+    return orc_quantize_gs(x, x_dt, scale, s_dt, zp, zp_dt, g_idx, out, out_dt, rows, cols, rdiv, cdiv, s_row_stride, cd, qtype, bits, NULL, s_dt);
+}
+
+int orc_dequantize_gs(const void* q, int q_dt, const void* scale, int s_dt, const void* zp, int zp_dt,
                    const int32_t* g_idx, void* out, int out_dt, int64_t rows, int64_t cols,
-                   int64_t rdiv, int64_t cdiv, int64_t s_row_stride) {
+                   int64_t rdiv, int64_t cdiv, int64_t s_row_stride, const float* gs, int se_dt) {
     if (!is_float_dt(s_dt) || !is_float_dt(out_dt)) return ORC_E_DTYPE;
+    if (!gs) se_dt = s_dt;
 #pragma omp parallel for schedule(static)
     for (int64_t r = 0; r < rows; ++r) {
         int64_t sbase = (r / rdiv) * s_row_stride;
         for (int64_t c = 0; c < cols; ++c) {
             int64_t si = sbase + (g_idx ? (int64_t)g_idx[c] : c / cdiv);
-            float v = rnd(load_as_f32(q, r * cols + c, q_dt), s_dt);       /* x_q.to(scale.dtype), :562 */
-            float sv = load_as_f32(scale, si, s_dt);
-            if (zp) v = rnd(v - rnd(load_as_f32(zp, si, zp_dt), s_dt), s_dt); /* :564-565 */
-            v = rnd(v * sv, s_dt);                                          /* :567 */
+            float v = rnd(load_as_f32(q, r * cols + c, q_dt), se_dt);      /* x_q.to(scale.dtype), :562 */
+            float sv = eff_scale(load_as_f32(scale, si, s_dt), gs, se_dt);
+            if (zp) v = rnd(v - rnd(load_as_f32(zp, si, zp_dt), se_dt), se_dt); /* :564-565 */
+            v = rnd(v * sv, se_dt);                                         /* :567 */
             store_from_f32(out, r * cols + c, out_dt, v);                   /* :569-570 / forward_helpers.py:171 */
         }
     }
     return ORC_OK;
 }
 
-int orc_fake_quantize(const void* x, int x_dt, const void* scale, int s_dt, const void* zp, int zp_dt,
+int orc_dequantize(const void* q, int q_dt, const void* scale, int s_dt, const void* zp, int zp_dt,
+                   const int32_t* g_idx, void* out, int out_dt, int64_t rows, int64_t cols,
+                   int64_t rdiv, int64_t cdiv, int64_t s_row_stride) {
+    return orc_dequantize_gs(q, q_dt, scale, s_dt, zp, zp_dt, g_idx, out, out_dt, rows, cols, rdiv, cdiv, s_row_stride, NULL, s_dt);
+}
+
+int orc_fake_quantize_gs(const void* x, int x_dt, const void* scale, int s_dt, const void* zp, int zp_dt,
                       const int32_t* g_idx, void* out, int out_dt, int64_t rows, int64_t cols,
-                      int64_t rdiv, int64_t cdiv, int64_t s_row_stride, int cd, int qtype, int bits) {
+                      int64_t rdiv, int64_t cdiv, int64_t s_row_stride, int cd, int qtype, int bits,
+                      const float* gs, int se_dt) {
     if (!is_float_dt(x_dt) || !is_float_dt(s_dt) || !is_float_dt(cd) || !is_float_dt(out_dt)) return ORC_E_DTYPE;
+    if (!gs) se_dt = s_dt;
     float qmin, qmax;
     q_range(qtype, bits, &qmin, &qmax);
 #pragma omp parallel for schedule(static)
@@ -372,16 +399,22 @@ int orc_fake_quantize(const void* x, int x_dt, const void* scale, int s_dt, cons
         for (int64_t c = 0; c < cols; ++c) {
             int64_t si = sbase + (g_idx ? (int64_t)g_idx[c] : c / cdiv);
             float xv = load_as_f32(x, r * cols + c, x_dt);
-            float sv = load_as_f32(scale, si, s_dt);
+            float sv = eff_scale(load_as_f32(scale, si, s_dt), gs, se_dt);
             float zraw = zp ? load_as_f32(zp, si, zp_dt) : 0.0f;
             float qv = quant_core(xv, sv, zp != NULL, rnd(zraw, x_dt), cd, qtype, qmin, qmax);
-            float d = rnd(qv, s_dt);                                /* quantized.to(scale.dtype), :209 */
-            if (zp) d = rnd(d - rnd(zraw, s_dt), s_dt);            /* :210-211 */
-            d = rnd(d * sv, s_dt);                                  /* :213 */
+            float d = rnd(qv, se_dt);                               /* quantized.to(scale.dtype), :209 */
+            if (zp) d = rnd(d - rnd(zraw, se_dt), se_dt);          /* :210-211 */
+            d = rnd(d * sv, se_dt);                                 /* :213 */
             store_from_f32(out, r * cols + c, out_dt, d);
         }
     }
     return ORC_OK;
+}
+
+int orc_fake_quantize(const void* x, int x_dt, const void* scale, int s_dt, const void* zp, int zp_dt,
+                      const int32_t* g_idx, void* out, int out_dt, int64_t rows, int64_t cols,
+                      int64_t rdiv, int64_t cdiv, int64_t s_row_stride, int cd, int qtype, int bits) {
+    return orc_fake_quantize_gs(x, x_dt, scale, s_dt, zp, zp_dt, g_idx, out, out_dt, rows, cols, rdiv, cdiv, s_row_stride, cd, qtype, bits, NULL, s_dt);
 }
 
 /* ------------------------------------------------------------------------- */

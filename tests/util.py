@@ -49,3 +49,15 @@ def same_values(a: torch.Tensor, b: torch.Tensor, what: str = "") -> None:
 
     if a.dtype != b.dtype or a.shape != b.shape or not torch.equal(a, b):
         pytest.fail(f"{what}: {diff_report(a, b)}", pytrace=False)
+
+
+def same_nan(a: torch.Tensor, b: torch.Tensor, what: str = "") -> None:
+    """bit-exact (sign of zero included) except that any NaN matches any NaN (payloads are not part of the contract)"""
+    import pytest
+
+    if a.dtype != b.dtype or a.shape != b.shape:
+        pytest.fail(f"{what}: {diff_report(a, b)}", pytrace=False)
+    na, nb = a.isnan(), b.isnan()
+    if not torch.equal(na, nb):
+        pytest.fail(f"{what}: NaN positions differ ({int(na.sum())} vs {int(nb.sum())})", pytrace=False)
+    same(torch.where(na, torch.zeros_like(a), a), torch.where(nb, torch.zeros_like(b), b), what)
