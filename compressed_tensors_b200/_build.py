@@ -22,6 +22,7 @@ LIB = os.path.join(HERE, "libct_b200.so")
 SOURCES = [
     "runtime.cu",
     "generic.cu",
+    "fp4.cu",
     "fast_pack.cu",
     "fast_quant.cu",
     "fast_fake.cu",

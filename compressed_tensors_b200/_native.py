@@ -37,9 +37,11 @@ DT = {
 }
 
 # ct_batch_op_t
-OP_QUANTIZE_PACK, OP_UNPACK_DEQUANTIZE, OP_QUANTIZE, OP_DEQUANTIZE, OP_FAKE_QUANTIZE, OP_PACK_INT32, OP_UNPACK_INT32, OP_OBSERVE_QUANTIZE_PACK = range(8)
+(OP_QUANTIZE_PACK, OP_UNPACK_DEQUANTIZE, OP_QUANTIZE, OP_DEQUANTIZE, OP_FAKE_QUANTIZE, OP_PACK_INT32, OP_UNPACK_INT32,
+ OP_OBSERVE_QUANTIZE_PACK, OP_QUANTIZE_PACK_FP4, OP_UNPACK_DEQUANTIZE_FP4) = range(10)
 
-Q_INT, Q_FLOAT = 0, 1
+Q_INT, Q_FLOAT, Q_FP4 = 0, 1, 2
+DT_E8M0 = 8  # uint8 MX scale exponent as stored (CT_E8M0)
 
 
 class QuantDesc(ctypes.Structure):
@@ -59,6 +61,9 @@ class QuantDesc(ctypes.Structure):
         ("out_dtype", ctypes.c_int32),
         ("qtype", ctypes.c_int32),
         ("num_bits", ctypes.c_int32),
+        ("global_scale", ctypes.c_void_p),
+        ("seff_dtype", ctypes.c_int32),
+        ("_reserved", ctypes.c_int32),
     ]
 
 
@@ -86,6 +91,13 @@ _PROTOS = {
     "ct_quantize_pack_int32": (_int, [_descp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "ct_unpack_dequantize_int32": (_int, [_descp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "ct_observe_quantize_pack_int32": (_int, [_descp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "ct_cast_to_fp4": (_int, [_vp, _int, _vp, _i64, _int, _vp]),
+    "ct_pack_fp4": (_int, [_vp, _int, _vp, _i64, _i64, _int, _vp]),
+    "ct_unpack_fp4": (_int, [_vp, _vp, _int, _i64, _i64, _int, _vp]),
+    "ct_quantize_pack_fp4": (_int, [_descp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "ct_unpack_dequantize_fp4": (_int, [_descp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "ct_mx_scale_compress": (_int, [_vp, _int, _vp, _i64, _int, _vp]),
+    "ct_mx_scale_decompress": (_int, [_vp, _vp, _i64, _int, _vp]),
     "ct_batched": (_int, [_int, _int, _descp, _vp, _vp, _vp, _vp, _int, _vp]),
     "ct_pack_bitmasks": (_int, [_vp, _vp, _i64, _i64, _int, _vp]),
     "ct_unpack_bitmasks": (_int, [_vp, _vp, _i64, _i64, _int, _vp]),

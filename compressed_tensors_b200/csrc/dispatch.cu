@@ -30,7 +30,10 @@ static int validate_desc(const ct_quant_desc* d) {
         set_error("num_bits %d outside [1, 8]", d->num_bits);
         return CT_E_BITS;
     }
-    if (d->qtype == CT_Q_FLOAT && d->num_bits != 8) { set_error("float quantization supports num_bits == 8 only"); return CT_E_BITS; }
+    if (d->qtype == CT_Q_FLOAT && d->num_bits != 8) { set_error("fp8 quantization needs num_bits == 8"); return CT_E_BITS; }
+    if (d->qtype == CT_Q_FP4 && d->num_bits != 4) { set_error("fp4 quantization needs num_bits == 4"); return CT_E_BITS; }
+    if (d->qtype != CT_Q_INT && d->qtype != CT_Q_FLOAT && d->qtype != CT_Q_FP4) { set_error("bad qtype %d", d->qtype); return CT_E_ARG; }
+    if (d->global_scale && !is_float_dt(d->seff_dtype)) { set_error("seff_dtype must be a float dtype when a global scale is given"); return CT_E_DTYPE; }
     if (d->rdiv <= 0 || d->cdiv <= 0) { set_error("rdiv/cdiv must be positive"); return CT_E_SHAPE; }
     return CT_OK;
 }
@@ -84,6 +87,7 @@ static Plan plan_one(int op, const ct_quant_desc& d, const void* in, const void*
     const int64_t n = d.rows * d.cols;
     if (g_idx || n == 0 || n % 8 != 0 || (n / 8) >= 0x7fffffffLL) return p;
     if (!aligned16(in) || !aligned16(out)) return p;
+    if (d.global_scale || d.qtype == CT_Q_FP4) return p;   // two-level scales / FP4 rounding: fp4 ops have their own plans (below), the rest is generic
     int64_t D;
     bool two_d = false;
     if (!flat_divisor(d, D)) {
@@ -230,6 +234,10 @@ static int run_generic(int op, const ct_quant_desc& d, const void* in, const voi
     case CT_OP_QUANTIZE: return launch_generic_quant(G_QUANTIZE, d, in, scale, zp, g_idx, out, st);
     case CT_OP_DEQUANTIZE: return launch_generic_quant(G_DEQUANTIZE, d, in, scale, zp, g_idx, out, st);
     case CT_OP_FAKE_QUANTIZE: return launch_generic_quant(G_FAKE, d, in, scale, zp, g_idx, out, st);
+    case CT_OP_QUANTIZE_PACK_FP4:
+        return launch_generic_quantpack_fp4(d, in, scale, zp, g_idx, reinterpret_cast<uint8_t*>(out), st);
+    case CT_OP_UNPACK_DEQUANTIZE_FP4:
+        return launch_generic_unpackdeq_fp4(d, reinterpret_cast<const uint8_t*>(in), scale, zp, g_idx, out, st);
     case CT_OP_OBSERVE_QUANTIZE_PACK:
         set_error("fused observe+quantize+pack supports bf16/fp16 group quantization with group_size in {32,64,128,256}, "
                   "4- or 8-bit codes, 16-byte aligned contiguous tensors; run the observer and quantize_pack separately otherwise");
@@ -240,14 +248,19 @@ static int run_generic(int op, const ct_quant_desc& d, const void* in, const voi
 }
 
 static int check_dtypes(int op, const ct_quant_desc& d, bool has_zp) {
-    const bool quantizing = (op == CT_OP_QUANTIZE_PACK || op == CT_OP_QUANTIZE || op == CT_OP_FAKE_QUANTIZE || op == CT_OP_OBSERVE_QUANTIZE_PACK);
-    if (!is_float_dt(d.scale_dtype)) { set_error("scale dtype %d is not a float dtype", d.scale_dtype); return CT_E_DTYPE; }
+    const bool quantizing = (op == CT_OP_QUANTIZE_PACK || op == CT_OP_QUANTIZE || op == CT_OP_FAKE_QUANTIZE || op == CT_OP_OBSERVE_QUANTIZE_PACK ||
+                             op == CT_OP_QUANTIZE_PACK_FP4);
+    const bool fp4_op = (op == CT_OP_QUANTIZE_PACK_FP4 || op == CT_OP_UNPACK_DEQUANTIZE_FP4);
+    if (fp4_op && (d.qtype != CT_Q_FP4 || d.cols % 2 != 0)) { set_error("fp4 ops need qtype fp4 and an even number of columns"); return d.cols % 2 ? CT_E_SHAPE : CT_E_DTYPE; }
+    const bool stored_scale = (op == CT_OP_UNPACK_DEQUANTIZE_FP4 && (d.scale_dtype == CT_F8E4M3 || d.scale_dtype == CT_E8M0));
+    if (stored_scale && !is_float_dt(d.seff_dtype)) { set_error("stored (fp8 / E8M0) scales need seff_dtype = the float dtype they decode to"); return CT_E_DTYPE; }
+    if (!is_float_dt(d.scale_dtype) && !stored_scale) { set_error("scale dtype %d is not a float dtype", d.scale_dtype); return CT_E_DTYPE; }
     if (quantizing && (!is_float_dt(d.x_dtype) || !is_float_dt(d.compute_dtype))) {
         set_error("x / compute dtype must be float (got %d / %d)", d.x_dtype, d.compute_dtype);
         return CT_E_DTYPE;
     }
     if (has_zp && dt_size(d.zp_dtype) == 0) { set_error("bad zero-point dtype %d", d.zp_dtype); return CT_E_DTYPE; }
-    if ((op == CT_OP_DEQUANTIZE || op == CT_OP_UNPACK_DEQUANTIZE || op == CT_OP_FAKE_QUANTIZE) && !is_float_dt(d.out_dtype)) {
+    if ((op == CT_OP_DEQUANTIZE || op == CT_OP_UNPACK_DEQUANTIZE || op == CT_OP_FAKE_QUANTIZE || op == CT_OP_UNPACK_DEQUANTIZE_FP4) && !is_float_dt(d.out_dtype)) {
         set_error("output dtype %d is not a float dtype", d.out_dtype);
         return CT_E_DTYPE;
     }
@@ -395,11 +408,52 @@ static int run_bits(bool pack, const void* in, void* out, int64_t rows, int64_t 
     return launch_generic_unpack(reinterpret_cast<const int32_t*>(in), reinterpret_cast<int8_t*>(out), rows, cols, bits, packed_dim, stream);
 }
 
+// small elementwise FP4 / MX entry points: device checks + one generic launch
+template <class F>
+static int run_simple(int device, int64_t rows, int64_t cols, const void* in, const void* out, F launch) {
+    if (rows < 0 || cols < 0) { set_error("negative shape"); return CT_E_SHAPE; }
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (rows * cols == 0) return CT_OK;
+    if (!in || !out) { set_error("null tensor pointer"); return CT_E_ARG; }
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    return launch();
+}
+
 }  // namespace ctb
 
 using namespace ctb;
 
 extern "C" {
+
+int ct_cast_to_fp4(const void* x, int dtype, void* out, int64_t n, int device, void* stream) {
+    if (!is_float_dt(dtype)) { set_error("cast_to_fp4 needs a float dtype"); return CT_E_DTYPE; }
+    return run_simple(device, 1, n, x, out, [&] { return launch_cast_to_fp4(x, dtype, out, n, reinterpret_cast<cudaStream_t>(stream)); });
+}
+int ct_pack_fp4(const void* x, int dtype, uint8_t* packed, int64_t rows, int64_t cols, int device, void* stream) {
+    if (!is_float_dt(dtype)) { set_error("pack_fp4 needs a float dtype"); return CT_E_DTYPE; }
+    if (cols % 2 != 0) { set_error("tensor must have an even number of columns for nvfp4 compression"); return CT_E_SHAPE; }
+    return run_simple(device, rows, cols, x, packed, [&] { return launch_pack_fp4(x, dtype, packed, rows, cols, reinterpret_cast<cudaStream_t>(stream)); });
+}
+int ct_unpack_fp4(const uint8_t* packed, void* out, int out_dtype, int64_t rows, int64_t cols, int device, void* stream) {
+    if (!is_float_dt(out_dtype)) { set_error("unpack_fp4 needs a float output dtype"); return CT_E_DTYPE; }
+    if (cols % 2 != 0) { set_error("unpack_fp4 needs an even number of columns"); return CT_E_SHAPE; }
+    return run_simple(device, rows, cols, packed, out, [&] { return launch_unpack_fp4(packed, out, out_dtype, rows, cols, reinterpret_cast<cudaStream_t>(stream)); });
+}
+int ct_quantize_pack_fp4(const ct_quant_desc* d, const void* x, const void* scale, const void* zp, const int32_t* g_idx, uint8_t* packed, int device, void* stream) {
+    return run_one(CT_OP_QUANTIZE_PACK_FP4, d, x, scale, zp, g_idx, packed, device, stream);
+}
+int ct_unpack_dequantize_fp4(const ct_quant_desc* d, const uint8_t* packed, const void* scale, const void* zp, const int32_t* g_idx, void* out, int device, void* stream) {
+    return run_one(CT_OP_UNPACK_DEQUANTIZE_FP4, d, packed, scale, zp, g_idx, out, device, stream);
+}
+int ct_mx_scale_compress(const void* scale, int dtype, uint8_t* out, int64_t n, int device, void* stream) {
+    if (!is_float_dt(dtype)) { set_error("mx_scale_compress needs a float dtype"); return CT_E_DTYPE; }
+    return run_simple(device, 1, n, scale, out, [&] { return launch_mx_scale_compress(scale, dtype, out, n, reinterpret_cast<cudaStream_t>(stream)); });
+}
+int ct_mx_scale_decompress(const uint8_t* in, void* out_bf16, int64_t n, int device, void* stream) {
+    return run_simple(device, 1, n, in, out_bf16, [&] { return launch_mx_scale_decompress(in, out_bf16, n, reinterpret_cast<cudaStream_t>(stream)); });
+}
 
 int ct_pack_int32(const int8_t* in, int32_t* out, int64_t rows, int64_t cols, int bits, int packed_dim, int device, void* stream) {
     return run_bits(true, in, out, rows, cols, bits, packed_dim, device, reinterpret_cast<cudaStream_t>(stream));

@@ -40,6 +40,17 @@ int launch_generic_unpackdeq(const ct_quant_desc& d, const int32_t* packed, cons
 int launch_generic_pack(const int8_t* in, int32_t* out, int64_t rows, int64_t cols, int bits, int packed_dim, cudaStream_t stream);
 int launch_generic_unpack(const int32_t* in, int8_t* out, int64_t rows, int64_t cols, int bits, int packed_dim, cudaStream_t stream);
 
+// ---- FP4 / MX (fp4.cu) ----------------------------------------------------------------------------
+int launch_cast_to_fp4(const void* x, int dt, void* out, int64_t n, cudaStream_t st);
+int launch_pack_fp4(const void* x, int dt, uint8_t* out, int64_t rows, int64_t cols, cudaStream_t st);
+int launch_unpack_fp4(const uint8_t* in, void* out, int out_dt, int64_t rows, int64_t cols, cudaStream_t st);
+int launch_generic_quantpack_fp4(const ct_quant_desc& d, const void* x, const void* scale, const void* zp,
+                                 const int32_t* g_idx, uint8_t* packed, cudaStream_t st);
+int launch_generic_unpackdeq_fp4(const ct_quant_desc& d, const uint8_t* packed, const void* scale, const void* zp,
+                                 const int32_t* g_idx, void* out, cudaStream_t st);
+int launch_mx_scale_compress(const void* s, int dt, uint8_t* out, int64_t n, cudaStream_t st);
+int launch_mx_scale_decompress(const uint8_t* in, void* out_bf16, int64_t n, cudaStream_t st);
+
 // ---- dispatch (dispatch.cu): one tensor or a table of tensors ---------------------------------
 int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in, const void* const* scale,
                 const void* const* zp, const int32_t* const* g_idx, void* const* out, int device, cudaStream_t stream);

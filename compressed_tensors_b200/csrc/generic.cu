@@ -3,48 +3,9 @@
 // bit widths 1..8, packed_dim 0 and 1, mixed x / scale / zero-point dtypes.  These are the
 // catch-all behind the streaming fast path (dispatch.cu decides); they are coalesced and
 // bit-exact but not tuned for the roofline.
-#include "engine.h"
-#include "quant_core.cuh"
+#include "generic.cuh"
 
 namespace ctb {
-
-struct GParams {
-    int64_t rows, cols, rdiv, cdiv, srs;
-    int x_dt, s_dt, zp_dt, cd, q_dt, out_dt, qtype, bits;
-    const void* in;
-    const void* scale;
-    const void* zp;
-    const int32_t* gidx;
-    void* out;
-    float qmin, qmax;
-};
-
-__device__ __forceinline__ int64_t scale_index(const GParams& p, int64_t r, int64_t c) {
-    int64_t rb = (p.rdiv == 1) ? r : (p.rdiv == CT_DIV_INF ? 0 : r / p.rdiv);
-    int64_t cb;
-    if (p.gidx) cb = p.gidx[c];
-    else cb = (p.cdiv == CT_DIV_INF) ? 0 : c / p.cdiv;
-    return rb * p.srs + cb;
-}
-
-// quantized value (in compute dtype, as fp32) of x[r, c]
-__device__ __forceinline__ float quant_at(const GParams& p, int64_t r, int64_t c) {
-    const int64_t si = scale_index(p, r, c);
-    const float x = load_as_f32(p.in, r * p.cols + c, p.x_dt);
-    const float s = load_as_f32(p.scale, si, p.s_dt);
-    float z = 0.f;
-    if (p.zp) z = rnd_dt(load_as_f32(p.zp, si, p.zp_dt), p.x_dt);   // zero_point.to(x.dtype)
-    return quant_scalar(x, s, p.zp != nullptr, z, p.cd, p.qtype, p.qmin, p.qmax);
-}
-
-// dequantized value of code q (already widened to fp32) at [r, c], rounded per op to scale dtype
-__device__ __forceinline__ float dequant_at(const GParams& p, float q, int64_t r, int64_t c) {
-    const int64_t si = scale_index(p, r, c);
-    float v = rnd_dt(q, p.s_dt);
-    const float s = load_as_f32(p.scale, si, p.s_dt);
-    if (p.zp) v = rnd_dt(__fsub_rn(v, rnd_dt(load_as_f32(p.zp, si, p.zp_dt), p.s_dt)), p.s_dt);
-    return rnd_dt(__fmul_rn(v, s), p.s_dt);
-}
 
 __global__ void __launch_bounds__(256) generic_quant_kernel(const __grid_constant__ GParams p, int mode) {
     const int64_t n = p.rows * p.cols;
@@ -209,29 +170,6 @@ __global__ void __launch_bounds__(256) unpackdeq_generic_kernel(const __grid_con
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-static GParams make_params(const ct_quant_desc& d, const void* in, const void* scale, const void* zp,
-                           const int32_t* gidx, void* out) {
-    GParams p;
-    p.rows = d.rows; p.cols = d.cols; p.rdiv = d.rdiv; p.cdiv = d.cdiv; p.srs = d.s_row_stride;
-    p.x_dt = d.x_dtype; p.s_dt = d.scale_dtype; p.zp_dt = d.zp_dtype; p.cd = d.compute_dtype;
-    p.q_dt = d.q_dtype; p.out_dt = d.out_dtype; p.qtype = d.qtype; p.bits = d.num_bits;
-    p.in = in; p.scale = scale; p.zp = zp; p.gidx = gidx; p.out = out;
-    if (d.qtype == CT_Q_INT) {
-        const float r = (float)(1 << d.num_bits);
-        p.qmax = r / 2 - 1; p.qmin = -r / 2;
-    } else {
-        p.qmax = 448.f; p.qmin = -448.f;
-    }
-    return p;
-}
-
-static unsigned grid_for(int64_t work_items) {
-    int64_t b = (work_items + 255) / 256;
-    if (b < 1) b = 1;
-    if (b > 148 * 32) b = 148 * 32;
-    return (unsigned)b;
-}
-
 int launch_generic_quant(int mode, const ct_quant_desc& d, const void* in, const void* scale, const void* zp,
                          const int32_t* g_idx, void* out, cudaStream_t stream) {
     const int64_t n = d.rows * d.cols;

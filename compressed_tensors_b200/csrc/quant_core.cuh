@@ -193,6 +193,10 @@ __device__ __forceinline__ float load_as_f32(const void* p, int64_t i, int dt) {
     case CT_F8E4M3: return e4m3_to_f32(reinterpret_cast<const uint8_t*>(p)[i]);
     case CT_I32: return __int2float_rn(reinterpret_cast<const int32_t*>(p)[i]);
     case CT_I64: return __ll2float_rn(reinterpret_cast<const int64_t*>(p)[i]);
+    case CT_E8M0: {   // stored MX scale: 2^(e - 127) decoded through bfloat16 (mx_utils.py:43-44), so e = 255 is +inf
+        const int e = (int)reinterpret_cast<const uint8_t*>(p)[i];
+        return e == 255 ? __int_as_float(0x7f800000) : ldexpf(1.0f, e - 127);
+    }
     default: return 0.f;
     }
 }
@@ -202,12 +206,33 @@ __device__ __forceinline__ float clamp_nan(float v, float lo, float hi) {
 }
 __device__ __forceinline__ uint8_t f32_to_e4m3_byte(float v) { return (uint8_t)(f32x2_to_e4m3x2(v, 0.f) & 0xffu); }
 
+// FP4_E2M1_DATA.cast_to_fp4 (quantization/utils/fp4_utils.py:77-98) on one value: |x| snapped by the closed / open
+// interval ladder, times torch.sign(x) -- so +-0 -> +0, small negatives -> -0, NaN stays NaN
+__device__ __forceinline__ float fp4_round(float v) {
+    const float a = fabsf(v);
+    float r = a <= 0.25f ? 0.0f : a < 0.75f ? 0.5f : a <= 1.25f ? 1.0f : a < 1.75f ? 1.5f : a <= 2.5f ? 2.0f : a < 3.5f ? 3.0f : a <= 5.0f ? 4.0f : 6.0f;
+    if (v != v) return v;
+    return v > 0.f ? r : (v < 0.f ? -r : 0.0f);
+}
+// nibble of an fp4 VALUE (compressors/nvfp4/helpers.py:141-156): index of |v| in the E2M1 table, bit 3 = sign bit
+__device__ __forceinline__ uint32_t fp4_nibble(float v) {
+    const int a = abs((int)(int8_t)(int)(v * 2.0f));
+    const uint32_t idx = a == 1 ? 1u : a == 2 ? 2u : a == 3 ? 3u : a == 4 ? 4u : a == 6 ? 5u : a == 8 ? 6u : a >= 12 ? 7u : 0u;
+    return idx | ((__float_as_uint(v) >> 28) & 8u);
+}
+__device__ __forceinline__ float fp4_value(uint32_t nib) {
+    const float mag = (nib & 4u) ? ((nib & 2u) ? ((nib & 1u) ? 6.0f : 4.0f) : ((nib & 1u) ? 3.0f : 2.0f))
+                                 : ((nib & 2u) ? ((nib & 1u) ? 1.5f : 1.0f) : ((nib & 1u) ? 0.5f : 0.0f));
+    return (nib & 8u) ? -mag : mag;
+}
+
 // value of `quantized_ground` before the final .to(dtype), in compute dtype cd
 __device__ __forceinline__ float quant_scalar(float x, float s, bool has_zp, float zp_in_xdt, int cd, int qtype, float qmin, float qmax) {
     float t = rnd_dt(__fdiv_rn(x, s), cd);
     if (has_zp) t = rnd_dt(__fadd_rn(t, zp_in_xdt), cd);
     t = clamp_nan(t, qmin, qmax);
     if (qtype == CT_Q_INT) t = rintf(t);
+    else if (qtype == CT_Q_FP4) t = fp4_round(t);
     else t = (t != t) ? t : e4m3_to_f32(f32_to_e4m3_byte(t));
     return t;
 }

@@ -40,6 +40,13 @@ __all__ = [
     "bitmask_compress",
     "bitmask_decompress",
     "batched",
+    "cast_to_fp4",
+    "pack_fp4_to_uint8",
+    "unpack_fp4_from_uint8",
+    "quantize_pack_fp4",
+    "unpack_dequantize_fp4",
+    "compress_mx_scale",
+    "decompress_mx_scale",
 ]
 
 _FLOAT_DTYPES = (torch.float32, torch.float16, torch.bfloat16)
@@ -158,7 +165,7 @@ def _type_name(args) -> str:
 class _Problem:
     """resolved 2-D view of one quantization call"""
 
-    __slots__ = ("rows", "cols", "rdiv", "cdiv", "srs", "scale", "zp", "g_idx", "strategy")
+    __slots__ = ("rows", "cols", "rdiv", "cdiv", "srs", "scale", "zp", "g_idx", "strategy", "gs")
 
 
 def _resolve(x: torch.Tensor, scale: torch.Tensor, zero_point: Optional[torch.Tensor], args, g_idx) -> _Problem:
@@ -166,6 +173,7 @@ def _resolve(x: torch.Tensor, scale: torch.Tensor, zero_point: Optional[torch.Te
     p = _Problem()
     p.strategy = strategy
     p.g_idx = None
+    p.gs = None
     cols = x.shape[-1] if x.ndim >= 1 else 1
     rows = x.numel() // max(cols, 1) if x.numel() else 0
     p.rows, p.cols = rows, cols
@@ -236,8 +244,10 @@ def _resolve(x: torch.Tensor, scale: torch.Tensor, zero_point: Optional[torch.Te
 def _qparams(args) -> Tuple[int, int]:
     qtype = N.Q_FLOAT if _type_name(args) == "float" else N.Q_INT
     bits = int(getattr(args, "num_bits", 8))
+    if qtype == N.Q_FLOAT and bits == 4:
+        return N.Q_FP4, 4   # FP4 E2M1 (quant_args.py:484-485)
     if qtype == N.Q_FLOAT and bits != 8:
-        raise NotImplementedError("Only num_bits in (8) are supported for float quantization on this path")
+        raise NotImplementedError("Only num_bits in (4, 8) are supported")
     if qtype == N.Q_INT and not 1 <= bits <= 8:
         raise NotImplementedError(f"integer quantization on this path supports 1..8 bits, got {bits}")
     return qtype, bits
@@ -248,7 +258,8 @@ def _check_float(t: torch.Tensor, what: str):
         raise NotImplementedError(f"{what} dtype {t.dtype} is not supported by compressed_tensors_b200 (fp32/fp16/bf16 only)")
 
 
-def _desc(p: _Problem, x_dt, s_dt, zp_dt, cd, q_dt, out_dt, qtype, bits) -> N.QuantDesc:
+def _desc(p: _Problem, x_dt, s_dt, zp_dt, cd, q_dt, out_dt, qtype, bits, se_dt=None) -> N.QuantDesc:
+    """se_dt: dtype of scale / global_scale (or, for stored fp8 / E8M0 scales, the float dtype they decode to)"""
     d = N.QuantDesc()
     d.rows, d.cols, d.rdiv, d.cdiv, d.s_row_stride = p.rows, p.cols, p.rdiv, p.cdiv, p.srs
     d.x_dtype = N.DT.get(x_dt, N.DT_NONE)
@@ -258,6 +269,8 @@ def _desc(p: _Problem, x_dt, s_dt, zp_dt, cd, q_dt, out_dt, qtype, bits) -> N.Qu
     d.q_dtype = N.DT.get(q_dt, N.DT_NONE)
     d.out_dtype = N.DT.get(out_dt, N.DT_NONE)
     d.qtype, d.num_bits = qtype, bits
+    d.global_scale = None
+    d.seff_dtype = N.DT.get(se_dt, N.DT_NONE)
     return d
 
 
@@ -266,9 +279,12 @@ def _run(fn_name: str, op: int, d: N.QuantDesc, p: _Problem, src: torch.Tensor, 
     lib = N.lib()
     on_cpu = not src.is_cuda
     idx = _dev_index(src, p.scale)
+    gs = getattr(p, "gs", None)
     if (
         on_cpu
         and p.g_idx is None
+        and gs is None
+        and op not in (N.OP_QUANTIZE_PACK_FP4, N.OP_UNPACK_DEQUANTIZE_FP4)
         and src.numel() * src.element_size() >= _HOST_PIPELINE_MIN_BYTES
         and not p.scale.is_cuda
     ):
@@ -284,14 +300,32 @@ def _run(fn_name: str, op: int, d: N.QuantDesc, p: _Problem, src: torch.Tensor, 
     sc = _to_dev(p.scale, idx)
     zp = _to_dev(p.zp, idx)
     gi = _to_dev(p.g_idx.to(torch.int32) if p.g_idx is not None else None, idx)
+    gs_dev = _to_dev(gs, idx)   # one float32 on the device, read by the kernel (kept alive until the call returns)
+    d.global_scale = gs_dev.data_ptr() if gs_dev is not None else None
     out = torch.empty(out_shape, dtype=out_dtype, device=s_dev.device)
     rc = getattr(lib, fn_name)(ctypes.byref(d), N.ptr(s_dev), N.ptr(sc), N.ptr(zp), N.ptr(gi), N.ptr(out), idx, N.stream_ptr(idx))
     N.check(rc, fn_name)
     return out.cpu() if on_cpu else out
 
 
-def _apply_global_scale(scale, global_scale):
-    return scale if global_scale is None else scale / global_scale
+def _global_scale(scale, global_scale):
+    """
+    `scale = scale / global_scale` (forward_helpers.py:535-536, 559-560, 196-197).  A float32 global scale of one
+    element held in a >= 1-D tensor (what generate_gparam returns) is handed to the kernels, which form the quotient
+    per group in registers; any other form is divided here with torch, exactly like the reference.
+    Returns (scale, gs tensor or None, dtype of the effective scale).
+    """
+    if global_scale is None:
+        return scale, None, scale.dtype
+    if global_scale.dtype == torch.float32 and global_scale.numel() == 1 and global_scale.ndim >= 1 and scale.dtype in _FLOAT_DTYPES:
+        return scale, global_scale.reshape(1).contiguous(), torch.result_type(scale, global_scale)
+    scale = scale / global_scale
+    return scale, None, scale.dtype
+
+
+def _like(scale, dtype):
+    """a stand-in with the scale's dimensionality for torch.result_type (0-dim tensors promote differently)"""
+    return torch.empty(scale.shape, dtype=dtype, device="meta")
 
 
 # --------------------------------------------------------------------------------------------
@@ -300,11 +334,11 @@ def _apply_global_scale(scale, global_scale):
 @torch.no_grad()
 def quantize(x, scale, zero_point, args, dtype: Optional[torch.dtype] = None, g_idx=None, global_scale=None) -> torch.Tensor:
     """reference: quantization/lifecycle/forward.py:36-73"""
-    scale = _apply_global_scale(scale, global_scale)
+    scale, gs, se = _global_scale(scale, global_scale)
     _check_float(x, "input")
     _check_float(scale, "scale")
     qtype, bits = _qparams(args)
-    cd = torch.result_type(x, scale)
+    cd = torch.result_type(x, scale if gs is None else _like(scale, se))
     strategy = _strategy_name(args)
     if strategy in ("group", "tensor_group"):
         out_dtype = dtype if dtype is not None else x.dtype  # forward_helpers.py:134,171
@@ -317,7 +351,8 @@ def quantize(x, scale, zero_point, args, dtype: Optional[torch.dtype] = None, g_
         return torch.empty(x.shape, dtype=out_dtype, device=x.device)
     if out_dtype not in N.DT:
         raise NotImplementedError(f"quantize(dtype={out_dtype}) is not supported")
-    d = _desc(p, x.dtype, p.scale.dtype, p.zp.dtype if p.zp is not None else None, cd, out_dtype, out_dtype, qtype, bits)
+    p.gs = gs
+    d = _desc(p, x.dtype, p.scale.dtype, p.zp.dtype if p.zp is not None else None, cd, out_dtype, out_dtype, qtype, bits, se)
     x2 = x.reshape(p.rows, p.cols)
     out = _run("ct_quantize", N.OP_QUANTIZE, d, p, x2, (p.rows, p.cols), out_dtype)
     return out.reshape(x.shape)
@@ -350,11 +385,11 @@ def dequantize(x_q, scale, zero_point=None, args=None, dtype: Optional[torch.dty
         args = _infer_dequant_args(x_q, scale)
     if dtype is None:
         dtype = scale.dtype
-    scale = _apply_global_scale(scale, global_scale)
+    scale, gs, se = _global_scale(scale, global_scale)
     _check_float(scale, "scale")
     strategy = _strategy_name(args)
     # the dtype argument is honoured only on the group path
-    out_dtype = dtype if strategy in ("group", "tensor_group") else scale.dtype
+    out_dtype = dtype if strategy in ("group", "tensor_group") else se
     p = _resolve(x_q, scale, zero_point, args, g_idx)
     if strategy == "block":
         # inferred block sizes may not cover the tensor (forward.py:118-126); the reference pads
@@ -366,7 +401,8 @@ def dequantize(x_q, scale, zero_point=None, args=None, dtype: Optional[torch.dty
         return torch.empty(x_q.shape, dtype=out_dtype, device=x_q.device)
     if x_q.dtype not in N.DT or out_dtype not in _FLOAT_DTYPES:
         raise NotImplementedError(f"dequantize from {x_q.dtype} to {out_dtype} is not supported")
-    d = _desc(p, None, p.scale.dtype, p.zp.dtype if p.zp is not None else None, None, x_q.dtype, out_dtype, N.Q_INT, 8)
+    p.gs = gs
+    d = _desc(p, None, p.scale.dtype, p.zp.dtype if p.zp is not None else None, None, x_q.dtype, out_dtype, N.Q_INT, 8, se)
     q2 = x_q.reshape(p.rows, p.cols)
     out = _run("ct_dequantize", N.OP_DEQUANTIZE, d, p, q2, (p.rows, p.cols), out_dtype)
     return out.reshape(x_q.shape)
@@ -375,19 +411,20 @@ def dequantize(x_q, scale, zero_point=None, args=None, dtype: Optional[torch.dty
 @torch.no_grad()
 def fake_quantize(x, scale, zero_point, args, g_idx=None, global_scale=None) -> torch.Tensor:
     """reference: quantization/lifecycle/forward.py:148-181"""
-    scale = _apply_global_scale(scale, global_scale)
+    scale, gs, se = _global_scale(scale, global_scale)
     _check_float(x, "input")
     _check_float(scale, "scale")
     qtype, bits = _qparams(args)
-    cd = torch.result_type(x, scale)
+    cd = torch.result_type(x, scale if gs is None else _like(scale, se))
     strategy = _strategy_name(args)
-    out_dtype = x.dtype if strategy in ("group", "tensor_group") else scale.dtype
+    out_dtype = x.dtype if strategy in ("group", "tensor_group") else se
     p = _resolve(x, scale, zero_point, args, g_idx)
     if x.device.type == "meta":
         return torch.empty(x.shape, dtype=out_dtype, device="meta")
     if x.numel() == 0:
         return torch.empty(x.shape, dtype=out_dtype, device=x.device)
-    d = _desc(p, x.dtype, p.scale.dtype, p.zp.dtype if p.zp is not None else None, cd, None, out_dtype, qtype, bits)
+    p.gs = gs
+    d = _desc(p, x.dtype, p.scale.dtype, p.zp.dtype if p.zp is not None else None, cd, None, out_dtype, qtype, bits, se)
     x2 = x.reshape(p.rows, p.cols)
     out = _run("ct_fake_quantize", N.OP_FAKE_QUANTIZE, d, p, x2, (p.rows, p.cols), out_dtype)
     return out.reshape(x.shape)
@@ -408,18 +445,19 @@ def quantize_pack(x, scale, zero_point, args, g_idx=None, global_scale=None) -> 
             zp = zero_point[i] if (zero_point is not None and zero_point.ndim == x.ndim) else zero_point
             outs.append(quantize_pack(x[i], sc, zp, args, g_idx, global_scale))
         return torch.stack(outs)
-    scale = _apply_global_scale(scale, global_scale)
+    scale, gs, se = _global_scale(scale, global_scale)
     _check_float(x, "input")
     _check_float(scale, "scale")
     qtype, bits = _qparams(args)
     if qtype != N.Q_INT:
         raise ValueError("pack-quantized compression needs integer quantization")
-    cd = torch.result_type(x, scale)
+    cd = torch.result_type(x, scale if gs is None else _like(scale, se))
     p = _resolve(x, scale, zero_point, args, g_idx)
+    p.gs = gs
     out_shape = (p.rows, math.ceil(p.cols * bits / 32))
     if x.device.type == "meta":
         return torch.empty(out_shape, dtype=torch.int32, device="meta")
-    d = _desc(p, x.dtype, p.scale.dtype, p.zp.dtype if p.zp is not None else None, cd, torch.int8, None, qtype, bits)
+    d = _desc(p, x.dtype, p.scale.dtype, p.zp.dtype if p.zp is not None else None, cd, torch.int8, None, qtype, bits, se)
     return _run("ct_quantize_pack_int32", N.OP_QUANTIZE_PACK, d, p, x.reshape(p.rows, p.cols), out_shape, torch.int32)
 
 
@@ -457,6 +495,137 @@ def unpack_dequantize(packed, scale, zero_point, num_bits: int, shape: Sequence[
         return torch.empty(shape, dtype=out_dtype, device="meta")
     d = _desc(p, None, p.scale.dtype, p.zp.dtype if p.zp is not None else None, None, torch.int8, out_dtype, N.Q_INT, int(num_bits))
     return _run("ct_unpack_dequantize_int32", N.OP_UNPACK_DEQUANTIZE, d, p, packed, shape, out_dtype)
+
+
+# --------------------------------------------------------------------------------------------
+# FP4 (E2M1) and MX formats
+# --------------------------------------------------------------------------------------------
+def _simple(fn_name: str, src: torch.Tensor, out_shape, out_dtype, call) -> torch.Tensor:
+    """one elementwise FP4 / MX kernel on `src` (CPU tensors are staged through the GPU)"""
+    if src.device.type == "meta":
+        return torch.empty(out_shape, dtype=out_dtype, device="meta")
+    idx = _dev_index(src)
+    s_dev = _to_dev(src.contiguous(), idx)
+    out = torch.empty(out_shape, dtype=out_dtype, device=s_dev.device)
+    N.check(call(N.lib(), s_dev, out, idx), fn_name)
+    return out.cpu() if not src.is_cuda else out
+
+
+@torch.no_grad()
+def cast_to_fp4(x: torch.Tensor) -> torch.Tensor:
+    """reference: quantization/utils/fp4_utils.py:77-98 (returns a new tensor; the reference writes in place on a temporary)"""
+    _check_float(x, "input")
+    return _simple("ct_cast_to_fp4", x, x.shape, x.dtype,
+                   lambda lib, a, o, i: lib.ct_cast_to_fp4(N.ptr(a), N.DT[a.dtype], N.ptr(o), a.numel(), i, N.stream_ptr(i)))
+
+
+@torch.no_grad()
+def pack_fp4_to_uint8(x: torch.Tensor) -> torch.Tensor:
+    """reference: compressors/nvfp4/helpers.py:108-158"""
+    m, n = x.shape
+    if n % 2 != 0:
+        raise ValueError("tensor must have an even number of columns for nvfp4 compression")
+    _check_float(x, "input")
+    return _simple("ct_pack_fp4", x, (m, n // 2), torch.uint8,
+                   lambda lib, a, o, i: lib.ct_pack_fp4(N.ptr(a), N.DT[a.dtype], N.ptr(o), m, n, i, N.stream_ptr(i)))
+
+
+@torch.no_grad()
+def unpack_fp4_from_uint8(a: torch.Tensor, m: int, n: int, dtype: Optional[torch.dtype] = torch.bfloat16) -> torch.Tensor:
+    """reference: compressors/nvfp4/helpers.py:162-193"""
+    assert a.dtype == torch.uint8
+    if dtype not in _FLOAT_DTYPES:
+        raise NotImplementedError(f"unpack_fp4_from_uint8 to {dtype} is not supported")
+    if a.numel() * 2 != m * n or n % 2 != 0:
+        raise ValueError(f"{a.numel()} packed bytes do not hold a [{m}, {n}] fp4 tensor")
+    return _simple("ct_unpack_fp4", a, (m, n), dtype,
+                   lambda lib, t, o, i: lib.ct_unpack_fp4(N.ptr(t), N.ptr(o), N.DT[dtype], m, n, i, N.stream_ptr(i)))
+
+
+@torch.no_grad()
+def compress_mx_scale(scale: torch.Tensor, scale_dtype: torch.dtype = torch.uint8) -> torch.Tensor:
+    """reference: compressors/mx_utils.py:18-31 (E8M0: 127 + floor(log2(scale)))"""
+    _check_float(scale, "scale")
+    out = _simple("ct_mx_scale_compress", scale, scale.shape, torch.uint8,
+                  lambda lib, a, o, i: lib.ct_mx_scale_compress(N.ptr(a), N.DT[a.dtype], N.ptr(o), a.numel(), i, N.stream_ptr(i)))
+    return out.to(scale_dtype)
+
+
+@torch.no_grad()
+def decompress_mx_scale(scale: torch.Tensor) -> torch.Tensor:
+    """reference: compressors/mx_utils.py:34-44 (uint8 exponent -> bfloat16 power of two)"""
+    if scale.dtype != torch.uint8:
+        scale = scale.to(torch.uint8)
+    return _simple("ct_mx_scale_decompress", scale, scale.shape, torch.bfloat16,
+                   lambda lib, a, o, i: lib.ct_mx_scale_decompress(N.ptr(a), N.ptr(o), a.numel(), i, N.stream_ptr(i)))
+
+
+@torch.no_grad()
+def quantize_pack_fp4(x, scale, zero_point, args, g_idx=None, global_scale=None) -> torch.Tensor:
+    """quantize(FP4 args) -> pack_fp4_to_uint8 in one pass (compressors/nvfp4/base.py:82-90): x [R, C] float ->
+    uint8 [R, C/2].  NVFP4: group 16 + global_scale; MXFP4: group 32, power-of-two scales."""
+    if x.ndim != 2:
+        raise ValueError("fp4 packing needs a 2-D weight")
+    if x.shape[1] % 2 != 0:
+        raise ValueError("tensor must have an even number of columns for nvfp4 compression")
+    scale, gs, se = _global_scale(scale, global_scale)
+    _check_float(x, "input")
+    _check_float(scale, "scale")
+    qtype, bits = _qparams(args)
+    if qtype != N.Q_FP4:
+        raise ValueError("fp4 packing needs FLOAT quantization with num_bits == 4")
+    cd = torch.result_type(x, scale if gs is None else _like(scale, se))
+    p = _resolve(x, scale, zero_point, args, g_idx)
+    p.gs = gs
+    out_shape = (p.rows, p.cols // 2)
+    if x.device.type == "meta":
+        return torch.empty(out_shape, dtype=torch.uint8, device="meta")
+    d = _desc(p, x.dtype, p.scale.dtype, p.zp.dtype if p.zp is not None else None, cd, x.dtype, None, qtype, bits, se)
+    return _run("ct_quantize_pack_fp4", N.OP_QUANTIZE_PACK_FP4, d, p, x.reshape(p.rows, p.cols), out_shape, torch.uint8)
+
+
+@torch.no_grad()
+def unpack_dequantize_fp4(packed, scale, global_scale=None, dtype: torch.dtype = torch.bfloat16, stored_scale: Optional[str] = None) -> torch.Tensor:
+    """
+    unpack_fp4_from_uint8 -> dequantize in one pass (compressors/nvfp4/base.py:111-128): uint8 [R, C/2] -> `dtype` [R, C].
+    `scale` is either the float scale the reference hands to dequantize (scale.to(dtype)), or the STORED scale:
+    stored_scale="fp8" (float8_e4m3fn, NVFP4) / "e8m0" (uint8 exponents, MX), decoded in registers to `dtype`
+    exactly like _decompress_scale does.
+    """
+    if packed.dtype != torch.uint8 or packed.ndim != 2:
+        raise ValueError("packed fp4 weights are 2-D uint8")
+    if dtype not in _FLOAT_DTYPES:
+        raise NotImplementedError(f"unpack_dequantize_fp4 to {dtype} is not supported")
+    m, n = packed.shape[0], packed.shape[1] * 2
+    if stored_scale is None:
+        _check_float(scale, "scale")
+        s_code, base_dt = None, scale.dtype
+    elif stored_scale == "fp8":
+        if scale.dtype != torch.float8_e4m3fn:
+            raise ValueError("stored NVFP4 scales are float8_e4m3fn")
+        s_code, base_dt = N.DT[torch.float8_e4m3fn], dtype
+    elif stored_scale == "e8m0":
+        if scale.dtype != torch.uint8:
+            raise ValueError("stored MX scales are uint8 exponents")
+        s_code, base_dt = N.DT_E8M0, dtype
+    else:
+        raise ValueError(f"unknown stored_scale {stored_scale!r}")
+    if global_scale is not None:
+        if not (global_scale.dtype == torch.float32 and global_scale.numel() == 1 and global_scale.ndim >= 1):
+            raise NotImplementedError("global_scale must be a float32 tensor of shape [1]")
+        gs, se = global_scale.reshape(1).contiguous(), torch.result_type(_like(scale, base_dt), global_scale)
+    else:
+        gs, se = None, base_dt
+    like = torch.empty((m, n), dtype=torch.int8, device="meta")
+    args = _infer_dequant_args(like, scale)
+    out_dtype = dtype if _strategy_name(args) in ("group", "tensor_group") else se
+    p = _resolve(like, scale, None, args, None)
+    p.gs = gs
+    if packed.device.type == "meta":
+        return torch.empty((m, n), dtype=out_dtype, device="meta")
+    d = _desc(p, None, torch.float32, None, None, None, out_dtype, N.Q_FP4, 4, se)
+    d.scale_dtype = s_code if s_code is not None else N.DT[scale.dtype]
+    return _run("ct_unpack_dequantize_fp4", N.OP_UNPACK_DEQUANTIZE_FP4, d, p, packed, (m, n), out_dtype)
 
 
 @torch.no_grad()

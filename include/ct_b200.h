@@ -52,10 +52,12 @@ typedef enum ct_dtype_t {
     CT_F8E4M3 = 4,         /* torch.float8_e4m3fn */
     CT_I32 = 5,
     CT_U8 = 6,             /* also torch.bool */
-    CT_I64 = 7
+    CT_I64 = 7,
+    CT_E8M0 = 8            /* uint8 biased power-of-two exponent: an MX scale as STORED (compressors/mx_utils.py:18-44) */
 } ct_dtype_t;
 
-typedef enum ct_qtype_t { CT_Q_INT = 0, CT_Q_FLOAT = 1 } ct_qtype_t;
+/* CT_Q_FLOAT = fp8 e4m3 (num_bits 8); CT_Q_FP4 = fp4 e2m1 (num_bits 4: values 0, .5, 1, 1.5, 2, 3, 4, 6 and negatives) */
+typedef enum ct_qtype_t { CT_Q_INT = 0, CT_Q_FLOAT = 1, CT_Q_FP4 = 2 } ct_qtype_t;
 
 #define CT_DIV_INF INT64_MAX
 
@@ -82,6 +84,12 @@ typedef struct ct_quant_desc {
     int32_t out_dtype;      /* float output of dequantize / fake_quantize */
     int32_t qtype;          /* ct_qtype_t */
     int32_t num_bits;
+    /* NVFP4-style two-level scaling (forward_helpers.py:535-536, 559-560, 196-197): when global_scale != NULL
+     * (DEVICE pointer to one float32) every op first forms  scale = scale / global_scale  in
+     * seff_dtype = result_type(scale, global_scale), and "scale dtype" below means seff_dtype. */
+    const void* global_scale;
+    int32_t seff_dtype;
+    int32_t _reserved;
 } ct_quant_desc;
 
 /* ---- library / device ---------------------------------------------------- */
@@ -136,6 +144,25 @@ int ct_unpack_dequantize_int32(const ct_quant_desc* d, const int32_t* packed, co
 int ct_observe_quantize_pack_int32(const ct_quant_desc* d, const void* x, void* scale_out, void* zp_out, int32_t* packed,
                                    int device, void* stream);
 
+/* ---- FP4 (E2M1) and MX formats -------------------------
+ * cast_to_fp4: quantization/utils/fp4_utils.py:77-98 (x and out share a float dtype).
+ * pack_fp4 / unpack_fp4: compressors/nvfp4/helpers.py:108-158 / :162-193 -- x [rows, cols] of VALID fp4 values
+ *   <-> uint8 [rows, cols/2], element 2j in the low nibble, bit 3 of a nibble = sign (so -0.0 survives).
+ * quantize_pack_fp4 / unpack_dequantize_fp4: the bodies of NVFP4PackedCompressor / MXFP4PackedCompressor
+ *   .compress / .decompress (compressors/nvfp4/base.py:73-93, 111-128) in one pass: quantize (d->qtype =
+ *   CT_Q_FP4, group 16 with d->global_scale for NVFP4, group 32 for MXFP4) -> nibbles, and nibbles -> dequantize.
+ *   For the decompress direction the scale may be given AS STORED: CT_F8E4M3 (NVFP4) or CT_E8M0 (MXFP4).
+ * mx_scale_compress / decompress: compressors/mx_utils.py:18-31 / :34-44 (E8M0 encode of float scales; decode to bf16). */
+int ct_cast_to_fp4(const void* x, int dtype, void* out, int64_t n, int device, void* stream);
+int ct_pack_fp4(const void* x, int dtype, uint8_t* packed, int64_t rows, int64_t cols, int device, void* stream);
+int ct_unpack_fp4(const uint8_t* packed, void* out, int out_dtype, int64_t rows, int64_t cols, int device, void* stream);
+int ct_quantize_pack_fp4(const ct_quant_desc* d, const void* x, const void* scale, const void* zp, const int32_t* g_idx,
+                         uint8_t* packed, int device, void* stream);
+int ct_unpack_dequantize_fp4(const ct_quant_desc* d, const uint8_t* packed, const void* scale, const void* zp,
+                             const int32_t* g_idx, void* out, int device, void* stream);
+int ct_mx_scale_compress(const void* scale, int dtype, uint8_t* out, int64_t n, int device, void* stream);
+int ct_mx_scale_decompress(const uint8_t* in, void* out_bf16, int64_t n, int device, void* stream);
+
 /* ---- multi-tensor (whole-model) launches -------------------------------------
  * One persistent launch over `n` independent tensors: the body of the module loop of
  * ModelCompressor.compress_model / decompress_model
@@ -149,7 +176,9 @@ typedef enum ct_batch_op_t {
     CT_OP_FAKE_QUANTIZE = 4,      /* in x        -> out float */
     CT_OP_PACK_INT32 = 5,         /* in int8 codes -> out packed int32 (packed_dim 1; desc: rows, cols, num_bits; no scale) */
     CT_OP_UNPACK_INT32 = 6,       /* in packed   -> out int8 codes */
-    CT_OP_OBSERVE_QUANTIZE_PACK = 7 /* in x      -> out packed int32; scale[i] / zp[i] are OUTPUTS (see ct_observe_quantize_pack_int32) */
+    CT_OP_OBSERVE_QUANTIZE_PACK = 7, /* in x     -> out packed int32; scale[i] / zp[i] are OUTPUTS (see ct_observe_quantize_pack_int32) */
+    CT_OP_QUANTIZE_PACK_FP4 = 8,  /* in x        -> out uint8 nibbles (ct_quantize_pack_fp4) */
+    CT_OP_UNPACK_DEQUANTIZE_FP4 = 9 /* in nibbles -> out float (ct_unpack_dequantize_fp4) */
 } ct_batch_op_t;
 int ct_batched(int op, int n, const ct_quant_desc* descs, const void* const* in, const void* const* scale,
                const void* const* zp, void* const* out, int device, void* stream);
