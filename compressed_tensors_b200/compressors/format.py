@@ -12,8 +12,10 @@ from ..quantization.utils.helpers import is_module_quantized
 
 __all__ = ["infer_model_format", "infer_module_format", "COMPRESSION_FORMAT_PRIORITY"]
 
-# the FP4 / MX formats of the reference's list are not registered in this engine
 COMPRESSION_FORMAT_PRIORITY: List[CompressionFormat] = [
+    CompressionFormat.mxfp4_pack_quantized,
+    CompressionFormat.mxfp8_quantized,
+    CompressionFormat.nvfp4_pack_quantized,
     CompressionFormat.int_quantized,
     CompressionFormat.pack_quantized,
     CompressionFormat.float_quantized,
@@ -25,10 +27,6 @@ COMPRESSION_FORMAT_PRIORITY: List[CompressionFormat] = [
 def infer_module_format(module_type: type, scheme: QuantizationScheme) -> CompressionFormat:
     from .base import BaseCompressor
 
-    w = scheme.weights
-    if w is not None and w.type == "float" and (w.num_bits == 4 or w.scale_dtype == torch.uint8):
-        # nvfp4-pack-quantized / mxfp4-pack-quantized / mxfp8-quantized of the reference's priority list
-        raise NotImplementedError("FP4 / MX (nvfp4, mxfp4, mxfp8) compression is outside this engine's path (SURVEY 8(f) rank 2)")
     for fmt in COMPRESSION_FORMAT_PRIORITY:
         if BaseCompressor.get_value_from_registry(fmt.value).can_compress(module_type, scheme):
             return fmt

@@ -43,6 +43,14 @@ class FP8_E4M3_DATA:
 class FP4_E2M1_DATA:
     exponent, mantissa, bits = 2, 1, 4
     max, min = 6.0, -6.0
+    dtype = None
+
+    @staticmethod
+    def cast_to_fp4(x: torch.Tensor) -> torch.Tensor:
+        """round to the nearest E2M1 value, same dtype (quant_args.py:55-67 -> fp4_utils.py:77-98); one CUDA kernel"""
+        from ..ops import cast_to_fp4
+
+        return cast_to_fp4(x)
 
 
 class QuantizationType(str, Enum):

@@ -23,6 +23,7 @@ __all__ = [
     "compute_dynamic_scales_and_zp",
     "is_module_quantized",
     "strategy_cdiv",
+    "generate_gparam",
     "maybe_pad_tensor_for_block_quant",
 ]
 
@@ -47,8 +48,8 @@ def calculate_range(quantization_args: QuantizationArgs, device) -> tuple[Tensor
 def calculate_qparams(min_vals: Tensor, max_vals: Tensor, quantization_args: QuantizationArgs,
                       global_scale: Tensor | None = None) -> tuple[Tensor, Tensor]:
     """observer rule of the reference (helpers.py:50-137), same op order so the scales agree bit for bit"""
-    if quantization_args.type == QuantizationType.FLOAT and quantization_args.num_bits == 4:
-        raise NotImplementedError("FP4 / MX scale generation is outside this engine's path (SURVEY 8(f) rank 2)")
+    from .mxfp_utils import generate_mx_scales, maybe_convert_from_mx_exp, should_generate_mx_scales
+
     min_vals = torch.min(min_vals, torch.zeros_like(min_vals))
     max_vals = torch.max(max_vals, torch.zeros_like(max_vals))
     device = min_vals.device
@@ -56,9 +57,14 @@ def calculate_qparams(min_vals: Tensor, max_vals: Tensor, quantization_args: Qua
     bit_range = bit_max - bit_min
     if quantization_args.symmetric:
         max_val_pos = torch.max(torch.abs(min_vals), torch.abs(max_vals))
-        scales = max_val_pos / (float(bit_range) / 2)
+        if should_generate_mx_scales(quantization_args):
+            scales = generate_mx_scales(x=max_val_pos, num_bits=quantization_args.num_bits)
+        else:
+            scales = max_val_pos / (float(bit_range) / 2)
         zero_points = torch.zeros(scales.shape, device=device, dtype=min_vals.dtype)
     else:
+        if quantization_args.num_bits == 4 and quantization_args.type == QuantizationType.FLOAT:
+            raise NotImplementedError("Asymmetric Quantization is not supported for FP4")
         scales = (max_vals - min_vals) / float(bit_range)
         zero_points = bit_min - (min_vals / scales)
         zero_points = torch.clamp(zero_points, bit_min, bit_max)
@@ -66,6 +72,7 @@ def calculate_qparams(min_vals: Tensor, max_vals: Tensor, quantization_args: Qua
         scales = global_scale * scales
     if quantization_args.scale_dtype is not None:
         scales = round_to_quantized_type_dtype(scales, dtype=quantization_args.scale_dtype)
+    scales = maybe_convert_from_mx_exp(quantization_args, scales)
     eps_dtype = quantization_args.scale_dtype if quantization_args.scale_dtype is not None else scales.dtype
     if eps_dtype == FP8_E4M3_DATA.dtype:
         eps = 0.125
@@ -76,6 +83,19 @@ def calculate_qparams(min_vals: Tensor, max_vals: Tensor, quantization_args: Qua
     if scales.ndim == 0:
         scales, zero_points = scales.reshape(1), zero_points.reshape(1)
     return scales, zero_points
+
+
+def generate_gparam(updated_min_val: Tensor, updated_max_val: Tensor, scale_data=FP8_E4M3_DATA, quant_data=FP4_E2M1_DATA,
+                    dtype: torch.dtype | None = torch.float32) -> Tensor:
+    """global scale of a tensor: maps its max |x| onto (max of the local-scale dtype) x (max of the element dtype), so
+    that NVFP4's fp8 group scales use their whole range (helpers.py:308-337); NaN / inf results become 1.0"""
+    lo = torch.min(updated_min_val, torch.zeros_like(updated_min_val))
+    hi = torch.max(updated_max_val, torch.zeros_like(updated_max_val))
+    top = torch.max(torch.abs(lo), torch.abs(hi))
+    top = torch.clamp(top, min=torch.finfo(top.dtype).tiny)
+    g = scale_data.max * quant_data.max / top
+    g = torch.nan_to_num(g, nan=1.0, posinf=1.0, neginf=1.0)
+    return g.to(dtype).reshape([1])
 
 
 def compute_dynamic_scales_and_zp(value: Tensor, args: QuantizationArgs, module: Module = None, global_scale: Tensor | None = None):

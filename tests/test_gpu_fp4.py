@@ -136,3 +136,140 @@ def test_fp4_pack_round_trip_full_size():
     assert torch.equal(back.view(torch.int16), v.view(torch.int16))
     # idempotence of the cast on its own outputs
     assert torch.equal(ops.cast_to_fp4(v.abs()).view(torch.int16), v.abs().view(torch.int16))
+
+
+# ---- compressors: state dict in -> state dict out, against the reference's own outputs --------------------------
+def _cls(fmt):
+    from compressed_tensors_b200.compressors import MXFP4PackedCompressor, MXFP8QuantizationCompressor, NVFP4PackedCompressor
+
+    return {"nvfp4": NVFP4PackedCompressor, "mxfp4": MXFP4PackedCompressor, "mxfp8": MXFP8QuantizationCompressor}[fmt]
+
+
+def _same_state(got, want, what):
+    got = {k: v for k, v in got.items() if v is not None}
+    assert set(got) == set(want), (what, sorted(got), sorted(want))
+    for k, w in want.items():
+        g = got[k].data if isinstance(got[k], torch.nn.Parameter) else got[k]
+        if w.dtype == torch.float8_e4m3fn:
+            g, w = g.view(torch.uint8), w.view(torch.uint8)
+        same(g.cpu(), w, f"{what}[{k}]")
+
+
+@pytest.mark.parametrize("i", range(len(G["compressors"])))
+@pytest.mark.parametrize("where", [DEV, "cpu"])
+def test_fp4_mx_compressors_golden(i, where):
+    from compressed_tensors_b200.quantization import QuantizationScheme
+
+    c = G["compressors"][i]
+    cls = _cls(c["format"])
+    extra = {"zp_dtype": torch.uint8} if c["format"].startswith("mx") else {}
+    scheme = QuantizationScheme(targets=["Linear"], weights=QuantizationArgs(**{**c["args"], **extra}))
+    state = {k: v.to(where) for k, v in c["state"].items()}
+    comp = cls.compress(state, scheme)
+    assert set(state) == set(c["state"]), "input must not be mutated"
+    _same_state(comp, c["compressed"], f"{c['format']} compress")
+    assert all(v.device.type == torch.device(where).type for v in comp.values() if v is not None)
+    back = cls.decompress(comp, scheme)
+    _same_state(back, c["decompressed"], f"{c['format']} decompress")
+
+
+# ---- the reference's own tests for these formats (tests/test_compressors/test_fp4_quant.py, test_fp4_optimizations.py,
+# ---- test_mxfp4_quant.py, test_mxfp8_quant.py), re-expressed against this package -------------------------------------
+def test_ref_pack_unpack_preserves_sign_of_zero():
+    x = torch.tensor([[-0.5, -6.0, -0.5, -1.5, -1.0, 6.0, 0.0, -0.0], [-1.0, -6.0, -0.5, -0.0, 0.5, 0.5, -0.0, 0.0],
+                      [-3.0, -6.0, -0.5, -2.0, -0.5, -1.5, -0.0, -0.0], [1.5, 6.0, -0.0, -0.5, 1.0, 1.0, -0.0, 0.0]], dtype=torch.bfloat16, device=DEV)
+    packed = ops.pack_fp4_to_uint8(x)
+    assert packed.dtype == torch.uint8
+    back = ops.unpack_fp4_from_uint8(packed, *x.shape, dtype=torch.bfloat16)
+    assert back.dtype == torch.bfloat16 and torch.equal(back, x) and torch.equal(torch.signbit(back), torch.signbit(x))
+
+
+@pytest.mark.parametrize("x", [torch.tensor([[0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0]]), torch.tensor([[-0.5, -1.0, -1.5, -2.0, -3.0, -4.0, -6.0, -0.0]]),
+                               torch.tensor([[0.0, -0.5, 1.0, -1.5, 2.0, -3.0, 4.0, -6.0]])])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+def test_ref_pack_matches_nearest_index_search(x, dt):
+    x = x.to(dtype=dt, device=DEV)
+    table = FP4.to(device=DEV, dtype=dt)
+    idx = torch.argmin(torch.abs(x.abs().unsqueeze(-1) - table), dim=-1).to(torch.int8) + (torch.signbit(x).to(torch.int8) << 3)
+    idx = idx.reshape(-1, 2)
+    want = (idx[:, 0].to(torch.uint8) | (idx[:, 1].to(torch.uint8) << 4)).reshape(x.shape[0], x.shape[1] // 2)
+    assert torch.equal(ops.pack_fp4_to_uint8(x), want)
+
+
+def test_ref_pack_non_contiguous():
+    base = torch.tensor([[0.0, -0.5, 1.0, -1.5], [2.0, -3.0, 4.0, -6.0], [0.5, -1.0, 1.5, -2.0], [3.0, -4.0, 6.0, -0.0]], dtype=torch.bfloat16, device=DEV)
+    x = base[:, ::2]
+    assert not x.is_contiguous()
+    assert torch.equal(ops.pack_fp4_to_uint8(x), ops.pack_fp4_to_uint8(x.contiguous()))
+
+
+def test_ref_compress_scale_defaults():
+    from compressed_tensors_b200.compressors import MXFP4PackedCompressor, MXFP8QuantizationCompressor, NVFP4PackedCompressor
+
+    s = torch.randn(10, dtype=torch.bfloat16, device=DEV).abs() + 1e-6
+    assert NVFP4PackedCompressor._compress_scale(s, QuantizationArgs(num_bits=4, type="float", symmetric=True, group_size=16)).dtype == torch.float8_e4m3fn
+    assert MXFP4PackedCompressor._compress_scale(s, QuantizationArgs(num_bits=4, type="float", symmetric=True, group_size=32)).dtype == torch.uint8
+    assert MXFP4PackedCompressor._compress_scale(s, QuantizationArgs(num_bits=4, type="float", symmetric=True, group_size=32, scale_dtype=torch.uint8)).dtype == torch.uint8
+    assert MXFP8QuantizationCompressor._compress_scale(s, QuantizationArgs(num_bits=8, type="float", symmetric=True, group_size=32)).dtype == torch.uint8
+
+
+def test_ref_mxfp4_decompress_decodes_scales_and_restores_weight():
+    from compressed_tensors_b200.compressors import MXFP4PackedCompressor
+    from compressed_tensors_b200.quantization import QuantizationScheme
+
+    a = QuantizationArgs(num_bits=4, type="float", symmetric=True, group_size=32, scale_dtype=torch.uint8)
+    scale = torch.tensor([[0.25, 0.5]], dtype=torch.bfloat16, device=DEV)
+    packed = ops.pack_fp4_to_uint8(torch.tensor([[0.5, 1.0, 1.5, 2.0]], dtype=torch.bfloat16, device=DEV))
+    out = MXFP4PackedCompressor.decompress({"weight_packed": packed, "weight_scale": MXFP4PackedCompressor._compress_scale(scale, a)},
+                                           QuantizationScheme(targets=["Linear"], weights=a))
+    assert torch.equal(out["weight_scale"], scale)
+    assert torch.equal(out["weight"], torch.tensor([[0.125, 0.25, 0.75, 1.0]], dtype=torch.bfloat16, device=DEV))
+
+
+def test_ref_mxfp8_compress_decompress_and_scale_round_trip():
+    from compressed_tensors_b200.compressors import MXFP8QuantizationCompressor
+    from compressed_tensors_b200.quantization import QuantizationScheme
+    from compressed_tensors_b200.quantization.utils import calculate_qparams
+
+    a = QuantizationArgs(num_bits=8, type="float", strategy="group", group_size=32, scale_dtype=torch.uint8, zp_dtype=torch.uint8, symmetric=True)
+    w = torch.randn((512, 1024), device=DEV)
+    g = w.reshape(512, 32, 32)
+    scale, zp = calculate_qparams(g.amin(-1), g.amax(-1), a)
+    scheme = QuantizationScheme(targets=["Linear"], weights=a)
+    comp = MXFP8QuantizationCompressor.compress({"weight": w, "weight_scale": scale, "weight_zero_point": zp}, scheme)
+    assert comp["weight"].dtype == torch.float8_e4m3fn and comp["weight_scale"].dtype == torch.uint8
+    decoded = 2.0 ** (comp["weight_scale"].to(torch.int32) - 127).to(torch.float32)
+    assert torch.allclose(decoded, 2.0 ** torch.floor(torch.log2(scale)).to(torch.float32))
+    back = MXFP8QuantizationCompressor.decompress(comp, scheme)
+    assert back["weight"].shape == w.shape and torch.allclose(back["weight"].float(), w, atol=0.1, rtol=0.1)
+
+
+def test_nvfp4_model_compressor_round_trip():
+    """ModelCompressor over a small NVFP4A16 model: compress == per-module reference flow, decompress gives bf16 weights back"""
+    from compressed_tensors_b200.compressors import ModelCompressor
+    from compressed_tensors_b200.quantization import QuantizationConfig, QuantizationStatus, apply_quantization_config
+    from compressed_tensors_b200.quantization.utils import calculate_qparams, generate_gparam
+
+    model = torch.nn.Sequential(torch.nn.Linear(256, 128, bias=False), torch.nn.Linear(128, 64, bias=False)).to(DEV).to(torch.bfloat16)
+    apply_quantization_config(model, QuantizationConfig(config_groups={"NVFP4A16": ["Linear"]}))
+    dense = []
+    for lin in model:
+        a = lin.quantization_scheme.weights
+        w = lin.weight.data
+        gs = generate_gparam(w.min(), w.max())
+        g = w.unflatten(-1, (-1, 16))
+        s, z = calculate_qparams(g.amin(-1), g.amax(-1), a, global_scale=gs)
+        lin.weight_scale = torch.nn.Parameter(s, requires_grad=False)
+        lin.weight_global_scale = torch.nn.Parameter(gs, requires_grad=False)
+        lin.quantization_status = QuantizationStatus.FROZEN
+        dense.append(ops.fake_quantize(w, s, None, a, global_scale=gs))
+    mc = ModelCompressor.from_pretrained_model(model)
+    assert mc.quantization_config.format == "nvfp4-pack-quantized"
+    mc.compress_model(model)
+    for lin in model:
+        assert lin.weight_packed.dtype == torch.uint8 and lin.weight_scale.dtype == torch.float8_e4m3fn and not hasattr(lin, "weight")
+    mc.decompress_model(model)
+    for lin, want in zip(model, dense):
+        assert lin.weight.dtype == torch.bfloat16 and lin.weight.shape == want.shape
+        # fake_quantize used the float32 scale, decompress the fp8-stored one: equal because calculate_qparams already rounded it to fp8
+        assert torch.equal(lin.weight.data, want)
