@@ -23,6 +23,7 @@ SOURCES = [
     "runtime.cu",
     "generic.cu",
     "fp4.cu",
+    "fast_fp4.cu",
     "fast_pack.cu",
     "fast_quant.cu",
     "fast_fake.cu",

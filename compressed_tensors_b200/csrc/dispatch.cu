@@ -66,6 +66,9 @@ static Common make_common(int p_dt, int qtype, int bits) {
         const float r = (float)(1 << bits);
         cm.qmax = r / 2 - 1;
         cm.qmin = -r / 2;
+    } else if (qtype == CT_Q_FP4) {
+        cm.qmax = 6.f;
+        cm.qmin = -6.f;
     } else {
         cm.qmax = 448.f;
         cm.qmin = -448.f;
@@ -191,6 +194,65 @@ static Plan plan_one(int op, const ct_quant_desc& d, const void* in, const void*
     return p;
 }
 
+// FP4 fused ops as streaming jobs (fast_fp4.cu).  Both need GROUP strategy with full rows of scales and no g_idx.
+//   quantize+pack: x bf16 / fp16, units of 32 elements inside a row;  NVFP4 = group 16 + global scale (fp32 arithmetic, scale in
+//                  x's dtype or float32, zero point absent or fp8), MX-style = group % 32 == 0, scale and arithmetic in x's dtype
+//   unpack+dequantize: out bf16 / fp16, units of 16 elements; scale in the out dtype or as stored (fp8 / E8M0)
+static Plan plan_fp4(int op, const ct_quant_desc& d, const void* in, const void* scale, const void* zp,
+                     const int32_t* g_idx, void* out) {
+    Plan p;
+    p.fast = false;
+    memset(&p.job, 0, sizeof(p.job));
+    memset(&p.cm, 0, sizeof(p.cm));
+    p.sig = FastSig{0, 0, 0, 0, 1};
+    const int64_t n = d.rows * d.cols;
+    int64_t D;
+    if (g_idx || n == 0 || (n / 8) >= 0x7fffffffLL || !aligned16(in) || !aligned16(out)) return p;
+    if (!flat_divisor(d, D) || is_inf(D) || d.qtype != CT_Q_FP4) return p;
+    FastSig sig{0, 0, 0, 0, 1};
+    if (op == CT_OP_QUANTIZE_PACK_FP4) {
+        if (d.x_dtype != CT_BF16 && d.x_dtype != CT_F16) return p;
+        if (d.cols % 32 != 0 || !aligned16(scale) ) return p;
+        sig.op = F_FP4_QUANTPACK; sig.p_dt = d.x_dtype; sig.group = 4;
+        if (d.global_scale) {
+            if (D != 16 || d.seff_dtype != CT_F32 || d.compute_dtype != CT_F32) return p;
+            if (d.scale_dtype == d.x_dtype) sig.sel = 1;
+            else if (d.scale_dtype == CT_F32) sig.sel = 2;
+            else return p;
+            if (zp) { if (d.zp_dtype != CT_F8E4M3) return p; sig.zp = 1; }   // FZ_F8
+        } else {
+            if (D % 32 != 0 || d.scale_dtype != d.x_dtype || d.compute_dtype != d.x_dtype) return p;
+            sig.sel = 0;
+            if (zp) {
+                if (d.zp_dtype == CT_U8) sig.zp = 2;        // FZ_U8
+                else if (d.zp_dtype == CT_I8) sig.zp = 3;   // FZ_I8
+                else return p;
+            }
+        }
+    } else {
+        if (d.out_dtype != CT_BF16 && d.out_dtype != CT_F16) return p;
+        if (zp || d.cols % 16 != 0 || D % 16 != 0) return p;
+        sig.op = F_FP4_UNPACKDEQ; sig.p_dt = d.out_dtype; sig.group = 2;
+        if (d.scale_dtype == d.out_dtype) sig.sel = 0;          // FS_SAME
+        else if (d.scale_dtype == CT_F8E4M3) sig.sel = 2;       // FS_F8
+        else if (d.scale_dtype == CT_E8M0) sig.sel = 3;         // FS_E8M0
+        else return p;
+        if (d.global_scale ? d.seff_dtype != CT_F32 : (d.seff_dtype != d.out_dtype && d.scale_dtype != d.out_dtype)) return p;
+        if (((n / 8) * 4) % 16 != 0) return p;   // a partial last tile must still be a multiple of 16 bytes for the bulk copy
+    }
+    p.fast = true;
+    p.sig = sig;
+    p.job.in = reinterpret_cast<const uint8_t*>(in);
+    p.job.scale = scale;
+    p.job.zp = zp;
+    p.job.out = reinterpret_cast<uint8_t*>(out);
+    p.job.aux = d.global_scale;
+    p.job.n_chunks = (uint32_t)(n / 8);
+    p.job.dc = make_fastdiv((uint64_t)(D / 8));
+    p.cm = make_common(sig.p_dt, CT_Q_FP4, 4);
+    return p;
+}
+
 // standalone pack / unpack (packed_dim 1) as a streaming job; for these ops a chunk is 16 codes
 static Plan plan_bits(bool pack, int64_t rows, int64_t cols, int bits, const void* in, void* out) {
     Plan p;
@@ -219,6 +281,8 @@ static int launch_sig(const FastSig& s, const LaunchPlan& lp, int device, cudaSt
     case F_DEQUANT: return launch_fast_dequant(s, lp, device, st);
     case F_FAKE: return launch_fast_fake(s, lp, device, st);
     case F_OBSERVE_QP: return launch_fast_observe(s, lp, device, st);
+    case F_FP4_QUANTPACK:
+    case F_FP4_UNPACKDEQ: return launch_fast_fp4(s, lp, device, st);
     default: return launch_fast_bits(s, lp, device, st);
     }
 }
@@ -294,7 +358,8 @@ int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in
         rc = check_dtypes(op, descs[i], z != nullptr);
         if (rc) return rc;
         if (descs[i].rows * descs[i].cols > 0 && (!in[i] || !scale[i] || !out[i])) { set_error("null tensor pointer (tensor %d)", i); return CT_E_ARG; }
-        plans[i] = plan_one(op, descs[i], in[i], scale[i], z, g_idx ? g_idx[i] : nullptr, out[i]);
+        if (op == CT_OP_QUANTIZE_PACK_FP4 || op == CT_OP_UNPACK_DEQUANTIZE_FP4) plans[i] = plan_fp4(op, descs[i], in[i], scale[i], z, g_idx ? g_idx[i] : nullptr, out[i]);
+        else plans[i] = plan_one(op, descs[i], in[i], scale[i], z, g_idx ? g_idx[i] : nullptr, out[i]);
     }
     // group fast jobs by kernel signature (and clamp constants), one launch per group
     std::vector<char> done((size_t)n, 0);

@@ -7,7 +7,8 @@
 namespace ctb {
 
 // ---- fast (flat, streaming) path -------------------------------------------------------
-enum FastOp { F_QUANTPACK = 0, F_UNPACKDEQ = 1, F_QUANT = 2, F_DEQUANT = 3, F_FAKE = 4, F_PACK = 5, F_UNPACK = 6, F_OBSERVE_QP = 7 };
+enum FastOp { F_QUANTPACK = 0, F_UNPACKDEQ = 1, F_QUANT = 2, F_DEQUANT = 3, F_FAKE = 4, F_PACK = 5, F_UNPACK = 6, F_OBSERVE_QP = 7,
+              F_FP4_QUANTPACK = 8, F_FP4_UNPACKDEQ = 9 };
 
 struct FastSig {
     int op;      // FastOp
@@ -27,6 +28,7 @@ int launch_fast_fake(const FastSig&, const LaunchPlan&, int device, cudaStream_t
 int launch_fast_bits(const FastSig&, const LaunchPlan&, int device, cudaStream_t);
 int fast_group_quantpack(int p_dt, int bits);   // preferred unit size of the instantiated kernels
 int fast_group_quant(int p_dt);
+int launch_fast_fp4(const FastSig&, const LaunchPlan&, int device, cudaStream_t);       // fast_fp4.cu; sig.sel / sig.zp: see there
 int launch_fast_observe(const FastSig&, const LaunchPlan&, int device, cudaStream_t);   // fast_observe.cu; sig.group = lanes per quantization group
 
 // ---- generic path (any strategy, g_idx, ragged shapes, mixed dtypes) -----------------------

@@ -1,0 +1,214 @@
+// fp4_ops.cuh -- streaming functors of the FP4 formats (stream.cuh pipelines):
+//   Fp4NvQuantPackOp   x (bf16 / fp16) -> E2M1 nibbles, fp32 arithmetic with  scale / global_scale  per group of 16 (NVFP4)
+//   Fp4MxQuantPackOp   x (bf16 / fp16) -> E2M1 nibbles, arithmetic in x's dtype, one scale per group (MXFP4: group 32)
+//   Fp4UnpackDequantOp nibbles -> bf16 / fp16, scale as float, as stored fp8 (NVFP4) or as stored E8M0 exponent (MX)
+// Rounding to E2M1 is the hardware conversion (cvt.rn.satfinite.e2m1x2.f32, SASS F2FP...E2M1): round-to-nearest-even on the
+// E2M1 grid with saturation at +-6 IS the closed / open interval ladder of the reference's cast_to_fp4
+// (quantization/utils/fp4_utils.py:89-96; the ties 0.25, 1.25, 2.5, 5.0 go down, 0.75, 1.75, 3.5 go up) preceded by the
+// clamp to +-6 (quant_args.py:481).  The one difference -- the reference maps an exact -0.0 to +0.0 because it multiplies by
+// torch.sign(x) -- is removed by adding +0.0f first.
+#pragma once
+
+#include "ops.cuh"
+
+namespace ctb {
+
+// two floats -> one byte of two E2M1 codes, `lo` in the low nibble (compressors/nvfp4/helpers.py:154-156)
+__device__ __forceinline__ uint32_t f32x2_to_e2m1x2(float lo, float hi) {
+    uint16_t r;
+    asm("{ .reg .b8 t; cvt.rn.satfinite.e2m1x2.f32 t, %1, %2; cvt.u16.u8 %0, t; }" : "=h"(r) : "f"(hi), "f"(lo));
+    return (uint32_t)r;
+}
+// one byte of two E2M1 codes -> half2 bits (exact; code 8 is -0.0), low nibble in the low half
+__device__ __forceinline__ uint32_t e2m1x2_to_f16x2(uint32_t byte) {
+    uint32_t r;
+    uint16_t in = (uint16_t)byte;
+    asm("{ .reg .b8 t; cvt.u8.u16 t, %1; cvt.rn.f16x2.e2m1x2 %0, t; }" : "=r"(r) : "h"(in));
+    return r;
+}
+
+enum Fp4ScaleKind { FS_SAME = 0, FS_F32 = 1, FS_F8 = 2, FS_E8M0 = 3 };   // how the scale tensor is held
+enum Fp4ZpKind { FZ_NONE = 0, FZ_F8 = 1, FZ_U8 = 2, FZ_I8 = 3 };         // zero point of a symmetric scheme (zeros), added like the reference does
+
+template <int ZK>
+__device__ __forceinline__ float fp4_zp_value(uint32_t byte) {
+    if constexpr (ZK == FZ_F8) return e4m3_to_f32(byte);
+    else if constexpr (ZK == FZ_U8) return (float)(byte & 0xffu);
+    else if constexpr (ZK == FZ_I8) return (float)(int)(int8_t)(byte & 0xffu);
+    else return 0.f;
+}
+
+// ------------------------------------------------------------------------------------
+// NVFP4 quantize + pack.  unit = 4 chunks = 32 elements = two groups of 16 -> one 16-byte store.
+//   reference: scale = scale / global_scale (fp32); scaled = x / scale (fp32); scaled += zp.to(x.dtype); clamp; cast_to_fp4;
+//   .to(x.dtype); pack_fp4_to_uint8      (forward_helpers.py:535-546, nvfp4/base.py:82-90)
+// Division: q = RN(x / s) through the correctly rounded reciprocal r = RN(1/s) and one residual step
+//   q0 = x r,  e = fma(-q0, s, x),  q1 = fma(e, r, q0)
+// (exhaustively checked against div.rn for every 16-bit x and every scale significand by ct_selftest_fp4_division);
+// groups whose scale falls outside [2^-100, 2^100] take div.rn per element.
+// ------------------------------------------------------------------------------------
+struct Fp4NvRaw {
+    uint32_t s0, s1;   // the unit's two group scales (bit patterns)
+    uint32_t z;        // two zero-point bytes
+    float gs;
+};
+
+template <class P, int SK, int ZK>
+struct Fp4NvQuantPackOp {
+    static_assert(SK == FS_SAME || SK == FS_F32, "NVFP4 quantization takes float scales");
+    static constexpr int IN_BYTES = 16;
+    static constexpr int GROUP = 4;
+    using Raw = Fp4NvRaw;
+
+    __device__ static __forceinline__ Raw prefetch(const Job& J, uint32_t gc0) {
+        Raw r;
+        const uint32_t si = gc0 >> 1;   // group of 16 elements = 2 chunks; gc0 % 4 == 0 so si is even
+        if constexpr (SK == FS_F32) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const float*>(J.scale) + si));
+            r.s0 = v.x; r.s1 = v.y;
+        } else {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned short*>(J.scale) + si));
+            r.s0 = v & 0xffffu; r.s1 = v >> 16;
+        }
+        r.z = 0;
+        if constexpr (ZK != FZ_NONE) r.z = __ldg(reinterpret_cast<const unsigned short*>(reinterpret_cast<const uint8_t*>(J.zp) + si));
+        r.gs = __ldg(reinterpret_cast<const float*>(J.aux));
+        return r;
+    }
+    __device__ static __forceinline__ float scale_value(uint32_t bits) {
+        if constexpr (SK == FS_F32) return __uint_as_float(bits);
+        else { RawQP q; q.s = bits; q.z = 0; return scale_f32<P>(q); }
+    }
+    __device__ static __forceinline__ float quotient(float x, float s, float rcp, bool slow) {
+        if (slow) return __fdiv_rn(x, s);
+        const float q0 = __fmul_rn(x, rcp);
+        const float e = __fmaf_rn(-q0, s, x);
+        const float q1 = __fmaf_rn(e, rcp, q0);
+        return (q1 == q1) ? q1 : q0;     // q0 = +-inf (overflow): keep it, the conversion saturates
+    }
+    __device__ static __forceinline__ void run(const Job& J, const Common&, const Raw& r, uint32_t gc0, const uint32_t (&w)[4][4], int off) {
+        float s[2], rc[2], z[2];
+        bool slow[2];
+        s[0] = __fdiv_rn(scale_value(r.s0), r.gs);
+        s[1] = __fdiv_rn(scale_value(r.s1), r.gs);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const float a = fabsf(s[g]);
+            slow[g] = !(a >= 7.888609052210118e-31f && a <= 1.2676506002282294e30f);
+            rc[g] = __frcp_rn(s[g]);
+            // zero_point.to(x.dtype): fp8 / small integers are exact in bf16 and fp16
+            z[g] = fp4_zp_value<ZK>(r.z >> (8 * g));
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int g = ((k + off) >> 1) & 1;   // chunk (k + off) mod 4 belongs to group 0 or 1 of the unit
+            const float sg = g ? s[1] : s[0], rg = g ? rc[1] : rc[0], zg = g ? z[1] : z[0];
+            const bool sl = g ? slow[1] : slow[0];
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                // + zg: the reference's in-place add of the zero point; without one, + 0.0f turns an exact -0.0 into +0.0 (header)
+                const float t0 = __fadd_rn(quotient(P::lo(w[k][j]), sg, rg, sl), zg);
+                const float t1 = __fadd_rn(quotient(P::hi(w[k][j]), sg, rg, sl), zg);
+                word |= f32x2_to_e2m1x2(t0, t1) << (8 * j);
+            }
+            o[k] = word;
+        }
+        rotate_out<4, 1>(o, off);
+        store_words<4>(J.out + (size_t)gc0 * 4, o);
+    }
+};
+
+// ------------------------------------------------------------------------------------
+// MXFP4-style quantize + pack: arithmetic in x's dtype T (scale has the same dtype, no global scale), one scale per unit.
+//   unit = 4 chunks = 32 elements (needs group_size % 32 == 0)
+// ------------------------------------------------------------------------------------
+struct Fp4MxRaw {
+    uint32_t s;
+    uint32_t z;
+};
+template <class P, int ZK>
+struct Fp4MxQuantPackOp {
+    static constexpr int IN_BYTES = 16;
+    static constexpr int GROUP = 4;
+    using Raw = Fp4MxRaw;
+    __device__ static __forceinline__ Raw prefetch(const Job& J, uint32_t gc0) {
+        Raw r;
+        const uint32_t si = scale_index(J, gc0);
+        r.s = __ldg(reinterpret_cast<const unsigned short*>(J.scale) + si);
+        r.z = 0;
+        if constexpr (ZK != FZ_NONE) r.z = __ldg(reinterpret_cast<const uint8_t*>(J.zp) + si);
+        return r;
+    }
+    template <bool SLOW>
+    __device__ static __forceinline__ uint32_t chunk(const uint32_t (&w)[4], const ScaleCtx& sc, uint32_t zp2, const Common& cm) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t t = scaled_clamped2<P, ZK != FZ_NONE, SLOW>(w[j], sc, zp2, cm.qmin2, cm.qmax2);
+            word |= f32x2_to_e2m1x2(__fadd_rn(P::lo(t), 0.0f), __fadd_rn(P::hi(t), 0.0f)) << (8 * j);
+        }
+        return word;
+    }
+    __device__ static __forceinline__ void run(const Job& J, const Common& cm, const Raw& r, uint32_t gc0, const uint32_t (&w)[4][4], int off) {
+        RawQP q; q.s = r.s; q.z = 0;
+        const ScaleCtx sc = make_scale_ctx(scale_f32<P>(q));
+        const uint32_t zp2 = (ZK != FZ_NONE) ? dup2<P>(fp4_zp_value<ZK>(r.z)) : 0u;
+        uint32_t o[4];
+        if (sc.slow) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = chunk<true>(w[k], sc, zp2, cm);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = chunk<false>(w[k], sc, zp2, cm);
+        }
+        rotate_out<4, 1>(o, off);
+        store_words<4>(J.out + (size_t)gc0 * 4, o);
+    }
+};
+
+// ------------------------------------------------------------------------------------
+// unpack + dequantize: 8 nibbles (4 bytes) per chunk -> 8 x T; unit = 2 chunks = 16 elements, one scale.
+//   reference: unpack_fp4_from_uint8 -> (scale.to(T)) -> scale / global_scale -> x_q.to(scale.dtype) * scale -> .to(T)
+//   (nvfp4/base.py:111-128, forward_helpers.py:559-570).  A product of an E2M1 value (2 significant bits) and a scale of
+//   <= 24 bits is rounded once, to T, whichever of fp32 (global scale) or T the reference multiplies in.
+// ------------------------------------------------------------------------------------
+struct Fp4DqRaw {
+    uint32_t s;
+    float gs;
+};
+template <class P, int SK>
+struct Fp4UnpackDequantOp {
+    static constexpr int IN_BYTES = 4;
+    static constexpr int GROUP = 2;
+    using Raw = Fp4DqRaw;
+    __device__ static __forceinline__ Raw prefetch(const Job& J, uint32_t gc0) {
+        Raw r;
+        const uint32_t si = scale_index(J, gc0);
+        if constexpr (SK == FS_SAME) r.s = __ldg(reinterpret_cast<const unsigned short*>(J.scale) + si);
+        else r.s = __ldg(reinterpret_cast<const uint8_t*>(J.scale) + si);
+        r.gs = J.aux ? __ldg(reinterpret_cast<const float*>(J.aux)) : 0.f;
+        return r;
+    }
+    __device__ static __forceinline__ void run(const Job& J, const Common&, const Raw& r, uint32_t gc0, const uint32_t (&w)[2][1], int) {
+        float s;
+        if constexpr (SK == FS_SAME) { RawQP q; q.s = r.s; q.z = 0; s = scale_f32<P>(q); }
+        else if constexpr (SK == FS_F8) s = e4m3_to_f32(r.s);                                   // .to(T) of an e4m3 value is exact
+        else s = P::lo(P::pack((r.s & 0xffu) == 255u ? __int_as_float(0x7f800000) : ldexpf(1.0f, (int)(r.s & 0xffu) - 127), 0.f));  // 2^(e-127) -> bf16 -> T
+        if (J.aux) s = __fdiv_rn(s, r.gs);
+        uint32_t o[8];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t h2 = e2m1x2_to_f16x2((w[c][0] >> (8 * j)) & 0xffu);
+                const float a = __low2float(*reinterpret_cast<__half2*>(&h2)), b = __high2float(*reinterpret_cast<__half2*>(&h2));
+                o[4 * c + j] = P::pack(__fmul_rn(a, s), __fmul_rn(b, s));
+            }
+        }
+        store_words<8>(J.out + (size_t)gc0 * 16, o);
+    }
+};
+
+}  // namespace ctb

@@ -45,6 +45,7 @@ struct Job {
     FastDiv rd;            // rows per scale row (block height; "infinite" for a one-row scale)
     uint32_t srs;          // scale row stride
     uint32_t _pad2;
+    const void* aux;       // FP4 ops: the tensor's global scale (one float32) or nullptr
 };
 
 struct JobTable {

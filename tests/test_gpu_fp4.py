@@ -273,3 +273,79 @@ def test_nvfp4_model_compressor_round_trip():
         assert lin.weight.dtype == torch.bfloat16 and lin.weight.shape == want.shape
         # fake_quantize used the float32 scale, decompress the fp8-stored one: equal because calculate_qparams already rounded it to fp8
         assert torch.equal(lin.weight.data, want)
+
+
+# ---- streaming fast path specifics ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("exponent", [-100, -17, -1, 0, 1, 40, 100])
+def test_fp4_division_shortcut_is_exact(dt, exponent):
+    """every 16-bit x, every float32 scale significand: reciprocal + residual step gives the E2M1 code of the IEEE quotient"""
+    import ctypes
+
+    from compressed_tensors_b200 import _native as N
+
+    bad = ctypes.c_uint64(123)
+    N.check(N.lib().ct_selftest_fp4_division(N.DT[dt], exponent, ctypes.byref(bad), 0), "selftest")
+    assert bad.value == 0, f"{bad.value} mismatching (x, scale) pairs"
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("scale_dt", ["same", torch.float32])
+@pytest.mark.parametrize("zp_mode", [None, "zeros", "values"])
+def test_nvfp4_fast_path_zero_points_and_extremes(dt, scale_dt, zp_mode):
+    g = torch.Generator().manual_seed(11)
+    rows, cols = 96, 1024
+    x = (torch.randn(rows, cols, generator=g) * torch.exp2(torch.randint(-12, 6, (rows, cols // 16, 1), generator=g).float()).expand(-1, -1, 16).reshape(rows, cols)).to(dt)
+    x[0, :8] = torch.tensor([0.0, -0.0, float("inf"), -float("inf"), 65504.0, -65504.0, 1e-7, -1e-7]).to(dt)
+    gs = torch.tensor([2688.0 / 7.0])
+    s = (x.float().unflatten(-1, (-1, 16)).abs().amax(-1).clamp(1e-6, 3e4) / 6.0 * gs).clamp(max=448.0).to(torch.float8_e4m3fn).float().clamp_min(2.0 ** -9)
+    assert not s.isnan().any()
+    s[1, :4] = torch.tensor([2.0 ** -9, 448.0, 1.0, 3.5])
+    s = s.to(dt if scale_dt == "same" else scale_dt)
+    zp = None
+    if zp_mode == "zeros":
+        zp = torch.zeros(rows, cols // 16).to(torch.float8_e4m3fn)
+    elif zp_mode == "values":
+        zp = (torch.randint(-4, 5, (rows, cols // 16), generator=g).float() * 0.5).to(torch.float8_e4m3fn)
+    a = QuantizationArgs(**NV)
+    want = oracle.pack_fp4_to_uint8(oracle.quantize(x, s, zp, global_scale=gs, **okw(a)))
+    got = ops.quantize_pack_fp4(x.to(DEV), s.to(DEV), zp.to(DEV) if zp is not None else None, a, global_scale=gs.to(DEV))
+    same(got.cpu(), want, "quantize_pack_fp4 fast path")
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("zp_dt", [None, torch.uint8, torch.int8])
+@pytest.mark.parametrize("gsize", [32, 64])
+def test_mxfp4_fast_path(dt, zp_dt, gsize):
+    g = torch.Generator().manual_seed(5)
+    rows, cols = 64, 2048
+    x = (torch.randn(rows, cols, generator=g) * 0.7).to(dt)
+    x[0, :4] = torch.tensor([0.0, -0.0, 1e-6, -1e-6]).to(dt)
+    e = torch.floor(torch.log2(x.float().unflatten(-1, (-1, gsize)).abs().amax(-1).clamp_min(1e-20))) - 2
+    s = torch.exp2(e).to(dt)
+    s[2, :3] = torch.tensor([0.3, 1.7, 0.011]).to(dt)       # not powers of two: the exact-division machinery has to hold
+    zp = torch.zeros(rows, cols // gsize, dtype=zp_dt) if zp_dt is not None else None
+    if zp is not None:
+        zp[3, :2] = 1
+    a = QuantizationArgs(num_bits=4, type="float", symmetric=True, strategy="group", group_size=gsize)
+    want = oracle.pack_fp4_to_uint8(oracle.quantize(x, s, zp, **okw(a)))
+    got = ops.quantize_pack_fp4(x.to(DEV), s.to(DEV), zp.to(DEV) if zp is not None else None, a)
+    same(got.cpu(), want, "quantize_pack_fp4 (T arithmetic) fast path")
+    back = ops.unpack_dequantize_fp4(got, s.to(DEV), dtype=dt)
+    same(back.cpu(), oracle.dequantize(oracle.unpack_fp4_from_uint8(want, rows, cols, dt), s, None, dtype=dt), "unpack_dequantize_fp4 (float scale)")
+
+
+def test_fp4_full_size_properties():
+    """Llama-3-8B down_proj shape: fused == unfused through the C ABI, decompress(compress(w)) == fake_quantize(w)"""
+    rows, cols = 4096, 14336
+    w = (torch.randn(rows, cols, device=DEV) * 0.02).to(torch.bfloat16)
+    a = QuantizationArgs(**NV)
+    gs = (448.0 * 6.0 / w.float().abs().max()).reshape(1)
+    s = (w.float().unflatten(-1, (-1, 16)).abs().amax(-1) / 6.0 * gs).to(torch.float8_e4m3fn)
+    s = torch.where(s.float() == 0, torch.tensor(0.125, device=DEV).to(torch.float8_e4m3fn), s)
+    sb = s.to(torch.bfloat16)
+    packed = ops.quantize_pack_fp4(w, sb, None, a, global_scale=gs)
+    assert torch.equal(packed, ops.pack_fp4_to_uint8(ops.quantize(w, sb, None, a, global_scale=gs)))
+    back = ops.unpack_dequantize_fp4(packed, s, gs, stored_scale="fp8")
+    assert torch.equal(back, ops.fake_quantize(w, sb, None, a, global_scale=gs))
+    assert torch.equal(back, ops.dequantize(ops.unpack_fp4_from_uint8(packed, rows, cols, torch.bfloat16), sb, global_scale=gs, dtype=torch.bfloat16))
