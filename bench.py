@@ -294,6 +294,27 @@ def run_b200(a):
         extra["int4_pack"] = rate(lambda: ops.batched(N.OP_PACK_INT32, pack_probs, local), nel * 1.5, nel)
         extra["int4_unpack"] = rate(lambda: ops.batched(N.OP_UNPACK_INT32, unpack_probs, local), nel * 1.5, nel)
         del codes, pk
+        # NVFP4: fp4 e2m1, groups of 16, bf16 group scales (fp8-representable, as after calibration) and a
+        # float32 global scale per tensor; decompress reads the scales as stored (float8_e4m3fn)
+        nv = SimpleNamespace(strategy="tensor_group", group_size=16, block_structure=None, num_bits=4, type="float", symmetric=True)
+        gss = [(448.0 * 6.0 / w.abs().max().float()).reshape(1) for w in ws]
+        s8s = [(w.unflatten(-1, (-1, 16)).abs().amax(-1).float() / 6.0 * g).clamp(2.0 ** -9, 448.0).to(torch.float8_e4m3fn) for w, g in zip(ws, gss)]
+        sbs = [s.to(torch.bfloat16) for s in s8s]
+        nib = [torch.empty(w.shape[0], w.shape[1] // 2, dtype=torch.uint8, device=dev) for w in ws]
+        nback = [torch.empty_like(w) for w in ws]
+        cprobs, uprobs = [], []
+        for w, sb, s8_, g, o, b in zip(ws, sbs, s8s, gss, nib, nback):
+            p = ops._resolve(w, sb, None, nv, None)
+            d = ops._desc(p, w.dtype, sb.dtype, None, torch.float32, w.dtype, None, N.Q_FP4, 4, torch.float32)
+            d.global_scale = g.data_ptr()
+            cprobs.append((d, w, sb, None, o))
+            d2 = ops._desc(p, None, torch.float32, None, None, None, torch.bfloat16, N.Q_FP4, 4, torch.float32)
+            d2.scale_dtype = N.DT[torch.float8_e4m3fn]
+            d2.global_scale = g.data_ptr()
+            uprobs.append((d2, o, s8_, None, b))
+        extra["nvfp4_quantize_pack"] = rate(lambda: ops.batched(N.OP_QUANTIZE_PACK_FP4, cprobs, local), n_elems * (2 + 2 / 16 + 0.5), weight_bytes)
+        extra["nvfp4_unpack_dequantize"] = rate(lambda: ops.batched(N.OP_UNPACK_DEQUANTIZE_FP4, uprobs, local), n_elems * (0.5 + 1 / 16 + 2), weight_bytes)
+        del nib, nback, cprobs, uprobs, sbs, s8s
 
     # end to end through the plugin API on host (pinned) state dicts
     e2e = None

@@ -34,7 +34,7 @@ SOURCES = [
     "fast_observe.cu",
     "host_many.cu",
 ]
-HEADERS = ["common.cuh", "quant_core.cuh", "stream.cuh", "ops.cuh", "engine.h", "../../include/ct_b200.h"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + ["../../include/ct_b200.h"]   # every header: a stale object is a silent wrong build
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

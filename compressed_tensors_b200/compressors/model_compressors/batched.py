@@ -28,6 +28,101 @@ __all__ = ["compress_modules_batched", "decompress_modules_batched"]
 
 _BATCHABLE = (CompressionFormat.pack_quantized, CompressionFormat.naive_quantized, CompressionFormat.int_quantized,
               CompressionFormat.float_quantized)
+# fp4 nibble formats: batched on CUDA placements (one multi-tensor launch); host-resident modules take the per-module path
+_FP4 = (CompressionFormat.nvfp4_pack_quantized, CompressionFormat.mxfp4_pack_quantized)
+
+
+def _fp4_ok(module, fmt, place, key: str) -> bool:
+    if fmt not in _FP4 or place is None or place[0] != "cuda":
+        return False
+    if fmt == CompressionFormat.nvfp4_pack_quantized:
+        gs = module._parameters.get("weight_global_scale", None)
+        t = module._parameters.get(key)
+        return gs is not None and gs.device == t.device and gs.dtype == torch.float32 and gs.numel() == 1 and gs.ndim >= 1
+    return True
+
+
+def _compress_fp4_group(mods, fmt, place, force_format) -> None:
+    comp = BaseCompressor.get_value_from_registry(fmt.value)
+    probs, staged, keep = [], [], []
+    for m in mods:
+        scheme = m.quantization_scheme
+        scheme.format = fmt
+        args = scheme.weights
+        sd = get_direct_state_dict(m)
+        w, sc = sd["weight"], sd["weight_scale"]
+        gs = sd.get("weight_global_scale", None) if fmt == CompressionFormat.nvfp4_pack_quantized else None
+        try:
+            if w.shape[1] % 2 != 0:
+                raise ValueError("odd columns")
+            scale, gsv, se = ops._global_scale(sc, gs)
+            qtype, bits = ops._qparams(args)
+            if qtype != N.Q_FP4 or (gs is not None and gsv is None):
+                raise NotImplementedError
+            cd = torch.result_type(w, scale if gsv is None else ops._like(scale, se))
+            zp = sd.get("weight_zero_point", None)
+            p = ops._resolve(w, scale, zp, args, None)
+            d = ops._desc(p, w.dtype, p.scale.dtype, p.zp.dtype if p.zp is not None else None, cd, w.dtype, None, qtype, bits, se)
+            if gsv is not None:
+                d.global_scale = gsv.data_ptr()
+                keep.append(gsv)
+            out = torch.empty((p.rows, p.cols // 2), dtype=torch.uint8, device=w.device)
+        except (ValueError, NotImplementedError):
+            compress_module(m, force_format)
+            continue
+        probs.append((d, w.contiguous(), p.scale.contiguous(), p.zp.contiguous() if p.zp is not None else None, out))
+        staged.append((m, sd, out))
+    _run(N.OP_QUANTIZE_PACK_FP4, probs, place)
+    for m, sd, out in staged:
+        scheme = m.quantization_scheme
+        new = sd.copy()
+        new.pop("weight")
+        new["weight_packed"] = out
+        new["weight_scale"] = comp._compress_scale(sd["weight_scale"], scheme.weights)
+        replace_direct_state_dict(m, comp._remove_symmetric_zp(new, scheme))
+        m.quantization_status = QuantizationStatus.COMPRESSED
+
+
+def _decompress_fp4_group(mods, fmt, place, force_format) -> None:
+    comp = BaseCompressor.get_value_from_registry(fmt.value)
+    dense = torch.bfloat16   # like the reference: unpack_fp4_from_uint8's default dtype (nvfp4/base.py:116)
+    probs, staged, keep = [], [], []
+    for m in mods:
+        scheme = m.quantization_scheme
+        scheme.format = fmt
+        sd = get_direct_state_dict(m)
+        packed, sc = sd["weight_packed"], sd["weight_scale"]
+        gs = sd.get("weight_global_scale", None)
+        try:
+            if packed.dtype != torch.uint8 or packed.ndim != 2:
+                raise ValueError
+            stored = {torch.float8_e4m3fn: N.DT[torch.float8_e4m3fn], torch.uint8: N.DT_E8M0}.get(sc.dtype)
+            if stored is None or (gs is not None and not (gs.dtype == torch.float32 and gs.numel() == 1 and gs.ndim >= 1)):
+                raise NotImplementedError
+            rows, cols = packed.shape[0], packed.shape[1] * 2
+            like = torch.empty((rows, cols), dtype=torch.int8, device="meta")
+            p = ops._resolve(like, sc, None, ops._infer_dequant_args(like, sc), None)
+            se = torch.float32 if gs is not None else dense
+            d = ops._desc(p, None, torch.float32, None, None, None, dense, N.Q_FP4, 4, se)
+            d.scale_dtype = stored
+            if gs is not None:
+                gsv = gs.reshape(1).contiguous()
+                d.global_scale = gsv.data_ptr()
+                keep.append(gsv)
+            out = torch.empty((rows, cols), dtype=dense, device=packed.device)
+        except (ValueError, NotImplementedError):
+            decompress_module(m, force_format)
+            continue
+        probs.append((d, packed.contiguous(), p.scale.contiguous(), None, out))
+        new = sd.copy()
+        new.pop("weight_packed")
+        new["weight"] = out
+        new["weight_scale"] = comp._decompress_scale(sc, dense)
+        staged.append((m, new))
+    _run(N.OP_UNPACK_DEQUANTIZE_FP4, probs, place)
+    for m, new in staged:
+        replace_direct_state_dict(m, new)
+        m.quantization_status = QuantizationStatus.DECOMPRESSED
 
 
 def _placement(module, key: str):
@@ -69,13 +164,16 @@ def compress_modules_batched(modules, force_format: Optional[CompressionFormat] 
         if not isinstance(scheme, QuantizationScheme):
             continue
         fmt = _resolve_format(m, scheme, force_format)
-        place = _placement(m, "weight") if (fmt in _BATCHABLE and scheme.weights is not None) else None
-        if place is not None:
+        place = _placement(m, "weight") if (fmt in _BATCHABLE + _FP4 and scheme.weights is not None) else None
+        if place is not None and (fmt in _BATCHABLE or _fp4_ok(m, fmt, place, "weight")):
             groups[(fmt, place)].append(m)
         else:
             compress_module(m, force_format)
 
     for (fmt, place), mods in groups.items():
+        if fmt in _FP4:
+            _compress_fp4_group(mods, fmt, place, force_format)
+            continue
         comp = BaseCompressor.get_value_from_registry(fmt.value)
         pack = fmt == CompressionFormat.pack_quantized
         probs, staged = [], []
@@ -127,14 +225,17 @@ def decompress_modules_batched(modules, force_format: Optional[CompressionFormat
         if not isinstance(scheme, QuantizationScheme):
             continue
         fmt = _resolve_format(m, scheme, force_format)
-        key_t = "weight_packed" if fmt == CompressionFormat.pack_quantized else "weight"
-        place = _placement(m, key_t) if (fmt in _BATCHABLE and scheme.weights is not None) else None
-        if place is not None:
+        key_t = "weight_packed" if fmt in (CompressionFormat.pack_quantized,) + _FP4 else "weight"
+        place = _placement(m, key_t) if (fmt in _BATCHABLE + _FP4 and scheme.weights is not None) else None
+        if place is not None and (fmt in _BATCHABLE or _fp4_ok(m, fmt, place, key_t)):
             groups[(fmt, place)].append(m)
         else:
             decompress_module(m, force_format)
 
     for (fmt, place), mods in groups.items():
+        if fmt in _FP4:
+            _decompress_fp4_group(mods, fmt, place, force_format)
+            continue
         pack = fmt == CompressionFormat.pack_quantized
         probs, staged = [], []
         for m in mods:

@@ -231,8 +231,8 @@ static Plan plan_fp4(int op, const ct_quant_desc& d, const void* in, const void*
         }
     } else {
         if (d.out_dtype != CT_BF16 && d.out_dtype != CT_F16) return p;
-        if (zp || d.cols % 16 != 0 || D % 16 != 0) return p;
-        sig.op = F_FP4_UNPACKDEQ; sig.p_dt = d.out_dtype; sig.group = 2;
+        if (zp || d.cols % 8 != 0 || D % 8 != 0) return p;
+        sig.op = F_FP4_UNPACKDEQ; sig.p_dt = d.out_dtype; sig.group = 1;
         if (d.scale_dtype == d.out_dtype) sig.sel = 0;          // FS_SAME
         else if (d.scale_dtype == CT_F8E4M3) sig.sel = 2;       // FS_F8
         else if (d.scale_dtype == CT_E8M0) sig.sel = 3;         // FS_E8M0

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) fp4_division_selftest_kernel(unsigned lon
         const float rc = __frcp_rn(s);
         for (uint32_t xp = threadIdx.x; xp < 65536u; xp += blockDim.x) {
             const float x = P::lo(xp);
-            const float fast = __fadd_rn(Op::quotient(x, s, rc, false), 0.0f);
+            const float fast = Op::quotient(P::lo(Op::clamp_x(xp)), s, rc);   // exactly what chunk_fast does; nothing is added without a zero point
             const float ref = __fadd_rn(__fdiv_rn(x, s), 0.0f);
             if (x != x) continue;   // NaN weights are outside the bit-exact contract
             if (f32x2_to_e2m1x2(fast, 0.f) != f32x2_to_e2m1x2(ref, 0.f)) ++local;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) fp4_division_selftest_kernel(unsigned lon
 extern "C" int ct_selftest_fp4_division(int dtype, int scale_exponent, uint64_t* mismatches, int device) {
     using namespace ctb;
     if (!mismatches) { set_error("null output"); return CT_E_ARG; }
-    if (scale_exponent < -100 || scale_exponent > 100) { set_error("scale exponent outside the fast range [-100, 100]"); return CT_E_ARG; }
+    if (scale_exponent < -100 || scale_exponent > 9) { set_error("scale exponent outside the fast range [-100, 9] (|scale| in [2^-100, 2^10))"); return CT_E_ARG; }
     int rc = check_device(device);
     if (rc) return rc;
     DeviceGuard guard(device);

@@ -45,7 +45,7 @@ __device__ __forceinline__ float fp4_zp_value(uint32_t byte) {
 // Division: q = RN(x / s) through the correctly rounded reciprocal r = RN(1/s) and one residual step
 //   q0 = x r,  e = fma(-q0, s, x),  q1 = fma(e, r, q0)
 // (exhaustively checked against div.rn for every 16-bit x and every scale significand by ct_selftest_fp4_division);
-// groups whose scale falls outside [2^-100, 2^100] take div.rn per element.
+// groups whose effective scale falls outside [2^-100, 2^10] take div.rn per element.
 // ------------------------------------------------------------------------------------
 struct Fp4NvRaw {
     uint32_t s0, s1;   // the unit's two group scales (bit patterns)
@@ -67,8 +67,9 @@ struct Fp4NvQuantPackOp {
             const uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const float*>(J.scale) + si));
             r.s0 = v.x; r.s1 = v.y;
         } else {
-            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned short*>(J.scale) + si));
-            r.s0 = v & 0xffffu; r.s1 = v >> 16;
+            // raw word only: nothing in prefetch() may depend on a load (it would wait for it a whole tile early); run() splits it
+            r.s0 = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned short*>(J.scale) + si));
+            r.s1 = 0;
         }
         r.z = 0;
         if constexpr (ZK != FZ_NONE) r.z = __ldg(reinterpret_cast<const unsigned short*>(reinterpret_cast<const uint8_t*>(J.zp) + si));
@@ -79,41 +80,79 @@ struct Fp4NvQuantPackOp {
         if constexpr (SK == FS_F32) return __uint_as_float(bits);
         else { RawQP q; q.s = bits; q.z = 0; return scale_f32<P>(q); }
     }
-    __device__ static __forceinline__ float quotient(float x, float s, float rcp, bool slow) {
-        if (slow) return __fdiv_rn(x, s);
+    // fast quotient: reciprocal + one residual step (no branches).  |x| <= 2^14 here (clamp_x), |1/s| <= 2^100: no overflow
+    __device__ static __forceinline__ float quotient(float x, float s, float rcp) {
         const float q0 = __fmul_rn(x, rcp);
         const float e = __fmaf_rn(-q0, s, x);
-        const float q1 = __fmaf_rn(e, rcp, q0);
-        return (q1 == q1) ? q1 : q0;     // q0 = +-inf (overflow): keep it, the conversion saturates
+        return __fmaf_rn(e, rcp, q0);
+    }
+    // x pair clamped to +-2^14 (packed min / max).  With |s| <= 2^10 every |x| >= 2^14 quantizes to +-6 anyway (|x / s| >= 16),
+    // so the codes do not change, and the products above can no longer overflow to inf (inf - inf = NaN in the residual).
+    __device__ static __forceinline__ uint32_t clamp_x(uint32_t w) {
+        constexpr uint32_t HI = (P::DT == CT_BF16) ? 0x46804680u : 0x74007400u;   // 16384.0 as bf16 / fp16, both halves
+        return min2<P>(max2<P>(w, HI | 0x80008000u), HI);
+    }
+    // one chunk (8 elements, 4 packed words) -> 4 bytes of nibbles
+    __device__ static __forceinline__ uint32_t chunk_fast(const uint32_t (&w)[4], float s, float rcp, float z) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t xc = clamp_x(w[j]);
+            float t0 = quotient(P::lo(xc), s, rcp), t1 = quotient(P::hi(xc), s, rcp);
+            // the reference's in-place add of the zero point.  Without one nothing is added: the residual step already turns
+            // x = -0.0 into +0.0 (fma(+0, r, -0) = +0) and, with |s| <= 2^10, no non-zero 16-bit x underflows to -0.0
+            if constexpr (ZK != FZ_NONE) { t0 = __fadd_rn(t0, z); t1 = __fadd_rn(t1, z); }
+            word |= f32x2_to_e2m1x2(t0, t1) << (8 * j);
+        }
+        return word;
+    }
+    // out of line, everything by value: a unit whose effective scale is outside [2^-100, 2^10] (or 0 / inf / NaN) -> IEEE division
+    // per element.  One call per unit so that the caller's registers never have to be spilled to be indexed.
+    __device__ static __noinline__ uint4 unit_slow(uint4 c0, uint4 c1, uint4 c2, uint4 c3, float s0, float s1, float z0, float z1, int off) {
+        const uint4 c[4] = {c0, c1, c2, c3};
+        uint32_t o[4];
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const bool g = ((k + off) >> 1) & 1;
+            const float s = g ? s1 : s0, z = g ? z1 : z0;
+            const uint32_t w[4] = {c[k].x, c[k].y, c[k].z, c[k].w};
+            uint32_t word = 0;
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                const float t0 = __fadd_rn(__fdiv_rn(P::lo(w[j]), s), z);
+                const float t1 = __fadd_rn(__fdiv_rn(P::hi(w[j]), s), z);
+                word |= f32x2_to_e2m1x2(t0, t1) << (8 * j);
+            }
+            o[k] = word;
+        }
+        return make_uint4(o[0], o[1], o[2], o[3]);
     }
     __device__ static __forceinline__ void run(const Job& J, const Common&, const Raw& r, uint32_t gc0, const uint32_t (&w)[4][4], int off) {
         float s[2], rc[2], z[2];
-        bool slow[2];
-        s[0] = __fdiv_rn(scale_value(r.s0), r.gs);
-        s[1] = __fdiv_rn(scale_value(r.s1), r.gs);
+        const uint32_t b0 = (SK == FS_F32) ? r.s0 : (r.s0 & 0xffffu), b1 = (SK == FS_F32) ? r.s1 : (r.s0 >> 16);
+        s[0] = __fdiv_rn(scale_value(b0), r.gs);
+        s[1] = __fdiv_rn(scale_value(b1), r.gs);
+        bool slow = false;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
             const float a = fabsf(s[g]);
-            slow[g] = !(a >= 7.888609052210118e-31f && a <= 1.2676506002282294e30f);
+            slow |= !(a >= 7.888609052210118e-31f && a <= 1024.0f);   // [2^-100, 2^10]; NaN -> slow
             rc[g] = __frcp_rn(s[g]);
             // zero_point.to(x.dtype): fp8 / small integers are exact in bf16 and fp16
             z[g] = fp4_zp_value<ZK>(r.z >> (8 * g));
         }
         uint32_t o[4];
+        if (slow) {
+            const uint4 v = unit_slow(make_uint4(w[0][0], w[0][1], w[0][2], w[0][3]), make_uint4(w[1][0], w[1][1], w[1][2], w[1][3]),
+                                      make_uint4(w[2][0], w[2][1], w[2][2], w[2][3]), make_uint4(w[3][0], w[3][1], w[3][2], w[3][3]),
+                                      s[0], s[1], z[0], z[1], off);
+            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int g = ((k + off) >> 1) & 1;   // chunk (k + off) mod 4 belongs to group 0 or 1 of the unit
-            const float sg = g ? s[1] : s[0], rg = g ? rc[1] : rc[0], zg = g ? z[1] : z[0];
-            const bool sl = g ? slow[1] : slow[0];
-            uint32_t word = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                // + zg: the reference's in-place add of the zero point; without one, + 0.0f turns an exact -0.0 into +0.0 (header)
-                const float t0 = __fadd_rn(quotient(P::lo(w[k][j]), sg, rg, sl), zg);
-                const float t1 = __fadd_rn(quotient(P::hi(w[k][j]), sg, rg, sl), zg);
-                word |= f32x2_to_e2m1x2(t0, t1) << (8 * j);
+            for (int k = 0; k < 4; ++k) {
+                const bool g = ((k + off) >> 1) & 1;   // chunk (k + off) mod 4 belongs to group 0 or 1 of the unit
+                o[k] = chunk_fast(w[k], g ? s[1] : s[0], g ? rc[1] : rc[0], g ? z[1] : z[0]);
             }
-            o[k] = word;
         }
         rotate_out<4, 1>(o, off);
         store_words<4>(J.out + (size_t)gc0 * 4, o);
@@ -169,7 +208,8 @@ struct Fp4MxQuantPackOp {
 };
 
 // ------------------------------------------------------------------------------------
-// unpack + dequantize: 8 nibbles (4 bytes) per chunk -> 8 x T; unit = 2 chunks = 16 elements, one scale.
+// unpack + dequantize: 8 nibbles (4 bytes) per chunk -> 8 x T; unit = 1 chunk, so that a thread's output is ONE 16-byte store
+// (a 2-chunk unit wrote 32 bytes per thread in two half-coalesced stores: twice the L1->L2 write sectors, measured).
 //   reference: unpack_fp4_from_uint8 -> (scale.to(T)) -> scale / global_scale -> x_q.to(scale.dtype) * scale -> .to(T)
 //   (nvfp4/base.py:111-128, forward_helpers.py:559-570).  A product of an E2M1 value (2 significant bits) and a scale of
 //   <= 24 bits is rounded once, to T, whichever of fp32 (global scale) or T the reference multiplies in.
@@ -181,7 +221,7 @@ struct Fp4DqRaw {
 template <class P, int SK>
 struct Fp4UnpackDequantOp {
     static constexpr int IN_BYTES = 4;
-    static constexpr int GROUP = 2;
+    static constexpr int GROUP = 1;
     using Raw = Fp4DqRaw;
     __device__ static __forceinline__ Raw prefetch(const Job& J, uint32_t gc0) {
         Raw r;
@@ -191,23 +231,20 @@ struct Fp4UnpackDequantOp {
         r.gs = J.aux ? __ldg(reinterpret_cast<const float*>(J.aux)) : 0.f;
         return r;
     }
-    __device__ static __forceinline__ void run(const Job& J, const Common&, const Raw& r, uint32_t gc0, const uint32_t (&w)[2][1], int) {
+    __device__ static __forceinline__ void run(const Job& J, const Common&, const Raw& r, uint32_t gc0, const uint32_t (&w)[1][1], int) {
         float s;
         if constexpr (SK == FS_SAME) { RawQP q; q.s = r.s; q.z = 0; s = scale_f32<P>(q); }
         else if constexpr (SK == FS_F8) s = e4m3_to_f32(r.s);                                   // .to(T) of an e4m3 value is exact
         else s = P::lo(P::pack((r.s & 0xffu) == 255u ? __int_as_float(0x7f800000) : ldexpf(1.0f, (int)(r.s & 0xffu) - 127), 0.f));  // 2^(e-127) -> bf16 -> T
         if (J.aux) s = __fdiv_rn(s, r.gs);
-        uint32_t o[8];
+        uint32_t o[4];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint32_t h2 = e2m1x2_to_f16x2((w[c][0] >> (8 * j)) & 0xffu);
-                const float a = __low2float(*reinterpret_cast<__half2*>(&h2)), b = __high2float(*reinterpret_cast<__half2*>(&h2));
-                o[4 * c + j] = P::pack(__fmul_rn(a, s), __fmul_rn(b, s));
-            }
+        for (int j = 0; j < 4; ++j) {
+            uint32_t h2 = e2m1x2_to_f16x2((w[0][0] >> (8 * j)) & 0xffu);
+            const float a = __low2float(*reinterpret_cast<__half2*>(&h2)), b = __high2float(*reinterpret_cast<__half2*>(&h2));
+            o[j] = P::pack(__fmul_rn(a, s), __fmul_rn(b, s));
         }
-        store_words<8>(J.out + (size_t)gc0 * 16, o);
+        store_words<4>(J.out + (size_t)gc0 * 16, o);
     }
 };
 

@@ -236,7 +236,7 @@ int ct_host_run_many(int op, int n, const ct_quant_desc* descs, const void* cons
 int ct_selftest_division(int dtype, uint64_t* mismatches, int device);
 /* NVFP4 fast path: the E2M1 code obtained through the reciprocal + one-residual-step quotient must equal the code of the
  * IEEE quotient for every 16-bit x of `dtype` and every float32 scale significand at binary exponent `scale_exponent`
- * (within [-100, 100], the range the kernels use the shortcut in). */
+ * (within [-100, 9]: the kernels use the shortcut for |scale / global_scale| in [2^-100, 2^10]). */
 int ct_selftest_fp4_division(int dtype, int scale_exponent, uint64_t* mismatches, int device);
 
 #ifdef __cplusplus

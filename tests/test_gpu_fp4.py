@@ -277,7 +277,7 @@ def test_nvfp4_model_compressor_round_trip():
 
 # ---- streaming fast path specifics ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("exponent", [-100, -17, -1, 0, 1, 40, 100])
+@pytest.mark.parametrize("exponent", [-100, -60, -17, -1, 0, 1, 9])
 def test_fp4_division_shortcut_is_exact(dt, exponent):
     """every 16-bit x, every float32 scale significand: reciprocal + residual step gives the E2M1 code of the IEEE quotient"""
     import ctypes
@@ -349,3 +349,57 @@ def test_fp4_full_size_properties():
     back = ops.unpack_dequantize_fp4(packed, s, gs, stored_scale="fp8")
     assert torch.equal(back, ops.fake_quantize(w, sb, None, a, global_scale=gs))
     assert torch.equal(back, ops.dequantize(ops.unpack_fp4_from_uint8(packed, rows, cols, torch.bfloat16), sb, global_scale=gs, dtype=torch.bfloat16))
+
+
+@pytest.mark.parametrize("preset", ["NVFP4A16", "MXFP4A16", "MXFP8A16"])
+def test_model_compressor_batched_equals_per_module(preset):
+    """one multi-tensor launch (ModelCompressor) == the per-module compressor calls, both directions"""
+    import copy
+
+    from compressed_tensors_b200.compressors import ModelCompressor, compress_module, decompress_module
+    from compressed_tensors_b200.quantization import QuantizationConfig, QuantizationStatus, apply_quantization_config
+    from compressed_tensors_b200.quantization.utils import calculate_qparams, generate_gparam
+    from compressed_tensors_b200.utils import get_direct_state_dict
+
+    torch.manual_seed(3)
+    model = torch.nn.Sequential(torch.nn.Linear(512, 256, bias=False), torch.nn.Linear(256, 128, bias=False), torch.nn.Linear(128, 96, bias=False)).to(DEV).to(torch.bfloat16)
+    apply_quantization_config(model, QuantizationConfig(config_groups={preset: ["Linear"]}))
+    for lin in model:
+        a = lin.quantization_scheme.weights
+        w = lin.weight.data
+        g = w.unflatten(-1, (-1, a.group_size))
+        if preset.startswith("NV"):
+            gs = generate_gparam(w.min(), w.max())
+            lin.weight_global_scale.data.copy_(gs)
+            s, _ = calculate_qparams(g.amin(-1), g.amax(-1), a, global_scale=gs)
+        else:
+            s, _ = calculate_qparams(g.amin(-1), g.amax(-1), a)
+        lin.weight_scale.data.copy_(s)          # the parameter has the weight's dtype, as after calibration
+        lin.quantization_status = QuantizationStatus.FROZEN
+    single = copy.deepcopy(model)
+    mc = ModelCompressor.from_pretrained_model(model)
+    mc.compress_model(model)
+    for lin in single:
+        compress_module(lin)
+    for a, b in zip(model, single):
+        sa, sb = get_direct_state_dict(a), get_direct_state_dict(b)
+        assert set(sa) == set(sb), (sorted(sa), sorted(sb))
+        for k in sa:
+            x, y = sa[k], sb[k]
+            if x is None or y is None:
+                assert x is None and y is None, k
+                continue
+            if x.dtype == torch.float8_e4m3fn:
+                x, y = x.view(torch.uint8), y.view(torch.uint8)
+            assert x.dtype == y.dtype and torch.equal(x, y), (preset, k)
+    mc.decompress_model(model)
+    for lin in single:
+        decompress_module(lin)
+    for a, b in zip(model, single):
+        sa, sb = get_direct_state_dict(a), get_direct_state_dict(b)
+        assert set(sa) == set(sb)
+        for k in sa:
+            if sa[k] is None or sb[k] is None:
+                assert sa[k] is None and sb[k] is None, k
+                continue
+            assert sa[k].dtype == sb[k].dtype and torch.equal(sa[k].float(), sb[k].float()), (preset, k)

@@ -30,7 +30,9 @@ def build_problems(layers: int):
     f8 = SimpleNamespace(strategy="tensor", group_size=None, block_structure=None, num_bits=8, type="float", symmetric=True)
     s8 = [(w.abs().max().float() / 448).bfloat16().reshape(1) for w in ws]
     q8 = [torch.empty(w.shape, dtype=torch.float8_e4m3fn, device=dev) for w in ws]
-    P = {"quantpack": [], "unpackdeq": [], "fp8_q": [], "fp8_dq": [], "fake_w4": [], "observe_qp": []}
+    P = {"quantpack": [], "unpackdeq": [], "fp8_q": [], "fp8_dq": [], "fake_w4": [], "observe_qp": [], "nvfp4_qp": [], "nvfp4_ud": []}
+    nv = SimpleNamespace(strategy="tensor_group", group_size=16, block_structure=None, num_bits=4, type="float", symmetric=True)
+    keep = []
     sc_out = [torch.empty_like(s) for s in scs]
     for w, sc, o, b, s, q, so in zip(ws, scs, outs, back, s8, q8, sc_out):
         p = ops._resolve(w, sc, None, qa, None)
@@ -40,9 +42,24 @@ def build_problems(layers: int):
         P["fake_w4"].append((ops._desc(p, w.dtype, sc.dtype, None, torch.bfloat16, None, torch.bfloat16, N.Q_INT, 4), w, sc, None, b))
         p8 = ops._resolve(w, s, None, f8, None)
         P["fp8_q"].append((ops._desc(p8, w.dtype, s.dtype, None, torch.bfloat16, torch.float8_e4m3fn, None, N.Q_FLOAT, 8), w, s, None, q))
+        g = (448.0 * 6.0 / w.abs().max().float()).reshape(1)
+        s8n = (w.unflatten(-1, (-1, 16)).abs().amax(-1).float() / 6.0 * g).clamp(2.0 ** -9, 448.0).to(torch.float8_e4m3fn)
+        sbn = s8n.to(torch.bfloat16)
+        nib = torch.empty(w.shape[0], w.shape[1] // 2, dtype=torch.uint8, device=dev)
+        pn = ops._resolve(w, sbn, None, nv, None)
+        dn = ops._desc(pn, w.dtype, sbn.dtype, None, torch.float32, w.dtype, None, N.Q_FP4, 4, torch.float32)
+        dn.global_scale = g.data_ptr()
+        du = ops._desc(pn, None, torch.float32, None, None, None, torch.bfloat16, N.Q_FP4, 4, torch.float32)
+        du.scale_dtype = N.DT[torch.float8_e4m3fn]
+        du.global_scale = g.data_ptr()
+        keep.append(g)
+        P["nvfp4_qp"].append((dn, w, sbn, None, nib))
+        P["nvfp4_ud"].append((du, nib, s8n, None, b))
         P["fp8_dq"].append((ops._desc(p8, None, s.dtype, None, None, torch.float8_e4m3fn, torch.bfloat16, N.Q_INT, 8), q, s, None, b))
     OPS = {"quantpack": (N.OP_QUANTIZE_PACK, 2.515625), "unpackdeq": (N.OP_UNPACK_DEQUANTIZE, 2.515625),
-           "observe_qp": (N.OP_OBSERVE_QUANTIZE_PACK, 2.515625), "fp8_q": (N.OP_QUANTIZE, 3.0), "fp8_dq": (N.OP_DEQUANTIZE, 3.0), "fake_w4": (N.OP_FAKE_QUANTIZE, 4.0 + 2 / 128)}
+           "observe_qp": (N.OP_OBSERVE_QUANTIZE_PACK, 2.515625), "fp8_q": (N.OP_QUANTIZE, 3.0), "fp8_dq": (N.OP_DEQUANTIZE, 3.0), "fake_w4": (N.OP_FAKE_QUANTIZE, 4.0 + 2 / 128),
+           "nvfp4_qp": (N.OP_QUANTIZE_PACK_FP4, 2 + 2 / 16 + 0.5), "nvfp4_ud": (N.OP_UNPACK_DEQUANTIZE_FP4, 0.5 + 1 / 16 + 2)}
+    P["_keep"] = keep   # global-scale tensors referenced by address from the descriptors
     return P, OPS, n
 
 
