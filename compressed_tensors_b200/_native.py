@@ -112,7 +112,7 @@ _PROTOS = {
     "ct_host_run": (_int, [_int, _descp, _vp, _vp, _vp, _vp, _int]),
     "ct_host_run_many": (_int, [_int, _int, _descp, _vp, _vp, _vp, _vp, _int]),
     "ct_selftest_division": (_int, [_int, ctypes.POINTER(ctypes.c_uint64), _int]),
-    "ct_selftest_fp4_division": (_int, [_int, _int, ctypes.POINTER(ctypes.c_uint64), _int]),
+    "ct_selftest_fp4_division": (_int, [_int, _int, _int, ctypes.POINTER(ctypes.c_uint64), _int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

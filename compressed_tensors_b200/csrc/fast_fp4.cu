@@ -50,8 +50,10 @@ int launch_fast_fp4(const FastSig& s, const LaunchPlan& lp, int device, cudaStre
 
 // ---- selftest: the E2M1 code of quotient(x, s) (reciprocal + one residual step) must equal the code of div.rn(x, s) for
 // ---- every 16-bit x and every float32 scale significand, at several scale exponents inside the fast range ------------------
+// mode 0: E2M1 code of the quantization quotient (weights / effective scale).  mode 1: the float32 VALUE of scale / global_scale
+// for every 16-bit scale with |scale| in [2^-40, 2^14] (what Fp4UnpackDequantOp uses recip_div for).
 template <class P>
-__global__ void __launch_bounds__(256) fp4_division_selftest_kernel(unsigned long long* mismatches, int exp_field) {
+__global__ void __launch_bounds__(256) fp4_division_selftest_kernel(unsigned long long* mismatches, int exp_field, int mode) {
     using Op = Fp4NvQuantPackOp<P, FS_F32, FZ_NONE>;
     unsigned long long local = 0;
     for (uint32_t m = blockIdx.x; m < (1u << 23); m += gridDim.x) {
@@ -59,6 +61,12 @@ __global__ void __launch_bounds__(256) fp4_division_selftest_kernel(unsigned lon
         const float rc = __frcp_rn(s);
         for (uint32_t xp = threadIdx.x; xp < 65536u; xp += blockDim.x) {
             const float x = P::lo(xp);
+            if (mode == 1) {
+                const float a = fabsf(x);
+                if (!(a >= 9.094947017729282e-13f && a <= 16384.0f)) continue;
+                if (__float_as_uint(recip_div(x, s, rc)) != __float_as_uint(__fdiv_rn(x, s))) ++local;
+                continue;
+            }
             const float fast = Op::quotient(P::lo(Op::clamp_x(xp)), s, rc);   // exactly what chunk_fast does; nothing is added without a zero point
             const float ref = __fadd_rn(__fdiv_rn(x, s), 0.0f);
             if (x != x) continue;   // NaN weights are outside the bit-exact contract
@@ -71,10 +79,12 @@ __global__ void __launch_bounds__(256) fp4_division_selftest_kernel(unsigned lon
 
 }  // namespace ctb
 
-extern "C" int ct_selftest_fp4_division(int dtype, int scale_exponent, uint64_t* mismatches, int device) {
+extern "C" int ct_selftest_fp4_division(int dtype, int scale_exponent, int mode, uint64_t* mismatches, int device) {
     using namespace ctb;
     if (!mismatches) { set_error("null output"); return CT_E_ARG; }
-    if (scale_exponent < -100 || scale_exponent > 9) { set_error("scale exponent outside the fast range [-100, 9] (|scale| in [2^-100, 2^10))"); return CT_E_ARG; }
+    if (mode == 0 && (scale_exponent < -100 || scale_exponent > 9)) { set_error("scale exponent outside the fast range [-100, 9] (|scale| in [2^-100, 2^10))"); return CT_E_ARG; }
+    if (mode == 1 && (scale_exponent < -60 || scale_exponent > 59)) { set_error("global-scale exponent outside the fast range [-60, 59]"); return CT_E_ARG; }
+    if (mode != 0 && mode != 1) { set_error("mode must be 0 or 1"); return CT_E_ARG; }
     int rc = check_device(device);
     if (rc) return rc;
     DeviceGuard guard(device);
@@ -82,8 +92,8 @@ extern "C" int ct_selftest_fp4_division(int dtype, int scale_exponent, uint64_t*
     CT_CUDA_TRY(cudaMalloc(&d, sizeof(unsigned long long)));
     CT_CUDA_TRY(cudaMemset(d, 0, sizeof(unsigned long long)));
     const int ef = scale_exponent + 127;
-    if (dtype == CT_BF16) fp4_division_selftest_kernel<BF16><<<148 * 16, 256>>>(d, ef);
-    else if (dtype == CT_F16) fp4_division_selftest_kernel<F16><<<148 * 16, 256>>>(d, ef);
+    if (dtype == CT_BF16) fp4_division_selftest_kernel<BF16><<<148 * 16, 256>>>(d, ef, mode);
+    else if (dtype == CT_F16) fp4_division_selftest_kernel<F16><<<148 * 16, 256>>>(d, ef, mode);
     else { cudaFree(d); set_error("selftest supports bf16 / f16"); return CT_E_DTYPE; }
     count_launch();
     unsigned long long h = 0;

@@ -27,6 +27,15 @@ __device__ __forceinline__ uint32_t e2m1x2_to_f16x2(uint32_t byte) {
     return r;
 }
 
+// RN(x / s) through r = RN(1 / s) and one residual step: q0 = x r, e = fma(-q0, s, x), q1 = fma(e, r, q0).  No branches; the
+// callers keep the operands in ranges where nothing over- or underflows and ct_selftest_fp4_division checks the result
+// against div.rn exhaustively (every 16-bit x, every float32 significand of s).
+__device__ __forceinline__ float recip_div(float x, float s, float rcp) {
+    const float q0 = __fmul_rn(x, rcp);
+    const float e = __fmaf_rn(-q0, s, x);
+    return __fmaf_rn(e, rcp, q0);
+}
+
 enum Fp4ScaleKind { FS_SAME = 0, FS_F32 = 1, FS_F8 = 2, FS_E8M0 = 3 };   // how the scale tensor is held
 enum Fp4ZpKind { FZ_NONE = 0, FZ_F8 = 1, FZ_U8 = 2, FZ_I8 = 3 };         // zero point of a symmetric scheme (zeros), added like the reference does
 
@@ -81,11 +90,7 @@ struct Fp4NvQuantPackOp {
         else { RawQP q; q.s = bits; q.z = 0; return scale_f32<P>(q); }
     }
     // fast quotient: reciprocal + one residual step (no branches).  |x| <= 2^14 here (clamp_x), |1/s| <= 2^100: no overflow
-    __device__ static __forceinline__ float quotient(float x, float s, float rcp) {
-        const float q0 = __fmul_rn(x, rcp);
-        const float e = __fmaf_rn(-q0, s, x);
-        return __fmaf_rn(e, rcp, q0);
-    }
+    __device__ static __forceinline__ float quotient(float x, float s, float rcp) { return recip_div(x, s, rcp); }
     // x pair clamped to +-2^14 (packed min / max).  With |s| <= 2^10 every |x| >= 2^14 quantizes to +-6 anyway (|x / s| >= 16),
     // so the codes do not change, and the products above can no longer overflow to inf (inf - inf = NaN in the residual).
     __device__ static __forceinline__ uint32_t clamp_x(uint32_t w) {
@@ -216,7 +221,10 @@ struct Fp4MxQuantPackOp {
 // ------------------------------------------------------------------------------------
 struct Fp4DqRaw {
     uint32_t s;
-    float gs;
+};
+struct Fp4DqTile {
+    float gs, rgs;   // global scale of the tensor and its correctly rounded reciprocal
+    bool has, fast;  // fast: |gs| in [2^-60, 2^60] -> scale / gs by recip_div for |scale| in [2^-40, 2^14] (exhaustively checked)
 };
 template <class P, int SK>
 struct Fp4UnpackDequantOp {
@@ -228,15 +236,28 @@ struct Fp4UnpackDequantOp {
         const uint32_t si = scale_index(J, gc0);
         if constexpr (SK == FS_SAME) r.s = __ldg(reinterpret_cast<const unsigned short*>(J.scale) + si);
         else r.s = __ldg(reinterpret_cast<const uint8_t*>(J.scale) + si);
-        r.gs = J.aux ? __ldg(reinterpret_cast<const float*>(J.aux)) : 0.f;
         return r;
     }
-    __device__ static __forceinline__ void run(const Job& J, const Common&, const Raw& r, uint32_t gc0, const uint32_t (&w)[1][1], int) {
+    using Tile = Fp4DqTile;
+    __device__ static __forceinline__ Tile tile(const Job& J) {
+        Tile t;
+        t.has = J.aux != nullptr;
+        t.gs = t.has ? __ldg(reinterpret_cast<const float*>(J.aux)) : 1.0f;
+        t.rgs = __frcp_rn(t.gs);
+        const float a = fabsf(t.gs);
+        t.fast = a >= 8.673617379884035e-19f && a <= 1.152921504606847e18f;
+        return t;
+    }
+    __device__ static __forceinline__ void run(const Job& J, const Common&, const Raw& r, uint32_t gc0, const uint32_t (&w)[1][1], int, const Tile& tc) {
         float s;
         if constexpr (SK == FS_SAME) { RawQP q; q.s = r.s; q.z = 0; s = scale_f32<P>(q); }
         else if constexpr (SK == FS_F8) s = e4m3_to_f32(r.s);                                   // .to(T) of an e4m3 value is exact
         else s = P::lo(P::pack((r.s & 0xffu) == 255u ? __int_as_float(0x7f800000) : ldexpf(1.0f, (int)(r.s & 0xffu) - 127), 0.f));  // 2^(e-127) -> bf16 -> T
-        if (J.aux) s = __fdiv_rn(s, r.gs);
+        if (tc.has) {   // scale / global_scale, float32
+            const float a = fabsf(s);
+            if (tc.fast && a >= 9.094947017729282e-13f && a <= 16384.0f) s = recip_div(s, tc.gs, tc.rgs);
+            else s = __fdiv_rn(s, tc.gs);
+        }
         uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {

@@ -76,7 +76,22 @@ __device__ __forceinline__ Job job_at(const JobTable& t, int j) {
 //   static Raw prefetch(J, gc0);       issued BEFORE the data arrives; no dependent arithmetic
 //   static void run(J, cm, raw, gc0, w[GROUP][IN_BYTES/4], off);   gc0 = first chunk of the unit;
 //                                      w[k] holds chunk (k + off) mod GROUP (see swz_off)
+//   optional:  struct Tile;  static Tile tile(J);   evaluated once per (thread, tile) and passed to run() as a 7th argument:
+//                                      per-tensor constants that are too expensive to rebuild per unit
 // ------------------------------------------------------------------------------------
+
+template <class Op, class = void> struct HasTile { static constexpr bool value = false; };
+template <class Op> struct HasTile<Op, decltype((void)sizeof(typename Op::Tile))> { static constexpr bool value = true; };
+struct NoTile {};
+template <class Op> __device__ __forceinline__ auto op_tile(const Job& J) {
+    if constexpr (HasTile<Op>::value) return Op::tile(J);
+    else return NoTile{};
+}
+template <class Op, class W, class T>
+__device__ __forceinline__ void op_run(const Job& J, const Common& cm, const typename Op::Raw& r, uint32_t gc0, const W& w, int off, const T& tc) {
+    if constexpr (HasTile<Op>::value) Op::run(J, cm, r, gc0, w, off, tc);
+    else Op::run(J, cm, r, gc0, w, off);
+}
 
 template <int BYTES>
 __device__ __forceinline__ void lds_chunk(uint32_t saddr, uint32_t (&w)[BYTES / 4]) {
@@ -282,6 +297,7 @@ __global__ void __launch_bounds__(32 * (NCW + 1)) stream_tma_kernel(const __grid
                 }
             }
             const uint32_t sp = data0 + (uint32_t)s * TILE_BYTES;
+            const auto tc = op_tile<Op>(J);
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
                 const uint32_t c0 = (uint32_t)(it * CTHREADS + ctid) * G;
@@ -289,7 +305,7 @@ __global__ void __launch_bounds__(32 * (NCW + 1)) stream_tma_kernel(const __grid
                     uint32_t w[G][Op::IN_BYTES / 4];
 #pragma unroll
                     for (int k = 0; k < G; ++k) lds_chunk<Op::IN_BYTES>(sp + (c0 + ((k + off) & (G - 1))) * Op::IN_BYTES, w[k]);
-                    Op::run(J, cm, raw[it], base + c0, w, off);
+                    op_run<Op>(J, cm, raw[it], base + c0, w, off, tc);
                 }
             }
             __syncwarp();
@@ -334,10 +350,11 @@ __global__ void __launch_bounds__(DIRECT_THREADS) stream_direct_kernel(const __g
                 raw[it] = Op::prefetch(J, base + c0);
             }
         }
+        const auto tc = op_tile<Op>(J);
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
             const uint32_t c0 = (uint32_t)(it * DIRECT_THREADS + threadIdx.x) * G;
-            if (c0 < chunks) Op::run(J, cm, raw[it], base + c0, w[it], 0);
+            if (c0 < chunks) op_run<Op>(J, cm, raw[it], base + c0, w[it], 0, tc);
         }
     }
 }

@@ -236,8 +236,10 @@ int ct_host_run_many(int op, int n, const ct_quant_desc* descs, const void* cons
 int ct_selftest_division(int dtype, uint64_t* mismatches, int device);
 /* NVFP4 fast path: the E2M1 code obtained through the reciprocal + one-residual-step quotient must equal the code of the
  * IEEE quotient for every 16-bit x of `dtype` and every float32 scale significand at binary exponent `scale_exponent`
- * (within [-100, 9]: the kernels use the shortcut for |scale / global_scale| in [2^-100, 2^10]). */
-int ct_selftest_fp4_division(int dtype, int scale_exponent, uint64_t* mismatches, int device);
+ * (within [-100, 9]: the kernels use the shortcut for |scale / global_scale| in [2^-100, 2^10]).
+ * mode 1: the float32 value of  scale / global_scale  for every 16-bit scale with |scale| in [2^-40, 2^14] and every global-scale
+ * significand at exponent `scale_exponent` (within [-60, 59]) must equal div.rn bit for bit (used by the decompress kernel). */
+int ct_selftest_fp4_division(int dtype, int scale_exponent, int mode, uint64_t* mismatches, int device);
 
 #ifdef __cplusplus
 }

@@ -277,16 +277,17 @@ def test_nvfp4_model_compressor_round_trip():
 
 # ---- streaming fast path specifics ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("exponent", [-100, -60, -17, -1, 0, 1, 9])
-def test_fp4_division_shortcut_is_exact(dt, exponent):
-    """every 16-bit x, every float32 scale significand: reciprocal + residual step gives the E2M1 code of the IEEE quotient"""
+@pytest.mark.parametrize("mode,exponent", [(0, e) for e in (-100, -60, -17, -1, 0, 1, 9)] + [(1, e) for e in (-60, -13, 0, 8, 14, 59)])
+def test_fp4_division_shortcut_is_exact(dt, mode, exponent):
+    """every 16-bit x, every float32 significand of the divisor: reciprocal + residual step == IEEE division
+    (mode 0: the E2M1 code of weight / scale; mode 1: the float32 value of scale / global_scale)"""
     import ctypes
 
     from compressed_tensors_b200 import _native as N
 
     bad = ctypes.c_uint64(123)
-    N.check(N.lib().ct_selftest_fp4_division(N.DT[dt], exponent, ctypes.byref(bad), 0), "selftest")
-    assert bad.value == 0, f"{bad.value} mismatching (x, scale) pairs"
+    N.check(N.lib().ct_selftest_fp4_division(N.DT[dt], exponent, mode, ctypes.byref(bad), 0), "selftest")
+    assert bad.value == 0, f"{bad.value} mismatching (x, divisor) pairs"
 
 
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
