@@ -24,6 +24,7 @@ SOURCES = [
     "generic.cu",
     "fp4.cu",
     "fast_fp4.cu",
+    "convert.cu",
     "fast_pack.cu",
     "fast_quant.cu",
     "fast_fake.cu",

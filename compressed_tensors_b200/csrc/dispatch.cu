@@ -153,6 +153,11 @@ static Plan plan_one(int op, const ct_quant_desc& d, const void* in, const void*
         sig.group = fast_group_quant(p_dt);
         break;
     case CT_OP_DEQUANTIZE:
+        if (d.scale_dtype == CT_F32 && (d.out_dtype == CT_BF16 || d.out_dtype == CT_F16) && d.q_dtype == CT_F8E4M3 && !zp) {
+            // (q.to(float32) * scale).to(T): fp8 block checkpoints (DequantF32ScaleOp)
+            p_dt = d.out_dtype; sig.op = F_DEQUANT; sig.sel = 3; in_bytes_per_chunk = 8;
+            break;
+        }
         if (d.out_dtype != d.scale_dtype || !is_float_dt(d.out_dtype)) return p;
         if (d.q_dtype != CT_I8 && d.q_dtype != CT_F8E4M3) return p;
         p_dt = d.scale_dtype; sig.op = F_DEQUANT; sig.sel = (d.q_dtype == CT_F8E4M3) ? 2 : 1; in_bytes_per_chunk = 8;

@@ -41,6 +41,9 @@ int launch_fast_quant(const FastSig& s, const LaunchPlan& lp, int device, cudaSt
 
 template <class P>
 static int dequant_p(const FastSig& s, const LaunchPlan& lp, int device, cudaStream_t st) {
+    if constexpr (P::DT != CT_F32) {
+        if (s.sel == 3 && s.zp == 0) return launch_stream<DequantF32ScaleOp<P>>(lp, device, st);   // fp8 codes, float32 scale, 16-bit output
+    }
     const int kind = (s.sel == QF8) ? QF8 : QI_WIDE;
     if (kind == QF8 && s.zp == 0) return launch_stream<DequantizeOp<P, QF8, 0>>(lp, device, st);
     if (kind == QF8 && s.zp == 1) return launch_stream<DequantizeOp<P, QF8, 1>>(lp, device, st);

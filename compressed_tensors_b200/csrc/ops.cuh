@@ -299,6 +299,33 @@ struct DequantizeOp {
 };
 
 // ------------------------------------------------------------------------------------
+// Dequantize with a float32 scale and a 16-bit output: (q.to(float32) * scale).to(T) -- two roundings, fp32 then T
+//   (the FP8 block checkpoints of entrypoints/convert/converters/fp8block_dequantizer.py:111-158: fp8 weight, float32
+//   weight_scale_inv per 128x128 block, bf16 result; also dequantize() with a float32 scale on the group path)
+// ------------------------------------------------------------------------------------
+template <class P>
+struct DequantF32ScaleOp {
+    static constexpr int IN_BYTES = 8;
+    static constexpr int GROUP = 1;
+    struct Raw { uint32_t s; };
+    __device__ static __forceinline__ Raw prefetch(const Job& J, uint32_t gc) {
+        Raw r;
+        r.s = __float_as_uint(__ldg(reinterpret_cast<const float*>(J.scale) + scale_index(J, gc)));
+        return r;
+    }
+    __device__ static __forceinline__ void run(const Job& J, const Common&, const Raw& r, uint32_t gc, const uint32_t (&wg)[1][2], int) {
+        const float s = __uint_as_float(r.s);
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t h2 = e4m3x2_to_f16x2((wg[0][k >> 1] >> (16 * (k & 1))) & 0xffffu);
+            o[k] = P::pack(__fmul_rn(__low2float(*reinterpret_cast<__half2*>(&h2)), s), __fmul_rn(__high2float(*reinterpret_cast<__half2*>(&h2)), s));
+        }
+        store_words<4>(J.out + (size_t)gc * 16, o);
+    }
+};
+
+// ------------------------------------------------------------------------------------
 // UnpackDequant: BITS*8 bits of the int32 bitstream -> 8 x T
 //   replaces unpack_from_int32 + dequantize (pack_quantized/base.py:159-166)
 // ------------------------------------------------------------------------------------

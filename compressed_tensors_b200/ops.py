@@ -47,6 +47,9 @@ __all__ = [
     "unpack_dequantize_fp4",
     "compress_mx_scale",
     "decompress_mx_scale",
+    "dequantize_block_fp8",
+    "awq_repack",
+    "awq_repack_zeros",
 ]
 
 _FLOAT_DTYPES = (torch.float32, torch.float16, torch.bfloat16)
@@ -626,6 +629,52 @@ def unpack_dequantize_fp4(packed, scale, global_scale=None, dtype: torch.dtype =
     d = _desc(p, None, torch.float32, None, None, None, out_dtype, N.Q_FP4, 4, se)
     d.scale_dtype = s_code if s_code is not None else N.DT[scale.dtype]
     return _run("ct_unpack_dequantize_fp4", N.OP_UNPACK_DEQUANTIZE_FP4, d, p, packed, (m, n), out_dtype)
+
+
+# --------------------------------------------------------------------------------------------
+# checkpoint-format conversions (entrypoints/convert)
+# --------------------------------------------------------------------------------------------
+@torch.no_grad()
+def dequantize_block_fp8(weight: torch.Tensor, scale_inv: torch.Tensor, block_size: Sequence[int], dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """(weight.to(float32) * scale_inv.to(float32) per block).to(dtype): entrypoints/convert/converters/fp8block_dequantizer.py:111-158.
+    weight float8_e4m3fn [R, C], scale_inv [ceil(R/bh), ceil(C/bw)]; one kernel, no padded copy."""
+    from types import SimpleNamespace
+
+    if weight.ndim != 2 or weight.dtype != torch.float8_e4m3fn:
+        raise ValueError("fp8 block dequantization needs a 2-D float8_e4m3fn weight")
+    if dtype not in _FLOAT_DTYPES:
+        raise NotImplementedError(f"dequantize_block_fp8 to {dtype} is not supported")
+    scale = scale_inv.to(torch.float32)   # qparam-sized; float32 already in the checkpoints this converter targets
+    args = SimpleNamespace(strategy="block", group_size=None, block_structure=[int(block_size[0]), int(block_size[1])])
+    p = _resolve(weight, scale, None, args, None)
+    if weight.device.type == "meta":
+        return torch.empty(weight.shape, dtype=dtype, device="meta")
+    if weight.numel() == 0:
+        return torch.empty(weight.shape, dtype=dtype, device=weight.device)
+    d = _desc(p, None, torch.float32, None, None, weight.dtype, dtype, N.Q_INT, 8, torch.float32)
+    return _run("ct_dequantize", N.OP_DEQUANTIZE, d, p, weight, tuple(weight.shape), dtype)
+
+
+def _awq(fn_name: str, src: torch.Tensor, out_shape, rows: int, n_out: int) -> torch.Tensor:
+    if src.dtype != torch.int32 or src.ndim != 2:
+        raise ValueError("AutoAWQ tensors are 2-D int32")
+    return _simple(fn_name, src, out_shape, torch.int32,
+                   lambda lib, a, o, i: getattr(lib, fn_name)(N.ptr(a), N.ptr(o), rows, n_out, i, N.stream_ptr(i)))
+
+
+@torch.no_grad()
+def awq_repack(qweight: torch.Tensor) -> torch.Tensor:
+    """AutoAWQ GEMM qweight int32 [K, N/8] -> compressed-tensors weight_packed int32 [N, ceil(K/8)]
+    (entrypoints/convert/converters/autoawq.py:120-126 with :179-262, one kernel)"""
+    k, nw = qweight.shape
+    return _awq("ct_awq_repack_int4", qweight, (nw * 8, (k + 7) // 8), k, nw * 8)
+
+
+@torch.no_grad()
+def awq_repack_zeros(qzeros: torch.Tensor) -> torch.Tensor:
+    """AutoAWQ qzeros int32 [G, N/8] -> weight_zero_point int32 [N/8, G] (packed along dim 0, contiguous; autoawq.py:124-128)"""
+    g, nw = qzeros.shape
+    return _awq("ct_awq_repack_zeros_int4", qzeros, (nw, g), g, nw * 8)
 
 
 @torch.no_grad()

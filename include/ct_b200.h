@@ -163,6 +163,16 @@ int ct_unpack_dequantize_fp4(const ct_quant_desc* d, const uint8_t* packed, cons
 int ct_mx_scale_compress(const void* scale, int dtype, uint8_t* out, int64_t n, int device, void* stream);
 int ct_mx_scale_decompress(const uint8_t* in, void* out_bf16, int64_t n, int device, void* stream);
 
+/* ---- checkpoint-format conversions ----------------------
+ * AutoAWQ GEMM -> pack-quantized: entrypoints/convert/converters/autoawq.py:120-128 with :179-262 (unpack_awq, reverse_awq_order,
+ * & 15, - 8, .T.contiguous(), pack_to_int32) in one pass.
+ *   qweight int32 [K, N/8] (AutoAWQ nibble order)  ->  weight_packed int32 [N, ceil(K/8)]
+ *   qzeros  int32 [G, N/8]                         ->  weight_zero_point int32 [N/8, G]  (packed along dim 0, contiguous)
+ * FP8 block checkpoints (fp8block_dequantizer.py:111-158) go through ct_dequantize with scale_dtype = CT_F32, BLOCK addressing and
+ * out_dtype = CT_BF16 / CT_F16. */
+int ct_awq_repack_int4(const int32_t* qweight, int32_t* weight_packed, int64_t K, int64_t N, int device, void* stream);
+int ct_awq_repack_zeros_int4(const int32_t* qzeros, int32_t* zero_point_packed, int64_t G, int64_t N, int device, void* stream);
+
 /* ---- multi-tensor (whole-model) launches -------------------------------------
  * One persistent launch over `n` independent tensors: the body of the module loop of
  * ModelCompressor.compress_model / decompress_model

@@ -27,7 +27,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libct_oracle.so")
 _SRC = os.path.join(_HERE, "ct_oracle_all.c")  # includes ct_oracle.c and ct_oracle_qparams.c
-_PARTS = [os.path.join(_HERE, f) for f in ("ct_oracle_all.c", "ct_oracle.c", "ct_oracle_qparams.c", "ct_oracle_fp4.c")]
+_PARTS = [os.path.join(_HERE, f) for f in ("ct_oracle_all.c", "ct_oracle.c", "ct_oracle_qparams.c", "ct_oracle_fp4.c", "ct_oracle_convert.c")]
 
 INT64_MAX = (1 << 63) - 1
 
@@ -72,6 +72,7 @@ def lib() -> ctypes.CDLL:
             "orc_semi_structured_from_dense orc_semi_structured_to_dense "
             "orc_quantize_gs orc_dequantize_gs orc_fake_quantize_gs "
             "orc_cast_to_fp4 orc_pack_fp4 orc_unpack_fp4 orc_mx_scale_compress orc_mx_scale_decompress "
+            "orc_awq_repack orc_awq_repack_zeros "
             "orc_num_threads"
         ).split():
             getattr(_lib, name).restype = ctypes.c_int
@@ -393,3 +394,29 @@ def decompress_mx_scale(scale: torch.Tensor) -> torch.Tensor:
     out = torch.empty(scale.shape, dtype=torch.bfloat16)
     _check(lib().orc_mx_scale_decompress(_p(scale), _p(out), _i64(scale.numel())), "decompress_mx_scale")
     return out
+
+
+# --------------------------------------------------------------------------- #
+# checkpoint converters -- ct_oracle_convert.c
+# --------------------------------------------------------------------------- #
+def awq_repack(qweight: torch.Tensor) -> torch.Tensor:
+    """entrypoints/convert/converters/autoawq.py: qweight int32 [K, N/8] -> weight_packed int32 [N, ceil(K/8)]"""
+    k, nw = qweight.shape
+    qweight = qweight.contiguous()
+    out = torch.empty((nw * 8, (k + 7) // 8), dtype=torch.int32)
+    _check(lib().orc_awq_repack(_p(qweight), _p(out), _i64(k), _i64(nw * 8)), "awq_repack")
+    return out
+
+
+def awq_repack_zeros(qzeros: torch.Tensor) -> torch.Tensor:
+    """qzeros int32 [G, N/8] -> weight_zero_point int32 [N/8, G]"""
+    g, nw = qzeros.shape
+    qzeros = qzeros.contiguous()
+    out = torch.empty((nw, g), dtype=torch.int32)
+    _check(lib().orc_awq_repack_zeros(_p(qzeros), _p(out), _i64(g), _i64(nw * 8)), "awq_repack_zeros")
+    return out
+
+
+def dequantize_block_fp8(weight: torch.Tensor, scale_inv: torch.Tensor, block, dtype=torch.bfloat16) -> torch.Tensor:
+    """entrypoints/convert/converters/fp8block_dequantizer.py:111-158: (w.to(f32) * s.to(f32) per block).to(dtype)"""
+    return dequantize(weight, scale_inv.to(torch.float32), None, strategy="block", block_structure=list(block)).to(dtype)

@@ -2,3 +2,4 @@
 #include "ct_oracle.c"
 #include "ct_oracle_qparams.c"
 #include "ct_oracle_fp4.c"
+#include "ct_oracle_convert.c"

@@ -1,0 +1,122 @@
+"""
+Robustness of the C ABI on the B200:
+  * thread safety -- the reference's convert_checkpoint calls decompress from a thread pool
+    (entrypoints/convert/convert_checkpoint.py:110-134): concurrent callers on separate CUDA streams must get the
+    results of a serial run, including launches that use the dynamic tile schedule (own scratch per launch);
+  * seeded randomized differential test against the CPU oracle across strategies / dtypes / shapes that straddle the
+    fast-path / generic-path boundary;
+  * stream semantics -- work is enqueued on the caller's current stream and nothing synchronises inside.
+"""
+import random
+from concurrent.futures import ThreadPoolExecutor
+
+import pytest
+import torch
+
+import oracle
+from compressed_tensors_b200 import _native as N
+from compressed_tensors_b200 import ops
+from compressed_tensors_b200.quantization import QuantizationArgs
+from tests.util import same
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _w4():
+    return QuantizationArgs(num_bits=4, type="int", symmetric=True, strategy="group", group_size=128)
+
+
+def test_concurrent_callers_on_separate_streams():
+    torch.manual_seed(0)
+    a = _w4()
+    shapes = [(4096, 4096), (1024, 4096), (14336, 4096), (512, 1024), (4096, 14336), (96, 256)]   # large ones take the dynamic schedule
+    work = []
+    for i, sh in enumerate(shapes * 2):
+        w = (torch.randn(sh, device=DEV) * 0.02).to(torch.bfloat16)
+        s = (w.float().unflatten(-1, (-1, 128)).abs().amax(-1) / 7.5).to(torch.bfloat16)
+        work.append((w, s))
+    serial = []
+    for w, s in work:
+        p = ops.quantize_pack(w, s, None, a)
+        serial.append((p, ops.unpack_dequantize(p, s, None, 4, w.shape)))
+    torch.cuda.synchronize()
+
+    def job(i):
+        w, s = work[i]
+        st = torch.cuda.Stream(device=DEV)
+        st.wait_stream(torch.cuda.default_stream(torch.device(DEV)))
+        with torch.cuda.stream(st):
+            out = []
+            for _ in range(3):   # several launches per thread so that calls overlap in time
+                p = ops.quantize_pack(w, s, None, a)
+                out = (p, ops.unpack_dequantize(p, s, None, 4, w.shape))
+            st.synchronize()
+        return i, out
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        for i, (p, d) in ex.map(job, range(len(work))):
+            assert torch.equal(p, serial[i][0]), f"packed words of job {i} differ under concurrency"
+            assert torch.equal(d.view(torch.int16), serial[i][1].view(torch.int16)), f"dequantized output of job {i} differs under concurrency"
+
+
+def test_enqueue_only_no_sync_and_stream_order():
+    """a long kernel on a side stream followed by ours on the same stream must see the long kernel's output"""
+    a = _w4()
+    st = torch.cuda.Stream(device=DEV)
+    w = torch.empty(8192, 8192, device=DEV, dtype=torch.bfloat16)
+    s = torch.full((8192, 64), 0.01, device=DEV, dtype=torch.bfloat16)
+    with torch.cuda.stream(st):
+        for _ in range(4):
+            w.normal_(0, 0.02)        # producer on the same stream: ordering is the only synchronisation
+        p = ops.quantize_pack(w, s, None, a)
+    st.synchronize()
+    assert torch.equal(p, ops.quantize_pack(w, s, None, a))
+
+
+_STRATS = ["tensor", "channel", "group", "group_row", "block", "token"]
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_randomized_differential_vs_oracle(seed):
+    rnd = random.Random(seed)
+    g = torch.Generator().manual_seed(seed)
+    dt = rnd.choice([torch.bfloat16, torch.float16, torch.float32])
+    sdt = dt if rnd.random() < 0.7 else rnd.choice([torch.bfloat16, torch.float16, torch.float32])
+    strat = rnd.choice(_STRATS)
+    qtype, bits = rnd.choice([("int", 4), ("int", 8), ("int", rnd.randint(1, 8)), ("float", 8), ("float", 4)])
+    gsz = rnd.choice([16, 32, 64, 128])
+    rows = rnd.choice([1, 3, 8, 33, 64, 257])
+    cols = gsz * rnd.choice([1, 2, 3, 8, 17]) if strat.startswith("group") or rnd.random() < 0.5 else rnd.choice([8, 24, 40, 100, 136, 1000])
+    x = (torch.randn(rows, cols, generator=g) * 10 ** rnd.uniform(-3, 1)).to(dt)
+    qmax = {"int": 2 ** (bits - 1) - 0.5, "float": 448.0 if bits == 8 else 6.0}[qtype]
+    kw = dict(num_bits=bits, type=qtype, symmetric=True)
+    if strat == "tensor":
+        a, shape = QuantizationArgs(strategy="tensor", **kw), (1,)
+    elif strat in ("channel", "token"):
+        a, shape = QuantizationArgs(strategy=strat, **({**kw, "dynamic": True} if strat == "token" else kw)), (rows, 1)
+    elif strat == "group":
+        a, shape = QuantizationArgs(strategy="group", group_size=gsz, **kw), (rows, cols // gsz)
+    elif strat == "group_row":
+        a, shape = QuantizationArgs(strategy="group", group_size=gsz, **kw), (1, cols // gsz)
+    else:
+        bh, bw = rnd.choice([(4, 8), (16, 16), (128, 128), (8, 24)])
+        a, shape = QuantizationArgs(strategy="block", block_structure=[bh, bw], **kw), (-(-rows // bh), -(-cols // bw))
+    s = ((torch.rand(shape, generator=g) + 0.25) * float(x.float().abs().max().clamp_min(1e-6)) / qmax).to(sdt)
+    zp = None
+    if qtype == "int" and rnd.random() < 0.4:
+        zp = torch.randint(-(2 ** (bits - 1)), 2 ** (bits - 1), shape, generator=g).to(torch.int8)
+    okw = dict(strategy=a.strategy, group_size=a.group_size, block_structure=a.block_structure, num_bits=bits, qtype=qtype)
+    qdt = torch.int8 if qtype == "int" else (torch.float8_e4m3fn if bits == 8 else None)
+    X, S, Z = x.to(DEV), s.to(DEV), zp.to(DEV) if zp is not None else None
+    what = f"seed {seed}: {strat} {dt} scale {sdt} {qtype}{bits} {rows}x{cols} zp={zp is not None}"
+    want_q = oracle.quantize(x, s, zp, dtype=qdt, **okw)
+    same(ops.quantize(X, S, Z, a, dtype=qdt).cpu(), want_q, "quantize " + what)
+    same(ops.fake_quantize(X, S, Z, a).cpu(), oracle.fake_quantize(x, s, zp, **okw), "fake_quantize " + what)
+    same(ops.dequantize(want_q.to(DEV), S, Z, args=a).cpu(), oracle.dequantize(want_q, s, zp, strategy=a.strategy, group_size=a.group_size,
+                                                                                block_structure=a.block_structure), "dequantize " + what)
+    if qtype == "int":
+        want_p = oracle.pack_to_int32(oracle.quantize(x, s, zp, dtype=torch.int8, **okw), bits)
+        same(ops.quantize_pack(X, S, Z, a).cpu(), want_p, "quantize_pack " + what)
+    elif bits == 4 and cols % 2 == 0:
+        same(ops.quantize_pack_fp4(X, S, Z, a).cpu(), oracle.pack_fp4_to_uint8(want_q), "quantize_pack_fp4 " + what)
