@@ -134,16 +134,15 @@ def test_convert_checkpoint_fp8_block_end_to_end(tmp_path, workers):
     src, dst = tmp_path / "src", tmp_path / "dst"
     src.mkdir()
     g = torch.Generator().manual_seed(0)
-    shards, wm, ref = {}, {}, {}
+    wm, ref = {}, {}
+    shards = {f"model-0000{s + 1}-of-00003.safetensors": {} for s in range(3)}
     for s in range(3):
         name = f"model-0000{s + 1}-of-00003.safetensors"
-        shards[name] = {}
         for l in range(2):
             w = (torch.randn(256, 384, generator=g) * 2).to(torch.float8_e4m3fn)
             sc = torch.rand(2, 3, generator=g) * 0.02 + 1e-3
             shards[name][f"model.layers.{s}.mlp.p{l}_proj.weight"] = w
             # the partner scale lives in the NEXT shard: the planner has to bring it over
-            shards.setdefault(f"model-0000{(s + 1) % 3 + 1}-of-00003.safetensors", {})
             ref[f"model.layers.{s}.mlp.p{l}_proj.weight"] = oracle.dequantize_block_fp8(w, sc, (128, 128), torch.bfloat16)
             wm[f"model.layers.{s}.mlp.p{l}_proj.weight"] = name
             other = f"model-0000{(s + 1) % 3 + 1}-of-00003.safetensors"
