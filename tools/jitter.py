@@ -39,6 +39,19 @@ def main():
     jobs = {k: (op, P[k], n * bpe) for k, (op, bpe) in OPS.items()}
     jobs["int4_pack"] = (N.OP_PACK_INT32, [(d, c, None, None, o) for d, c, o in zip(descs, codes, pk)], nel * 1.5)
     jobs["int4_unpack"] = (N.OP_UNPACK_INT32, [(d, o, None, None, c) for d, c, o in zip(descs, codes, pk)], nel * 1.5)
+    # checkpoint converters: FP8 128x128-block dequantize (DeepSeek-style shapes) and the AutoAWQ nibble transpose
+    from types import SimpleNamespace
+    blk = SimpleNamespace(strategy="block", group_size=None, block_structure=[128, 128])
+    fw = [torch.randn(7168, 4096, device=dev).to(torch.float8_e4m3fn) for _ in range(8)]
+    fs = [torch.rand(56, 32, device=dev) * 0.01 + 1e-4 for _ in fw]
+    fo = [torch.empty(w.shape, dtype=torch.bfloat16, device=dev) for w in fw]
+    fprobs = []
+    for w, sc, o in zip(fw, fs, fo):
+        p = ops._resolve(w, sc, None, blk, None)
+        fprobs.append((ops._desc(p, None, torch.float32, None, None, w.dtype, torch.bfloat16, N.Q_INT, 8, torch.float32), w, sc, None, o))
+    jobs["fp8_block_dq"] = (N.OP_DEQUANTIZE, fprobs, sum(w.numel() for w in fw) * 3.0)
+    awq_q = torch.randint(-2 ** 31, 2 ** 31 - 1, (14336, 4096 // 8), device=dev, dtype=torch.int64).to(torch.int32)
+    extra_fns = {"awq_repack": (lambda: ops.awq_repack(awq_q), 14336 * 4096 * 1.0)}
     for pipe in [int(p) for p in a.pipes.split(",")]:
         N.set_tuning(pipe, 4, 3)
         for name, (op, probs, nbytes) in jobs.items():
@@ -56,6 +69,19 @@ def main():
             print(json.dumps({"op": name, "pipe": {1: "tma-dynamic", 2: "tma-static"}[pipe], "GBps_best": round(nbytes / s[0] / 1e6, 1),
                               "GBps_median": round(nbytes / s[len(s) // 2] / 1e6, 1), "GBps_worst": round(nbytes / s[-1] / 1e6, 1),
                               "ms": [round(v, 3) for v in ms]}), flush=True)
+        for name, (fn, nbytes) in extra_fns.items():
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.launches)]
+            for e0, e1 in ev:
+                e0.record()
+                fn()
+                e1.record()
+            torch.cuda.synchronize()
+            s = sorted(e0.elapsed_time(e1) for e0, e1 in ev)
+            print(json.dumps({"op": name, "pipe": "plain grid launch (includes the output allocation)", "GBps_best": round(nbytes / s[0] / 1e6, 1),
+                              "GBps_median": round(nbytes / s[len(s) // 2] / 1e6, 1)}), flush=True)
 
 
 if __name__ == "__main__":
