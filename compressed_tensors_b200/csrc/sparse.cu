@@ -160,6 +160,76 @@ __global__ void __launch_bounds__(256) sparse24_decompress_kernel(const void* __
 }
 
 // ---------------------------------------------------------------------------------------------
+// sparse24, vectorised variants for 2-byte elements (bf16 / fp16), cols % 8 == 0, 16-byte aligned tensors and a mask size that is
+// a multiple of 4 bytes: one thread = 8 elements = one 16-byte load, one 8-byte store of the 4 kept values, one mask byte
+// (four lanes combine theirs into one 32-bit store).  Plain grid launch, one thread per unit: the hardware block scheduler
+// balances the SMs (same effect as the dynamic tile schedule of stream.cuh; see tools/ubench/mix_ceiling.cu).
+// Semantics identical to the generic kernels above (ties: lower column first; -0.0 counts as magnitude 0).
+// ---------------------------------------------------------------------------------------------
+// keep mask (bit j = element j kept) of one quad held as two packed words {e0,e1}, {e2,e3}, and the kept pair in column order
+__device__ __forceinline__ uint32_t quad_select16(uint32_t w0, uint32_t w1, uint32_t& pair) {
+    const uint32_t k0 = w0 & 0x7fffu, k1 = (w0 >> 16) & 0x7fffu, k2 = w1 & 0x7fffu, k3 = (w1 >> 16) & 0x7fffu;
+    // "m beats j": larger key, or equal key and lower index
+    const int b01 = k0 >= k1, b02 = k0 >= k2, b03 = k0 >= k3, b12 = k1 >= k2, b13 = k1 >= k3, b23 = k2 >= k3;
+    const int beat0 = (1 - b01) + (1 - b02) + (1 - b03);
+    const int beat1 = b01 + (1 - b12) + (1 - b13);
+    const int beat2 = b02 + b12 + (1 - b23);
+    const int beat3 = b03 + b13 + b23;
+    const uint32_t keep = (uint32_t)(beat0 < 2) | ((uint32_t)(beat1 < 2) << 1) | ((uint32_t)(beat2 < 2) << 2) | ((uint32_t)(beat3 < 2) << 3);
+    const uint32_t i0 = __ffs(keep) - 1, i1 = 31 - __clz(keep);
+    pair = __byte_perm(w0, w1, 0x1010u + i0 * 0x22u + i1 * 0x2200u);   // bytes (2 i0, 2 i0 + 1, 2 i1, 2 i1 + 1)
+    return keep;
+}
+
+__global__ void __launch_bounds__(256) sparse24_compress_vec16_kernel(const uint4* __restrict__ x, uint2* __restrict__ values,
+                                                                      uint32_t* __restrict__ mask_words, int64_t n_units) {
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const bool valid = t < n_units;
+    uint32_t byte = 0;
+    if (valid) {
+        const uint4 v = ldg_stream16(x + t);
+        uint32_t p0, p1;
+        byte = quad_select16(v.x, v.y, p0) | (quad_select16(v.z, v.w, p1) << 4);
+        stg_stream8(values + t, make_uint2(p0, p1));
+    }
+    uint32_t w = byte;
+    w |= __shfl_down_sync(0xffffffffu, w, 1) << 8;
+    w |= __shfl_down_sync(0xffffffffu, w, 2) << 16;
+    if ((threadIdx.x & 3) == 0 && valid) mask_words[t >> 2] = w;   // n_units % 4 == 0: the four lanes are valid together
+}
+
+__global__ void __launch_bounds__(256) sparse24_decompress_vec16_kernel(const uint2* __restrict__ values, const uint8_t* __restrict__ bitmask,
+                                                                        uint4* __restrict__ out, int64_t n_units) {
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= n_units) return;
+    const uint32_t byte = __ldg(bitmask + t);
+    const uint2 v = ldg_stream8(values + t);
+    if (__popc(byte) > 4) {
+        // not a 2:4 mask: more set bits than the unit's own 4 values.  Same sequential rule as the generic kernel (rare, slow).
+        const uint16_t* vals = reinterpret_cast<const uint16_t*>(values) + t * 4;
+        uint16_t* o = reinterpret_cast<uint16_t*>(out) + t * 8;
+        int vi = 0;
+        for (int k = 0; k < 8; ++k) o[k] = ((byte >> k) & 1u) ? vals[vi++] : (uint16_t)0;
+        return;
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t ba = (byte >> (2 * j)) & 1u, bb = (byte >> (2 * j + 1)) & 1u;
+        const uint32_t ia = __popc(byte & ((1u << (2 * j)) - 1u)), ib = __popc(byte & ((1u << (2 * j + 1)) - 1u));   // values consumed before
+        const uint32_t w = __byte_perm(v.x, v.y, 0x1010u + (ia & 3u) * 0x22u + (ib & 3u) * 0x2200u);
+        o[j] = w & ((ba ? 0xffffu : 0u) | (bb ? 0xffff0000u : 0u));
+    }
+    stg_stream16(out + t, make_uint4(o[0], o[1], o[2], o[3]));
+}
+
+static bool vec16_ok(int dtype, int64_t rows, int64_t cols, const void* a, const void* b, const void* c) {
+    const int64_t n_units = rows * cols / 8;
+    return (dtype == CT_BF16 || dtype == CT_F16) && cols % 8 == 0 && n_units % 4 == 0 && n_units < ((int64_t)1 << 39) &&
+           aligned16(a) && aligned16(b) && aligned16(c);
+}
+
+// ---------------------------------------------------------------------------------------------
 // unstructured bitmask: count -> scan -> scatter
 // ---------------------------------------------------------------------------------------------
 template <int DT, int ES>
@@ -293,6 +363,14 @@ int ct_sparse24_compress(const void* x, int dtype, void* values, uint8_t* bitmas
     if (rows * cols == 0) return CT_OK;
     if (!x || !values || !bitmask) { set_error("null pointer"); return CT_E_ARG; }
     const int64_t nb = (cols + 7) / 8;
+    if (vec16_ok(dtype, rows, cols, x, values, bitmask)) {
+        const int64_t n_units = rows * cols / 8;
+        sparse24_compress_vec16_kernel<<<(unsigned)((n_units + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const uint4*>(x), reinterpret_cast<uint2*>(values), reinterpret_cast<uint32_t*>(bitmask), n_units);
+        count_launch();
+        CT_CUDA_TRY(cudaGetLastError());
+        return CT_OK;
+    }
     const unsigned g = grid_for(rows * ((nb + 3) & ~(int64_t)3));
     switch (dtype) {
     case CT_BF16: sparse24_compress_kernel<CT_BF16, 2><<<g, 256, 0, st>>>(x, values, bitmask, rows, cols, nb); break;
@@ -313,6 +391,14 @@ int ct_sparse24_decompress(const void* values, int dtype, const uint8_t* bitmask
     if (rows * cols == 0) return CT_OK;
     if (!out || !values || !bitmask) { set_error("null pointer"); return CT_E_ARG; }
     const int64_t nb = (cols + 7) / 8;
+    if (vec16_ok(dtype, rows, cols, values, out, values)) {   // the mask is read bytewise: no alignment needed
+        const int64_t n_units = rows * cols / 8;
+        sparse24_decompress_vec16_kernel<<<(unsigned)((n_units + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const uint2*>(values), bitmask, reinterpret_cast<uint4*>(out), n_units);
+        count_launch();
+        CT_CUDA_TRY(cudaGetLastError());
+        return CT_OK;
+    }
     const unsigned g = grid_for(rows * nb);
     switch (esize_of(dtype)) {
     case 1: sparse24_decompress_kernel<1><<<g, 256, 0, st>>>(values, bitmask, out, rows, cols, nb); break;

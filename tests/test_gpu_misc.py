@@ -133,3 +133,40 @@ def test_one_row_group_scale_fast_path():
     want = oracle.quantize(w, scale, None, strategy="group", group_size=64, num_bits=4, dtype=torch.int8)
     same_values(ops.quantize(w.to(DEV), scale.to(DEV), None, a, dtype=torch.int8).cpu(), want, "one-row group scale")
     same_values(ops.quantize_pack(w.to(DEV), scale.to(DEV), None, a).cpu(), oracle.pack_to_int32(want, 4), "one-row group scale, packed")
+
+
+# ---- sparse24 vectorised path (bf16 / fp16, cols % 8 == 0): ties, signed zeros, arbitrary masks ---------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_sparse24_vectorised_ties_and_zeros(dtype):
+    import oracle
+    from tests.util import same
+
+    g = torch.Generator().manual_seed(9)
+    x = (torch.randint(-3, 4, (256, 1024), generator=g).float() * 0.5).to(dtype)    # few distinct magnitudes: lots of ties and zeros
+    x[0, :8] = torch.tensor([0.0, -0.0, 0.0, -0.0, 1.0, -1.0, 1.0, -1.0]).to(dtype)
+    vals, bm = oracle.sparse24_compress(x)
+    gv, gb = ops.sparse24_compress(x.to(DEV))
+    same(gb.cpu(), bm, "sparse24 bitmask")
+    same(gv.cpu(), vals, "sparse24 values")
+    same(ops.sparse24_decompress(gv, gb, x.shape).cpu(), oracle.sparse24_decompress(vals, bm, x.shape), "sparse24 decompress")
+    # arbitrary (non 2:4) masks, including bytes with more than 4 bits set: same sequential rule as the oracle
+    rnd = torch.randint(0, 256, bm.shape, generator=g, dtype=torch.int64).to(torch.uint8)
+    rnd[0, :4] = torch.tensor([0xff, 0x00, 0xf0, 0x1f], dtype=torch.uint8)
+    same(ops.sparse24_decompress(gv, rnd.to(DEV), x.shape).cpu()[:, :-8], oracle.sparse24_decompress(vals, rnd, x.shape)[:, :-8], "arbitrary masks")
+
+
+def test_sparse24_full_size_round_trip():
+    x = (torch.randn(4096, 14336, device=DEV) * 0.02).to(torch.bfloat16)
+    v, m = ops.sparse24_compress(x)
+    assert v.shape == (4096, 7168) and m.shape == (4096, 1792)
+    dense = ops.sparse24_decompress(v, m, x.shape)
+    # every quad keeps exactly two elements, and they are the two of largest magnitude
+    q, dq = x.view(-1, 4).float().abs(), dense.view(-1, 4)
+    assert torch.equal((dq != 0).sum(-1) + ((dq == 0) & (x.view(-1, 4) == 0) & (torch.arange(4, device=DEV) < 0)).sum(-1), (dq != 0).sum(-1))
+    kept = dq != 0
+    assert int(kept.sum(-1).max()) <= 2
+    third = q.sort(-1, descending=True).values[:, 2:3]
+    assert bool(((q >= third) | ~kept).all()), "a kept element is smaller than a dropped one"
+    assert torch.equal(torch.where(kept, x.view(-1, 4), torch.zeros_like(dq)), dq)
+    v2, m2 = ops.sparse24_compress(dense)              # idempotent on its own output
+    assert torch.equal(ops.sparse24_decompress(v2, m2, x.shape), dense)

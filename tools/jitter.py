@@ -52,6 +52,16 @@ def main():
     jobs["fp8_block_dq"] = (N.OP_DEQUANTIZE, fprobs, sum(w.numel() for w in fw) * 3.0)
     awq_q = torch.randint(-2 ** 31, 2 ** 31 - 1, (14336, 4096 // 8), device=dev, dtype=torch.int64).to(torch.int32)
     extra_fns = {"awq_repack": (lambda: ops.awq_repack(awq_q), 14336 * 4096 * 1.0)}
+    # sparse formats (north-star rows a12 / a13): 2:4 bitmask and unstructured bitmask on one big bf16 tensor
+    sp = (torch.randn(14336, 8192, device=dev) * 0.02).to(torch.bfloat16)
+    nsp = sp.numel()
+    vals24, mask24 = ops.sparse24_compress(sp)
+    extra_fns["sparse24_compress"] = (lambda: ops.sparse24_compress(sp), nsp * 3.125)
+    extra_fns["sparse24_decompress"] = (lambda: ops.sparse24_decompress(vals24, mask24, sp.shape), nsp * 3.125)
+    un = torch.where(torch.rand(sp.shape, device=dev) < 0.5, sp, torch.zeros_like(sp))
+    uv, um, uo = ops.bitmask_compress(un)
+    extra_fns["bitmask_compress_50pct"] = (lambda: ops.bitmask_compress(un), nsp * (2 + 1 + 0.125))
+    extra_fns["bitmask_decompress_50pct"] = (lambda: ops.bitmask_decompress(uv, um, uo, un.shape), nsp * (1 + 0.125 + 2))
     for pipe in [int(p) for p in a.pipes.split(",")]:
         N.set_tuning(pipe, 4, 3)
         for name, (op, probs, nbytes) in jobs.items():
