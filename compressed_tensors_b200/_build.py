@@ -25,6 +25,7 @@ SOURCES = [
     "fp4.cu",
     "fast_fp4.cu",
     "convert.cu",
+    "observe_channel.cu",
     "fast_pack.cu",
     "fast_quant.cu",
     "fast_fake.cu",

@@ -47,6 +47,8 @@ __all__ = [
     "unpack_dequantize_fp4",
     "compress_mx_scale",
     "decompress_mx_scale",
+    "observe_quantize",
+    "observe_quantize_pack",
     "dequantize_block_fp8",
     "awq_repack",
     "awq_repack_zeros",
@@ -727,6 +729,61 @@ def observe_quantize_pack(x: torch.Tensor, args) -> Tuple[torch.Tensor, torch.Te
     zp = None if symmetric else zp
     packed = quantize_pack(xd, scale, zp, args)
     return _back(packed, x), _back(scale, x), (_back(zp, x) if zp is not None else None)
+
+
+@torch.no_grad()
+def observe_quantize(x: torch.Tensor, args, pack: bool = False) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """Memoryless min-max observer + quantize (+ pack_to_int32 when `pack`) in ONE pass over the weight, for the strategies with a
+    fused kernel; returns (codes or packed words, scale, zero point or None) exactly as the reference's
+    min/max -> calculate_qparams (utils/helpers.py:50-137) -> quantize(dtype=args.pytorch_dtype()) [-> pack_to_int32] flow does.
+
+      CHANNEL (one scale per row): bf16 / fp16, cols % 8 == 0, cols <= 16384 -> `ct_observe_quantize_channel`
+                                   (int8 codes, float8_e4m3fn codes, or 4- / 8-bit packed int32)
+      GROUP + pack               : `observe_quantize_pack`
+    Everything else runs the observer with torch reductions on the device and then the quantize kernel."""
+    from .quantization.utils.helpers import calculate_qparams
+
+    qtype, bits = _qparams(args)
+    strategy = _strategy_name(args)
+    symmetric = bool(getattr(args, "symmetric", True))
+    if x.ndim != 2:
+        raise ValueError("observe_quantize expects a 2-D weight")
+    if pack and qtype != N.Q_INT:
+        raise ValueError("pack-quantized compression needs integer quantization")
+    if strategy == "group" and pack:
+        return observe_quantize_pack(x, args)
+    rows, cols = x.shape
+    idx = _dev_index(x)
+    xd = _to_dev(x, idx).contiguous()
+    qdt = torch.int32 if pack else (torch.float8_e4m3fn if qtype == N.Q_FLOAT else torch.int8)
+    fused_ok = (strategy == "channel" and x.dtype in (torch.bfloat16, torch.float16) and cols % 8 == 0 and 0 < cols <= 16384 and rows > 0
+                and qtype in (N.Q_INT, N.Q_FLOAT) and (bits in (4, 8) if pack else bits == 8) and (symmetric or qtype == N.Q_INT))
+    if fused_ok:
+        scale = torch.empty((rows, 1), dtype=x.dtype, device=xd.device)
+        zp = None if symmetric else torch.empty((rows, 1), dtype=torch.int8, device=xd.device)
+        out = torch.empty((rows, cols * bits // 32) if pack else (rows, cols), dtype=qdt, device=xd.device)
+        d = N.QuantDesc()
+        d.rows, d.cols, d.rdiv, d.cdiv, d.s_row_stride = rows, cols, 1, N.INF, 1
+        d.x_dtype = d.scale_dtype = d.compute_dtype = N.DT[x.dtype]
+        d.zp_dtype = N.DT_NONE if symmetric else N.DT[torch.int8]
+        d.q_dtype, d.out_dtype, d.qtype, d.num_bits = N.DT[qdt], N.DT_NONE, qtype, bits
+        rc = N.lib().ct_observe_quantize_channel(ctypes.byref(d), N.ptr(xd), N.ptr(scale), N.ptr(zp), N.ptr(out), idx, N.stream_ptr(idx))
+        N.check(rc, "observe_quantize")
+        return _back(out, x), _back(scale, x), (_back(zp, x) if zp is not None else None)
+    if strategy == "group":
+        group = int(getattr(args, "group_size"))
+        xr = xd.unflatten(-1, (-1, group))
+        mn, mx = xr.amin(-1), xr.amax(-1)
+    elif strategy == "channel":
+        mn, mx = xd.amin(-1, keepdim=True), xd.amax(-1, keepdim=True)
+    elif strategy == "tensor":
+        mn, mx = (t.reshape(1) for t in torch.aminmax(xd))
+    else:
+        raise NotImplementedError(f"observe_quantize does not support strategy {strategy}")
+    scale, zp = calculate_qparams(mn, mx, args)
+    zp = None if symmetric else zp
+    out = quantize_pack(xd, scale, zp, args) if pack else quantize(xd, scale, zp, args, dtype=qdt)
+    return _back(out, x), _back(scale, x), (_back(zp, x) if zp is not None else None)
 
 
 # --------------------------------------------------------------------------------------------

@@ -173,6 +173,15 @@ int ct_mx_scale_decompress(const uint8_t* in, void* out_bf16, int64_t n, int dev
 int ct_awq_repack_int4(const int32_t* qweight, int32_t* weight_packed, int64_t K, int64_t N, int device, void* stream);
 int ct_awq_repack_zeros_int4(const int32_t* qzeros, int32_t* zero_point_packed, int64_t G, int64_t N, int device, void* stream);
 
+/* one-pass min-max observer + quantize for CHANNEL-wise weight quantization (one scale per row): the same observer rule as
+ * above on the row's min / max, then quantize (forward_helpers.py:523-546) and, for d->q_dtype == CT_I32, pack_to_int32.
+ *   d->q_dtype = CT_I8 (num_bits 8)      -> int8 codes  [rows, cols]        (W8A8 / INT8 presets)
+ *   d->q_dtype = CT_F8E4M3 (CT_Q_FLOAT)  -> fp8 codes   [rows, cols]        (FP8_DYNAMIC preset; symmetric only)
+ *   d->q_dtype = CT_I32 (num_bits 4 | 8) -> packed int32 [rows, cols*bits/32] (W4A16 / W8A16 channel-wise)
+ * scale_out: x dtype [rows]; zp_out: int8 [rows] or NULL (symmetric).  bf16 / fp16, cols % 8 == 0, cols <= 16384; anything else
+ * returns CT_E_UNSUPPORTED. */
+int ct_observe_quantize_channel(const ct_quant_desc* d, const void* x, void* scale_out, void* zp_out, void* out, int device, void* stream);
+
 /* ---- multi-tensor (whole-model) launches -------------------------------------
  * One persistent launch over `n` independent tensors: the body of the module loop of
  * ModelCompressor.compress_model / decompress_model

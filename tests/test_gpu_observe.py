@@ -74,3 +74,61 @@ def test_unfused_cases_compose():
     ws, _ = orc_qparams(mn, mx, num_bits=4, symmetric=True)
     same(scale.cpu(), ws, "channel scale")
     same_values(packed.cpu(), oracle.pack_to_int32(oracle.quantize(w, ws, None, strategy="channel", num_bits=4, dtype=torch.int8), 4), "packed")
+
+
+# ---- channel-wise fused observer (ct_observe_quantize_channel) ------------------------------------------------------------
+def _chan_oracle(x, qtype, bits, symmetric, pack):
+    import oracle
+    from oracle.qparams import calculate_qparams as oq
+
+    mn, mx = x.amin(-1, keepdim=True), x.amax(-1, keepdim=True)
+    s, z = oq(mn, mx, num_bits=bits, qtype=qtype, symmetric=symmetric)
+    z = None if symmetric else z
+    kw = dict(strategy="channel", num_bits=bits, qtype=qtype)
+    q = oracle.quantize(x, s, z, dtype=(torch.float8_e4m3fn if qtype == "float" else torch.int8), **kw)
+    return (oracle.pack_to_int32(q, bits) if pack else q), s, z
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("kind", [("int", 8, True, False), ("int", 8, False, False), ("float", 8, True, False), ("int", 4, True, True),
+                                  ("int", 4, False, True), ("int", 8, True, True)])
+@pytest.mark.parametrize("shape", [(64, 4096), (33, 14336), (7, 8), (5, 1000), (16, 16384)])
+def test_channel_observer_vs_oracle(dt, kind, shape):
+    from compressed_tensors_b200.quantization import QuantizationArgs
+    from tests.util import same
+
+    qtype, bits, sym, pack = kind
+    g = torch.Generator().manual_seed(shape[1] + bits)
+    x = (torch.randn(shape, generator=g) * torch.exp2(torch.randint(-8, 2, (shape[0], 1), generator=g).float())).to(dt)
+    x[0] = 0                      # dead channel: scale falls back to eps
+    if shape[0] > 2:
+        x[1] = x[1].abs()         # one-sided channel
+        x[2] = -x[2].abs()
+    a = QuantizationArgs(num_bits=bits, type=qtype, symmetric=sym, strategy="channel")
+    q, s, z = ops.observe_quantize(x.to(DEV), a, pack=pack)
+    wq, ws, wz = _chan_oracle(x, qtype, bits, sym, pack)
+    same(s.cpu(), ws, "channel observer scale")
+    if sym:
+        assert z is None
+    else:
+        same(z.cpu(), wz, "channel observer zero point")
+    if wq.dtype == torch.float8_e4m3fn:
+        same(q.cpu().view(torch.uint8), wq.view(torch.uint8), "channel observer fp8 codes")
+    else:
+        same(q.cpu(), wq, "channel observer codes")
+
+
+def test_channel_observer_equals_unfused_flow_at_full_size():
+    from compressed_tensors_b200.quantization import QuantizationArgs
+    from compressed_tensors_b200.quantization.utils import calculate_qparams
+
+    x = (torch.randn(14336, 4096, device=DEV) * 0.02).to(torch.bfloat16)
+    for kw, pack in ((dict(num_bits=8, type="int", symmetric=True), False), (dict(num_bits=8, type="float", symmetric=True), False),
+                     (dict(num_bits=4, type="int", symmetric=False), True)):
+        a = QuantizationArgs(strategy="channel", **kw)
+        q, s, z = ops.observe_quantize(x, a, pack=pack)
+        s2, z2 = calculate_qparams(x.amin(-1, keepdim=True), x.amax(-1, keepdim=True), a)
+        z2 = None if a.symmetric else z2
+        assert torch.equal(s, s2) and (z is None or torch.equal(z, z2))
+        q2 = ops.quantize_pack(x, s2, z2, a) if pack else ops.quantize(x, s2, z2, a, dtype=a.pytorch_dtype())
+        assert torch.equal(q.view(torch.uint8) if q.dtype == torch.float8_e4m3fn else q, q2.view(torch.uint8) if q2.dtype == torch.float8_e4m3fn else q2)

@@ -58,6 +58,11 @@ def main():
     vals24, mask24 = ops.sparse24_compress(sp)
     extra_fns["sparse24_compress"] = (lambda: ops.sparse24_compress(sp), nsp * 3.125)
     extra_fns["sparse24_decompress"] = (lambda: ops.sparse24_decompress(vals24, mask24, sp.shape), nsp * 3.125)
+    from compressed_tensors_b200.quantization import QuantizationArgs
+    for nm, kw, pk, bpe in (("observe_channel_int8", dict(num_bits=8, type="int"), False, 3.0), ("observe_channel_fp8", dict(num_bits=8, type="float"), False, 3.0),
+                            ("observe_channel_w4pack", dict(num_bits=4, type="int"), True, 2.5)):
+        qa_c = QuantizationArgs(strategy="channel", symmetric=True, **kw)
+        extra_fns[nm] = ((lambda qa_c=qa_c, pk=pk: ops.observe_quantize(sp, qa_c, pack=pk)), nsp * bpe)
     un = torch.where(torch.rand(sp.shape, device=dev) < 0.5, sp, torch.zeros_like(sp))
     uv, um, uo = ops.bitmask_compress(un)
     extra_fns["bitmask_compress_50pct"] = (lambda: ops.bitmask_compress(un), nsp * (2 + 1 + 0.125))
