@@ -336,6 +336,124 @@ __global__ void __launch_bounds__(256) bitmask_move_kernel(const void* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// unstructured bitmask, vectorised variants for 2-byte elements, cols % 8 == 0, 16-byte aligned dense tensor.
+//   count : one block per row, 16-byte loads (4 per thread in flight), mask bytes combined four at a time into 32-bit stores
+//   move  : one block per row, segments of 256 units (2048 elements): 16-byte access to the dense side, block scan of the
+//           popcounts, the kept elements staged in shared memory so that the compact side is read / written coalesced
+// Plain grid launch over the rows (hardware block scheduler = dynamic balance).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t nonzero_byte16(const uint4& v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t byte = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        byte |= ((w[j] & 0x7fffu) != 0u ? 1u : 0u) << (2 * j);            // -0.0 == 0
+        byte |= ((w[j] & 0x7fff0000u) != 0u ? 1u : 0u) << (2 * j + 1);
+    }
+    return byte;
+}
+
+__global__ void __launch_bounds__(256) bitmask_count_vec16_kernel(const uint4* __restrict__ x, uint8_t* __restrict__ bitmask,
+                                                                  int64_t* __restrict__ counts, int units /* per row, % 4 == 0 */) {
+    __shared__ int warp_sums[8];
+    const int64_t r = blockIdx.x;
+    const uint4* row = x + r * units;
+    uint32_t* mrow = reinterpret_cast<uint32_t*>(bitmask + r * units);
+    int local = 0;
+    for (int b0 = 0; b0 < units; b0 += 256 * 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = b0 + u * 256 + threadIdx.x;
+            v[u] = (i < units) ? ldg_stream16(row + i) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = b0 + u * 256 + threadIdx.x;
+            uint32_t w = nonzero_byte16(v[u]);
+            local += __popc(w);
+            w |= __shfl_down_sync(0xffffffffu, w, 1) << 8;
+            w |= __shfl_down_sync(0xffffffffu, w, 2) << 16;
+            if ((threadIdx.x & 3) == 0 && i < units) mrow[i >> 2] = w;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += warp_sums[w];
+        counts[r] = t;
+    }
+}
+
+template <bool COMPRESS>
+__global__ void __launch_bounds__(256) bitmask_move_vec16_kernel(const void* __restrict__ src, const uint8_t* __restrict__ bitmask,
+                                                                 const int64_t* __restrict__ row_offsets, void* __restrict__ dst, int units) {
+    __shared__ uint16_t stage[2048];
+    __shared__ int warp_tot[8];
+    const int64_t r = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t pos = row_offsets[r];            // first compact element of this segment
+    const uint16_t* cin = reinterpret_cast<const uint16_t*>(src);     // compact side when expanding
+    uint16_t* cout = reinterpret_cast<uint16_t*>(dst);                // compact side when compressing
+    const uint4* din = reinterpret_cast<const uint4*>(src) + r * units;   // dense side when compressing
+    uint4* dout = reinterpret_cast<uint4*>(dst) + r * units;              // dense side when expanding
+    for (int b0 = 0; b0 < units; b0 += 256) {
+        const int i = b0 + threadIdx.x;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        uint32_t byte = 0;
+        if (i < units) {
+            if (COMPRESS) { v = ldg_stream16(din + i); byte = nonzero_byte16(v); }   // the mask is recomputed: one load less
+            else byte = __ldg(bitmask + r * units + i);
+        }
+        const int cnt = __popc(byte);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        int woff = 0, seg_total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int t = warp_tot[w];
+            if (w < warp) woff += t;
+            seg_total += t;
+        }
+        const int off = woff + incl - cnt;       // this thread's first slot in the segment's compact run
+        if (COMPRESS) {
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            int o = off;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if ((byte >> k) & 1u) stage[o++] = (uint16_t)(w[k >> 1] >> (16 * (k & 1)));
+            __syncthreads();
+            for (int j = threadIdx.x; j < seg_total; j += 256) cout[pos + j] = stage[j];   // coalesced
+        } else {
+            for (int j = threadIdx.x; j < seg_total; j += 256) stage[j] = cin[pos + j];    // coalesced
+            __syncthreads();
+            if (i < units) {
+                uint32_t e[8];
+                int o = off;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) e[k] = ((byte >> k) & 1u) ? (uint32_t)stage[o++] : 0u;
+                stg_stream16(dout + i, make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16)));
+            }
+        }
+        pos += seg_total;
+        __syncthreads();   // stage / warp_tot are reused by the next segment
+    }
+}
+
+static bool bitmask_vec16_ok(int dtype, int64_t rows, int64_t cols, const void* dense, const void* mask) {
+    return dt_size(dtype) == 2 && cols % 32 == 0 && cols / 8 < 0x7fffffffLL && rows > 0 && rows < 0x7fffffffLL && aligned16(dense) &&
+           (reinterpret_cast<uintptr_t>(mask) & 3u) == 0;
+}
+
 static unsigned grid_for(int64_t items) {
     int64_t b = (items + 255) / 256;
     if (b < 1) b = 1;
@@ -450,6 +568,9 @@ int ct_bitmask_count(const void* x, int dtype, uint8_t* bitmask, int64_t* row_of
     void* tmp = reinterpret_cast<uint8_t*>(workspace) + (((rows + 1) * sizeof(int64_t) + 255) & ~(size_t)255);
     CT_CUDA_TRY(cudaMemsetAsync(counts + rows, 0, sizeof(int64_t), st));
     const unsigned g = (unsigned)(rows < 148 * 8 ? rows : 148 * 8);
+    if (bitmask_vec16_ok(dtype, rows, cols, x, bitmask) && (dtype == CT_BF16 || dtype == CT_F16)) {
+        bitmask_count_vec16_kernel<<<(unsigned)rows, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), bitmask, counts, (int)(cols / 8));
+    } else
     switch (dtype) {
     case CT_BF16: bitmask_count_kernel<CT_BF16, 2><<<g, 256, 0, st>>>(x, bitmask, counts, rows, cols, nb); break;
     case CT_F16: bitmask_count_kernel<CT_F16, 2><<<g, 256, 0, st>>>(x, bitmask, counts, rows, cols, nb); break;
@@ -477,6 +598,9 @@ int ct_bitmask_compress(const void* x, int dtype, const uint8_t* bitmask, const 
     if (!x || !bitmask || !row_offsets) { set_error("null pointer"); return CT_E_ARG; }
     const int64_t nb = (cols + 7) / 8;
     const unsigned g = (unsigned)(rows < 148 * 8 ? rows : 148 * 8);
+    if ((dtype == CT_BF16 || dtype == CT_F16) && bitmask_vec16_ok(dtype, rows, cols, x, bitmask)) {
+        bitmask_move_vec16_kernel<true><<<(unsigned)rows, 256, 0, st>>>(x, bitmask, row_offsets, values, (int)(cols / 8));
+    } else
     switch (esize_of(dtype)) {
     case 1: bitmask_move_kernel<1, true><<<g, 256, 0, st>>>(x, bitmask, row_offsets, values, rows, cols, nb); break;
     case 2: bitmask_move_kernel<2, true><<<g, 256, 0, st>>>(x, bitmask, row_offsets, values, rows, cols, nb); break;
@@ -495,6 +619,9 @@ int ct_bitmask_decompress(const void* values, int dtype, const uint8_t* bitmask,
     if (!out || !bitmask || !row_offsets) { set_error("null pointer"); return CT_E_ARG; }
     const int64_t nb = (cols + 7) / 8;
     const unsigned g = (unsigned)(rows < 148 * 8 ? rows : 148 * 8);
+    if (bitmask_vec16_ok(dtype, rows, cols, out, bitmask)) {
+        bitmask_move_vec16_kernel<false><<<(unsigned)rows, 256, 0, st>>>(values, bitmask, row_offsets, out, (int)(cols / 8));
+    } else
     switch (esize_of(dtype)) {
     case 1: bitmask_move_kernel<1, false><<<g, 256, 0, st>>>(values, bitmask, row_offsets, out, rows, cols, nb); break;
     case 2: bitmask_move_kernel<2, false><<<g, 256, 0, st>>>(values, bitmask, row_offsets, out, rows, cols, nb); break;

@@ -167,3 +167,34 @@ def test_sparse24_full_size_round_trip():
     assert torch.equal(torch.where(kept, x.view(-1, 4), torch.zeros_like(dq)), dq)
     v2, m2 = ops.sparse24_compress(dense)              # idempotent on its own output
     assert torch.equal(ops.sparse24_decompress(v2, m2, x.shape), dense)
+
+
+# ---- unstructured bitmask, vectorised path (bf16 / fp16, cols % 32 == 0) ---------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape,density", [((64, 4096), 0.3), ((33, 2048), 0.5), ((5, 32), 1.0), ((7, 8192), 0.0), ((16, 14336), 0.9), ((3, 2080), 0.5)])
+def test_bitmask_vectorised_vs_oracle(dtype, shape, density):
+    import oracle
+    from tests.util import same
+
+    g = torch.Generator().manual_seed(shape[1])
+    x = (torch.randn(shape, generator=g) * 3).to(dtype)
+    x[torch.rand(shape, generator=g) >= density] = 0
+    if shape[0] > 2:
+        x[1] = 0                    # an empty row in the middle: its offset equals the next row's
+        x[2, ::7] = -0.0            # negative zeros are zeros
+    vals, bm, offs = oracle.bitmask_compress(x)
+    gv, gb, go = ops.bitmask_compress(x.to(DEV))
+    same(gb.cpu(), bm, "bitmask")
+    same(go.cpu(), offs, "row offsets")
+    same(gv.cpu(), vals, "values")
+    dense = ops.bitmask_decompress(gv, gb, go, x.shape)
+    same(dense.cpu(), oracle.bitmask_decompress(vals, bm, x.shape), "decompress")
+
+
+def test_bitmask_full_size_round_trip():
+    x = (torch.randn(4096, 14336, device=DEV) * 0.02).to(torch.bfloat16)
+    x = torch.where(torch.rand(x.shape, device=DEV) < 0.5, x, torch.zeros_like(x))
+    v, m, o = ops.bitmask_compress(x)
+    assert v.numel() == int((x != 0).sum()) and torch.equal(v, x[x != 0])
+    assert torch.equal(o, torch.cat([torch.zeros(1, dtype=torch.int64, device=DEV), (x != 0).sum(-1).cumsum(0)[:-1]]))
+    assert torch.equal(ops.bitmask_decompress(v, m, o, x.shape), x)
