@@ -14,26 +14,27 @@
 namespace ctb {
 
 enum ChanOut { CO_PACK4 = 0, CO_PACK8 = 1, CO_I8 = 2, CO_F8 = 3 };
-constexpr int CH_MAXU = 8;   // units (of 8 elements) per thread
+constexpr int CH_MAXU = 8;   // most units (of 8 elements) per thread: rows up to 16384 columns.  The kernel is instantiated for 2, 4 and
+                             // 8 units so that short rows do not pay for registers they do not use (more CTAs resident per SM)
 
 template <class P> __device__ __forceinline__ float ch_round_to_t(float v) { return P::lo(P::pack(v, 0.f)); }
 
-template <class P, int OUT, int ASYM>
+template <class P, int OUT, int ASYM, int MAXU>
 __global__ void __launch_bounds__(256) observe_channel_kernel(const uint4* __restrict__ x, void* __restrict__ scale_out, int8_t* __restrict__ zp_out,
                                                               uint8_t* __restrict__ out, int64_t rows, int units /* cols / 8 */, const __grid_constant__ Common cm) {
     __shared__ uint32_t red[2][8];
     __shared__ float qp[2];
     const int64_t r = blockIdx.x;
     const uint4* row = x + r * units;
-    uint4 v[CH_MAXU];
+    uint4 v[MAXU];
 #pragma unroll
-    for (int u = 0; u < CH_MAXU; ++u) {
+    for (int u = 0; u < MAXU; ++u) {
         const int i = u * 256 + threadIdx.x;
         v[u] = (i < units) ? ldg_stream16(row + i) : make_uint4(0, 0, 0, 0);   // 0 is neutral: the observer clamps min <= 0 <= max
     }
     uint32_t mn2 = v[0].x, mx2 = v[0].x;
 #pragma unroll
-    for (int u = 0; u < CH_MAXU; ++u) {
+    for (int u = 0; u < MAXU; ++u) {
         mn2 = min2<P>(min2<P>(mn2, v[u].x), min2<P>(v[u].y, min2<P>(v[u].z, v[u].w)));
         mx2 = max2<P>(max2<P>(mx2, v[u].x), max2<P>(v[u].y, max2<P>(v[u].z, v[u].w)));
     }
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(256) observe_channel_kernel(const uint4* __res
     constexpr int OW = (OUT == CO_PACK4) ? 1 : 2;   // output words per unit
     uint8_t* orow = out + (size_t)r * units * (4 * OW);
 #pragma unroll
-    for (int u = 0; u < CH_MAXU; ++u) {
+    for (int u = 0; u < MAXU; ++u) {
         const int i = u * 256 + threadIdx.x;
         if (i >= units) continue;
         const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
@@ -92,8 +93,11 @@ __global__ void __launch_bounds__(256) observe_channel_kernel(const uint4* __res
 
 template <class P, int OUT>
 static int launch_chan(bool asym, const uint4* x, void* s, int8_t* z, uint8_t* out, int64_t rows, int units, const Common& cm, cudaStream_t st) {
-    if (asym) observe_channel_kernel<P, OUT, 1><<<(unsigned)rows, 256, 0, st>>>(x, s, z, out, rows, units, cm);
-    else observe_channel_kernel<P, OUT, 0><<<(unsigned)rows, 256, 0, st>>>(x, s, z, out, rows, units, cm);
+    const int per_thread = (units + 255) / 256;
+#define CT_CHAN_LAUNCH(A, U) observe_channel_kernel<P, OUT, A, U><<<(unsigned)rows, 256, 0, st>>>(x, s, z, out, rows, units, cm)
+    if (asym) { if (per_thread <= 2) CT_CHAN_LAUNCH(1, 2); else if (per_thread <= 4) CT_CHAN_LAUNCH(1, 4); else CT_CHAN_LAUNCH(1, 8); }
+    else { if (per_thread <= 2) CT_CHAN_LAUNCH(0, 2); else if (per_thread <= 4) CT_CHAN_LAUNCH(0, 4); else CT_CHAN_LAUNCH(0, 8); }
+#undef CT_CHAN_LAUNCH
     count_launch();
     CT_CUDA_TRY(cudaGetLastError());
     return CT_OK;

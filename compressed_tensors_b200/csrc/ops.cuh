@@ -2,8 +2,9 @@
 //
 // Fast-path contract (checked on the host in dispatch.cu): x, scale and compute dtype are the
 // same float dtype P; zero point absent (ZP=0) or int8 (ZP=1); scale index = chunk / dc
-// (TENSOR, CHANNEL, GROUP with full rows of scales), and dc % GROUP == 0 so that every unit has
-// exactly one scale.
+// (TENSOR, CHANNEL, GROUP with full rows of scales) or the 2-D form (row / rd) * srs + col_chunk / dc
+// (BLOCK, one-row group scales), and dc % GROUP == 0 so that every unit has exactly one scale.
+// The FP4 functors (two scales per unit, float32 arithmetic) are in fp4_ops.cuh.
 #pragma once
 
 #include "quant_core.cuh"

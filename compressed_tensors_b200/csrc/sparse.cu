@@ -168,15 +168,15 @@ __global__ void __launch_bounds__(256) sparse24_decompress_kernel(const void* __
 // ---------------------------------------------------------------------------------------------
 // keep mask (bit j = element j kept) of one quad held as two packed words {e0,e1}, {e2,e3}, and the kept pair in column order
 __device__ __forceinline__ uint32_t quad_select16(uint32_t w0, uint32_t w1, uint32_t& pair) {
-    const uint32_t k0 = w0 & 0x7fffu, k1 = (w0 >> 16) & 0x7fffu, k2 = w1 & 0x7fffu, k3 = (w1 >> 16) & 0x7fffu;
-    // "m beats j": larger key, or equal key and lower index
-    const int b01 = k0 >= k1, b02 = k0 >= k2, b03 = k0 >= k3, b12 = k1 >= k2, b13 = k1 >= k3, b23 = k2 >= k3;
-    const int beat0 = (1 - b01) + (1 - b02) + (1 - b03);
-    const int beat1 = b01 + (1 - b12) + (1 - b13);
-    const int beat2 = b02 + b12 + (1 - b23);
-    const int beat3 = b03 + b13 + b23;
-    const uint32_t keep = (uint32_t)(beat0 < 2) | ((uint32_t)(beat1 < 2) << 1) | ((uint32_t)(beat2 < 2) << 2) | ((uint32_t)(beat3 < 2) << 3);
-    const uint32_t i0 = __ffs(keep) - 1, i1 = 31 - __clz(keep);
+    // composite = |x| bits << 2 | (3 - column): all four distinct, larger = wins (larger magnitude, or equal magnitude and lower
+    // column).  The two winners come out of a 4-input selection network of integer min / max.
+    const uint32_t c0 = ((w0 << 2) & 0x1fffcu) | 3u, c1 = ((w0 >> 14) & 0x1fffcu) | 2u;
+    const uint32_t c2 = ((w1 << 2) & 0x1fffcu) | 1u, c3 = ((w1 >> 14) & 0x1fffcu);
+    const uint32_t a = max(c0, c1), b = min(c0, c1), c = max(c2, c3), d = min(c2, c3);
+    const uint32_t first = max(a, c), second = max(min(a, c), max(b, d));
+    const uint32_t ia = 3u - (first & 3u), ib = 3u - (second & 3u);
+    const uint32_t keep = (1u << ia) | (1u << ib);
+    const uint32_t i0 = min(ia, ib), i1 = max(ia, ib);
     pair = __byte_perm(w0, w1, 0x1010u + i0 * 0x22u + i1 * 0x2200u);   // bytes (2 i0, 2 i0 + 1, 2 i1, 2 i1 + 1)
     return keep;
 }

@@ -7,7 +7,8 @@
 //           1-byte codes: 16 elements) and the scale / reciprocal is fetched once per unit.
 //   tile  = TILE_CHUNKS chunks = 8192 elements (16 KB of bf16) = one CTA's unit of work
 //   job   = one tensor; a launch covers a table of jobs (whole-model batches); tiles are numbered
-//           globally and dealt round-robin to a persistent grid of n_SM * ctas_per_sm CTAs.
+//           globally and CLAIMED from a device counter by a persistent grid of n_SM * ctas_per_sm CTAs
+//           (dynamic schedule, see stream_tma_kernel; small launches keep a static round-robin deal).
 //
 // Pipeline 1 ("tma"): warp-specialised.  One producer lane issues 1-D bulk async copies
 // (cp.async.bulk, the TMA engine without a tensor map) of whole input tiles into a ring of
