@@ -38,7 +38,7 @@ DT = {
 
 # ct_batch_op_t
 (OP_QUANTIZE_PACK, OP_UNPACK_DEQUANTIZE, OP_QUANTIZE, OP_DEQUANTIZE, OP_FAKE_QUANTIZE, OP_PACK_INT32, OP_UNPACK_INT32,
- OP_OBSERVE_QUANTIZE_PACK, OP_QUANTIZE_PACK_FP4, OP_UNPACK_DEQUANTIZE_FP4) = range(10)
+ OP_OBSERVE_QUANTIZE_PACK, OP_QUANTIZE_PACK_FP4, OP_UNPACK_DEQUANTIZE_FP4, OP_OBSERVE_QUANTIZE_PACK_FP4) = range(11)
 
 Q_INT, Q_FLOAT, Q_FP4 = 0, 1, 2
 DT_E8M0 = 8  # uint8 MX scale exponent as stored (CT_E8M0)
@@ -96,6 +96,7 @@ _PROTOS = {
     "ct_unpack_fp4": (_int, [_vp, _vp, _int, _i64, _i64, _int, _vp]),
     "ct_quantize_pack_fp4": (_int, [_descp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "ct_unpack_dequantize_fp4": (_int, [_descp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "ct_observe_quantize_pack_nvfp4": (_int, [_descp, _vp, _vp, _vp, _int, _vp]),
     "ct_mx_scale_compress": (_int, [_vp, _int, _vp, _i64, _int, _vp]),
     "ct_mx_scale_decompress": (_int, [_vp, _vp, _i64, _int, _vp]),
     "ct_awq_repack_int4": (_int, [_vp, _vp, _i64, _i64, _int, _vp]),

@@ -215,7 +215,12 @@ static Plan plan_fp4(int op, const ct_quant_desc& d, const void* in, const void*
     if (g_idx || n == 0 || (n / 8) >= 0x7fffffffLL || !aligned16(in) || !aligned16(out)) return p;
     if (!flat_divisor(d, D) || is_inf(D) || d.qtype != CT_Q_FP4) return p;
     FastSig sig{0, 0, 0, 0, 1};
-    if (op == CT_OP_QUANTIZE_PACK_FP4) {
+    if (op == CT_OP_OBSERVE_QUANTIZE_PACK_FP4) {
+        // scale (float8_e4m3fn [rows, cols / 16]) is an OUTPUT; NVFP4 only: group 16, float32 global scale given, no zero point
+        if ((d.x_dtype != CT_BF16 && d.x_dtype != CT_F16) || d.cols % 32 != 0 || D != 16 || !d.global_scale || zp) return p;
+        if ((reinterpret_cast<uintptr_t>(scale) & 1u) != 0) return p;
+        sig.op = F_FP4_QUANTPACK; sig.p_dt = d.x_dtype; sig.group = 4; sig.sel = 3;
+    } else if (op == CT_OP_QUANTIZE_PACK_FP4) {
         if (d.x_dtype != CT_BF16 && d.x_dtype != CT_F16) return p;
         if (d.cols % 32 != 0 || !aligned16(scale) ) return p;
         sig.op = F_FP4_QUANTPACK; sig.p_dt = d.x_dtype; sig.group = 4;
@@ -307,6 +312,10 @@ static int run_generic(int op, const ct_quant_desc& d, const void* in, const voi
         return launch_generic_quantpack_fp4(d, in, scale, zp, g_idx, reinterpret_cast<uint8_t*>(out), st);
     case CT_OP_UNPACK_DEQUANTIZE_FP4:
         return launch_generic_unpackdeq_fp4(d, reinterpret_cast<const uint8_t*>(in), scale, zp, g_idx, out, st);
+    case CT_OP_OBSERVE_QUANTIZE_PACK_FP4:
+        set_error("fused NVFP4 observe+quantize+pack supports bf16 / fp16 weights, group_size 16 with full rows of scales, cols %% 32 == 0, "
+                  "a float32 global scale, 16-byte aligned contiguous tensors; run the observer and quantize_pack_fp4 separately otherwise");
+        return CT_E_UNSUPPORTED;
     case CT_OP_OBSERVE_QUANTIZE_PACK:
         set_error("fused observe+quantize+pack supports bf16/fp16 group quantization with group_size in {32,64,128,256}, "
                   "4- or 8-bit codes, 16-byte aligned contiguous tensors; run the observer and quantize_pack separately otherwise");
@@ -318,8 +327,13 @@ static int run_generic(int op, const ct_quant_desc& d, const void* in, const voi
 
 static int check_dtypes(int op, const ct_quant_desc& d, bool has_zp) {
     const bool quantizing = (op == CT_OP_QUANTIZE_PACK || op == CT_OP_QUANTIZE || op == CT_OP_FAKE_QUANTIZE || op == CT_OP_OBSERVE_QUANTIZE_PACK ||
-                             op == CT_OP_QUANTIZE_PACK_FP4);
-    const bool fp4_op = (op == CT_OP_QUANTIZE_PACK_FP4 || op == CT_OP_UNPACK_DEQUANTIZE_FP4);
+                             op == CT_OP_QUANTIZE_PACK_FP4 || op == CT_OP_OBSERVE_QUANTIZE_PACK_FP4);
+    const bool fp4_op = (op == CT_OP_QUANTIZE_PACK_FP4 || op == CT_OP_UNPACK_DEQUANTIZE_FP4 || op == CT_OP_OBSERVE_QUANTIZE_PACK_FP4);
+    if (op == CT_OP_OBSERVE_QUANTIZE_PACK_FP4) {   // the scale is produced, as float8_e4m3fn
+        if (d.qtype != CT_Q_FP4 || d.cols % 2 != 0) { set_error("fp4 ops need qtype fp4 and an even number of columns"); return CT_E_DTYPE; }
+        if (!is_float_dt(d.x_dtype)) { set_error("x dtype must be float"); return CT_E_DTYPE; }
+        return CT_OK;
+    }
     if (fp4_op && (d.qtype != CT_Q_FP4 || d.cols % 2 != 0)) { set_error("fp4 ops need qtype fp4 and an even number of columns"); return d.cols % 2 ? CT_E_SHAPE : CT_E_DTYPE; }
     const bool stored_scale = (op == CT_OP_UNPACK_DEQUANTIZE_FP4 && (d.scale_dtype == CT_F8E4M3 || d.scale_dtype == CT_E8M0));
     if (stored_scale && !is_float_dt(d.seff_dtype)) { set_error("stored (fp8 / E8M0) scales need seff_dtype = the float dtype they decode to"); return CT_E_DTYPE; }
@@ -363,7 +377,7 @@ int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in
         rc = check_dtypes(op, descs[i], z != nullptr);
         if (rc) return rc;
         if (descs[i].rows * descs[i].cols > 0 && (!in[i] || !scale[i] || !out[i])) { set_error("null tensor pointer (tensor %d)", i); return CT_E_ARG; }
-        if (op == CT_OP_QUANTIZE_PACK_FP4 || op == CT_OP_UNPACK_DEQUANTIZE_FP4) plans[i] = plan_fp4(op, descs[i], in[i], scale[i], z, g_idx ? g_idx[i] : nullptr, out[i]);
+        if (op == CT_OP_QUANTIZE_PACK_FP4 || op == CT_OP_UNPACK_DEQUANTIZE_FP4 || op == CT_OP_OBSERVE_QUANTIZE_PACK_FP4) plans[i] = plan_fp4(op, descs[i], in[i], scale[i], z, g_idx ? g_idx[i] : nullptr, out[i]);
         else plans[i] = plan_one(op, descs[i], in[i], scale[i], z, g_idx ? g_idx[i] : nullptr, out[i]);
     }
     // group fast jobs by kernel signature (and clamp constants), one launch per group
@@ -513,6 +527,9 @@ int ct_unpack_fp4(const uint8_t* packed, void* out, int out_dtype, int64_t rows,
 }
 int ct_quantize_pack_fp4(const ct_quant_desc* d, const void* x, const void* scale, const void* zp, const int32_t* g_idx, uint8_t* packed, int device, void* stream) {
     return run_one(CT_OP_QUANTIZE_PACK_FP4, d, x, scale, zp, g_idx, packed, device, stream);
+}
+int ct_observe_quantize_pack_nvfp4(const ct_quant_desc* d, const void* x, void* scale_out_fp8, uint8_t* packed, int device, void* stream) {
+    return run_one(CT_OP_OBSERVE_QUANTIZE_PACK_FP4, d, x, scale_out_fp8, nullptr, nullptr, packed, device, stream);
 }
 int ct_unpack_dequantize_fp4(const ct_quant_desc* d, const uint8_t* packed, const void* scale, const void* zp, const int32_t* g_idx, void* out, int device, void* stream) {
     return run_one(CT_OP_UNPACK_DEQUANTIZE_FP4, d, packed, scale, zp, g_idx, out, device, stream);

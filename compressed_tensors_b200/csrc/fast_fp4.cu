@@ -11,7 +11,8 @@ namespace ctb {
         return CT_E_UNSUPPORTED;                                                                   \
     } while (0)
 
-// sig.sel: F_FP4_QUANTPACK: 0 = MX (arithmetic in T), 1 = NV with scale in T, 2 = NV with float32 scale
+// sig.sel: F_FP4_QUANTPACK: 0 = MX (arithmetic in T), 1 = NV with scale in T, 2 = NV with float32 scale, 3 = NV with the group
+//          observer fused in (scale is an OUTPUT, float8_e4m3fn)
 //          F_FP4_UNPACKDEQ: Fp4ScaleKind of the scale tensor (FS_SAME / FS_F8 / FS_E8M0)
 // sig.zp : Fp4ZpKind
 template <class P>
@@ -38,6 +39,11 @@ static int fp4_unpackdeq_p(const FastSig& s, const LaunchPlan& lp, int device, c
 }
 
 int launch_fast_fp4(const FastSig& s, const LaunchPlan& lp, int device, cudaStream_t st) {
+    if (s.op == F_FP4_QUANTPACK && s.sel == 3) {   // observe + quantize + pack (scale is an output)
+        if (s.p_dt == CT_BF16) return launch_stream<Fp4NvObserveQuantPackOp<BF16>>(lp, device, st);
+        if (s.p_dt == CT_F16) return launch_stream<Fp4NvObserveQuantPackOp<F16>>(lp, device, st);
+        SIG_FAIL(s);
+    }
     if (s.op == F_FP4_QUANTPACK) {
         if (s.p_dt == CT_BF16) return fp4_quantpack_p<BF16>(s, lp, device, st);
         if (s.p_dt == CT_F16) return fp4_quantpack_p<F16>(s, lp, device, st);

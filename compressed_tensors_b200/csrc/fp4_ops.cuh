@@ -165,6 +165,75 @@ struct Fp4NvQuantPackOp {
 };
 
 // ------------------------------------------------------------------------------------
+// NVFP4 observe + quantize + pack: the per-group part of the observer fused in front of Fp4NvQuantPackOp.
+//   reference: min / max per group of 16 -> calculate_qparams(args NVFP4, global_scale) (quantization/utils/helpers.py:50-137:
+//   max|x| / 6 in T, x global_scale in float32, clamp to +-448 and .to(float8_e4m3fn), 0 -> 0.125) -> quantize -> pack.
+//   The global scale (generate_gparam over the whole tensor, helpers.py:308-337) is an INPUT: it needs a grid-wide reduction
+//   that has to finish before any group can be scaled.  Outputs: nibbles and the group scales as stored (float8_e4m3fn).
+// J.scale is written here (uint8 [n / 16]); J.aux = global scale.
+// ------------------------------------------------------------------------------------
+template <class P>
+struct Fp4NvObserveQuantPackOp {
+    static constexpr int IN_BYTES = 16;
+    static constexpr int GROUP = 4;
+    struct Raw { float gs; };
+    __device__ static __forceinline__ Raw prefetch(const Job& J, uint32_t) {
+        Raw r;
+        r.gs = __ldg(reinterpret_cast<const float*>(J.aux));
+        return r;
+    }
+    // max |x| of one chunk as packed T2 (abs = clear the sign bits)
+    __device__ static __forceinline__ uint32_t chunk_amax2(const uint32_t (&w)[4]) {
+        return max2<P>(max2<P>(w[0] & 0x7fff7fffu, w[1] & 0x7fff7fffu), max2<P>(w[2] & 0x7fff7fffu, w[3] & 0x7fff7fffu));
+    }
+    __device__ static __forceinline__ void run(const Job& J, const Common&, const Raw& r, uint32_t gc0, const uint32_t (&w)[4][4], int off) {
+        using Q = Fp4NvQuantPackOp<P, FS_F32, FZ_NONE>;
+        const uint32_t m0 = chunk_amax2(w[0]), m1 = chunk_amax2(w[1]), m2 = chunk_amax2(w[2]), m3 = chunk_amax2(w[3]);
+        // register k holds chunk (k + off) mod 4; groups are chunks {0, 1} and {2, 3}
+        const bool odd = off & 1;
+        const uint32_t pa = odd ? max2<P>(m3, m0) : max2<P>(m0, m1);      // the pair that contains register 0
+        const uint32_t pb = odd ? max2<P>(m1, m2) : max2<P>(m2, m3);
+        const bool a_is_g0 = off < 2;                                        // off 0: regs {0,1} = chunks {0,1}; off 1: regs {3,0} = chunks {0,1}
+        const uint32_t g0 = a_is_g0 ? pa : pb, g1 = a_is_g0 ? pb : pa;
+        float s[2], rc[2];
+        uint32_t codes = 0;
+        bool slow = false;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const uint32_t gm = g ? g1 : g0;
+            const float amax = fmaxf(P::lo(gm), P::hi(gm));                              // max(|min(min, 0)|, |max(max, 0)|) = max |x|
+            const float st = P::lo(P::pack(__fdiv_rn(amax, 6.0f), 0.f));               // max_val_pos / (bit_range / 2), rounded to T
+            float sf = fminf(fmaxf(__fmul_rn(r.gs, st), -448.0f), 448.0f);              // global_scale * scales (float32), clamp
+            uint32_t byte = f32x2_to_e4m3x2(sf, 0.f) & 0xffu;                           // .to(float8_e4m3fn)
+            sf = e4m3_to_f32(byte);
+            if (sf == 0.f) { sf = 0.125f; byte = 0x20u; }                                // eps of the scale dtype; 0x20 = 0.125 in e4m3
+            if (sf != sf) byte = 0x7fu;
+            codes |= byte << (8 * g);
+            s[g] = __fdiv_rn(sf, r.gs);
+            const float a = fabsf(s[g]);
+            slow |= !(a >= 7.888609052210118e-31f && a <= 1024.0f);
+            rc[g] = __frcp_rn(s[g]);
+        }
+        reinterpret_cast<unsigned short*>(const_cast<void*>(J.scale))[gc0 >> 2] = (unsigned short)codes;   // two fp8 scales of this unit
+        uint32_t o[4];
+        if (slow) {
+            const uint4 v = Q::unit_slow(make_uint4(w[0][0], w[0][1], w[0][2], w[0][3]), make_uint4(w[1][0], w[1][1], w[1][2], w[1][3]),
+                                         make_uint4(w[2][0], w[2][1], w[2][2], w[2][3]), make_uint4(w[3][0], w[3][1], w[3][2], w[3][3]),
+                                         s[0], s[1], 0.f, 0.f, off);
+            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool g = ((k + off) >> 1) & 1;
+                o[k] = Q::chunk_fast(w[k], g ? s[1] : s[0], g ? rc[1] : rc[0], 0.f);
+            }
+        }
+        rotate_out<4, 1>(o, off);
+        store_words<4>(J.out + (size_t)gc0 * 4, o);
+    }
+};
+
+// ------------------------------------------------------------------------------------
 // MXFP4-style quantize + pack: arithmetic in x's dtype T (scale has the same dtype, no global scale), one scale per unit.
 //   unit = 4 chunks = 32 elements (needs group_size % 32 == 0)
 // ------------------------------------------------------------------------------------

@@ -158,6 +158,11 @@ int ct_pack_fp4(const void* x, int dtype, uint8_t* packed, int64_t rows, int64_t
 int ct_unpack_fp4(const uint8_t* packed, void* out, int out_dtype, int64_t rows, int64_t cols, int device, void* stream);
 int ct_quantize_pack_fp4(const ct_quant_desc* d, const void* x, const void* scale, const void* zp, const int32_t* g_idx,
                          uint8_t* packed, int device, void* stream);
+/* NVFP4 with the per-group observer fused in: given the tensor's global scale (d->global_scale, from generate_gparam,
+ * quantization/utils/helpers.py:308-337) computes every group-of-16 scale with calculate_qparams' rule (helpers.py:74-131: max|x| / 6
+ * in x's dtype, x global_scale in float32, clamp, .to(float8_e4m3fn), 0 -> 0.125), stores it AS float8_e4m3fn in scale_out
+ * [rows, cols / 16] and quantizes + packs with it in the same pass.  bf16 / fp16, cols % 32 == 0; CT_E_UNSUPPORTED otherwise. */
+int ct_observe_quantize_pack_nvfp4(const ct_quant_desc* d, const void* x, void* scale_out_fp8, uint8_t* packed, int device, void* stream);
 int ct_unpack_dequantize_fp4(const ct_quant_desc* d, const uint8_t* packed, const void* scale, const void* zp,
                              const int32_t* g_idx, void* out, int device, void* stream);
 int ct_mx_scale_compress(const void* scale, int dtype, uint8_t* out, int64_t n, int device, void* stream);
@@ -197,7 +202,8 @@ typedef enum ct_batch_op_t {
     CT_OP_UNPACK_INT32 = 6,       /* in packed   -> out int8 codes */
     CT_OP_OBSERVE_QUANTIZE_PACK = 7, /* in x     -> out packed int32; scale[i] / zp[i] are OUTPUTS (see ct_observe_quantize_pack_int32) */
     CT_OP_QUANTIZE_PACK_FP4 = 8,  /* in x        -> out uint8 nibbles (ct_quantize_pack_fp4) */
-    CT_OP_UNPACK_DEQUANTIZE_FP4 = 9 /* in nibbles -> out float (ct_unpack_dequantize_fp4) */
+    CT_OP_UNPACK_DEQUANTIZE_FP4 = 9, /* in nibbles -> out float (ct_unpack_dequantize_fp4) */
+    CT_OP_OBSERVE_QUANTIZE_PACK_FP4 = 10 /* in x -> out nibbles; scale[i] (float8_e4m3fn) is an OUTPUT (ct_observe_quantize_pack_nvfp4) */
 } ct_batch_op_t;
 int ct_batched(int op, int n, const ct_quant_desc* descs, const void* const* in, const void* const* scale,
                const void* const* zp, void* const* out, int device, void* stream);
