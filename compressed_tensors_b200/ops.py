@@ -49,6 +49,7 @@ __all__ = [
     "decompress_mx_scale",
     "observe_quantize",
     "observe_quantize_pack",
+    "observe_quantize_pack_nvfp4",
     "dequantize_block_fp8",
     "awq_repack",
     "awq_repack_zeros",
@@ -729,6 +730,46 @@ def observe_quantize_pack(x: torch.Tensor, args) -> Tuple[torch.Tensor, torch.Te
     zp = None if symmetric else zp
     packed = quantize_pack(xd, scale, zp, args)
     return _back(packed, x), _back(scale, x), (_back(zp, x) if zp is not None else None)
+
+
+@torch.no_grad()
+def observe_quantize_pack_nvfp4(x: torch.Tensor, args, global_scale: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """NVFP4 "calibrate + compress" of one weight: returns (weight_packed uint8 [R, C/2], weight_scale float8_e4m3fn [R, C/16],
+    weight_global_scale float32 [1]) -- what the reference produces with
+        global_scale = generate_gparam(w.min(), w.max())                                   (utils/helpers.py:308-337)
+        scale, _     = calculate_qparams(group min, group max, args, global_scale)         (utils/helpers.py:50-137)
+        NVFP4PackedCompressor.compress({"weight", "weight_scale", "weight_global_scale"})  (compressors/nvfp4/base.py:73-93)
+    The global scale needs the whole tensor first (one torch min/max reduction unless it is given); everything per group --
+    max |x|, the fp8 scale, quantize, nibble packing -- is ONE more pass (`ct_observe_quantize_pack_nvfp4`): the weight is read twice
+    instead of three times and neither the float scale tensor nor the unpacked fp4 values ever exist."""
+    from .quantization.utils.helpers import calculate_qparams, generate_gparam
+
+    qtype, bits = _qparams(args)
+    group = int(getattr(args, "group_size", 0) or 0)
+    if qtype != N.Q_FP4 or _strategy_name(args) != "tensor_group" or group != 16:
+        raise ValueError("observe_quantize_pack_nvfp4 needs NVFP4 args (float, 4 bits, tensor_group, group_size 16)")
+    if x.ndim != 2:
+        raise ValueError("observe_quantize_pack_nvfp4 expects a 2-D weight")
+    rows, cols = x.shape
+    idx = _dev_index(x)
+    xd = _to_dev(x, idx).contiguous()
+    gs = _to_dev(global_scale, idx) if global_scale is not None else generate_gparam(xd.min(), xd.max())
+    gs = gs.reshape(1).to(torch.float32).contiguous()
+    if x.dtype in (torch.bfloat16, torch.float16) and cols % 32 == 0 and rows > 0:
+        scale = torch.empty((rows, cols // 16), dtype=torch.float8_e4m3fn, device=xd.device)
+        packed = torch.empty((rows, cols // 2), dtype=torch.uint8, device=xd.device)
+        d = N.QuantDesc()
+        d.rows, d.cols, d.rdiv, d.cdiv, d.s_row_stride = rows, cols, 1, 16, cols // 16
+        d.x_dtype, d.scale_dtype, d.compute_dtype = N.DT[x.dtype], N.DT[torch.float8_e4m3fn], N.DT[torch.float32]
+        d.zp_dtype, d.q_dtype, d.out_dtype, d.qtype, d.num_bits = N.DT_NONE, N.DT[x.dtype], N.DT_NONE, N.Q_FP4, 4
+        d.global_scale, d.seff_dtype = gs.data_ptr(), N.DT[torch.float32]
+        rc = N.lib().ct_observe_quantize_pack_nvfp4(ctypes.byref(d), N.ptr(xd), N.ptr(scale), N.ptr(packed), idx, N.stream_ptr(idx))
+        N.check(rc, "observe_quantize_pack_nvfp4")
+        return _back(packed, x), _back(scale, x), _back(gs, x)
+    g = xd.unflatten(-1, (-1, 16))
+    scale, _ = calculate_qparams(g.amin(-1), g.amax(-1), args, global_scale=gs)
+    packed = quantize_pack_fp4(xd, scale, None, args, global_scale=gs)
+    return _back(packed, x), _back(scale.to(torch.float8_e4m3fn), x), _back(gs, x)
 
 
 @torch.no_grad()

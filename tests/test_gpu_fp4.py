@@ -404,3 +404,39 @@ def test_model_compressor_batched_equals_per_module(preset):
                 assert sa[k] is None and sb[k] is None, k
                 continue
             assert sa[k].dtype == sb[k].dtype and torch.equal(sa[k].float(), sb[k].float()), (preset, k)
+
+
+# ---- NVFP4 with the group observer fused in (ct_observe_quantize_pack_nvfp4) ---------------------------------------------------
+@pytest.mark.parametrize("i", [i for i, c in enumerate(G["nvfp4"]) if c["scale"].dtype == torch.float32 and c["x"].dtype != torch.float32 and c["x"].shape[1] % 32 == 0])
+def test_nvfp4_fused_observer_golden(i):
+    """the reference's generate_gparam -> calculate_qparams -> quantize -> pack chain, from its own outputs"""
+    c = G["nvfp4"][i]
+    a = qa(c["args"])
+    packed, scale, gs = ops.observe_quantize_pack_nvfp4(c["x"].to(DEV), a)
+    same(gs.cpu(), c["global_scale"], "global scale")
+    same(scale.cpu().view(torch.uint8), c["qparams_scale"].to(torch.float8_e4m3fn).view(torch.uint8), "fp8 group scales")
+    same(packed.cpu(), oracle.pack_fp4_to_uint8(c["q"]), "nibbles")
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(64, 256), (128, 4096), (33, 1056), (5, 48)])
+def test_nvfp4_fused_observer_vs_unfused(dt, shape):
+    from compressed_tensors_b200.quantization.utils import calculate_qparams, generate_gparam
+
+    g = torch.Generator().manual_seed(shape[0])
+    x = (torch.randn(shape, generator=g) * torch.exp2(torch.randint(-10, 3, (shape[0], shape[1] // 16, 1), generator=g).float()).expand(-1, -1, 16).reshape(shape)).to(dt)
+    x[0, :16] = 0                       # dead group: scale falls back to 0.125
+    x[-1, -16:] = x[-1, -16:].abs()     # one-sided group
+    a = QuantizationArgs(**NV, scale_dtype=torch.float8_e4m3fn)
+    xd = x.to(DEV)
+    gs = generate_gparam(xd.min(), xd.max())
+    grp = xd.unflatten(-1, (-1, 16))
+    s, _ = calculate_qparams(grp.amin(-1), grp.amax(-1), a, global_scale=gs)
+    want_packed = ops.quantize_pack_fp4(xd, s, None, a, global_scale=gs)
+    packed, scale, gs2 = ops.observe_quantize_pack_nvfp4(xd, a)
+    assert torch.equal(gs2, gs)
+    assert torch.equal(scale.view(torch.uint8), s.to(torch.float8_e4m3fn).view(torch.uint8)), "group scales"
+    assert torch.equal(packed, want_packed), "nibbles"
+    # and against the CPU oracle end to end
+    os_ = oracle.quantize(x, s.cpu(), None, global_scale=gs.cpu(), **okw(a))
+    same(packed.cpu(), oracle.pack_fp4_to_uint8(os_), "nibbles vs oracle")

@@ -54,11 +54,12 @@ def build_problems(layers: int):
         du.global_scale = g.data_ptr()
         keep.append(g)
         P["nvfp4_qp"].append((dn, w, sbn, None, nib))
+        P.setdefault("nvfp4_observe_qp", []).append((dn, w, torch.empty_like(s8n), None, nib))
         P["nvfp4_ud"].append((du, nib, s8n, None, b))
         P["fp8_dq"].append((ops._desc(p8, None, s.dtype, None, None, torch.float8_e4m3fn, torch.bfloat16, N.Q_INT, 8), q, s, None, b))
     OPS = {"quantpack": (N.OP_QUANTIZE_PACK, 2.515625), "unpackdeq": (N.OP_UNPACK_DEQUANTIZE, 2.515625),
            "observe_qp": (N.OP_OBSERVE_QUANTIZE_PACK, 2.515625), "fp8_q": (N.OP_QUANTIZE, 3.0), "fp8_dq": (N.OP_DEQUANTIZE, 3.0), "fake_w4": (N.OP_FAKE_QUANTIZE, 4.0 + 2 / 128),
-           "nvfp4_qp": (N.OP_QUANTIZE_PACK_FP4, 2 + 2 / 16 + 0.5), "nvfp4_ud": (N.OP_UNPACK_DEQUANTIZE_FP4, 0.5 + 1 / 16 + 2)}
+           "nvfp4_qp": (N.OP_QUANTIZE_PACK_FP4, 2 + 2 / 16 + 0.5), "nvfp4_observe_qp": (N.OP_OBSERVE_QUANTIZE_PACK_FP4, 2 + 1 / 16 + 0.5), "nvfp4_ud": (N.OP_UNPACK_DEQUANTIZE_FP4, 0.5 + 1 / 16 + 2)}
     P["_keep"] = keep   # global-scale tensors referenced by address from the descriptors
     return P, OPS, n
 
