@@ -56,6 +56,12 @@ __device__ __forceinline__ float fp4_zp_value(uint32_t byte) {
 // (exhaustively checked against div.rn for every 16-bit x and every scale significand by ct_selftest_fp4_division);
 // groups whose effective scale falls outside [2^-100, 2^10] take div.rn per element.
 // ------------------------------------------------------------------------------------
+// per-tile constants of the ops that divide a scale by the tensor's global scale
+struct Fp4DqTile {
+    float gs, rgs;   // global scale of the tensor and its correctly rounded reciprocal
+    bool has, fast;  // fast: |gs| in [2^-60, 2^60] -> scale / gs by recip_div for |scale| in [2^-40, 2^14] (exhaustively checked)
+};
+
 struct Fp4NvRaw {
     uint32_t s0, s1;   // the unit's two group scales (bit patterns)
     uint32_t z;        // two zero-point bytes
@@ -176,17 +182,29 @@ template <class P>
 struct Fp4NvObserveQuantPackOp {
     static constexpr int IN_BYTES = 16;
     static constexpr int GROUP = 4;
-    struct Raw { float gs; };
-    __device__ static __forceinline__ Raw prefetch(const Job& J, uint32_t) {
-        Raw r;
-        r.gs = __ldg(reinterpret_cast<const float*>(J.aux));
+    using Raw = NoRaw;
+    __device__ static __forceinline__ Raw prefetch(const Job&, uint32_t) { return {}; }
+    // per tile: the tensor's global scale, its reciprocal, and whether scale / global_scale may use recip_div (as in Fp4DqTile)
+    using Tile = Fp4DqTile;
+    __device__ static __forceinline__ Tile tile(const Job& J) {
+        Tile t;
+        t.has = true;
+        t.gs = __ldg(reinterpret_cast<const float*>(J.aux));
+        t.rgs = __frcp_rn(t.gs);
+        const float a = fabsf(t.gs);
+        t.fast = a >= 8.673617379884035e-19f && a <= 1.152921504606847e18f;
+        return t;
+    }
+    // packed max(|a|, |b|): max.xorsign.abs takes the larger magnitude (its sign is the xor of the input signs, cleared at the end)
+    __device__ static __forceinline__ uint32_t amax2(uint32_t a, uint32_t b) {
+        uint32_t r;
+        if constexpr (P::DT == CT_BF16) asm("max.xorsign.abs.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+        else asm("max.xorsign.abs.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
         return r;
     }
-    // max |x| of one chunk as packed T2 (abs = clear the sign bits)
-    __device__ static __forceinline__ uint32_t chunk_amax2(const uint32_t (&w)[4]) {
-        return max2<P>(max2<P>(w[0] & 0x7fff7fffu, w[1] & 0x7fff7fffu), max2<P>(w[2] & 0x7fff7fffu, w[3] & 0x7fff7fffu));
-    }
-    __device__ static __forceinline__ void run(const Job& J, const Common&, const Raw& r, uint32_t gc0, const uint32_t (&w)[4][4], int off) {
+    // max |x| of one chunk as packed T2
+    __device__ static __forceinline__ uint32_t chunk_amax2(const uint32_t (&w)[4]) { return amax2(amax2(w[0], w[1]), amax2(w[2], w[3])) & 0x7fff7fffu; }
+    __device__ static __forceinline__ void run(const Job& J, const Common&, const Raw&, uint32_t gc0, const uint32_t (&w)[4][4], int off, const Tile& tc) {
         using Q = Fp4NvQuantPackOp<P, FS_F32, FZ_NONE>;
         const uint32_t m0 = chunk_amax2(w[0]), m1 = chunk_amax2(w[1]), m2 = chunk_amax2(w[2]), m3 = chunk_amax2(w[3]);
         // register k holds chunk (k + off) mod 4; groups are chunks {0, 1} and {2, 3}
@@ -202,14 +220,19 @@ struct Fp4NvObserveQuantPackOp {
         for (int g = 0; g < 2; ++g) {
             const uint32_t gm = g ? g1 : g0;
             const float amax = fmaxf(P::lo(gm), P::hi(gm));                              // max(|min(min, 0)|, |max(max, 0)|) = max |x|
-            const float st = P::lo(P::pack(__fdiv_rn(amax, 6.0f), 0.f));               // max_val_pos / (bit_range / 2), rounded to T
-            float sf = fminf(fmaxf(__fmul_rn(r.gs, st), -448.0f), 448.0f);              // global_scale * scales (float32), clamp
+            // max_val_pos / (bit_range / 2) in float32, then rounded to T.  recip_div is exact for 16-bit numerators in
+            // [2^-40, 2^14] (ct_selftest_fp4_division, mode 1; the divisor 6.0 is one of the float32 significands it covers)
+            const float q6 = (amax >= 9.094947017729282e-13f && amax <= 16384.0f) ? recip_div(amax, 6.0f, 0.16666667163372039794921875f)
+                                                                                   : __fdiv_rn(amax, 6.0f);
+            const float st = P::lo(P::pack(q6, 0.f));
+            float sf = fminf(fmaxf(__fmul_rn(tc.gs, st), -448.0f), 448.0f);             // global_scale * scales (float32), clamp
             uint32_t byte = f32x2_to_e4m3x2(sf, 0.f) & 0xffu;                           // .to(float8_e4m3fn)
             sf = e4m3_to_f32(byte);
             if (sf == 0.f) { sf = 0.125f; byte = 0x20u; }                                // eps of the scale dtype; 0x20 = 0.125 in e4m3
             if (sf != sf) byte = 0x7fu;
             codes |= byte << (8 * g);
-            s[g] = __fdiv_rn(sf, r.gs);
+            // scale / global_scale: an e4m3 value (within [2^-9, 448]) over the global scale, same shortcut as the decompress kernel
+            s[g] = (tc.fast && sf == sf) ? recip_div(sf, tc.gs, tc.rgs) : __fdiv_rn(sf, tc.gs);
             const float a = fabsf(s[g]);
             slow |= !(a >= 7.888609052210118e-31f && a <= 1024.0f);
             rc[g] = __frcp_rn(s[g]);
@@ -291,10 +314,7 @@ struct Fp4MxQuantPackOp {
 struct Fp4DqRaw {
     uint32_t s;
 };
-struct Fp4DqTile {
-    float gs, rgs;   // global scale of the tensor and its correctly rounded reciprocal
-    bool has, fast;  // fast: |gs| in [2^-60, 2^60] -> scale / gs by recip_div for |scale| in [2^-40, 2^14] (exhaustively checked)
-};
+
 template <class P, int SK>
 struct Fp4UnpackDequantOp {
     static constexpr int IN_BYTES = 4;
