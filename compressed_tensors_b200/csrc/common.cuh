@@ -29,6 +29,7 @@ struct Tuning {
     int stages;       // ring depth for the TMA variant
     int ctas_per_sm;  // persistent CTAs per SM
     int dynamic;      // TMA variant: 1 = tiles claimed from a device counter (default), 0 = static round-robin deal
+    int auto_shape;   // 1 when stages / ctas_per_sm are the defaults (not set by env / ct_set_tuning): ops may use their own preference
 };
 constexpr int DYNAMIC_MIN_TILES_PER_SM = 24;   // below this many tiles per SM a launch keeps the static deal (no scratch, no memset)
 Tuning tuning();

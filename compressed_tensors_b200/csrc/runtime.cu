@@ -30,7 +30,7 @@ int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 // ---- tuning ---------------------------------------------------------------------------------
 static std::mutex g_tune_mu;
-static Tuning g_tune = {-1, 0, 0, 1};
+static Tuning g_tune = {-1, 0, 0, 1, 0};
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -51,6 +51,7 @@ Tuning tuning() {
         g_tune.ctas_per_sm = env_int("CT_B200_CTAS_PER_SM", 0);
     }
     Tuning t = g_tune;
+    t.auto_shape = (t.ctas_per_sm <= 0) ? 1 : 0;
     if (t.ctas_per_sm <= 0) t.ctas_per_sm = (t.pipe == 1) ? 3 : 8;
     return t;
 }

@@ -83,6 +83,8 @@ __device__ __forceinline__ Job job_at(const JobTable& t, int j) {
 
 template <class Op, class = void> struct HasTile { static constexpr bool value = false; };
 template <class Op> struct HasTile<Op, decltype((void)sizeof(typename Op::Tile))> { static constexpr bool value = true; };
+template <class Op, class = void> struct HasShape { static constexpr bool value = false; };
+template <class Op> struct HasShape<Op, decltype((void)Op::PREF_CTAS)> { static constexpr bool value = true; };
 struct NoTile {};
 template <class Op> __device__ __forceinline__ auto op_tile(const Job& J) {
     if constexpr (HasTile<Op>::value) return Op::tile(J);
@@ -379,6 +381,9 @@ int launch_stream(const LaunchPlan& lp, int device, cudaStream_t stream) {
         constexpr int TILE_BYTES = TILE_CHUNKS * Op::IN_BYTES;
         int stages = tn.stages;
         int ctas = tn.ctas_per_sm;
+        if constexpr (HasShape<Op>::value) {   // an op's measured preference, unless the caller tuned explicitly
+            if (tn.auto_shape) { stages = Op::PREF_STAGES; ctas = Op::PREF_CTAS; }
+        }
         if (stages < 2) stages = 2;
         if (stages > MAX_STAGES) stages = MAX_STAGES;
         // keep stages * tile * ctas within ~200 KB of shared memory per SM

@@ -120,3 +120,29 @@ def test_randomized_differential_vs_oracle(seed):
         same(ops.quantize_pack(X, S, Z, a).cpu(), want_p, "quantize_pack " + what)
     elif bits == 4 and cols % 2 == 0:
         same(ops.quantize_pack_fp4(X, S, Z, a).cpu(), oracle.pack_fp4_to_uint8(want_q), "quantize_pack_fp4 " + what)
+
+
+def test_per_tensor_launches_are_cuda_graph_capturable():
+    """single-tensor entry points only enqueue (kernel + stream-ordered scratch from the library's pool): a sequence of them can be
+    captured once and replayed -- the way a caller would hide launch latency for the 224 small launches of a per-module loop"""
+    a = _w4()
+    ws = [(torch.randn(sh, device=DEV) * 0.02).to(torch.bfloat16) for sh in ((1024, 4096), (4096, 4096), (14336, 4096))]
+    ss = [(w.float().unflatten(-1, (-1, 128)).abs().amax(-1) / 7.5).to(torch.bfloat16) for w in ws]
+    want = [ops.quantize_pack(w, s, None, a) for w, s in zip(ws, ss)]
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(device=DEV)
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        for w, s in zip(ws, ss):          # warm-up on the capture stream
+            ops.quantize_pack(w, s, None, a)
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            outs = [ops.quantize_pack(w, s, None, a) for w, s in zip(ws, ss)]
+    for w in ws:
+        w.mul_(-1.0)                      # new inputs in the captured buffers
+    graph.replay()
+    torch.cuda.synchronize()
+    for o, w, s in zip(outs, ws, ss):
+        assert torch.equal(o, ops.quantize_pack(w, s, None, a))
+    assert not torch.equal(outs[0], want[0])

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--layers", type=int, default=8)
     ap.add_argument("--launches", type=int, default=40)
     ap.add_argument("--pipes", default="1,2")
+    ap.add_argument("--tune", default="", help="comma list of stages:ctas_per_sm to compare on the streaming ops (per-launch medians), e.g. 4:3,6:2,8:2")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
@@ -67,6 +68,26 @@ def main():
     uv, um, uo = ops.bitmask_compress(un)
     extra_fns["bitmask_compress_50pct"] = (lambda: ops.bitmask_compress(un), nsp * (2 + 1 + 0.125))
     extra_fns["bitmask_decompress_50pct"] = (lambda: ops.bitmask_decompress(uv, um, uo, un.shape), nsp * (1 + 0.125 + 2))
+    if a.tune:
+        for cfg in a.tune.split(","):
+            st, ct = (int(v) for v in cfg.split(":"))
+            N.set_tuning(1, st, ct)
+            rec = {"stages": st, "ctas_per_sm": ct}
+            for name in ("quantpack", "unpackdeq", "fp8_q", "fp8_dq", "fake_w4", "nvfp4_qp", "nvfp4_ud"):
+                op, probs, nbytes = jobs[name]
+                for _ in range(3):
+                    ops.batched(op, probs, 0)
+                torch.cuda.synchronize()
+                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.launches)]
+                for e0, e1 in ev:
+                    e0.record()
+                    ops.batched(op, probs, 0)
+                    e1.record()
+                torch.cuda.synchronize()
+                ms = sorted(e0.elapsed_time(e1) for e0, e1 in ev)
+                rec[name] = round(nbytes / ms[len(ms) // 2] / 1e6, 1)
+            print(json.dumps(rec), flush=True)
+        return
     for pipe in [int(p) for p in a.pipes.split(",")]:
         N.set_tuning(pipe, 4, 3)
         for name, (op, probs, nbytes) in jobs.items():
