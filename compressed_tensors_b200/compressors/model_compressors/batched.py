@@ -28,12 +28,12 @@ __all__ = ["compress_modules_batched", "decompress_modules_batched"]
 
 _BATCHABLE = (CompressionFormat.pack_quantized, CompressionFormat.naive_quantized, CompressionFormat.int_quantized,
               CompressionFormat.float_quantized)
-# fp4 nibble formats: batched on CUDA placements (one multi-tensor launch); host-resident modules take the per-module path
+# fp4 nibble formats: one multi-tensor launch on CUDA placements, the cross-tensor host pipeline for host-resident modules
 _FP4 = (CompressionFormat.nvfp4_pack_quantized, CompressionFormat.mxfp4_pack_quantized)
 
 
 def _fp4_ok(module, fmt, place, key: str) -> bool:
-    if fmt not in _FP4 or place is None or place[0] != "cuda":
+    if fmt not in _FP4 or place is None:
         return False
     if fmt == CompressionFormat.nvfp4_pack_quantized:
         gs = module._parameters.get("weight_global_scale", None)
@@ -66,7 +66,7 @@ def _compress_fp4_group(mods, fmt, place, force_format) -> None:
             if gsv is not None:
                 d.global_scale = gsv.data_ptr()
                 keep.append(gsv)
-            out = torch.empty((p.rows, p.cols // 2), dtype=torch.uint8, device=w.device)
+            out = _empty((p.rows, p.cols // 2), torch.uint8, w)
         except (ValueError, NotImplementedError):
             compress_module(m, force_format)
             continue
@@ -109,7 +109,7 @@ def _decompress_fp4_group(mods, fmt, place, force_format) -> None:
                 gsv = gs.reshape(1).contiguous()
                 d.global_scale = gsv.data_ptr()
                 keep.append(gsv)
-            out = torch.empty((rows, cols), dtype=dense, device=packed.device)
+            out = _empty((rows, cols), dense, packed)
         except (ValueError, NotImplementedError):
             decompress_module(m, force_format)
             continue

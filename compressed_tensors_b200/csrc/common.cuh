@@ -54,7 +54,7 @@ static inline int dt_size(int dt) {
     switch (dt) {
     case CT_F32: case CT_I32: return 4;
     case CT_F16: case CT_BF16: return 2;
-    case CT_I8: case CT_U8: case CT_F8E4M3: return 1;
+    case CT_I8: case CT_U8: case CT_F8E4M3: case CT_E8M0: return 1;
     case CT_I64: return 8;
     default: return 0;
     }

@@ -35,6 +35,8 @@ static int row_bytes(int op, const ct_quant_desc& d, size_t& in_row, size_t& out
     case CT_OP_QUANTIZE: in_row = (size_t)d.cols * dt_size(d.x_dtype); out_row = (size_t)d.cols * dt_size(d.q_dtype); break;
     case CT_OP_DEQUANTIZE: in_row = (size_t)d.cols * dt_size(d.q_dtype); out_row = (size_t)d.cols * dt_size(d.out_dtype); break;
     case CT_OP_FAKE_QUANTIZE: in_row = (size_t)d.cols * dt_size(d.x_dtype); out_row = (size_t)d.cols * dt_size(d.out_dtype); break;
+    case CT_OP_QUANTIZE_PACK_FP4: in_row = (size_t)d.cols * dt_size(d.x_dtype); out_row = (size_t)d.cols / 2; break;
+    case CT_OP_UNPACK_DEQUANTIZE_FP4: in_row = (size_t)d.cols / 2; out_row = (size_t)d.cols * dt_size(d.out_dtype); break;
     default: set_error("unknown op %d", op); return CT_E_ARG;
     }
     if (in_row == 0 || out_row == 0) { set_error("bad dtype in descriptor"); return CT_E_DTYPE; }
@@ -61,7 +63,8 @@ extern "C" int ct_host_run_many(int op, int n, const ct_quant_desc* descs, const
     DeviceGuard guard(device);
 
     constexpr size_t CHUNK = 32u << 20;   // bytes of streamed input per chunk
-    struct T { size_t in_row, out_row, s_off, z_off, s_bytes, z_bytes; int64_t rpc; };
+    struct T { size_t in_row, out_row, s_off, z_off, s_bytes, z_bytes, g_off; int64_t rpc; };   // g_off: the tensor's global scale (HOST pointer in
+                                                                                                // the descriptor of this entry point), uploaded to aux
     std::vector<T> ts((size_t)n);
     size_t aux_total = 0, max_in = 0, max_out = 0;
     for (int i = 0; i < n; ++i) {
@@ -76,6 +79,7 @@ extern "C" int ct_host_run_many(int op, int n, const ct_quant_desc* descs, const
         t.z_bytes = (zp && zp[i]) ? (size_t)ns * dt_size(d.zp_dtype) : 0;
         t.s_off = aux_total; aux_total += up256(t.s_bytes);
         t.z_off = aux_total; aux_total += up256(t.z_bytes);
+        t.g_off = aux_total; aux_total += d.global_scale ? 256 : 0;
         int64_t rpc = (int64_t)(CHUNK / t.in_row);
         if (rpc < 1) rpc = 1;
         if (d.rdiv != CT_DIV_INF && d.rdiv > 1) rpc = (rpc + d.rdiv - 1) / d.rdiv * d.rdiv;
@@ -116,6 +120,7 @@ extern "C" int ct_host_run_many(int op, int n, const ct_quant_desc* descs, const
         cudaStream_t s0 = S.st[slot];
         CT_CUDA_TRY(cudaMemcpyAsync(aux + t.s_off, scale[i], t.s_bytes, cudaMemcpyHostToDevice, s0));
         if (t.z_bytes) CT_CUDA_TRY(cudaMemcpyAsync(aux + t.z_off, zp[i], t.z_bytes, cudaMemcpyHostToDevice, s0));
+        if (d.global_scale) CT_CUDA_TRY(cudaMemcpyAsync(aux + t.g_off, d.global_scale, sizeof(float), cudaMemcpyHostToDevice, s0));
         cudaEvent_t ev;
         CT_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CT_CUDA_TRY(cudaEventRecord(ev, s0));
@@ -130,6 +135,7 @@ extern "C" int ct_host_run_many(int op, int n, const ct_quant_desc* descs, const
             CT_CUDA_TRY(cudaMemcpyAsync(S.in[slot], reinterpret_cast<const uint8_t*>(in[i]) + (size_t)r0 * t.in_row, (size_t)nr * t.in_row, cudaMemcpyHostToDevice, st));
             ct_quant_desc sub = d;
             sub.rows = nr;
+            if (d.global_scale) sub.global_scale = aux + t.g_off;
             const int64_t sblock = row_scaled ? (r0 / d.rdiv) * d.s_row_stride : 0;
             const void* sc = aux + t.s_off + (size_t)sblock * dt_size(d.scale_dtype);
             const void* zz = t.z_bytes ? aux + t.z_off + (size_t)sblock * dt_size(d.zp_dtype) : nullptr;

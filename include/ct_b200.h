@@ -251,6 +251,7 @@ int ct_host_run(int op, const ct_quant_desc* d, const void* in, const void* scal
 /* The same op over n host-resident tensors (a CPU-resident model: the body of ModelCompressor.compress_model /
  * decompress_model for state dicts that live in host memory), pipelined ACROSS tensors: all row chunks form one
  * queue through 4 staging slots, so the PCIe copy engines do not drain between tensors.  Blocking. */
+/* (for the FP4 ops d->global_scale is a HOST pointer here, like every other pointer of these two entry points) */
 int ct_host_run_many(int op, int n, const ct_quant_desc* descs, const void* const* in, const void* const* scale,
                      const void* const* zp, void* const* out, int device);
 

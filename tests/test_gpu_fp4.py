@@ -353,8 +353,10 @@ def test_fp4_full_size_properties():
 
 
 @pytest.mark.parametrize("preset", ["NVFP4A16", "MXFP4A16", "MXFP8A16"])
-def test_model_compressor_batched_equals_per_module(preset):
-    """one multi-tensor launch (ModelCompressor) == the per-module compressor calls, both directions"""
+@pytest.mark.parametrize("where", [DEV, "cpu"])
+def test_model_compressor_batched_equals_per_module(preset, where):
+    """one multi-tensor launch (ModelCompressor; the cross-tensor host pipeline for a CPU-resident model) == the per-module
+    compressor calls, both directions"""
     import copy
 
     from compressed_tensors_b200.compressors import ModelCompressor, compress_module, decompress_module
@@ -363,7 +365,7 @@ def test_model_compressor_batched_equals_per_module(preset):
     from compressed_tensors_b200.utils import get_direct_state_dict
 
     torch.manual_seed(3)
-    model = torch.nn.Sequential(torch.nn.Linear(512, 256, bias=False), torch.nn.Linear(256, 128, bias=False), torch.nn.Linear(128, 96, bias=False)).to(DEV).to(torch.bfloat16)
+    model = torch.nn.Sequential(torch.nn.Linear(512, 256, bias=False), torch.nn.Linear(256, 128, bias=False), torch.nn.Linear(128, 96, bias=False)).to(where).to(torch.bfloat16)
     apply_quantization_config(model, QuantizationConfig(config_groups={preset: ["Linear"]}))
     for lin in model:
         a = lin.quantization_scheme.weights
@@ -393,6 +395,7 @@ def test_model_compressor_batched_equals_per_module(preset):
             if x.dtype == torch.float8_e4m3fn:
                 x, y = x.view(torch.uint8), y.view(torch.uint8)
             assert x.dtype == y.dtype and torch.equal(x, y), (preset, k)
+            assert x.device.type == torch.device(where).type, (k, x.device)
     mc.decompress_model(model)
     for lin in single:
         decompress_module(lin)
