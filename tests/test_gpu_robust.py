@@ -7,6 +7,7 @@ Robustness of the C ABI on the B200:
     fast-path / generic-path boundary;
   * stream semantics -- work is enqueued on the caller's current stream and nothing synchronises inside.
 """
+import ctypes
 import random
 from concurrent.futures import ThreadPoolExecutor
 
@@ -146,3 +147,44 @@ def test_per_tensor_launches_are_cuda_graph_capturable():
     for o, w, s in zip(outs, ws, ss):
         assert torch.equal(o, ops.quantize_pack(w, s, None, a))
     assert not torch.equal(outs[0], want[0])
+
+
+# ---- error behaviour of the newer entry points: the reference's exception types, never a silent fallback ---------------------------
+def test_error_paths_raise_like_the_reference():
+    from compressed_tensors_b200.compressors import NVFP4PackedCompressor
+    from compressed_tensors_b200.quantization import QuantizationScheme
+
+    x = torch.randn(8, 30, device=DEV).to(torch.bfloat16)
+    with pytest.raises(ValueError, match="even number of columns"):
+        ops.pack_fp4_to_uint8(torch.zeros(3, 7, device=DEV))
+    with pytest.raises(ValueError):
+        ops.unpack_fp4_from_uint8(torch.zeros(3, 4, dtype=torch.uint8, device=DEV), 3, 6)          # 12 bytes do not hold 3 x 6
+    with pytest.raises(ValueError, match="divisble"):
+        ops.quantize(x, torch.ones(8, 2, device=DEV, dtype=torch.bfloat16), None, QuantizationArgs(num_bits=4, type="float", strategy="group", group_size=16))
+    with pytest.raises(ValueError):
+        ops.awq_repack(torch.zeros(8, 4, device=DEV))                                             # not int32
+    with pytest.raises(ValueError, match="NVFP4 args"):
+        ops.observe_quantize_pack_nvfp4(x, _w4())
+    with pytest.raises(NotImplementedError):
+        ops.cast_to_fp4(torch.zeros(4, dtype=torch.int32, device=DEV))
+    # the raw ABI refuses what the fused kernels do not cover instead of running something else
+    d = N.QuantDesc()
+    d.rows, d.cols, d.rdiv, d.cdiv, d.s_row_stride = 4, 24, 1, N.INF, 1
+    d.x_dtype = d.scale_dtype = d.compute_dtype = N.DT[torch.float32]
+    d.zp_dtype, d.q_dtype, d.out_dtype, d.qtype, d.num_bits = N.DT_NONE, N.DT[torch.int8], N.DT_NONE, N.Q_INT, 8
+    xf = torch.zeros(4, 24, device=DEV)
+    s = torch.zeros(4, 1, device=DEV)
+    o = torch.zeros(4, 24, dtype=torch.int8, device=DEV)
+    rc = N.lib().ct_observe_quantize_channel(ctypes.byref(d), N.ptr(xf), N.ptr(s), None, N.ptr(o), 0, N.stream_ptr(0))
+    assert rc == N.CT_E_UNSUPPORTED and "fused channel observer" in N.last_error()
+    # ... while the Python op falls back to observer + quantize as separate GPU kernels and still matches the oracle
+    a = QuantizationArgs(num_bits=8, type="int", symmetric=True, strategy="channel")
+    xr = torch.randn(4, 24, device=DEV)
+    q, sc, _ = ops.observe_quantize(xr, a)
+    from oracle.qparams import calculate_qparams as oq
+    ws, _ = oq(xr.cpu().amin(-1, keepdim=True), xr.cpu().amax(-1, keepdim=True), num_bits=8, qtype="int", symmetric=True)
+    assert torch.equal(sc.cpu(), ws) and torch.equal(q.cpu(), oracle.quantize(xr.cpu(), ws, None, strategy="channel", num_bits=8, dtype=torch.int8))
+    # a compressor fed the wrong scheme fails loudly as well
+    with pytest.raises(ValueError):
+        NVFP4PackedCompressor.compress({"weight": x, "weight_scale": torch.ones(8, 2, device=DEV, dtype=torch.bfloat16)},
+                                       QuantizationScheme(targets=["Linear"], weights=_w4()))
