@@ -4,6 +4,7 @@
 // drains between tensors; every tensor's scales / zero points are uploaded once into a per-call aux
 // area and published to the other slots with an event.  Blocking: returns when all outputs are in
 // host memory.  (ct_host_run, one tensor per call, restarts the pipeline for every tensor.)
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -11,7 +12,9 @@
 
 namespace ctb {
 
-constexpr int MSLOT = 4;
+constexpr int MSLOT = 8;   // slots allocated; CT_B200_HOST_SLOTS (default 4) of them are used
+static int host_slots() { const char* v = getenv("CT_B200_HOST_SLOTS"); int n = v ? atoi(v) : 4; return n < 2 ? 2 : (n > MSLOT ? MSLOT : n); }
+static size_t host_chunk() { const char* v = getenv("CT_B200_HOST_CHUNK_MB"); int n = v ? atoi(v) : 32; return (size_t)(n < 1 ? 1 : (n > 512 ? 512 : n)) << 20; }
 
 struct ManyScratch {
     std::mutex mu;
@@ -62,7 +65,8 @@ extern "C" int ct_host_run_many(int op, int n, const ct_quant_desc* descs, const
     if (n == 0) return CT_OK;
     DeviceGuard guard(device);
 
-    constexpr size_t CHUNK = 32u << 20;   // bytes of streamed input per chunk
+    const size_t CHUNK = host_chunk();   // bytes of streamed input per chunk
+    const int NS = host_slots();
     struct T { size_t in_row, out_row, s_off, z_off, s_bytes, z_bytes, g_off; int64_t rpc; };   // g_off: the tensor's global scale (HOST pointer in
                                                                                                 // the descriptor of this entry point), uploaded to aux
     std::vector<T> ts((size_t)n);
@@ -127,7 +131,7 @@ extern "C" int ct_host_run_many(int op, int n, const ct_quant_desc* descs, const
         evs.push_back(ev);
         const bool row_scaled = (d.rdiv != CT_DIV_INF);
         bool first = true;
-        for (int64_t r0 = 0; r0 < d.rows; r0 += t.rpc, slot = (slot + 1) % MSLOT) {
+        for (int64_t r0 = 0; r0 < d.rows; r0 += t.rpc, slot = (slot + 1) % NS) {
             const int64_t nr = (d.rows - r0 < t.rpc) ? d.rows - r0 : t.rpc;
             cudaStream_t st = S.st[slot];
             if (!first) CT_CUDA_TRY(cudaStreamWaitEvent(st, ev, 0));
