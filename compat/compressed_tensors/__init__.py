@@ -1,19 +1,21 @@
 """
-compressed_tensors_b200 -- B200-native (sm_100a) engine behind the compressed-tensors
-compress()/decompress() and quantize()/dequantize() path.
+Drop-in alias: with `<repo>/compat` on sys.path, `import compressed_tensors` (and every `compressed_tensors.<sub.module>` path of
+SURVEY.md Appendix C) resolves to the B200 engine, so code written against vllm-project/compressed-tensors -- including the
+reference's own hot-path tests -- runs on this package without editing its imports:
 
-Layout
-  csrc/            hand-written CUDA kernels + the C ABI (include/ct_b200.h) -> libct_b200.so
-  _native.py       ctypes binding of the C ABI (fails loudly when the library / GPU is missing)
-  ops.py           tensor-level front end mirroring the reference's per-tensor functions
-  quantization/, compressors/, config/, registry/, distributed/, utils/
-                   host-side mirror of the reference's plugin / operator interface for this path
+    PYTHONPATH=/path/to/repo/compat:/path/to/repo python -m pytest <reference>/tests/test_compressors/test_pack_quant.py
+
+The package's modules are loaded under the `compressed_tensors.*` names (its `__path__` points at compressed_tensors_b200/), and all
+imports inside the package are relative, so one consistent namespace results (its own registry, one native library handle).
+Do not mix it with `import compressed_tensors_b200` in the same process: that would be a second copy of the registry.
 """
+import importlib
+import os
+
+_IMPL = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "compressed_tensors_b200")
+__path__ = [_IMPL]
 __version__ = "0.1.0"
 
-
-# The reference star-exports its sub-packages at the top level (src/compressed_tensors/__init__.py:6-22).  Here the same names
-# resolve lazily, so that `import compressed_tensors_b200` stays cheap and does not need torch / the native library.
 _LAZY = {
     "ModelCompressor": "compressors", "BaseCompressor": "compressors", "PackedQuantizationCompressor": "compressors",
     "IntQuantizationCompressor": "compressors", "FloatQuantizationCompressor": "compressors", "NaiveQuantizationCompressor": "compressors",
@@ -27,7 +29,5 @@ _LAZY = {
 
 def __getattr__(name):
     if name in _LAZY:
-        import importlib
-
         return getattr(importlib.import_module(f"{__name__}.{_LAZY[name]}"), name)
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -6,7 +6,26 @@ import os
 import torch
 import torch.distributed as dist
 
-__all__ = ["is_distributed", "init_dist", "as_broadcastable", "module_size"]
+__all__ = ["is_distributed", "init_dist", "as_broadcastable", "module_size", "set_source_process", "get_source_rank"]
+
+import contextlib
+
+_SRC_RANK = 0
+
+
+@contextlib.contextmanager
+def set_source_process(src_rank: int):
+    """temporarily make `src_rank` the rank that broadcasts (mirror of distributed/utils.py:33-49)"""
+    global _SRC_RANK
+    keep, _SRC_RANK = _SRC_RANK, src_rank
+    try:
+        yield
+    finally:
+        _SRC_RANK = keep
+
+
+def get_source_rank() -> int:
+    return _SRC_RANK
 
 
 def is_distributed() -> bool:

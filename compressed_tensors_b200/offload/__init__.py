@@ -1,0 +1,41 @@
+"""
+Touch points of the reference's `offload` sub-package that the hot path and its tests import.
+The offload caches themselves (CPU / disk / device caches, dispatch hooks) are control plane and out of scope: this engine keeps
+modules where the caller put them, so these helpers are the "no offloading" behaviour of the reference functions
+(src/compressed_tensors/offload/__init__.py:113-149 and friends) -- a plain in-place update, a no-op context, the module's device.
+"""
+from __future__ import annotations
+
+import contextlib
+
+import torch
+
+__all__ = ["update_offload_parameter", "disable_onloading", "get_execution_device", "is_distributed"]
+
+
+def update_offload_parameter(module: torch.nn.Module, name: str, data: torch.Tensor):
+    """copy `data` into an existing parameter / buffer of a (non-offloaded) module"""
+    if name not in module._parameters and name not in module._buffers:
+        raise AttributeError(f"{type(module)} has no attribute {name}")
+    with torch.no_grad():
+        getattr(module, name).copy_(data)
+
+
+@contextlib.contextmanager
+def disable_onloading():
+    """nothing is ever offloaded here, so there is nothing to disable"""
+    yield
+
+
+def get_execution_device(module: torch.nn.Module, default: torch.device | None = None) -> torch.device:
+    for t in module.parameters(recurse=False):
+        return t.device
+    for t in module.buffers(recurse=False):
+        return t.device
+    return default if default is not None else torch.device("cpu")
+
+
+def is_distributed() -> bool:
+    from ..distributed import is_distributed as _d
+
+    return _d()

@@ -19,7 +19,19 @@ from ..quant_config import QuantizationStatus
 from ..quant_scheme import QuantizationScheme
 from ..utils.helpers import compute_dynamic_scales_and_zp
 
-__all__ = ["quantize", "dequantize", "fake_quantize", "set_forward_quantized", "forward_quantize"]
+__all__ = ["quantize", "dequantize", "fake_quantize", "set_forward_quantized", "forward_quantize", "_process_quantization"]
+
+
+@torch.no_grad()
+def _process_quantization(x: torch.Tensor, scale: torch.Tensor, zero_point: torch.Tensor, args: QuantizationArgs,
+                          g_idx: torch.Tensor | None = None, dtype: torch.dtype | None = None, do_quantize: bool = True,
+                          do_dequantize: bool = True, global_scale: torch.Tensor | None = None) -> torch.Tensor:
+    """the dispatcher behind quantize / dequantize / fake_quantize (forward.py:184-241): one CUDA kernel per combination"""
+    if do_quantize and do_dequantize:
+        return ops.fake_quantize(x, scale, zero_point, args, g_idx=g_idx, global_scale=global_scale)
+    if do_quantize:
+        return ops.quantize(x, scale, zero_point, args, dtype=dtype, g_idx=g_idx, global_scale=global_scale)
+    return ops.dequantize(x, scale, zero_point, args=args, dtype=dtype, g_idx=g_idx, global_scale=global_scale)
 
 
 @torch.no_grad()

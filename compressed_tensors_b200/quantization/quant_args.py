@@ -73,21 +73,31 @@ class DynamicType(str, Enum):
 
 
 class ActivationOrdering(str, Enum):
-    """GROUP (alias dynamic): columns grouped by g_idx; WEIGHT (alias static): calibration-only reorder"""
+    """GROUP: columns grouped by g_idx (weights stay in their original order); WEIGHT: calibration-only reorder.
+    DYNAMIC / STATIC are the reference's aliases (quant_args.py:138-166): distinct members that compare and hash equal to
+    GROUP / WEIGHT."""
 
     GROUP = "group"
     WEIGHT = "weight"
+    DYNAMIC = "dynamic"
+    STATIC = "static"
 
-    @classmethod
-    def _missing_(cls, value):
-        alias = {"dynamic": cls.GROUP, "static": cls.WEIGHT}
-        if isinstance(value, str) and value.lower() in alias:
-            return alias[value.lower()]
-        if isinstance(value, str):
-            for m in cls:
-                if m.value == value.lower():
-                    return m
-        return None
+    @staticmethod
+    def get_aliases() -> dict:
+        return {"dynamic": "group", "static": "weight"}
+
+    def _canon(self, v):
+        v = v.value if isinstance(v, Enum) else v
+        return self.get_aliases().get(v, v)
+
+    def __eq__(self, other):
+        return self._canon(self) == self._canon(other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __hash__(self):
+        return hash(self._canon(self))
 
 
 class TorchDtype:

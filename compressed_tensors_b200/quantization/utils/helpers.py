@@ -24,6 +24,7 @@ __all__ = [
     "is_module_quantized",
     "strategy_cdiv",
     "generate_gparam",
+    "calculate_block_padding",
     "maybe_pad_tensor_for_block_quant",
 ]
 
@@ -143,11 +144,17 @@ def strategy_cdiv(value: int, divisor: int, strategy=None, strict: bool = False)
     return out
 
 
-def maybe_pad_tensor_for_block_quant(tensor: Tensor, block_structure: tuple[int, int]) -> Tensor:
-    """zero-pad the last two dims up to multiples of the block (helpers.py:374-428)"""
+def calculate_block_padding(shape, block_structure) -> tuple[int, int]:
+    """(rows, cols) of zero padding that make the last two dims multiples of the block (helpers.py:374-397)"""
+    if len(shape) < 2:
+        raise ValueError(f"Tensor must be at least 2D, got shape {shape}")
     bh, bw = block_structure
-    rows, cols = tensor.shape[-2], tensor.shape[-1]
-    pr, pc = (-rows) % bh, (-cols) % bw
+    return (-shape[-2]) % bh, (-shape[-1]) % bw
+
+
+def maybe_pad_tensor_for_block_quant(tensor: Tensor, block_structure: tuple[int, int]) -> Tensor:
+    """zero-pad the last two dims up to multiples of the block (helpers.py:400-428)"""
+    pr, pc = calculate_block_padding(tensor.shape, block_structure)
     if pr == 0 and pc == 0:
         return tensor
     return torch.nn.functional.pad(tensor, (0, pc, 0, pr), mode="constant", value=0)

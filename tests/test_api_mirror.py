@@ -28,6 +28,7 @@ from compressed_tensors_b200.compressors.format import infer_model_format, infer
 from compressed_tensors_b200.config import BitmaskConfig, CompressionFormat, Sparse24BitMaskConfig, SparsityCompressionConfig, SparsityStructure
 from compressed_tensors_b200.distributed import greedy_bin_packing
 from compressed_tensors_b200.quantization import (
+    ActivationOrdering,
     QuantizationArgs,
     QuantizationConfig,
     QuantizationScheme,
@@ -80,7 +81,8 @@ def test_quantization_args_validation():
     assert QuantizationArgs(num_bits=4).pytorch_dtype() == torch.int8
     assert QuantizationArgs(block_structure="128x128", strategy="block").block_structure == [128, 128]
     assert QuantizationArgs(strategy="group", group_size=128, actorder=True).actorder == "group"
-    assert QuantizationArgs(strategy="group", group_size=128, actorder="static").actorder == "weight"
+    static = QuantizationArgs(strategy="group", group_size=128, actorder="static").actorder
+    assert static == "static" and static == ActivationOrdering.WEIGHT and ActivationOrdering.DYNAMIC == ActivationOrdering.GROUP   # aliases, as in the reference
     assert QuantizationArgs(dynamic=True, strategy="token").observer is None
     assert QuantizationArgs().observer == "memoryless_minmax"
     for bad in (dict(strategy="token"), dict(strategy="group"), dict(group_size=64, strategy="channel"), dict(group_size=-2),
