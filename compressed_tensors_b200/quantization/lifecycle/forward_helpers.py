@@ -14,7 +14,7 @@ import torch
 from ... import ops
 from ..quant_args import QuantizationArgs
 
-__all__ = ["_quantize", "_dequantize", "_quantize_dequantize"]
+__all__ = ["_quantize", "_dequantize", "_quantize_dequantize", "_is_fp8_supported"]
 
 
 def _bcast_args(x: torch.Tensor, scale: torch.Tensor, args):
@@ -41,3 +41,12 @@ def _dequantize(x_q, scale, zero_point=None, dtype=None, global_scale=None):
 @torch.no_grad()
 def _quantize_dequantize(x, scale, zero_point, q_min, q_max, args: QuantizationArgs, global_scale=None):
     return ops.fake_quantize(x, scale, zero_point, _bcast_args(x, scale, args), global_scale=global_scale)
+
+
+def _is_fp8_supported(device: torch.device) -> bool:
+    """native fp8 conversions: every device this engine runs on (sm_100a) has them (forward_helpers.py:346-354)"""
+    device = torch.device(device)
+    if device.type == "cuda":
+        major, _ = torch.cuda.get_device_capability(device)
+        return major >= 9
+    return False

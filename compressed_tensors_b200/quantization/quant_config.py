@@ -60,11 +60,31 @@ DEFAULT_QUANTIZATION_METHOD = "compressed-tensors"
 DEFAULT_QUANTIZATION_FORMAT = "fakequant"
 
 
+def _map_to_checkpoint_names(model: Module, ignore_list: list) -> list:
+    """HF module names -> checkpoint names for the ignore list: transformers v5 may rename weight keys on load
+    (`model._weight_conversions`); the same reverse mapping save_pretrained applies to weights (quant_config.py:31-53)"""
+    conversions = getattr(model, "_weight_conversions", None)
+    if not conversions:
+        return ignore_list
+    inverted = [c.reverse_transform() for c in reversed(conversions)]
+    out = []
+    for name in ignore_list:
+        for rev in inverted:
+            renamed, matched = rev.rename_source_key(name)
+            if matched is not None:
+                name = renamed
+        out.append(name)
+    return out
+
+
 def _vllm_module_type(name: str) -> str:
     """MoE router / gate layers are matched as 'Linear' when configs are loaded (quant_config.py:370-382)"""
     if "ExpertMLP" not in name and any(k in name for k in ("Router", "Gate", "Gating")):
         return "Linear"
     return name
+
+
+get_vllm_module_type = _vllm_module_type   # the reference's public name
 
 
 class QuantizationConfig(BaseModel):
@@ -116,6 +136,7 @@ class QuantizationConfig(BaseModel):
                       else CompressionFormat.dense.value)
         elif isinstance(format, list):
             format = CompressionFormat.mixed_precision.value if len(format) > 1 else format[0]
+        ignore = _map_to_checkpoint_names(model, ignore)
         return QuantizationConfig(config_groups=groups, quantization_status=status, kv_cache_scheme=None,
                                   global_compression_ratio=None, format=format, ignore=ignore)
 
@@ -130,3 +151,25 @@ class QuantizationConfig(BaseModel):
             if scheme.output_activations is not None and not scheme.output_activations.dynamic:
                 return True
         return False
+
+    def merge(self, config: "QuantizationConfig") -> None:
+        """
+        Fold another config into this one, in place (quant_config.py:308-363): its groups are appended under non-colliding names
+        (this config keeps precedence), plain names in `ignore` that the new groups target are dropped (regex entries stay), the
+        format becomes mixed-precision when the groups disagree, the status becomes the later of the two.
+        """
+        import warnings
+
+        from ..utils.helpers import find_unique_name
+        from ..utils.match import match_name
+
+        warnings.warn("Attempting to merge quantization configs. This is not a straightforward task and can lead to quantization configs "
+                      "that fail to load. For best results, use complex targets lists instead of complex ingore lists")
+        new_targets = [t for scheme in config.config_groups.values() for t in scheme.targets]
+        self.ignore = [i for i in (self.ignore or []) if i.startswith("re:") or not any(match_name(i, t) for t in new_targets)]
+        for name, scheme in config.config_groups.items():
+            self.config_groups[find_unique_name(name, self.config_groups.keys())] = scheme
+        formats = set(scheme.format for scheme in self.config_groups.values())
+        self.format = next(iter(formats)) if len(formats) == 1 else CompressionFormat.mixed_precision.value
+        if config.quantization_status > self.quantization_status:
+            self.quantization_status = config.quantization_status

@@ -12,7 +12,7 @@ import torch
 
 from ..ops import pack_bitmasks, unpack_bitmasks
 
-__all__ = ["getattr_chain", "patch_attr", "tensor_follows_mask_structure", "pack_bitmasks", "unpack_bitmasks", "TensorStateDict"]
+__all__ = ["getattr_chain", "patch_attr", "tensor_follows_mask_structure", "pack_bitmasks", "unpack_bitmasks", "TensorStateDict", "find_unique_name"]
 
 TensorStateDict = dict[str, torch.Tensor]
 _MISSING = object()
@@ -59,3 +59,18 @@ def tensor_follows_mask_structure(tensor: torch.Tensor, mask: str = "2:4") -> bo
     if not bool(torch.all(zeros >= n)):
         raise ValueError()
     return True
+
+
+def find_unique_name(name: str, existing_names) -> str:
+    """`name` if it is free, else its base (without a trailing _N) with the next free counter: group_0 -> group_1 (helpers.py:506-535)"""
+    import re
+
+    used = set(existing_names)
+    if name not in used:
+        return name
+    m = re.match(r"^(.+?)_(\d+)$", name)
+    base, n = (m.group(1), int(m.group(2))) if m else (name, 0)
+    n += 1
+    while f"{base}_{n}" in used:
+        n += 1
+    return f"{base}_{n}"
