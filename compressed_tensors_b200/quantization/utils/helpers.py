@@ -46,11 +46,12 @@ def calculate_range(quantization_args: QuantizationArgs, device) -> tuple[Tensor
     return torch.tensor(lo, device=device), torch.tensor(hi, device=device)
 
 
-def _divisor(value: float, device) -> Tensor:
-    """the Python-float divisor of the reference's formulas as a 0-dim float32 tensor ON THE DEVICE: same dtype semantics
-    (a 0-dim tensor does not promote), but torch's CUDA kernels then perform a true IEEE division -- with a Python scalar they
-    multiply by its reciprocal, which differs from the CPU result (the pinned one) by an ulp now and then"""
-    return torch.tensor(value, dtype=torch.float32, device=device)
+def _divisor(value: float, like: Tensor) -> Tensor:
+    """the Python-float divisor of the reference's formulas as a 0-dim tensor of `like`'s dtype ON ITS DEVICE: the result dtype
+    is the one a Python scalar gives (also when `like` is 0-dim itself, the TENSOR strategy), the value is rounded to that
+    dtype as the CPU kernels do with a scalar, and torch's CUDA kernels then perform a true IEEE division -- with a Python
+    scalar they multiply by its reciprocal, which differs from the CPU result (the pinned one) by an ulp now and then"""
+    return torch.tensor(value, dtype=like.dtype, device=like.device)
 
 
 def calculate_qparams(min_vals: Tensor, max_vals: Tensor, quantization_args: QuantizationArgs,
@@ -68,12 +69,12 @@ def calculate_qparams(min_vals: Tensor, max_vals: Tensor, quantization_args: Qua
         if should_generate_mx_scales(quantization_args):
             scales = generate_mx_scales(x=max_val_pos, num_bits=quantization_args.num_bits)
         else:
-            scales = max_val_pos / _divisor(float(bit_range) / 2, device)
+            scales = max_val_pos / _divisor(float(bit_range) / 2, max_val_pos)
         zero_points = torch.zeros(scales.shape, device=device, dtype=min_vals.dtype)
     else:
         if quantization_args.num_bits == 4 and quantization_args.type == QuantizationType.FLOAT:
             raise NotImplementedError("Asymmetric Quantization is not supported for FP4")
-        scales = (max_vals - min_vals) / _divisor(float(bit_range), device)
+        scales = (max_vals - min_vals) / _divisor(float(bit_range), max_vals)
         zero_points = bit_min - (min_vals / scales)
         zero_points = torch.clamp(zero_points, bit_min, bit_max)
     if global_scale is not None:
