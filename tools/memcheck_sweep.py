@@ -41,7 +41,8 @@ def quant_family(rows, cols, dt):
                 ops.fake_quantize(x, s, z, a)
                 if qtype == "int" and cols % (32 // bits) == 0:
                     p = ops.quantize_pack(x, s, z, a)
-                    ops.unpack_dequantize(p, s, z, bits, (rows, cols))
+                    if a.strategy != "block" or (rows % 128 == 0 and cols % 128 == 0):  # args=None inference needs whole blocks (forward.py:118-120)
+                        ops.unpack_dequantize(p, s, z, bits, (rows, cols))
     for bits in (2, 3, 4, 8):
         codes = torch.randint(-(2 ** (bits - 1)), 2 ** (bits - 1), (rows, cols), device=DEV, dtype=torch.int8)
         for dim in (0, 1):
