@@ -115,7 +115,7 @@ class TorchDtype:
             raise ValueError(f"{v!r} is not a torch dtype")
 
         return core_schema.no_info_plain_validator_function(
-            parse, serialization=core_schema.plain_serializer_function_ser_schema(str, when_used="json")
+            parse, serialization=core_schema.plain_serializer_function_ser_schema(str)  # in python mode too (utils/type.py:50-54)
         )
 
 

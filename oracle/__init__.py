@@ -166,8 +166,14 @@ def _addressing(x2d_shape, scale: torch.Tensor, strategy: str, group_size, block
 
 def _prep(x, scale, zero_point, g_idx, strategy):
     x2 = x.reshape(-1, x.shape[-1]).contiguous() if x.ndim != 2 else x.contiguous()
-    s = scale.contiguous()
-    z = zero_point.contiguous() if zero_point is not None else None
+    s, z = scale, zero_point
+    if strategy in ("channel", "token", "attn_head") and scale.numel() not in (1, x2.shape[0]) and scale.ndim >= 1 and scale.shape[-1] == 1:
+        # plain broadcasting against the leading dims of x (forward.py:229-241), e.g. attn_head: scale [H, 1, 1] vs x [B, H, S, D]
+        lead = tuple(x.shape[:-1]) + (1,)
+        s = scale.expand(lead)
+        z = zero_point.expand(lead) if zero_point is not None else None
+    s = s.contiguous()
+    z = z.contiguous() if z is not None else None
     gi = None
     if g_idx is not None and strategy in ("group", "tensor_group") and g_idx.device.type != "meta" and not bool((g_idx == -1).any()):
         gi = g_idx.to(torch.int32).contiguous()

@@ -80,3 +80,18 @@ def pytest_configure(config):
             for fn in ("pack_to_int32", "unpack_from_int32", "pack_fp4_to_uint8", "unpack_fp4_from_uint8", "pack_bitmasks", "unpack_bitmasks"):
                 if hasattr(mod, fn) and getattr(getattr(mod, fn), "__module__", "").startswith("compressed_tensors.ops"):
                     setattr(mod, fn, getattr(ops, fn))
+
+    # The reference's ModelCompressor / lifecycle test files import a `torchrun` decorator from tests/test_offload/conftest.py,
+    # whose module body needs torch.accelerator (a GPU) and the offload subsystem (out of scope).  The tests
+    # that USE the decorator are `requires_gpu(2)` and skip here anyway; a stand-in module lets the rest of those files import.
+    import types
+
+    import pytest
+
+    stub = types.ModuleType("tests.test_offload.conftest")
+
+    def torchrun(world_size=1, init_dist=False):
+        return lambda fn: pytest.mark.skip(reason="torchrun harness of the reference's offload tests is not mirrored")(fn)
+
+    stub.torchrun = torchrun
+    sys.modules.setdefault("tests.test_offload.conftest", stub)

@@ -225,3 +225,35 @@ def test_fused_qdq_equals_sequential(kw, dtype):
     q = quantize(x, scale, None, args, dtype=args.pytorch_dtype())
     seq = dequantize(q, scale, None, args=args)
     assert torch.equal(fake_quantize(x, scale, None, args).to(seq.dtype), seq)
+
+
+# --------------------------------------------------------------------------- #
+# test_static_lifecycle.py: the reference's known answers for fake_quantize, strategy by strategy (tests/kat_static.py)
+# --------------------------------------------------------------------------- #
+from tests import kat_static  # noqa: E402
+
+
+@pytest.mark.parametrize("case", kat_static.CASES, ids=[c[0] for c in kat_static.CASES])
+def test_static_lifecycle_known_answers(case):
+    out, want = kat_static.run(case, lambda x, s, z, a, gs: fake_quantize(x, s, z, a, global_scale=gs), device=DEV)
+    assert out.dtype == torch.bfloat16 and out.device.type == "cuda"
+    assert torch.equal(out.cpu(), want), (out.cpu(), want)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_attn_head_strategy_matches_oracle(dt, symmetric):
+    """attn_head: one scale per head, shape [heads, 1, 1], broadcast against [batch, heads, seq, head_dim] (forward.py:229-241)"""
+    import oracle
+
+    torch.manual_seed(3)
+    x = (torch.randn(3, 8, 17, 64) * 2).to(dt)
+    args = QuantizationArgs(num_bits=8, type="int", symmetric=symmetric, strategy="attn_head")
+    s = (torch.rand(8, 1, 1) * 0.05 + 0.01).to(dt)
+    z = None if symmetric else torch.randint(-20, 20, (8, 1, 1)).to(torch.int8)
+    kw = dict(strategy="attn_head", num_bits=8, qtype="int")
+    X, S, Z = x.to(DEV), s.to(DEV), None if z is None else z.to(DEV)
+    want_q = oracle.quantize(x, s, z, dtype=torch.int8, **kw)
+    assert torch.equal(quantize(X, S, Z, args, dtype=torch.int8).cpu(), want_q)
+    assert torch.equal(fake_quantize(X, S, Z, args).cpu(), oracle.fake_quantize(x, s, z, **kw))
+    assert torch.equal(dequantize(want_q.to(DEV), S, Z, args=args).cpu(), oracle.dequantize(want_q, s, z, strategy="attn_head"))

@@ -274,3 +274,19 @@ def test_semi_structured_golden():
             assert (back.view(torch.int32) != c["back"].view(torch.int32)).sum() < 0.05 * back.numel()
         else:
             assert bits_equal(back, c["back"]), diff_report(back, c["back"])
+
+
+# --------------------------------------------------------------------------- #
+# known answers held by the reference's own lifecycle tests (tests/kat_static.py)
+# --------------------------------------------------------------------------- #
+from tests import kat_static  # noqa: E402
+
+
+@pytest.mark.parametrize("case", kat_static.CASES, ids=[c[0] for c in kat_static.CASES])
+def test_static_lifecycle_known_answers(case):
+    def fq(x, s, z, a, gs):
+        return oracle.fake_quantize(x, s, z, strategy=a.strategy, group_size=a.group_size, block_structure=a.block_structure,
+                                    num_bits=a.num_bits, qtype=a.type, global_scale=gs)
+
+    out, want = kat_static.run(case, fq)
+    assert out.dtype == torch.bfloat16 and torch.equal(out, want), diff_report(out, want)
