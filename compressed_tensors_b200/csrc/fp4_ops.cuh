@@ -27,6 +27,32 @@ __device__ __forceinline__ uint32_t e2m1x2_to_f16x2(uint32_t byte) {
     return r;
 }
 
+// eight floats -> one word of eight E2M1 codes, element 0 in the low nibble of byte 0.  The four byte results are packed with a
+// PTX vector move, which ptxas folds into the conversions' merge operand (F2FP...PACK_AB_MERGE_C chained through C): four
+// instructions per word, no shifts / masks / permutes
+__device__ __forceinline__ uint32_t f32x8_to_e2m1x8(float f0, float f1, float f2, float f3, float f4, float f5, float f6, float f7) {
+    uint32_t r;
+    asm("{ .reg .b8 t0, t1, t2, t3;\n"
+        "cvt.rn.satfinite.e2m1x2.f32 t0, %2, %1;\n"
+        "cvt.rn.satfinite.e2m1x2.f32 t1, %4, %3;\n"
+        "cvt.rn.satfinite.e2m1x2.f32 t2, %6, %5;\n"
+        "cvt.rn.satfinite.e2m1x2.f32 t3, %8, %7;\n"
+        "mov.b32 %0, {t0, t1, t2, t3}; }"
+        : "=r"(r) : "f"(f0), "f"(f1), "f"(f2), "f"(f3), "f"(f4), "f"(f5), "f"(f6), "f"(f7));
+    return r;
+}
+// one word of eight E2M1 codes -> four half2 (byte j -> h[j], low nibble in the low half); the byte selection is part of the
+// conversion instruction (F2FP.F16.E2M1.UNPACK_B Rd, Rs.Bj)
+__device__ __forceinline__ void e2m1x8_to_f16x8(uint32_t w, uint32_t (&h)[4]) {
+    asm("{ .reg .b8 t0, t1, t2, t3;\n"
+        "mov.b32 {t0, t1, t2, t3}, %4;\n"
+        "cvt.rn.f16x2.e2m1x2 %0, t0;\n"
+        "cvt.rn.f16x2.e2m1x2 %1, t1;\n"
+        "cvt.rn.f16x2.e2m1x2 %2, t2;\n"
+        "cvt.rn.f16x2.e2m1x2 %3, t3; }"
+        : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]) : "r"(w));
+}
+
 // RN(x / s) through r = RN(1 / s) and one residual step: q0 = x r, e = fma(-q0, s, x), q1 = fma(e, r, q0).  No branches; the
 // callers keep the operands in ranges where nothing over- or underflows and ct_selftest_fp4_division checks the result
 // against div.rn exhaustively (every 16-bit x, every float32 significand of s).
@@ -103,19 +129,21 @@ struct Fp4NvQuantPackOp {
         constexpr uint32_t HI = (P::DT == CT_BF16) ? 0x46804680u : 0x74007400u;   // 16384.0 as bf16 / fp16, both halves
         return min2<P>(max2<P>(w, HI | 0x80008000u), HI);
     }
-    // one chunk (8 elements, 4 packed words) -> 4 bytes of nibbles
+    // one chunk (8 elements, 4 packed words) -> 4 bytes of nibbles.  CLAMP = false: the caller knows every |x| <= 2^14 already
+    // (the fused observer has the group's max |x| in hand), so clamp_x would be the identity
+    template <bool CLAMP = true>
     __device__ static __forceinline__ uint32_t chunk_fast(const uint32_t (&w)[4], float s, float rcp, float z) {
-        uint32_t word = 0;
+        float t[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t xc = clamp_x(w[j]);
-            float t0 = quotient(P::lo(xc), s, rcp), t1 = quotient(P::hi(xc), s, rcp);
+            const uint32_t xc = CLAMP ? clamp_x(w[j]) : w[j];
+            t[2 * j] = quotient(P::lo(xc), s, rcp);
+            t[2 * j + 1] = quotient(P::hi(xc), s, rcp);
             // the reference's in-place add of the zero point.  Without one nothing is added: the residual step already turns
             // x = -0.0 into +0.0 (fma(+0, r, -0) = +0) and, with |s| <= 2^10, no non-zero 16-bit x underflows to -0.0
-            if constexpr (ZK != FZ_NONE) { t0 = __fadd_rn(t0, z); t1 = __fadd_rn(t1, z); }
-            word |= f32x2_to_e2m1x2(t0, t1) << (8 * j);
+            if constexpr (ZK != FZ_NONE) { t[2 * j] = __fadd_rn(t[2 * j], z); t[2 * j + 1] = __fadd_rn(t[2 * j + 1], z); }
         }
-        return word;
+        return f32x8_to_e2m1x8(t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
     }
     // out of line, everything by value: a unit whose effective scale is outside [2^-100, 2^10] (or 0 / inf / NaN) -> IEEE division
     // per element.  One call per unit so that the caller's registers never have to be spilled to be indexed.
@@ -204,6 +232,36 @@ struct Fp4NvObserveQuantPackOp {
     }
     // max |x| of one chunk as packed T2
     __device__ static __forceinline__ uint32_t chunk_amax2(const uint32_t (&w)[4]) { return amax2(amax2(w[0], w[1]), amax2(w[2], w[3])) & 0x7fff7fffu; }
+    // group scale as the reference derives it from max |x| (calculate_qparams, helpers.py:50-137): the stored e4m3 byte and its value
+    //   DIV = true : IEEE divisions; DIV = false: recip_div, valid for amax == 0 or amax in [2^-40, 2^14] (selftest mode 1; 6.0 is
+    //   one of the float32 significands it covers) -- the caller checks the range
+    template <bool DIV>
+    __device__ static __forceinline__ float group_scale(float amax, float gs, uint32_t& byte) {
+        const float q6 = DIV ? __fdiv_rn(amax, 6.0f) : recip_div(amax, 6.0f, 0.16666667163372039794921875f);   // max_val_pos / (bit_range / 2)
+        const float st = P::lo(P::pack(q6, 0.f));                                                                  // ... in T
+        float sf = fminf(fmaxf(__fmul_rn(gs, st), -448.0f), 448.0f);             // global_scale * scales (float32), clamp
+        byte = f32x2_to_e4m3x2(sf, 0.f) & 0xffu;                                  // .to(float8_e4m3fn)
+        sf = e4m3_to_f32(byte);
+        if (sf == 0.f) { sf = 0.125f; byte = 0x20u; }                             // eps of the scale dtype; 0x20 = 0.125 in e4m3
+        if (sf != sf) byte = 0x7fu;
+        return sf;
+    }
+    struct SlowOut {
+        uint4 nibbles;
+        uint32_t codes;
+    };
+    // out of line, everything by value: a unit with a group outside the ranges the shortcuts are proven for (max |x| above 2^14 or
+    // below 2^-40, a global scale outside [2^-60, 2^60], an effective scale outside [2^-100, 2^10], NaN) -> IEEE division everywhere
+    __device__ static __noinline__ SlowOut unit_slow_observe(uint4 c0, uint4 c1, uint4 c2, uint4 c3, float amax0, float amax1, float gs, int off) {
+        using Q = Fp4NvQuantPackOp<P, FS_F32, FZ_NONE>;
+        uint32_t b0, b1;
+        const float s0 = __fdiv_rn(group_scale<true>(amax0, gs, b0), gs);
+        const float s1 = __fdiv_rn(group_scale<true>(amax1, gs, b1), gs);
+        SlowOut r;
+        r.nibbles = Q::unit_slow(c0, c1, c2, c3, s0, s1, 0.f, 0.f, off);
+        r.codes = b0 | (b1 << 8);
+        return r;
+    }
     __device__ static __forceinline__ void run(const Job& J, const Common&, const Raw&, uint32_t gc0, const uint32_t (&w)[4][4], int off, const Tile& tc) {
         using Q = Fp4NvQuantPackOp<P, FS_F32, FZ_NONE>;
         const uint32_t m0 = chunk_amax2(w[0]), m1 = chunk_amax2(w[1]), m2 = chunk_amax2(w[2]), m3 = chunk_amax2(w[3]);
@@ -213,44 +271,39 @@ struct Fp4NvObserveQuantPackOp {
         const uint32_t pb = odd ? max2<P>(m1, m2) : max2<P>(m2, m3);
         const bool a_is_g0 = off < 2;                                        // off 0: regs {0,1} = chunks {0,1}; off 1: regs {3,0} = chunks {0,1}
         const uint32_t g0 = a_is_g0 ? pa : pb, g1 = a_is_g0 ? pb : pa;
-        float s[2], rc[2];
+        float amax[2], s[2], rc[2];
         uint32_t codes = 0;
-        bool slow = false;
+        bool slow = !tc.fast;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
             const uint32_t gm = g ? g1 : g0;
-            const float amax = fmaxf(P::lo(gm), P::hi(gm));                              // max(|min(min, 0)|, |max(max, 0)|) = max |x|
-            // max_val_pos / (bit_range / 2) in float32, then rounded to T.  recip_div is exact for 16-bit numerators in
-            // [2^-40, 2^14] (ct_selftest_fp4_division, mode 1; the divisor 6.0 is one of the float32 significands it covers)
-            const float q6 = (amax >= 9.094947017729282e-13f && amax <= 16384.0f) ? recip_div(amax, 6.0f, 0.16666667163372039794921875f)
-                                                                                   : __fdiv_rn(amax, 6.0f);
-            const float st = P::lo(P::pack(q6, 0.f));
-            float sf = fminf(fmaxf(__fmul_rn(tc.gs, st), -448.0f), 448.0f);             // global_scale * scales (float32), clamp
-            uint32_t byte = f32x2_to_e4m3x2(sf, 0.f) & 0xffu;                           // .to(float8_e4m3fn)
-            sf = e4m3_to_f32(byte);
-            if (sf == 0.f) { sf = 0.125f; byte = 0x20u; }                                // eps of the scale dtype; 0x20 = 0.125 in e4m3
-            if (sf != sf) byte = 0x7fu;
+            amax[g] = fmaxf(P::lo(gm), P::hi(gm));                                       // max(|min(min, 0)|, |max(max, 0)|) = max |x|
+            // amax <= 2^14 also means clamp_x is the identity for every element of the group (chunk_fast<false> below)
+            slow |= !(amax[g] <= 16384.0f && (amax[g] >= 9.094947017729282e-13f || amax[g] == 0.f));
+            uint32_t byte;
+            const float sf = group_scale<false>(amax[g], tc.gs, byte);
             codes |= byte << (8 * g);
             // scale / global_scale: an e4m3 value (within [2^-9, 448]) over the global scale, same shortcut as the decompress kernel
-            s[g] = (tc.fast && sf == sf) ? recip_div(sf, tc.gs, tc.rgs) : __fdiv_rn(sf, tc.gs);
+            s[g] = recip_div(sf, tc.gs, tc.rgs);
             const float a = fabsf(s[g]);
-            slow |= !(a >= 7.888609052210118e-31f && a <= 1024.0f);
+            slow |= !(a >= 7.888609052210118e-31f && a <= 1024.0f);                     // [2^-100, 2^10]; NaN -> slow
             rc[g] = __frcp_rn(s[g]);
         }
-        reinterpret_cast<unsigned short*>(const_cast<void*>(J.scale))[gc0 >> 2] = (unsigned short)codes;   // two fp8 scales of this unit
         uint32_t o[4];
         if (slow) {
-            const uint4 v = Q::unit_slow(make_uint4(w[0][0], w[0][1], w[0][2], w[0][3]), make_uint4(w[1][0], w[1][1], w[1][2], w[1][3]),
-                                         make_uint4(w[2][0], w[2][1], w[2][2], w[2][3]), make_uint4(w[3][0], w[3][1], w[3][2], w[3][3]),
-                                         s[0], s[1], 0.f, 0.f, off);
-            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+            const SlowOut v = unit_slow_observe(make_uint4(w[0][0], w[0][1], w[0][2], w[0][3]), make_uint4(w[1][0], w[1][1], w[1][2], w[1][3]),
+                                                make_uint4(w[2][0], w[2][1], w[2][2], w[2][3]), make_uint4(w[3][0], w[3][1], w[3][2], w[3][3]),
+                                                amax[0], amax[1], tc.gs, off);
+            o[0] = v.nibbles.x; o[1] = v.nibbles.y; o[2] = v.nibbles.z; o[3] = v.nibbles.w;
+            codes = v.codes;
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const bool g = ((k + off) >> 1) & 1;
-                o[k] = Q::chunk_fast(w[k], g ? s[1] : s[0], g ? rc[1] : rc[0], 0.f);
+                o[k] = Q::template chunk_fast<false>(w[k], g ? s[1] : s[0], g ? rc[1] : rc[0], 0.f);
             }
         }
+        reinterpret_cast<unsigned short*>(const_cast<void*>(J.scale))[gc0 >> 2] = (unsigned short)codes;   // two fp8 scales of this unit
         rotate_out<4, 1>(o, off);
         store_words<4>(J.out + (size_t)gc0 * 4, o);
     }
@@ -279,13 +332,14 @@ struct Fp4MxQuantPackOp {
     }
     template <bool SLOW>
     __device__ static __forceinline__ uint32_t chunk(const uint32_t (&w)[4], const ScaleCtx& sc, uint32_t zp2, const Common& cm) {
-        uint32_t word = 0;
+        float f[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t t = scaled_clamped2<P, ZK != FZ_NONE, SLOW>(w[j], sc, zp2, cm.qmin2, cm.qmax2);
-            word |= f32x2_to_e2m1x2(__fadd_rn(P::lo(t), 0.0f), __fadd_rn(P::hi(t), 0.0f)) << (8 * j);
+            f[2 * j] = __fadd_rn(P::lo(t), 0.0f);
+            f[2 * j + 1] = __fadd_rn(P::hi(t), 0.0f);
         }
-        return word;
+        return f32x8_to_e2m1x8(f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7]);
     }
     __device__ static __forceinline__ void run(const Job& J, const Common& cm, const Raw& r, uint32_t gc0, const uint32_t (&w)[4][4], int off) {
         RawQP q; q.s = r.s; q.z = 0;
@@ -319,10 +373,8 @@ template <class P, int SK>
 struct Fp4UnpackDequantOp {
     static constexpr int IN_BYTES = 4;
     static constexpr int GROUP = 1;
-    // 56 registers: four CTAs fit per SM, and this write-dominated op likes the extra warps (tools/jitter.py --tune: 6473 GB/s at
-    // 3 stages x 4 CTAs against 6146 at the default 4 x 3)
-    static constexpr int PREF_STAGES = 3;
-    static constexpr int PREF_CTAS = 4;
+    // launch shape: the default (4 stages x 3 CTAs per SM).  With the byte selection folded into the conversions the kernel no
+    // longer gains from a fourth CTA (tools/jitter.py --tune, same run: 6287 GB/s at 4 x 3, 5749 at 3 x 4, 5704 at 4 x 4)
     using Raw = Fp4DqRaw;
     __device__ static __forceinline__ Raw prefetch(const Job& J, uint32_t gc0) {
         Raw r;
@@ -351,11 +403,11 @@ struct Fp4UnpackDequantOp {
             if (tc.fast && a >= 9.094947017729282e-13f && a <= 16384.0f) s = recip_div(s, tc.gs, tc.rgs);
             else s = __fdiv_rn(s, tc.gs);
         }
-        uint32_t o[4];
+        uint32_t o[4], h[4];
+        e2m1x8_to_f16x8(w[0][0], h);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            uint32_t h2 = e2m1x2_to_f16x2((w[0][0] >> (8 * j)) & 0xffu);
-            const float a = __low2float(*reinterpret_cast<__half2*>(&h2)), b = __high2float(*reinterpret_cast<__half2*>(&h2));
+            const float a = __low2float(*reinterpret_cast<__half2*>(&h[j])), b = __high2float(*reinterpret_cast<__half2*>(&h[j]));
             o[j] = P::pack(__fmul_rn(a, s), __fmul_rn(b, s));
         }
         store_words<4>(J.out + (size_t)gc0 * 16, o);

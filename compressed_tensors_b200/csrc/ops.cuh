@@ -273,11 +273,13 @@ struct DequantizeOp {
         const uint32_t s2 = scale_t2<P>(r), zp2 = zp_t2<P, ZP>(r);
         float f[8];
         if constexpr (KIND == QF8) {
+            uint32_t h[4];
+            e4m3x4_to_f16x4(w[0], h[0], h[1]);
+            e4m3x4_to_f16x4(w[1], h[2], h[3]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                uint32_t h2 = e4m3x2_to_f16x2((w[k >> 1] >> (16 * (k & 1))) & 0xffffu);
-                f[2 * k] = __low2float(*reinterpret_cast<__half2*>(&h2));
-                f[2 * k + 1] = __high2float(*reinterpret_cast<__half2*>(&h2));
+                f[2 * k] = __low2float(*reinterpret_cast<__half2*>(&h[k]));
+                f[2 * k + 1] = __high2float(*reinterpret_cast<__half2*>(&h[k]));
             }
         } else {
             const uint32_t w0 = w[0] ^ 0x80808080u, w1 = w[1] ^ 0x80808080u;  // int8 -> offset-128 unsigned
@@ -316,12 +318,12 @@ struct DequantF32ScaleOp {
     }
     __device__ static __forceinline__ void run(const Job& J, const Common&, const Raw& r, uint32_t gc, const uint32_t (&wg)[1][2], int) {
         const float s = __uint_as_float(r.s);
-        uint32_t o[4];
+        uint32_t o[4], h[4];
+        e4m3x4_to_f16x4(wg[0][0], h[0], h[1]);
+        e4m3x4_to_f16x4(wg[0][1], h[2], h[3]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t h2 = e4m3x2_to_f16x2((wg[0][k >> 1] >> (16 * (k & 1))) & 0xffffu);
-            o[k] = P::pack(__fmul_rn(__low2float(*reinterpret_cast<__half2*>(&h2)), s), __fmul_rn(__high2float(*reinterpret_cast<__half2*>(&h2)), s));
-        }
+        for (int k = 0; k < 4; ++k)
+            o[k] = P::pack(__fmul_rn(__low2float(*reinterpret_cast<__half2*>(&h[k])), s), __fmul_rn(__high2float(*reinterpret_cast<__half2*>(&h[k])), s));
         store_words<4>(J.out + (size_t)gc * 16, o);
     }
 };

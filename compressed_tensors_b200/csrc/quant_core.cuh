@@ -170,6 +170,14 @@ __device__ __forceinline__ uint32_t e4m3x2_to_f16x2(uint32_t two_bytes) {
     asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(r) : "h"(in));
     return r;
 }
+// one word of four e4m3 bytes -> two half2 (bytes 0,1 -> h0; bytes 2,3 -> h1): the half-word selection is part of the conversion
+// instruction (F2FP.F16.E4M3.UNPACK_B Rd, Rs.H1), no shift / mask
+__device__ __forceinline__ void e4m3x4_to_f16x4(uint32_t w, uint32_t& h0, uint32_t& h1) {
+    asm("{ .reg .b16 a, b;\n"
+        "mov.b32 {a, b}, %2;\n"
+        "cvt.rn.f16x2.e4m3x2 %0, a;\n"
+        "cvt.rn.f16x2.e4m3x2 %1, b; }" : "=r"(h0), "=r"(h1) : "r"(w));
+}
 __device__ __forceinline__ float e4m3_to_f32(uint32_t byte) {
     uint32_t h2 = e4m3x2_to_f16x2(byte & 0xffu);
     return __low2float(*reinterpret_cast<__half2*>(&h2));

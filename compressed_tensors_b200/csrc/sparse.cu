@@ -12,6 +12,7 @@
 // Thread mapping: one lane owns 8 consecutive columns = one bitmask byte; the byte is formed with
 // compare + shift inside the lane, and lanes exchange bytes with warp shuffles so that every
 // fourth lane issues one aligned 32-bit store of four mask bytes.
+#include <cstdlib>
 #include <cub/device/device_scan.cuh>
 
 #include "engine.h"
@@ -339,8 +340,9 @@ __global__ void __launch_bounds__(256) bitmask_move_kernel(const void* __restric
 // ---------------------------------------------------------------------------------------------
 // unstructured bitmask, vectorised variants for 2-byte elements, cols % 8 == 0, 16-byte aligned dense tensor.
 //   count : one block per row, 16-byte loads (4 per thread in flight), mask bytes combined four at a time into 32-bit stores
-//   move  : one block per row, segments of 256 units (2048 elements): 16-byte access to the dense side, block scan of the
-//           popcounts, the kept elements staged in shared memory so that the compact side is read / written coalesced
+//   move  : one block per row, up to 4 segments of 256 units (2048 elements) per iteration: 16-byte access to the dense side
+//           (4 loads per thread in flight), block scan of the popcounts, the kept elements staged in shared memory so that the
+//           compact side is read / written coalesced, as 4-byte words
 // Plain grid launch over the rows (hardware block scheduler = dynamic balance).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t nonzero_byte16(const uint4& v) {
@@ -388,65 +390,120 @@ __global__ void __launch_bounds__(256) bitmask_count_vec16_kernel(const uint4* _
     }
 }
 
-template <bool COMPRESS>
+// U segments of 256 units (2048 elements) per block iteration: U independent 16-byte loads per thread in flight, U warp scans
+// interleaved, ONE pair of block barriers for 2048 * U elements, and the compact side moved as 4-byte words.
+template <bool COMPRESS, int U>
 __global__ void __launch_bounds__(256) bitmask_move_vec16_kernel(const void* __restrict__ src, const uint8_t* __restrict__ bitmask,
                                                                  const int64_t* __restrict__ row_offsets, void* __restrict__ dst, int units) {
-    __shared__ uint16_t stage[2048];
-    __shared__ int warp_tot[8];
+    __shared__ __align__(16) uint16_t stage[2048 * U];
+    __shared__ int warp_tot[U][8];
     const int64_t r = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int64_t pos = row_offsets[r];            // first compact element of this segment
+    int64_t pos = row_offsets[r];            // first compact element of this iteration
     const uint16_t* cin = reinterpret_cast<const uint16_t*>(src);     // compact side when expanding
     uint16_t* cout = reinterpret_cast<uint16_t*>(dst);                // compact side when compressing
     const uint4* din = reinterpret_cast<const uint4*>(src) + r * units;   // dense side when compressing
     uint4* dout = reinterpret_cast<uint4*>(dst) + r * units;              // dense side when expanding
-    for (int b0 = 0; b0 < units; b0 += 256) {
-        const int i = b0 + threadIdx.x;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        uint32_t byte = 0;
-        if (i < units) {
-            if (COMPRESS) { v = ldg_stream16(din + i); byte = nonzero_byte16(v); }   // the mask is recomputed: one load less
-            else byte = __ldg(bitmask + r * units + i);
-        }
-        const int cnt = __popc(byte);
-        int incl = cnt;
+    for (int b0 = 0; b0 < units; b0 += 256 * U) {
+        uint4 v[U];
+        uint32_t byte[U];
+        int cnt[U], incl[U], off[U];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        int woff = 0, seg_total = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const int t = warp_tot[w];
-            if (w < warp) woff += t;
-            seg_total += t;
-        }
-        const int off = woff + incl - cnt;       // this thread's first slot in the segment's compact run
-        if (COMPRESS) {
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            int o = off;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if ((byte >> k) & 1u) stage[o++] = (uint16_t)(w[k >> 1] >> (16 * (k & 1)));
-            __syncthreads();
-            for (int j = threadIdx.x; j < seg_total; j += 256) cout[pos + j] = stage[j];   // coalesced
-        } else {
-            for (int j = threadIdx.x; j < seg_total; j += 256) stage[j] = cin[pos + j];    // coalesced
-            __syncthreads();
+        for (int u = 0; u < U; ++u) {
+            const int i = b0 + u * 256 + threadIdx.x;
+            v[u] = make_uint4(0, 0, 0, 0);
+            byte[u] = 0;
             if (i < units) {
-                uint32_t e[8];
-                int o = off;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) e[k] = ((byte >> k) & 1u) ? (uint32_t)stage[o++] : 0u;
-                stg_stream16(dout + i, make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16)));
+                if (COMPRESS) v[u] = ldg_stream16(din + i);             // the mask is recomputed: one load less
+                else byte[u] = __ldg(bitmask + r * units + i);
             }
         }
-        pos += seg_total;
-        __syncthreads();   // stage / warp_tot are reused by the next segment
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (COMPRESS) byte[u] = nonzero_byte16(v[u]);
+            cnt[u] = __popc(byte[u]);
+            incl[u] = cnt[u];
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int n = __shfl_up_sync(0xffffffffu, incl[u], o);
+                if (lane >= o) incl[u] += n;
+            }
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) warp_tot[u][warp] = incl[u];
+        }
+        __syncthreads();
+        int total = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            int before = 0, seg = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const int t = warp_tot[u][w];
+                if (w < warp) before += t;
+                seg += t;
+            }
+            off[u] = total + before + incl[u] - cnt[u];      // this thread's first slot in the iteration's compact run
+            total += seg;
+        }
+        // compact run [pos, pos + total): one 2-byte element to reach 4-byte alignment, then pairs, then a possible last element
+        const uintptr_t caddr = reinterpret_cast<uintptr_t>((COMPRESS ? static_cast<const uint16_t*>(cout) : cin) + pos);
+        const int head = (int)((caddr >> 1) & 1) & (total > 0 ? 1 : 0);
+        const int pairs = (total - head) >> 1;
+        const int tail = total - head - 2 * pairs;
+        if (COMPRESS) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                int o = off[u];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if ((byte[u] >> k) & 1u) stage[o++] = (uint16_t)(w[k >> 1] >> (16 * (k & 1)));
+            }
+            __syncthreads();
+            if (threadIdx.x == 0 && head) cout[pos] = stage[0];
+            uint32_t* c32 = reinterpret_cast<uint32_t*>(cout + pos + head);
+            for (int j = threadIdx.x; j < pairs; j += 256) c32[j] = (uint32_t)stage[head + 2 * j] | ((uint32_t)stage[head + 2 * j + 1] << 16);   // coalesced
+            if (threadIdx.x == 32 && tail) cout[pos + total - 1] = stage[total - 1];
+        } else {
+            if (threadIdx.x == 0 && head) stage[0] = cin[pos];
+            const uint32_t* c32 = reinterpret_cast<const uint32_t*>(cin + pos + head);
+            for (int j = threadIdx.x; j < pairs; j += 256) {                                                                                       // coalesced
+                const uint32_t two = __ldg(c32 + j);
+                stage[head + 2 * j] = (uint16_t)two;
+                stage[head + 2 * j + 1] = (uint16_t)(two >> 16);
+            }
+            if (threadIdx.x == 32 && tail) stage[total - 1] = cin[pos + total - 1];
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = b0 + u * 256 + threadIdx.x;
+                if (i < units) {
+                    uint32_t e[8];
+                    int o = off[u];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) e[k] = ((byte[u] >> k) & 1u) ? (uint32_t)stage[o++] : 0u;
+                    stg_stream16(dout + i, make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16)));
+                }
+            }
+        }
+        pos += total;
+        __syncthreads();   // stage / warp_tot are reused by the next iteration
     }
+}
+
+// rows shorter than one 4-segment iteration keep the single-segment shape (less shared memory, more blocks per SM)
+template <bool COMPRESS>
+static void launch_bitmask_move_vec16(const void* src, const uint8_t* bitmask, const int64_t* row_offsets, void* dst, int64_t rows, int units, cudaStream_t st) {
+    int cap = COMPRESS ? 2 : 4;   // compress keeps its 16-byte loads in registers: 4 segments cost 79 registers (3 blocks per SM)
+    if (const char* e = getenv("CT_B200_BITMASK_SEGMENTS")) cap = atoi(e);   // measurement aid (tools/jitter.py)
+    if (units > 512 && cap >= 4) bitmask_move_vec16_kernel<COMPRESS, 4><<<(unsigned)rows, 256, 0, st>>>(src, bitmask, row_offsets, dst, units);
+    else if (units > 256 && cap >= 2) bitmask_move_vec16_kernel<COMPRESS, 2><<<(unsigned)rows, 256, 0, st>>>(src, bitmask, row_offsets, dst, units);
+    else bitmask_move_vec16_kernel<COMPRESS, 1><<<(unsigned)rows, 256, 0, st>>>(src, bitmask, row_offsets, dst, units);
 }
 
 static bool bitmask_vec16_ok(int dtype, int64_t rows, int64_t cols, const void* dense, const void* mask) {
@@ -599,7 +656,7 @@ int ct_bitmask_compress(const void* x, int dtype, const uint8_t* bitmask, const 
     const int64_t nb = (cols + 7) / 8;
     const unsigned g = (unsigned)(rows < 148 * 8 ? rows : 148 * 8);
     if ((dtype == CT_BF16 || dtype == CT_F16) && bitmask_vec16_ok(dtype, rows, cols, x, bitmask)) {
-        bitmask_move_vec16_kernel<true><<<(unsigned)rows, 256, 0, st>>>(x, bitmask, row_offsets, values, (int)(cols / 8));
+        launch_bitmask_move_vec16<true>(x, bitmask, row_offsets, values, rows, (int)(cols / 8), st);
     } else
     switch (esize_of(dtype)) {
     case 1: bitmask_move_kernel<1, true><<<g, 256, 0, st>>>(x, bitmask, row_offsets, values, rows, cols, nb); break;
@@ -620,7 +677,7 @@ int ct_bitmask_decompress(const void* values, int dtype, const uint8_t* bitmask,
     const int64_t nb = (cols + 7) / 8;
     const unsigned g = (unsigned)(rows < 148 * 8 ? rows : 148 * 8);
     if (bitmask_vec16_ok(dtype, rows, cols, out, bitmask)) {
-        bitmask_move_vec16_kernel<false><<<(unsigned)rows, 256, 0, st>>>(values, bitmask, row_offsets, out, (int)(cols / 8));
+        launch_bitmask_move_vec16<false>(values, bitmask, row_offsets, out, rows, (int)(cols / 8), st);
     } else
     switch (esize_of(dtype)) {
     case 1: bitmask_move_kernel<1, false><<<g, 256, 0, st>>>(values, bitmask, row_offsets, out, rows, cols, nb); break;

@@ -278,11 +278,15 @@ __global__ void __launch_bounds__(32 * (NCW + 1)) stream_tma_kernel(const __grid
                 if (c0 < chunks) raw_next[it] = Op::prefetch(Jn, base + c0);
             }
         }
+        // per-tensor constants of the op (Op::tile): rebuilt only when the next tile belongs to another tensor
+        decltype(op_tile<Op>(Jn)) tc{};
+        bool new_job = true;
         while (tile < total_tiles) {
             // invariant: full[s] of `tile` has been waited for, `nxt` is the tile after it
             const Job J = Jn;
             const uint32_t base = (tile - J.tile_begin) * TILE_CHUNKS;
             const uint32_t chunks = min((uint32_t)TILE_CHUNKS, J.n_chunks - base);
+            if (new_job) { tc = op_tile<Op>(J); new_job = false; }
             typename Op::Raw raw[ITERS];
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) raw[it] = raw_next[it];
@@ -290,6 +294,7 @@ __global__ void __launch_bounds__(32 * (NCW + 1)) stream_tma_kernel(const __grid
                 if (nxt >= Jn.tile_end) {
                     while (nxt >= job_tile_end(tbl, j)) ++j;
                     Jn = job_at(tbl, j);
+                    new_job = true;
                 }
                 const uint32_t nbase = (nxt - Jn.tile_begin) * TILE_CHUNKS;
                 const uint32_t nchunks = min((uint32_t)TILE_CHUNKS, Jn.n_chunks - nbase);
@@ -300,7 +305,6 @@ __global__ void __launch_bounds__(32 * (NCW + 1)) stream_tma_kernel(const __grid
                 }
             }
             const uint32_t sp = data0 + (uint32_t)s * TILE_BYTES;
-            const auto tc = op_tile<Op>(J);
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
                 const uint32_t c0 = (uint32_t)(it * CTHREADS + ctid) * G;

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--launches", type=int, default=40)
     ap.add_argument("--pipes", default="1,2")
     ap.add_argument("--tune", default="", help="comma list of stages:ctas_per_sm to compare on the streaming ops (per-launch medians), e.g. 4:3,6:2,8:2")
+    ap.add_argument("--ops", default="", help="with --tune: comma list of streaming ops to time (default: the seven headline ops)")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
@@ -73,7 +74,7 @@ def main():
             st, ct = (int(v) for v in cfg.split(":"))
             N.set_tuning(1, st, ct)
             rec = {"stages": st, "ctas_per_sm": ct}
-            for name in ("quantpack", "unpackdeq", "fp8_q", "fp8_dq", "fake_w4", "nvfp4_qp", "nvfp4_ud"):
+            for name in (a.ops.split(",") if a.ops else ("quantpack", "unpackdeq", "fp8_q", "fp8_dq", "fake_w4", "nvfp4_qp", "nvfp4_ud")):
                 op, probs, nbytes = jobs[name]
                 for _ in range(3):
                     ops.batched(op, probs, 0)
