@@ -56,3 +56,37 @@ offload_module = _no_offload("offload_module")
 offload_model = _no_offload("offload_model")
 dispatch_model = _no_offload("dispatch_model")
 __all__ += ["set_onload_device", "offload_module", "offload_model", "dispatch_model"]
+
+
+class OffloadCache(dict):
+    """the type the reference's offloaded modules use for `module._parameters` / `_buffers` (offload/cache/base.py).  Nothing here ever
+    creates one: `isinstance(module._parameters, OffloadCache)` is how callers ask "is this module offloaded?", and the answer is no."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("compressed_tensors_b200 does not offload modules (DESIGN.md section 7)")
+
+
+def module_size(module: torch.nn.Module, recurse: bool = True) -> int:
+    """bytes of the module's parameters and buffers (offload/utils.py:144-158); the weight of a module in greedy_bin_packing"""
+    from itertools import chain
+
+    return sum((t.nbytes for t in chain(module.parameters(recurse=recurse), module.buffers(recurse=recurse))), 0)
+
+
+def to_meta(module: torch.nn.Module) -> None:
+    """replace the module's direct parameters and buffers by meta tensors of the same shape / dtype (offload/utils.py:189-209): what
+    the ranks that do not own a module keep while its owner compresses it"""
+    from ..utils.module import get_direct_state_dict, replace_direct_state_dict
+
+    state = get_direct_state_dict(module)
+    replace_direct_state_dict(module, {k: (v.to("meta") if v is not None else None) for k, v in state.items()})
+
+
+@contextlib.contextmanager
+def as_single_threaded():
+    """the reference swaps its distributed offload caches for the local ones inside this context (offload/utils.py:212-240); without
+    offload caches there is nothing to swap"""
+    yield
+
+
+__all__ += ["OffloadCache", "module_size", "to_meta", "as_single_threaded"]

@@ -50,3 +50,24 @@ def _is_fp8_supported(device: torch.device) -> bool:
         major, _ = torch.cuda.get_device_capability(device)
         return major >= 9
     return False
+
+
+def adapt_scale_and_zp_for_triton(scale: torch.Tensor, zero_point: torch.Tensor | None, num_rows: int):
+    """qparams as one contiguous row per weight row (forward_helpers.py:357-384): 0-d / 1-d / one-row tensors are broadcast over
+    `num_rows`.  The reference's Triton kernels need this layout; the CUDA kernels here address the original qparams directly
+    (DESIGN.md section 4), so only the reference's benchmark helpers call it."""
+    def rows(t):
+        if t is None:
+            return None
+        if t.ndim == 0:
+            t = t.expand(num_rows, 1)
+        elif t.ndim == 1:
+            t = t.unsqueeze(1).expand(num_rows, 1)
+        elif t.shape[0] == 1:
+            t = t.expand(num_rows, -1)
+        return t.contiguous()
+
+    return rows(scale), rows(zero_point)
+
+
+__all__.append("adapt_scale_and_zp_for_triton")

@@ -29,7 +29,7 @@ SURFACE = {
                      "ActivationOrdering", "DynamicType", "FP8_E4M3_DATA", "FP4_E2M1_DATA", "apply_quantization_config",
                      "initialize_module_for_quantization", "preset_name_to_scheme", "is_preset_scheme", "KVCacheScaleType", "QuantizationMetadata"],
     "quantization.lifecycle.forward": ["quantize", "dequantize", "fake_quantize", "forward_quantize", "set_forward_quantized", "_process_quantization"],
-    "quantization.lifecycle.forward_helpers": ["_quantize", "_dequantize", "_quantize_dequantize"],
+    "quantization.lifecycle.forward_helpers": ["_quantize", "_dequantize", "_quantize_dequantize", "_is_fp8_supported", "adapt_scale_and_zp_for_triton"],
     "quantization.lifecycle.initialize": ["initialize_module_for_quantization"],
     "quantization.quant_args": ["round_to_quantized_type_args", "round_to_quantized_type_dtype"],
     "quantization.utils": ["calculate_qparams", "calculate_range", "is_module_quantized", "compute_dynamic_scales_and_zp", "generate_gparam", "strategy_cdiv",
@@ -41,7 +41,9 @@ SURFACE = {
     "utils.match": ["match_name", "match_quantizable_tensors", "is_match"],
     "utils.safetensors_load": ["get_checkpoint_files", "get_weight_map", "update_safetensors_index", "load_tensors_from_inverse_weight_map", "find_config_path"],
     "distributed": ["greedy_bin_packing", "replace_module_parallel", "init_dist", "is_distributed", "set_source_process", "as_broadcastable"],
-    "offload": ["update_offload_parameter", "disable_onloading", "get_execution_device"],
+    "offload": ["update_offload_parameter", "disable_onloading", "get_execution_device", "is_distributed", "offload_module", "set_onload_device",
+                "OffloadCache", "to_meta", "as_single_threaded", "module_size"],
+    "compressors.model_compressors": ["ModelCompressor"],
     "transform": ["TransformConfig", "TransformArgs", "TransformScheme", "TransformLocation"],
     "quantization.quant_metadata": ["KVCacheScaleType", "QuantizationMetadata"],
     "quantization.lifecycle.helpers": ["enable_quantization", "disable_quantization"],
