@@ -27,7 +27,15 @@ _LAZY = {
 }
 
 
+_STAR = ("compressors", "config", "quantization", "registry", "utils")   # the sub-packages the reference star-exports (__init__.py:6-22)
+
+
 def __getattr__(name):
     if name in _LAZY:
         return getattr(importlib.import_module(f"{__name__}.{_LAZY[name]}"), name)
+    if not name.startswith("_"):
+        for sub in _STAR:
+            mod = importlib.import_module(f"{__name__}.{sub}")
+            if name in getattr(mod, "__all__", ()) or (not hasattr(mod, "__all__") and hasattr(mod, name)):
+                return getattr(mod, name)
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -25,9 +25,17 @@ _LAZY = {
 }
 
 
-def __getattr__(name):
-    if name in _LAZY:
-        import importlib
+_STAR = ("compressors", "config", "quantization", "registry", "utils")   # the sub-packages the reference star-exports
 
+
+def __getattr__(name):
+    import importlib
+
+    if name in _LAZY:
         return getattr(importlib.import_module(f"{__name__}.{_LAZY[name]}"), name)
+    if not name.startswith("_"):
+        for sub in _STAR:
+            mod = importlib.import_module(f"{__name__}.{sub}")
+            if name in getattr(mod, "__all__", ()) or (not hasattr(mod, "__all__") and hasattr(mod, name)):
+                return getattr(mod, name)
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

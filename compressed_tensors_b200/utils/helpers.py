@@ -12,7 +12,9 @@ import torch
 
 from ..ops import pack_bitmasks, unpack_bitmasks
 
-__all__ = ["getattr_chain", "patch_attr", "tensor_follows_mask_structure", "pack_bitmasks", "unpack_bitmasks", "TensorStateDict", "find_unique_name"]
+__all__ = ["getattr_chain", "patch_attr", "patch_attrs", "tensor_follows_mask_structure", "pack_bitmasks", "unpack_bitmasks", "TensorStateDict",
+           "find_unique_name", "get_nested_value", "ParameterizedDefaultDict", "fix_fsdp_module_name", "replace_module",
+           "is_compressed_tensors_config", "deprecated", "shard_tensor", "combine_shards"]
 
 TensorStateDict = dict[str, torch.Tensor]
 _MISSING = object()
@@ -74,3 +76,106 @@ def find_unique_name(name: str, existing_names) -> str:
     while f"{base}_{n}" in used:
         n += 1
     return f"{base}_{n}"
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# small host-side utilities of the reference's utils/helpers.py that its callers (llm-compressor, transformers, vLLM) import
+# ---------------------------------------------------------------------------------------------------------------------------
+@contextlib.contextmanager
+def patch_attrs(bases, attr: str, values):
+    """patch_attr over parallel sequences of objects and values; every original is restored on exit (helpers.py:376-400)"""
+    with contextlib.ExitStack() as stack:
+        for base, value in zip(bases, values):
+            stack.enter_context(patch_attr(base, attr, value))
+        yield
+
+
+def get_nested_value(data_dict, path: str, default=None):
+    """data_dict["a"]["b"] for path "a.b"; `default` when a level is missing or not subscriptable (helpers.py:139-146)"""
+    node = data_dict
+    for key in path.split("."):
+        try:
+            node = node[key]
+        except (KeyError, TypeError):
+            return default
+    return node
+
+
+class ParameterizedDefaultDict(dict):
+    """a defaultdict whose factory receives the missing key (a tuple key is splatted into positional arguments);
+    `get(*key, factory_kwargs=...)` additionally forwards keyword arguments to the factory (helpers.py:403-433)"""
+
+    def __init__(self, default_factory):
+        super().__init__()
+        self.default_factory = default_factory
+        self._factory_kwargs = {}
+
+    def __missing__(self, key):
+        args = key if isinstance(key, tuple) else (key,)
+        value = self[key] = self.default_factory(*args, **self._factory_kwargs)
+        return value
+
+    def get(self, *args, factory_kwargs=None):
+        with patch_attr(self, "_factory_kwargs", dict(factory_kwargs or {})):
+            return self[args]
+
+
+_FSDP_WRAPPER = "_fsdp_wrapped_module"
+
+
+def fix_fsdp_module_name(name: str) -> str:
+    """module name without FSDP's wrapper component, wherever it sits (helpers.py:74-84)"""
+    return ".".join(part for part in name.split(".") if part != _FSDP_WRAPPER)
+
+
+def replace_module(model: torch.nn.Module, name: str, new_module: torch.nn.Module) -> None:
+    """model.<name> = new_module for a dotted submodule name (helpers.py:112-121)"""
+    parent_name, _, child = name.rpartition(".")
+    setattr(model.get_submodule(parent_name) if parent_name else model, child, new_module)
+
+
+def is_compressed_tensors_config(compression_config) -> bool:
+    """True for an instance of transformers' CompressedTensorsConfig, False when transformers is absent (helpers.py:124-136)"""
+    try:
+        from transformers.utils.quantization_config import CompressedTensorsConfig
+    except ImportError:
+        return False
+    return isinstance(compression_config, CompressedTensorsConfig)
+
+
+def deprecated(future_name: str | None = None, message: str | None = None):
+    """decorator: DeprecationWarning on every call, pointing at `future_name` unless `message` replaces the text (helpers.py:180-207)"""
+    import functools
+    import warnings
+
+    def decorator(func):
+        text = message
+        if text is None:
+            text = f"{func.__name__} is deprecated and will be removed in a future release"
+            if future_name is not None:
+                text += f". Please use {future_name} instead."
+
+        @functools.wraps(func)
+        def wrapped(*args, **kwargs):
+            warnings.warn(text, DeprecationWarning, stacklevel=2)
+            return func(*args, **kwargs)
+
+        return wrapped
+
+    return decorator
+
+
+def shard_tensor(tensor: torch.Tensor, shard_sizes, dim: int = 0) -> list:
+    """views of `tensor` of the given sizes along `dim`; the sizes must add up (helpers.py:241-270)"""
+    if sum(shard_sizes) != tensor.size(dim):
+        raise ValueError("Sum of shard_sizes must equal the size of the tensor along the specified dimension.")
+    return list(torch.split(tensor, list(shard_sizes), dim=dim))
+
+
+def combine_shards(shards, dim: int = 0) -> torch.Tensor:
+    """the shards of one dtype joined along `dim` into a new tensor (helpers.py:273-303)"""
+    if not shards:
+        raise ValueError("The list of shards is empty.")
+    if len({shard.dtype for shard in shards}) > 1:
+        raise ValueError("All shards must have the same dtype.")
+    return torch.cat(list(shards), dim=dim)

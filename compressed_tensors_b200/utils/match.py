@@ -1,16 +1,21 @@
 """
-Name matching for checkpoint tensors (mirror of utils/match.py:422-445 `match_name` and :469-528 `match_quantizable_tensors`).
-Only the name-based matchers the checkpoint converters need live here; module/class matching for live models is in
-quantization/lifecycle/apply.py.
+Target matching of the reference's utils/match.py: names and regexes against checkpoint tensor names (`match_name`,
+`match_quantizable_tensors`, what the model-free converters use) and against the modules / parameters of a live model (`is_match`,
+`match_named_modules`, `match_named_parameters`, `match_targets`, `match_modules_set`, `is_narrow_match`), which
+`apply_quantization_config` and llm-compressor's modifiers use to decide where a scheme applies.
 """
 from __future__ import annotations
 
+import logging
 import re
 from typing import Iterable, Iterator, Mapping, Optional
 
 import torch
 
-__all__ = ["match_name", "match_quantizable_tensors", "is_match", "match_named_modules", "match_named_parameters", "match_targets"]
+_LOGGER = logging.getLogger(__name__)
+
+__all__ = ["match_name", "match_quantizable_tensors", "is_match", "match_named_modules", "match_named_parameters", "match_targets",
+           "get_lowest_common_ancestor_name", "match_modules_set", "is_narrow_match"]
 
 
 def match_name(name: str, target: str, fused: Optional[Mapping[str, Iterable[str]]] = None) -> bool:
@@ -72,17 +77,19 @@ def match_named_modules(model: torch.nn.Module, targets, ignore=None, fused: Opt
                     yield name, module
                 break
     if warn_on_fail:
-        import logging
-
         for t in unmatched:
-            logging.getLogger(__name__).warning(f"Could not match `{t}` in instance of {model.__class__.__name__}")
+            _LOGGER.warning(f"Could not match `{t}` in instance of {model.__class__.__name__}")
 
 
 def match_named_parameters(model: torch.nn.Module, targets, ignore=None, fused: Optional[Mapping[str, Iterable[str]]] = None, warn_on_fail: bool = False):
     """(qualified name, parent module, parameter) for parameters whose qualified name matches (utils/match.py:73-113)"""
     targets, ignore = list(targets or []), list(ignore or [])
     unmatched = set(targets)
+    from .internal import InternalModule
+
     for module_name, module in model.named_modules():
+        if isinstance(module, InternalModule):      # helper modules (observers, transforms) never take part in matching
+            continue
         for pname, param in module.named_parameters(recurse=False):
             fqn = f"{module_name}.{pname}"
             for t in targets:
@@ -91,10 +98,8 @@ def match_named_parameters(model: torch.nn.Module, targets, ignore=None, fused: 
                     if not any(match_name(fqn, i, fused) for i in ignore):
                         yield fqn, module, param
     if warn_on_fail:
-        import logging
-
         for t in unmatched:
-            logging.getLogger(__name__).warning(f"Could not match `{t}` in instance of {model.__class__.__name__}")
+            _LOGGER.warning(f"Could not match `{t}` in instance of {model.__class__.__name__}")
 
 
 def match_targets(name: str, module: torch.nn.Module, targets) -> list:
@@ -103,3 +108,63 @@ def match_targets(name: str, module: torch.nn.Module, targets) -> list:
     out = [t for t in targets if match_name(name, t)]
     out += [t for t in targets if _match_class(module, t) and t not in out]
     return out
+
+
+def get_lowest_common_ancestor_name(names) -> str:
+    """dotted name of the deepest module that contains every named module (None entries are skipped; "" is the root).  A module is
+    its own ancestor: ["a.b", "a.b.c"] -> "a.b", but ["abc", "ab"] -> "" because components, not characters, are compared
+    (utils/match.py:154-178)"""
+    paths = [n.split(".") if n else [] for n in names if n is not None]
+    if not paths:
+        return ""
+    shared = []
+    for parts in zip(*paths):
+        if any(p != parts[0] for p in parts):
+            break
+        shared.append(parts[0])
+    return ".".join(shared)
+
+
+def match_modules_set(model: torch.nn.Module, targets, ignore=None, error_on_module_rematch: bool = True):
+    """Walk named_modules() once and yield one group per "parent context": a list with one entry per target, each entry the list of
+    modules that matched that target inside the context -- e.g. (q_proj, k_proj, v_proj) per attention block, or one layernorm plus
+    ALL experts' up_proj per MoE layer.  A group is complete once every target has at least one match; it is closed (yielded) when the
+    next match would move the common ancestor of the group's members.  Leftover matches that never complete a group are an error
+    (utils/match.py:181-341)."""
+    targets, ignore = list(targets or []), list(ignore or [])
+    groups: dict = {t: [] for t in targets}
+    missing = set(targets)
+    context = None
+    for name, module in model.named_modules():
+        hits = [t for t in targets if is_match(name, module, t, ignore)]
+        if len(hits) > 1 and error_on_module_rematch:
+            raise ValueError(f"module: {name} was matched with multiple targets: {set(hits)} which is unexpected "
+                             "disable this check by setting `error_on_module_rematch = False`")
+        for t in hits:
+            widened = get_lowest_common_ancestor_name([name, context])
+            if not missing and widened != context:
+                # the group is complete and this match lives outside its context: hand the group out and start the next one here
+                yield [groups[x] for x in targets]
+                groups, missing, widened = {x: [] for x in targets}, set(targets), name
+            groups[t].append(module)
+            missing.discard(t)
+            context = widened
+    if len(missing) == len(set(targets)):
+        return                                   # nothing matched at all
+    if missing:
+        raise ValueError(f"Found a final incomplete set with matches found for keys: {set(targets) - missing} "
+                         f"but no matches found for keys: {missing}")
+    yield [groups[x] for x in targets]
+
+
+def is_narrow_match(model: torch.nn.Module, targets, name: str, module: Optional[torch.nn.Module] = None) -> bool:
+    """some target matches the module itself but neither its parent nor any of its descendants (utils/match.py:384-419)"""
+    targets = [targets] if isinstance(targets, str) else list(targets)
+    module = module if module is not None else model.get_submodule(name)
+    parent_name = name.rsplit(".", 1)[0]
+    parent = model.get_submodule(parent_name)
+
+    def below(target: str) -> bool:
+        return any(is_match(f"{name}.{child_name}", child, target) for child_name, child in module.named_modules() if child_name)
+
+    return any(is_match(name, module, t) and not is_match(parent_name, parent, t) and not below(t) for t in targets)

@@ -16,7 +16,8 @@ from safetensors import safe_open
 __all__ = [
     "InverseWeightMap", "load_tensors_from_inverse_weight_map", "find_config_path", "get_quantization_config",
     "find_safetensors_index_path", "find_safetensors_index_file", "get_weight_map", "update_safetensors_index",
-    "is_weights_file", "get_checkpoint_files",
+    "is_weights_file", "get_checkpoint_files", "get_safetensors_header", "match_param_name", "get_weight_mappings",
+    "get_nested_weight_mappings", "get_quantization_parameter_to_path_mapping", "is_quantization_param",
 ]
 
 CONFIG_NAME = "config.json"
@@ -119,3 +120,64 @@ def load_tensors_from_inverse_weight_map(inverse_weight_map: InverseWeightMap,
                 else:
                     tensors[name] = f.get_tensor(name)
     return tensors
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# name -> file maps of a saved (possibly compressed) checkpoint, as the reference's loaders use them (safetensors_load.py:302-538)
+# ---------------------------------------------------------------------------------------------------------------------------
+def get_safetensors_header(safetensors_path: str) -> dict:
+    """the JSON header of one .safetensors file: 8-byte little-endian length, then that many bytes of JSON"""
+    import struct
+
+    with open(safetensors_path, "rb") as f:
+        (n,) = struct.unpack("<Q", f.read(8))
+        return json.loads(f.read(n))
+
+
+def match_param_name(full_name: str, param_name: str) -> Optional[str]:
+    """"model.layers.0.q_proj" for ("model.layers.0.q_proj.weight_packed", "weight_packed"); None when the suffix differs"""
+    suffix = "." + param_name
+    return full_name[: -len(suffix)] if full_name.endswith(suffix) and len(full_name) > len(suffix) else None
+
+
+def get_weight_mappings(path_to_model_or_tensors: str) -> dict[str, str]:
+    """tensor name -> file holding it, for one .safetensors file, a directory with model.safetensors, or a sharded directory with
+    an index (paths joined onto the directory)"""
+    path = str(path_to_model_or_tensors)
+    if os.path.isfile(path):
+        return {name: path for name in get_safetensors_header(path) if name != "__metadata__"}
+    single, index = os.path.join(path, SAFE_WEIGHTS_NAME), os.path.join(path, SAFE_WEIGHTS_INDEX_NAME)
+    if os.path.exists(single):
+        return {name: single for name in get_safetensors_header(single) if name != "__metadata__"}
+    if os.path.exists(index):
+        with open(index, "r", encoding="utf-8") as f:
+            return {name: os.path.join(path, shard) for name, shard in json.load(f)["weight_map"].items()}
+    raise ValueError(f"Could not find a safetensors weight or index file at {path}")
+
+
+def get_nested_weight_mappings(model_path: str, params_to_nest: Iterable[str], return_unmatched_params: bool = False):
+    """{module: {param: file}} for the tensor names that end in one of `params_to_nest`; optionally also the flat map of the names
+    that matched none (what a second, stacked compressor still needs)"""
+    params_to_nest = list(params_to_nest)
+    nested: dict[str, dict[str, str]] = {}
+    unmatched: dict[str, str] = {}
+    for name, location in get_weight_mappings(model_path).items():
+        hit = False
+        for param in params_to_nest:
+            module = match_param_name(name, param)
+            if module:
+                nested.setdefault(module, {})[param] = location
+                hit = True
+        if not hit and return_unmatched_params:
+            unmatched[name] = location
+    return (nested, unmatched) if return_unmatched_params else nested
+
+
+def is_quantization_param(name: str) -> bool:
+    """a tensor name that ends in "_scale" (global scales included), "zero_point" or "g_idx" (safetensors_load.py:524-538)"""
+    return name.endswith(("_scale", "zero_point", "g_idx"))
+
+
+def get_quantization_parameter_to_path_mapping(model_path: str) -> dict[str, str]:
+    """the quantization parameters of a checkpoint and the files they live in"""
+    return {name: path for name, path in get_weight_mappings(model_path).items() if is_quantization_param(name)}

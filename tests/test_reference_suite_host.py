@@ -49,21 +49,31 @@ FILES = {
     "test_transform/test_transform_args.py": 3,
     "test_transform/test_transform_config.py": 4,
     "test_transform/test_transform_scheme.py": 3,
+    "test_utils/test_type.py": 5,
+    "test_utils/test_helpers.py": 7,
+    "test_utils/test_safetensors_load.py": 3,
+    "test_utils/test_match.py": 60,
 }
-# tests that need the Hugging Face Hub (no network in the build container) or an out-of-scope subsystem
-DESELECT = {"test_quantization/test_quant_config.py": "not map_to_checkpoint_names",
-            # the offloaded variant needs the reference's offload subsystem (out of scope; the shim refuses loudly)
-            "test_quantization/test_quant_metadata.py": "not True"}
+# deselected everywhere: tests that need the Hugging Face Hub (no network in the build container) or the reference's offload subsystem
+# (out of scope; the shim refuses loudly)
+DESELECT = "not map_to_checkpoint_names and not llama_stories and not (test_clear and True)"
+
+# one pytest process per directory of the reference's test tree (its conftest.py files are per directory); ~10 s each
+GROUPS: dict = {}
+for _path, _n in FILES.items():
+    GROUPS.setdefault(os.path.dirname(_path), []).append(_path)
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="the reference checkout is only mounted in the build container")
-@pytest.mark.parametrize("path", sorted(FILES))
-def test_reference_file_passes_on_the_host_mirror(path):
+@pytest.mark.parametrize("group", sorted(GROUPS))
+def test_reference_files_pass_on_the_host_mirror(group):
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests", "reference_compat"), os.path.join(ROOT, "compat"), ROOT]))
-    extra = ["-k", DESELECT[path]] if path in DESELECT else []
-    r = subprocess.run([sys.executable, "-m", "pytest", "-p", "oracle_patch", os.path.join(REF_TESTS, path), "-q", "-p", "no:cacheprovider", *extra],
+    paths = [os.path.join(REF_TESTS, p) for p in GROUPS[group]]
+    r = subprocess.run([sys.executable, "-m", "pytest", "-p", "oracle_patch", *paths, "-q", "-rp", "-p", "no:cacheprovider", "-k", DESELECT],
                        capture_output=True, text=True, env=env, cwd="/tmp", timeout=900)
-    tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:]
-    m = re.search(r"(\d+) passed", tail)
+    lines = r.stdout.strip().splitlines()
+    tail = lines[-1] if lines else r.stderr[-500:]
     assert r.returncode == 0 and "failed" not in tail and "error" not in tail, r.stdout[-3000:]
-    assert m and int(m.group(1)) >= FILES[path], tail
+    for p in GROUPS[group]:
+        passed = sum(1 for line in lines if line.startswith("PASSED") and f"/{p}::" in line)
+        assert passed >= FILES[p], f"{p}: {passed} passed, expected at least {FILES[p]}\n{tail}"
