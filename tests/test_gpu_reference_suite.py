@@ -257,3 +257,61 @@ def test_attn_head_strategy_matches_oracle(dt, symmetric):
     assert torch.equal(quantize(X, S, Z, args, dtype=torch.int8).cpu(), want_q)
     assert torch.equal(fake_quantize(X, S, Z, args).cpu(), oracle.fake_quantize(x, s, z, **kw))
     assert torch.equal(dequantize(want_q.to(DEV), S, Z, args=args).cpu(), oracle.dequantize(want_q, s, z, strategy="attn_head"))
+
+
+# --------------------------------------------------------------------------- #
+# test_compress_decompress_module.py: every preset through compress_module / decompress_module on the device, Linear and Embedding
+# (the reference runs this file on "cuda" only: its body is @requires_gpu)
+# --------------------------------------------------------------------------- #
+from compressed_tensors_b200.compressors.base import compress_module, decompress_module  # noqa: E402
+from compressed_tensors_b200.config import CompressionFormat  # noqa: E402
+from compressed_tensors_b200.quantization import ActivationOrdering, initialize_module_for_quantization, preset_name_to_scheme  # noqa: E402
+from compressed_tensors_b200.utils import get_direct_state_dict  # noqa: E402
+
+_F, _G = CompressionFormat, ActivationOrdering.GROUP
+_LINEAR_PRESETS = [
+    ("UNQUANTIZED", _F.dense, None), ("W8A16", _F.pack_quantized, None), ("W4A16", _F.pack_quantized, None), ("W4A16", _F.pack_quantized, _G),
+    ("W4A16_ASYM", _F.pack_quantized, None), ("W4A16_ASYM", _F.pack_quantized, _G), ("W8A8", _F.int_quantized, None), ("W4A8", _F.int_quantized, None),
+    ("W4AFP8", _F.int_quantized, None), ("FP8", _F.float_quantized, None), ("FP8_DYNAMIC", _F.float_quantized, None), ("FP8_BLOCK", _F.float_quantized, None),
+    ("NVFP4A16", _F.nvfp4_pack_quantized, None), ("NVFP4", _F.nvfp4_pack_quantized, None), ("MXFP4A16", _F.mxfp4_pack_quantized, None), ("MXFP4", _F.mxfp4_pack_quantized, None),
+]
+_EMBEDDING_PRESETS = [
+    ("UNQUANTIZED", _F.dense, None), ("W8A16", _F.pack_quantized, None), ("W4A16", _F.pack_quantized, None), ("W4A16", _F.pack_quantized, _G),
+    ("W4A16_ASYM", _F.pack_quantized, None), ("NVFP4A16", _F.nvfp4_pack_quantized, None), ("MXFP4A16", _F.mxfp4_pack_quantized, None),
+]
+
+
+def _compress_decompress_module(scheme_name, expected_format, actorder, module, targets):
+    module = module.to(dtype=torch.bfloat16, device=DEV)
+    scheme = preset_name_to_scheme(scheme_name, list(targets))
+    if actorder is not None:
+        scheme.weights.actorder = actorder
+    initialize_module_for_quantization(module, scheme)
+    with torch.no_grad():
+        for _, param in list(module.named_parameters()):
+            param.fill_(1)
+    pre = {n: (t.shape, t.dtype) for n, t in get_direct_state_dict(module).items() if t is not None}
+    w = module.weight.detach().clone()
+    compress_module(module)
+    assert module.quantization_scheme.format == expected_format
+    decompress_module(module)
+    for n, t in get_direct_state_dict(module).items():
+        if n in pre:
+            assert t.shape == pre[n][0] and t.dtype == pre[n][1], (n, t.shape, t.dtype, pre[n])
+            assert t.device.type == "cuda"
+    # values: the reference's fill sets every parameter to 1 -- scales AND (for the symmetric presets too) zero points, which the
+    # symmetric formats do not store -- so only the trivially exact cases are compared here; value parity of every format is the
+    # subject of the tests above and of tests/test_gpu_compressors.py
+    if scheme.weights is None:
+        assert torch.equal(module.weight.detach(), w)
+    assert bool(torch.isfinite(module.weight.detach().float()).all())
+
+
+@pytest.mark.parametrize("scheme_name,expected_format,actorder", _LINEAR_PRESETS, ids=[f"{n}-{a.value if a else 'none'}" for n, _, a in _LINEAR_PRESETS])
+def test_compress_decompress_module(scheme_name, expected_format, actorder):
+    _compress_decompress_module(scheme_name, expected_format, actorder, torch.nn.Linear(256, 256, bias=False), ("Linear",))
+
+
+@pytest.mark.parametrize("scheme_name,expected_format,actorder", _EMBEDDING_PRESETS, ids=[f"{n}-{a.value if a else 'none'}" for n, _, a in _EMBEDDING_PRESETS])
+def test_compress_decompress_embedding(scheme_name, expected_format, actorder):
+    _compress_decompress_module(scheme_name, expected_format, actorder, torch.nn.Embedding(256, 256), ("Embedding",))
