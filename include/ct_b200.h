@@ -191,7 +191,10 @@ int ct_observe_quantize_channel(const ct_quant_desc* d, const void* x, void* sca
  * One persistent launch over `n` independent tensors: the body of the module loop of
  * ModelCompressor.compress_model / decompress_model
  * (compressors/model_compressors/model_compressor.py:153-172, :183-207).
- * descs / pointer tables are HOST arrays of length n; tensor i uses descs[i], x[i], ... */
+ * descs / pointer tables are HOST arrays of length n; tensor i uses descs[i], x[i], ...
+ * Enqueue-only like every device entry point, with one caveat for CUDA graphs: when more than one tensor shares a launch, the
+ * job table is uploaded with a host-to-device copy from pageable memory, which a stream capture rejects; the single-tensor entry
+ * points (no table) can be captured and replayed (tests/test_gpu_robust.py). */
 typedef enum ct_batch_op_t {
     CT_OP_QUANTIZE_PACK = 0,      /* in x        -> out packed int32 */
     CT_OP_UNPACK_DEQUANTIZE = 1,  /* in packed   -> out float */

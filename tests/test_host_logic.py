@@ -34,6 +34,16 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in N.lib().ct_version()
 
 
+def test_every_declared_symbol_cites_the_reference_and_is_mapped_in_integration_md():
+    """include/ct_b200.h says which reference interface each entry point replaces (file:line); INTEGRATION.md maps every symbol"""
+    hdr = open(os.path.join(ROOT, "include", "ct_b200.h")).read()
+    declared = set(re.findall(r"\b(ct_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)))
+    integ = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = sorted(n for n in declared if n not in integ)
+    assert not missing, f"INTEGRATION.md does not mention {missing}"
+    assert len(re.findall(r"\.py:\d+", hdr)) >= 20, "the header should cite reference file:line for its entry points"
+
+
 def test_no_cpu_path():
     """without a GPU every compute entry point must refuse (never fall back)"""
     if torch.cuda.is_available():
