@@ -315,3 +315,21 @@ def test_compress_decompress_module(scheme_name, expected_format, actorder):
 @pytest.mark.parametrize("scheme_name,expected_format,actorder", _EMBEDDING_PRESETS, ids=[f"{n}-{a.value if a else 'none'}" for n, _, a in _EMBEDDING_PRESETS])
 def test_compress_decompress_embedding(scheme_name, expected_format, actorder):
     _compress_decompress_module(scheme_name, expected_format, actorder, torch.nn.Embedding(256, 256), ("Embedding",))
+
+
+_ATTN = __import__("tests.golden", fromlist=["load"]).load("attn")
+
+
+@pytest.mark.parametrize("i", range(len(_ATTN)))
+def test_attn_head_golden(i):
+    """the reference's own outputs for the ATTN_HEAD strategy (tests/golden/make_golden_attn.py) through the CUDA kernels"""
+    from tests.util import bits_equal
+
+    c = _ATTN[i]
+    args = QuantizationArgs(**{k: v for k, v in c["args"].items() if v is not None})
+    x, s, z = c["x"].to(DEV), c["scale"].to(DEV), c["zp"].to(DEV)
+    q = quantize(x, s, z, args, dtype=c["q"].dtype).cpu()
+    qa, qb = (q.view(torch.uint8), c["q"].view(torch.uint8)) if q.dtype == torch.float8_e4m3fn else (q, c["q"])
+    assert torch.equal(qa, qb)
+    assert bits_equal(dequantize(c["q"].to(DEV), s, z, args=args).cpu(), c["dq"])
+    assert bits_equal(fake_quantize(x, s, z, args).cpu(), c["fq"])

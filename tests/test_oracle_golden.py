@@ -290,3 +290,23 @@ def test_static_lifecycle_known_answers(case):
 
     out, want = kat_static.run(case, fq)
     assert out.dtype == torch.bfloat16 and torch.equal(out, want), diff_report(out, want)
+
+
+# --------------------------------------------------------------------------- #
+# ATTN_HEAD strategy: scale [heads, 1, 1] against [batch, heads, seq, head_dim] (tests/golden/make_golden_attn.py)
+# --------------------------------------------------------------------------- #
+_ATTN = load("attn")
+
+
+@pytest.mark.parametrize("i", range(len(_ATTN)))
+def test_attn_head_golden(i):
+    c = _ATTN[i]
+    a = c["args"]
+    kw = dict(strategy="attn_head", num_bits=a["num_bits"], qtype=a["type"])
+    q = oracle.quantize(c["x"], c["scale"], c["zp"], dtype=c["q"].dtype, **kw)
+    qa, qb = (q.view(torch.uint8), c["q"].view(torch.uint8)) if q.dtype == torch.float8_e4m3fn else (q, c["q"])
+    assert torch.equal(qa, qb), "quantize: " + diff_report(qa, qb)
+    dq = oracle.dequantize(c["q"], c["scale"], c["zp"], strategy="attn_head")
+    assert bits_equal(dq, c["dq"]), "dequantize: " + diff_report(dq, c["dq"])
+    fq = oracle.fake_quantize(c["x"], c["scale"], c["zp"], **kw)
+    assert bits_equal(fq, c["fq"]), "fake_quantize: " + diff_report(fq, c["fq"])
