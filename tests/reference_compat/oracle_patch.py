@@ -19,6 +19,11 @@ def pytest_configure(config):
     import oracle
     import compressed_tensors.ops as ops
 
+    _PATCHED = ("quantize", "dequantize", "fake_quantize", "quantize_pack", "unpack_dequantize", "pack_to_int32", "unpack_from_int32", "cast_to_fp4",
+                "pack_fp4_to_uint8", "unpack_fp4_from_uint8", "compress_mx_scale", "decompress_mx_scale", "quantize_pack_fp4", "unpack_dequantize_fp4",
+                "awq_repack", "awq_repack_zeros", "dequantize_block_fp8", "pack_bitmasks", "unpack_bitmasks")
+    _ORIGINAL = {name: getattr(ops, name) for name in _PATCHED}
+
     def kw(args):
         s = getattr(args, "strategy", None); s = getattr(s, "value", s)
         t = getattr(args, "type", "int"); t = getattr(t, "value", t)
@@ -74,6 +79,24 @@ def pytest_configure(config):
     ops.dequantize_block_fp8 = lambda w, s, block, dtype=torch.bfloat16: oracle.dequantize_block_fp8(w, s, block, dtype)
     ops.pack_bitmasks = lambda b: oracle.pack_bitmasks(b)
     ops.unpack_bitmasks = lambda p, shape: oracle.unpack_bitmasks(p, shape)
+    # meta tensors (the non-owner ranks of the distributed path, shape-only validation in the converters) never reach a kernel in the
+    # product either: the front end answers with an empty meta tensor of the right shape.  Keep that behaviour under the patch.
+    import functools
+
+    def meta_aware(name, patched):
+        original = _ORIGINAL[name]
+
+        @functools.wraps(patched)
+        def call(*args, **kwargs):
+            if any(isinstance(a, torch.Tensor) and a.device.type == "meta" for a in list(args) + list(kwargs.values())):
+                return original(*args, **kwargs)
+            return patched(*args, **kwargs)
+
+        return call
+
+    for _name in _PATCHED:
+        setattr(ops, _name, meta_aware(_name, getattr(ops, _name)))
+
     # modules that bound the names at import time
     for name, mod in list(sys.modules.items()):
         if name.startswith("compressed_tensors.") and mod is not None and mod is not ops:

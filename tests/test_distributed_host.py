@@ -1,0 +1,150 @@
+"""
+World-size-2 `gloo` tests of the distributed ModelCompressor path on CPU (no GPU, no NCCL): the host logic of the multi-GPU row --
+LPT bin packing of modules over ranks, owner-compresses / others-mirror-on-meta, the tensor recouple, distributed decompress, the
+decompress-on-first-forward hook -- with the tensor-level ops backed by the CPU oracle (tests/reference_compat/oracle_patch.py, test
+infrastructure; the CUDA kernels under the same flow are covered by tests/test_gpu_distributed.py over NCCL).
+The scenarios follow the reference's tests/test_compressors/distributed/test_distributed_compression.py:87-330 and
+tests/test_compressors/model_compressors/test_model_compressor_distributed.py:80-340, which need two GPUs.
+"""
+import os
+import subprocess
+import sys
+import textwrap
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_WORKER = textwrap.dedent(
+    """
+    import copy, os, sys
+    root = sys.argv[1]
+    sys.path[:0] = [os.path.join(root, "tests", "reference_compat"), os.path.join(root, "compat"), root]
+    import oracle_patch
+    oracle_patch.pytest_configure(None)          # compressed_tensors.ops -> CPU oracle (this process has no GPU)
+    import torch, torch.distributed as dist
+    from compressed_tensors import ModelCompressor
+    from compressed_tensors.config import CompressionFormat
+    from compressed_tensors.distributed import is_distributed
+    from compressed_tensors.quantization import QuantizationConfig, QuantizationStatus, apply_quantization_config
+    from compressed_tensors.quantization.lifecycle.forward import fake_quantize
+    from compressed_tensors.quantization.utils import calculate_qparams
+    from compressed_tensors.utils import get_direct_state_dict
+
+    dist.init_process_group("gloo")
+    rank = dist.get_rank()
+    assert is_distributed() and dist.get_world_size() == 2
+
+    class Net(torch.nn.Sequential):
+        def forward(self, x):                    # layers have unequal widths (unequal work per module); a forward only needs the first
+            return self.proj0(x)
+
+    def build(n_layers, width=128, with_extras=True):
+        torch.manual_seed(1234)                  # same weights on every rank, as after loading a checkpoint
+        layers = [torch.nn.Linear(width * (1 + i % 3), width, bias=False) for i in range(n_layers)]
+        model = Net()
+        for i, layer in enumerate(layers):
+            model.add_module(f"proj{i}", layer.to(torch.bfloat16))
+        if with_extras:
+            model.add_module("norm", torch.nn.LayerNorm(width).to(torch.bfloat16))
+            model.add_module("lm_head", torch.nn.Linear(width, 32, bias=False).to(torch.bfloat16))
+        return model
+
+    def quantize_config(model, preset):
+        apply_quantization_config(model, QuantizationConfig(config_groups={preset: ["Linear"]}, ignore=["lm_head"]))
+        for m in model.modules():                # memoryless min-max calibration of the weights
+            scheme = getattr(m, "quantization_scheme", None)
+            if scheme is None or scheme.weights is None:
+                continue
+            for base in ("input", "output"):     # static activation qparams are allocated uninitialised (torch.empty), like in the reference
+                if hasattr(m, f"{base}_scale"):
+                    getattr(m, f"{base}_scale").data.fill_(0.5)
+                if hasattr(m, f"{base}_zero_point"):
+                    getattr(m, f"{base}_zero_point").data.zero_()
+            a, w = scheme.weights, m.weight.data
+            if a.strategy == "group":
+                g = w.unflatten(-1, (-1, a.group_size))
+                lo, hi = g.amin(-1), g.amax(-1)
+            elif a.strategy == "channel":
+                lo, hi = w.amin(-1, keepdim=True), w.amax(-1, keepdim=True)
+            else:
+                lo, hi = w.amin().reshape(1), w.amax().reshape(1)
+            s, z = calculate_qparams(lo, hi, a)
+            m.weight_scale.data = s.to(m.weight_scale.dtype)
+            if hasattr(m, "weight_zero_point"):
+                m.weight_zero_point.data = z.to(m.weight_zero_point.dtype)
+
+    def state(model):
+        out = {}
+        for n, m in model.named_modules():
+            for k, v in get_direct_state_dict(m).items():
+                if v is not None:
+                    out[f"{n}.{k}"] = v
+        return out
+
+    def same_on_all_ranks(model, what):
+        flat = torch.cat([(v.view(torch.uint8) if v.dtype == torch.float8_e4m3fn else v).flatten().double() for v in state(model).values()])
+        other = flat.clone()
+        dist.broadcast(other, src=0)
+        assert torch.equal(flat, other), f"{what}: ranks disagree"
+
+    for preset, n_layers in (("W4A16", 5), ("W4A16_ASYM", 4), ("W8A8", 3), ("FP8", 10), ("W4A16", 1)):
+        model = build(n_layers)
+        quantize_config(model, preset)
+        reference = copy.deepcopy(model)
+        fq = {n: fake_quantize(m.weight.data, m.weight_scale, getattr(m, "weight_zero_point", None), m.quantization_scheme.weights)
+              for n, m in model.named_modules() if getattr(m, "quantization_scheme", None) is not None and m.quantization_scheme.weights is not None}
+
+        mc = ModelCompressor.from_pretrained_model(model)
+        mc.compress_model(model)                                     # distributed: follows is_distributed()
+        ModelCompressor.from_pretrained_model(reference).compress_model(reference, distributed=False)   # every module on this rank
+        a, b = state(model), state(reference)
+        assert set(a) == set(b), (preset, sorted(set(a) ^ set(b)))
+        for k in a:
+            x, y = (a[k].view(torch.uint8), b[k].view(torch.uint8)) if a[k].dtype == torch.float8_e4m3fn else (a[k], b[k])
+            assert a[k].dtype == b[k].dtype and a[k].device.type == "cpu" and torch.equal(x, y), f"{preset} {k}: differs from the single-process result"
+        same_on_all_ranks(model, f"{preset} compressed")
+        n_comp = sum(1 for m in model.modules() if getattr(m, "quantization_status", None) == QuantizationStatus.COMPRESSED)
+        assert n_comp == n_layers, (preset, n_comp)                  # lm_head (ignored) and the norm are untouched
+        assert model.lm_head.weight.dtype == torch.bfloat16 and not hasattr(model.lm_head, "quantization_scheme")
+        assert mc.quantization_config.quantization_status == QuantizationStatus.COMPRESSED
+        assert hasattr(model, "ct_decompress_hook")
+
+        if preset == "W8A8":
+            model(torch.randn(2, model.proj0.in_features).to(torch.bfloat16))   # the hook decompresses on the first forward
+            assert not hasattr(model, "ct_decompress_hook")
+        else:
+            mc.decompress_model(model)                               # distributed decompress (the reference leaves it as a TODO)
+        for n, m in model.named_modules():
+            if n in fq:
+                assert m.weight.dtype == torch.bfloat16 and torch.equal(m.weight.data, fq[n]), f"{preset} {n}: decompress != fake_quantize"
+        same_on_all_ranks(model, f"{preset} decompressed")
+
+    # nothing to compress: no quantized modules, and an empty model
+    plain = build(3)
+    before = {k: v.clone() for k, v in state(plain).items()}
+    ModelCompressor(quantization_config=None).compress_model(plain)
+    assert all(torch.equal(v, before[k]) for k, v in state(plain).items())
+    ModelCompressor(quantization_config=None).compress_model(torch.nn.Sequential())
+
+    # a forced format wins over the inferred one on every rank
+    forced = build(4)
+    quantize_config(forced, "W8A16")                                 # would infer pack-quantized
+    ModelCompressor.from_pretrained_model(forced, quantization_format="int-quantized").compress_model(forced)
+    assert all(m.quantization_scheme.format == CompressionFormat.int_quantized.value and m.weight.dtype == torch.int8
+               for n, m in forced.named_modules() if n.startswith("proj"))
+    same_on_all_ranks(forced, "forced format")
+
+    dist.barrier()
+    dist.destroy_process_group()
+    print("OK", rank)
+    """
+)
+
+
+def test_distributed_model_compressor_two_ranks_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29543", str(script), ROOT], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + "\n".join(line for line in r.stderr.splitlines() if "Error" in line or "assert" in line or "File" in line)[-4000:]
+    assert r.stdout.count("OK") == 2
