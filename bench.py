@@ -441,6 +441,7 @@ def cpu_sample():
 def cpu_baseline(max_seconds: float):
     import oracle
 
+    oracle.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     ws, scs, tmp = cpu_sample()
     wbytes = sum(w.numel() * 2 for w in ws)
     oracle_compress_layer(ws, scs, tmp)  # warm-up (also builds the .so)
@@ -463,6 +464,8 @@ def run_reference(a):
         return
     import oracle
 
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would time a 1-thread baseline
+    oracle.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     ws, scs, tmp = cpu_sample()
     wbytes = sum(w.numel() * 2 for w in ws)
     for _ in range(max(1, min(a.warmup, 3))):

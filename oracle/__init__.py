@@ -76,11 +76,19 @@ def lib() -> ctypes.CDLL:
             "orc_num_threads"
         ).split():
             getattr(_lib, name).restype = ctypes.c_int
+        _lib.orc_set_num_threads.restype = None
+        _lib.orc_set_num_threads.argtypes = [ctypes.c_int]
     return _lib
 
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+def set_num_threads(n: int) -> int:
+    """use `n` OpenMP threads from now on (bench.py's CPU legs: torchrun exports OMP_NUM_THREADS=1 to its workers); returns the new maximum"""
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
 
 
 def _p(t: Optional[torch.Tensor]):

@@ -589,6 +589,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the CPU baseline legs of bench.py ask for all host threads explicitly */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------------- */
 /* 2:4 "semi-structured" (CUTLASS / marlin-24) value + metadata layout        */
 /* utils/semi_structured_conversions.py:33-60 (meta reordering offsets),      */
