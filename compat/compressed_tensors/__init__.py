@@ -35,7 +35,10 @@ def __getattr__(name):
         return getattr(importlib.import_module(f"{__name__}.{_LAZY[name]}"), name)
     if not name.startswith("_"):
         for sub in _STAR:
-            mod = importlib.import_module(f"{__name__}.{sub}")
+            try:
+                mod = importlib.import_module(f"{__name__}.{sub}")
+            except ImportError:      # hasattr() on the package must stay a question, not an import failure
+                continue
             if name in getattr(mod, "__all__", ()) or (not hasattr(mod, "__all__") and hasattr(mod, name)):
                 return getattr(mod, name)
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
