@@ -77,3 +77,13 @@ def test_reference_files_pass_on_the_host_mirror(group):
     for p in GROUPS[group]:
         passed = sum(1 for line in lines if line.startswith("PASSED") and f"/{p}::" in line)
         assert passed >= FILES[p], f"{p}: {passed} passed, expected at least {FILES[p]}\n{tail}"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="the reference checkout is only mounted in the build container")
+def test_host_mirror_matches_the_reference_under_fuzz():
+    """random QuantizationArgs / QuantizationScheme constructions and qparam computations give the same values -- or the same
+    exception type -- in the reference and in the mirror (tests/reference_compat/fuzz_host_mirror.py, ~2500 comparisons)"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "reference_compat", "fuzz_host_mirror.py"), "300"],
+                       capture_output=True, text=True, cwd="/tmp", timeout=600)
+    lines = [line for line in r.stdout.splitlines() if "checked" in line]
+    assert r.returncode == 0 and len(lines) == 3 and all(line.endswith(" 0 mismatches") for line in lines), r.stdout[-2000:] + r.stderr[-1000:]
