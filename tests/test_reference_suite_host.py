@@ -87,3 +87,13 @@ def test_host_mirror_matches_the_reference_under_fuzz():
                        capture_output=True, text=True, cwd="/tmp", timeout=600)
     lines = [line for line in r.stdout.splitlines() if "checked" in line]
     assert r.returncode == 0 and len(lines) == 3 and all(line.endswith(" 0 mismatches") for line in lines), r.stdout[-2000:] + r.stderr[-1000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="the reference checkout is only mounted in the build container")
+def test_oracle_matches_the_reference_under_fuzz():
+    """fresh random cases, beyond the committed goldens: the CPU oracle against the reference's own quantize / dequantize / fake_quantize
+    (every strategy, int 2..8 / fp8 / fp4, three dtypes) and pack / unpack functions (tests/reference_compat/fuzz_oracle.py)"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "reference_compat", "fuzz_oracle.py"), "200"],
+                       capture_output=True, text=True, cwd="/tmp", timeout=600)
+    lines = [line for line in r.stdout.splitlines() if "checked" in line]
+    assert r.returncode == 0 and len(lines) == 2 and all(line.endswith(" 0 mismatches") for line in lines), r.stdout[-2000:] + r.stderr[-1000:]
