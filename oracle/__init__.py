@@ -167,7 +167,9 @@ def _addressing(x2d_shape, scale: torch.Tensor, strategy: str, group_size, block
         return 1, g, (ngroups if srows > 1 else 0)
     if strategy == "block":
         bh, bw = block_structure
-        ncb = math.ceil(cols / bw)
+        nrb, ncb = math.ceil(rows / bh), math.ceil(cols / bw)
+        if scale.numel() != nrb * ncb:      # the reference fails on the broadcast (forward_helpers.py:62-115); never index past the scale
+            raise ValueError(f"block scale has {scale.numel()} elements, expected {nrb}x{ncb}")
         return bh, bw, ncb
     raise ValueError(strategy)
 

@@ -16,8 +16,18 @@ import torch
 
 
 def pytest_configure(config):
+    apply("compressed_tensors")
+    _stub_reference_test_harness()
+
+
+def apply(package: str = "compressed_tensors"):
+    """rebind `<package>.ops` (the drop-in alias by default; tests/reference_compat/fuzz_compressors.py passes "compressed_tensors_b200",
+    because there the name `compressed_tensors` is the reference itself) to the CPU oracle"""
+    import importlib
+
     import oracle
-    import compressed_tensors.ops as ops
+
+    ops = importlib.import_module(package + ".ops")
 
     _PATCHED = ("quantize", "dequantize", "fake_quantize", "quantize_pack", "unpack_dequantize", "pack_to_int32", "unpack_from_int32", "cast_to_fp4",
                 "pack_fp4_to_uint8", "unpack_fp4_from_uint8", "compress_mx_scale", "decompress_mx_scale", "quantize_pack_fp4", "unpack_dequantize_fp4",
@@ -99,10 +109,13 @@ def pytest_configure(config):
 
     # modules that bound the names at import time
     for name, mod in list(sys.modules.items()):
-        if name.startswith("compressed_tensors.") and mod is not None and mod is not ops:
+        if name.startswith(package + ".") and mod is not None and mod is not ops:
             for fn in ("pack_to_int32", "unpack_from_int32", "pack_fp4_to_uint8", "unpack_fp4_from_uint8", "pack_bitmasks", "unpack_bitmasks"):
-                if hasattr(mod, fn) and getattr(getattr(mod, fn), "__module__", "").startswith("compressed_tensors.ops"):
+                if hasattr(mod, fn) and getattr(getattr(mod, fn), "__module__", "") == package + ".ops":
                     setattr(mod, fn, getattr(ops, fn))
+
+
+def _stub_reference_test_harness():
 
     # The reference's ModelCompressor / lifecycle test files import a `torchrun` decorator from tests/test_offload/conftest.py,
     # whose module body needs torch.accelerator (a GPU) and the offload subsystem (out of scope).  The tests

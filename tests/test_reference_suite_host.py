@@ -97,3 +97,13 @@ def test_oracle_matches_the_reference_under_fuzz():
                        capture_output=True, text=True, cwd="/tmp", timeout=600)
     lines = [line for line in r.stdout.splitlines() if "checked" in line]
     assert r.returncode == 0 and len(lines) == 2 and all(line.endswith(" 0 mismatches") for line in lines), r.stdout[-2000:] + r.stderr[-1000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="the reference checkout is only mounted in the build container")
+def test_compressor_plugins_match_the_reference_under_fuzz():
+    """compress() / decompress() of every registered quantization format on random weights, schemes and strategies: same keys, dtypes,
+    shapes and bits as the reference's classes (tests/reference_compat/fuzz_compressors.py; oracle-backed ops, CPU)"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "reference_compat", "fuzz_compressors.py"), "150"],
+                       capture_output=True, text=True, cwd="/tmp", timeout=600)
+    lines = [line for line in r.stdout.splitlines() if "checked" in line]
+    assert r.returncode == 0 and len(lines) == 1 and " 0 mismatches" in lines[0], r.stdout[-2000:] + r.stderr[-1000:]
