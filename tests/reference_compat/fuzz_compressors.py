@@ -67,8 +67,48 @@ FORMATS = {
 }
 
 
+def fuzz_converters(n):
+    """AutoAWQConverter.process and FP8BlockDequantizer._create_dequantized_weight (entrypoints/convert/converters/autoawq.py:109-262,
+    fp8block_dequantizer.py:111-158) on random checkpoints tensors"""
+    from compressed_tensors.entrypoints.convert import AutoAWQConverter as RAwq, FP8BlockDequantizer as RFp8
+
+    from compressed_tensors_b200.entrypoints.convert import AutoAWQConverter as MAwq, FP8BlockDequantizer as MFp8
+
+    rnd = random.Random(22)
+    g = torch.Generator().manual_seed(22)
+    checked = bad = 0
+    for case in range(n):
+        gsz = rnd.choice([8, 32, 128])
+        k, nn, zp = gsz * rnd.choice([1, 2, 5]), 8 * rnd.choice([1, 3, 8, 65]), rnd.random() < 0.7
+        t = {"m.q_proj.qweight": torch.randint(-2 ** 31, 2 ** 31 - 1, (k, nn // 8), generator=g, dtype=torch.int64).to(torch.int32),
+             "m.q_proj.scales": (torch.rand(k // gsz, nn, generator=g) * 0.02).to(torch.float16)}
+        if zp:
+            t["m.q_proj.qzeros"] = torch.randint(-2 ** 31, 2 ** 31 - 1, (k // gsz, nn // 8), generator=g, dtype=torch.int64).to(torch.int32)
+        want = RAwq(group_size=gsz, zero_point=zp).process({a: b.clone() for a, b in t.items()})
+        got = MAwq(group_size=gsz, zero_point=zp).process({a: b.clone() for a, b in t.items()})
+        checked += 1
+        err = same_dict(dict(got), dict(want), "autoawq")
+        if err:
+            bad += 1
+            print(f"converter case {case} k={k} n={nn} g={gsz} zp={zp}: {err}")
+        r, c = rnd.choice([8, 130, 256]), rnd.choice([8, 136, 300])
+        bs = rnd.choice([(128, 128), (32, 64)])
+        dt = rnd.choice([torch.bfloat16, torch.float16])
+        w = (torch.randn(r, c, generator=g) * 3).to(FP8)
+        si = torch.randn(-(-r // bs[0]), -(-c // bs[1]), generator=g).abs() * 0.01 + 1e-4
+        want = RFp8(weight_block_size=bs, dtype=dt)._create_dequantized_weight(w, si)
+        got = MFp8(weight_block_size=bs, dtype=dt)._create_dequantized_weight(w, si)
+        checked += 1
+        if got.dtype != want.dtype or got.shape != want.shape or not torch.equal(bits(got), bits(want)):
+            bad += 1
+            print(f"converter case {case} fp8 block {r}x{c} {bs} {dt}: differs")
+    return checked, bad
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+    c_checked, c_bad = fuzz_converters(max(20, n // 4))
+    print(f"converters: {c_checked} checked, {c_bad} mismatches", flush=True)
     rnd = random.Random(21)
     g = torch.Generator().manual_seed(21)
     checked = bad = skipped = 0
@@ -157,7 +197,7 @@ def main():
             if bad <= 10:
                 print(f"case {case} {fmt} {dt} {rows}x{cols} {kw}: {err}")
     print(f"compressors: {checked} checked, {bad} mismatches ({skipped} schema-rejected cases skipped)", flush=True)
-    sys.exit(1 if bad else 0)
+    sys.exit(1 if (bad or c_bad) else 0)
 
 
 if __name__ == "__main__":
