@@ -107,3 +107,14 @@ def test_compressor_plugins_match_the_reference_under_fuzz():
                        capture_output=True, text=True, cwd="/tmp", timeout=600)
     lines = [line for line in r.stdout.splitlines() if "checked" in line]
     assert r.returncode == 0 and len(lines) == 2 and all(" 0 mismatches" in line for line in lines), r.stdout[-2000:] + r.stderr[-1000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="the reference checkout is only mounted in the build container")
+def test_model_compressor_matches_the_reference_under_fuzz():
+    """ModelCompressor end to end on random small models and presets, next to the reference's: module state dicts after
+    apply_quantization_config, after compress_model and after decompress_model, and the quantization_config written to config.json
+    (tests/reference_compat/fuzz_model_compressor.py; oracle-backed ops, CPU)"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "reference_compat", "fuzz_model_compressor.py"), "30"],
+                       capture_output=True, text=True, cwd="/tmp", timeout=600)
+    lines = [line for line in r.stdout.splitlines() if "checked" in line]
+    assert r.returncode == 0 and len(lines) == 1 and lines[0].endswith(" 0 mismatches"), r.stdout[-2000:] + r.stderr[-600:]
