@@ -139,6 +139,14 @@ def fuzz_pack(n):
         code = compress_mx_scale(sc, torch.uint8)
         checked += 2
         bad += (not same(oracle.compress_mx_scale(sc, torch.uint8), code)) + (not same(oracle.decompress_mx_scale(code), decompress_mx_scale(code)))
+    from compressed_tensors.utils.helpers import pack_bitmasks, unpack_bitmasks
+
+    for _ in range(n // 2):                       # bitmask bit order (utils/helpers.py:306-343), ragged widths
+        shape = (rnd.choice([1, 5, 64]), rnd.choice([1, 7, 8, 9, 63, 64, 200]))
+        mask = torch.rand(shape, generator=g) < rnd.random()
+        want = pack_bitmasks(mask)
+        checked += 2
+        bad += (not same(oracle.pack_bitmasks(mask), want)) + (not same(oracle.unpack_bitmasks(want, list(shape)), unpack_bitmasks(want, list(shape))))
     return checked, bad
 
 
