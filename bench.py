@@ -352,6 +352,29 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+def _bind_to_gpu_numa(device_index: int):
+    """Opt-in experiment (CT_BENCH_NUMA=1, default off, not part of any reported number yet): run this rank on the CPUs NVML names as
+    local to its GPU, so that the pinned host buffers of the e2e leg are first-touched on that socket.  Returns the previous affinity
+    (to restore) or None when anything is missing."""
+    if os.environ.get("CT_BENCH_NUMA", "0") != "1" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        before = os.sched_getaffinity(0)
+        cpus &= before
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return before
+    except Exception:  # noqa: BLE001  (no NVML, no permission: keep the launcher's affinity)
+        return None
+
+
 def run_e2e(ws, scs, a, dist_on, world):
     """The same pass end to end through the public API: ModelCompressor.compress_model() on a HOST-resident
     model (pinned weights and scales), i.e. the call llm-compressor makes before save_pretrained.  Every step
@@ -364,6 +387,7 @@ def run_e2e(ws, scs, a, dist_on, world):
 
     layers = min(a.e2e_layers, len(ws) // len(LAYER_SHAPES))
     n = layers * len(LAYER_SHAPES)
+    previous_affinity = _bind_to_gpu_numa(ws[0].device.index or 0)
     hw = [w.cpu().pin_memory() for w in ws[:n]]
     hs = [s.cpu().pin_memory() for s in scs[:n]]
     wbytes = sum(t.numel() * 2 for t in hw)
@@ -404,9 +428,13 @@ def run_e2e(ws, scs, a, dist_on, world):
         dt = float(t.item())
     packed = mods[0].weight_packed
     assert packed.dtype == torch.int32 and not packed.is_cuda and mods[-1].quantization_status == QuantizationStatus.COMPRESSED
-    return {"value": round(world * wbytes / dt / 1e9, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "api": "ModelCompressor.compress_model(model) on a host-resident (pinned) model", "tensors_per_step": n, "steps": steps,
-            "ms_per_step": round(dt * 1e3, 2)}
+    out = {"value": round(world * wbytes / dt / 1e9, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "api": "ModelCompressor.compress_model(model) on a host-resident (pinned) model", "tensors_per_step": n, "steps": steps,
+           "ms_per_step": round(dt * 1e3, 2)}
+    if previous_affinity is not None:
+        out["cpu_affinity"] = "GPU-local CPUs (CT_BENCH_NUMA=1)"
+        os.sched_setaffinity(0, previous_affinity)      # the CPU baseline leg counts its threads from the launcher's affinity
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
