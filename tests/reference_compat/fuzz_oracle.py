@@ -7,6 +7,7 @@ this runs the same comparison on fresh random cases:
 
   quant   quantize / dequantize / fake_quantize: tensor, channel, group (with and without g_idx), block, token (3-D), tensor_group with a
           global scale, attn_head (4-D); int 2..8 bits symmetric / asymmetric, fp8, fp4; bf16 / fp16 / fp32 inputs, scale dtype equal or not
+          (and once more with the scale addressing computed by the PRODUCT's front end, ops._resolve, feeding the oracle's C arithmetic)
   pack    pack_to_int32 / unpack_from_int32 for 1..8 bits on both dims, ragged widths; fp4 nibble pack / unpack; MX scale codes
 Prints "<part>: N checked, M mismatches" and exits non-zero on any mismatch.
 """
@@ -44,6 +45,27 @@ def bits(t):
 
 def same(a, b):
     return a.dtype == b.dtype and a.shape == b.shape and torch.equal(bits(a.contiguous()), bits(b.contiguous()))
+
+
+def product_addressing_quantize(x, scale, zp, args, g_idx, out_dtype):
+    import ctypes
+
+    from compressed_tensors_b200 import ops
+
+    p = ops._resolve(x, scale, zp, args, g_idx)
+    cd = torch.result_type(x, scale)
+    x2 = x.reshape(p.rows, p.cols).contiguous()
+    out = torch.empty(p.rows, p.cols, dtype=out_dtype)
+    sc = p.scale.contiguous()
+    z = p.zp.contiguous() if p.zp is not None else None
+    gi = p.g_idx.to(torch.int32).contiguous() if p.g_idx is not None else None
+    qt = getattr(args.type, "value", args.type)
+    rc = oracle.lib().orc_quantize(oracle._p(x2), oracle.DT[x2.dtype], oracle._p(sc), oracle.DT[sc.dtype], oracle._p(z),
+                                   oracle.DT[z.dtype] if z is not None else -1, oracle._p(gi), oracle._p(out), oracle.DT[out.dtype],
+                                   ctypes.c_int64(p.rows), ctypes.c_int64(p.cols), ctypes.c_int64(p.rdiv), ctypes.c_int64(p.cdiv),
+                                   ctypes.c_int64(p.srs), oracle.DT[cd], 0 if qt == "int" else 1, args.num_bits)
+    assert rc == 0
+    return out.reshape(x.shape)
 
 
 def fuzz_quant(n):
@@ -102,7 +124,15 @@ def fuzz_quant(n):
             continue
         got = [oracle.quantize(x, s, zp, dtype=qdt, **okw), oracle.fake_quantize(x, s, zp, **okw),
                oracle.dequantize(want_q, s, zp, strategy=args.strategy, group_size=args.group_size, block_structure=args.block_structure, g_idx=g_idx, global_scale=gs)]
-        for name, a, b in zip(("quantize", "fake_quantize", "dequantize"), got, (want_q, want_fq, want_dq)):
+        if gs is None:
+            # the PRODUCT's front end (ops._resolve: strategy -> scale addressing, broadcasting, g_idx handling; pure Python) driving the
+            # oracle's C arithmetic must land on the reference's result as well
+            got.append(product_addressing_quantize(x, s, zp, args, g_idx, want_q.dtype))
+            names = ("quantize", "fake_quantize", "dequantize", "quantize via the product's addressing")
+            wants = (want_q, want_fq, want_dq, want_q)
+        else:
+            names, wants = ("quantize", "fake_quantize", "dequantize"), (want_q, want_fq, want_dq)
+        for name, a, b in zip(names, got, wants):
             checked += 1
             if not same(a, b):
                 bad += 1
