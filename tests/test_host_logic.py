@@ -58,6 +58,25 @@ def test_no_cpu_path():
     assert "no CPU path" in N.last_error() or "CUDA" in N.last_error()
 
 
+def test_only_test_infrastructure_touches_the_oracle():
+    """oracle/ is the checker: nothing in the product package, the drop-in alias or tools/ may import it; bench.py only inside its CPU legs
+    (cpu_baseline, the reference arm), __graft_entry__ only inside build() / smoke()"""
+    pat = re.compile(r"^\s*(import oracle\b|from oracle\b)", re.M)
+    for top in ("compressed_tensors_b200", "compat", "tools", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    src = open(os.path.join(dirpath, f), errors="replace").read()
+                    assert not pat.search(src) and "libct_oracle" not in src and "orc_" not in src, os.path.join(dirpath, f)
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    for m in pat.finditer(bench):
+        fn = re.findall(r"^def (\w+)", bench[: m.start()], flags=re.M)[-1]
+        assert fn in ("cpu_baseline", "run_reference", "oracle_compress_layer"), f"bench.py imports the oracle inside {fn}()"
+    entry = open(os.path.join(ROOT, "__graft_entry__.py")).read()
+    for m in pat.finditer(entry):
+        assert re.findall(r"^def (\w+)", entry[: m.start()], flags=re.M)[-1] in ("build", "smoke")
+
+
 def test_error_messages_match_reference():
     with pytest.raises(ValueError, match="Tensor must be quantized to torch.int8 before packing"):
         ops.pack_to_int32(torch.zeros(2, 2, dtype=torch.int32), 4)
