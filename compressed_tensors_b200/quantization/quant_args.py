@@ -17,6 +17,11 @@ from pydantic import BaseModel, ConfigDict, Field, field_serializer, field_valid
 from pydantic_core import core_schema
 
 __all__ = [
+    "FloatArgs",
+    "BFLOAT16_DATA",
+    "FLOAT16_DATA",
+    "FLOAT32_DATA",
+    "FLOAT64_DATA",
     "FP8_DTYPE",
     "FP8_E4M3_DATA",
     "FP4_E2M1_DATA",
@@ -33,14 +38,40 @@ __all__ = [
 FP8_DTYPE = torch.float8_e4m3fn
 
 
-class FP8_E4M3_DATA:
+class FloatArgs:
+    """format constants of a floating-point type (quant_args.py:40-46): the E8M0 / MX helpers read exponent and mantissa widths from these"""
+    exponent: int
+    mantissa: int
+    bits = None
+    max = None
+    min = None
+    dtype = None
+
+
+class BFLOAT16_DATA(FloatArgs):
+    exponent, mantissa = 8, 7
+
+
+class FLOAT16_DATA(FloatArgs):
+    exponent, mantissa = 5, 10
+
+
+class FLOAT32_DATA(FloatArgs):
+    exponent, mantissa = 8, 23
+
+
+class FLOAT64_DATA(FloatArgs):
+    exponent, mantissa = 11, 52
+
+
+class FP8_E4M3_DATA(FloatArgs):
     exponent, mantissa, bits = 4, 3, 8
     max = torch.finfo(torch.float8_e4m3fn).max   # 448
     min = torch.finfo(torch.float8_e4m3fn).min
     dtype = torch.float8_e4m3fn
 
 
-class FP4_E2M1_DATA:
+class FP4_E2M1_DATA(FloatArgs):
     exponent, mantissa, bits = 2, 1, 4
     max, min = 6.0, -6.0
     dtype = None

@@ -27,6 +27,12 @@ class QuantizationStatus(str, Enum):
     COMPRESSED = "compressed"
     DECOMPRESSED = "decompressed"
 
+    @classmethod
+    def lifecycle_order(cls) -> list:
+        """the statuses in life-cycle order (the reference's method of this name returns None, quant_config.py:79-84; the list is what
+        its docstring promises and what `LIFECYCLE_ORDER` holds)"""
+        return list(LIFECYCLE_ORDER)
+
     def _rank(self) -> int:
         return LIFECYCLE_ORDER.index(self)
 

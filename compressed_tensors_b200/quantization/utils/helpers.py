@@ -26,6 +26,10 @@ __all__ = [
     "generate_gparam",
     "calculate_block_padding",
     "maybe_pad_tensor_for_block_quant",
+    "is_model_quantized",
+    "module_type",
+    "get_torch_bit_depth",
+    "can_quantize",
 ]
 
 
@@ -159,3 +163,30 @@ def maybe_pad_tensor_for_block_quant(tensor: Tensor, block_structure: tuple[int,
     if pr == 0 and pc == 0:
         return tensor
     return torch.nn.functional.pad(tensor, (0, pc, 0, pr), mode="constant", value=0)
+
+
+def is_model_quantized(model: Module) -> bool:
+    """some module of the model carries a non-empty quantization scheme (helpers.py:252-260)"""
+    return any(is_module_quantized(m) for m in model.modules())
+
+
+def module_type(module: Module) -> str:
+    """class name of the module, the string "targets" are matched against (helpers.py:263-270)"""
+    return type(module).__name__
+
+
+def get_torch_bit_depth(value: Tensor) -> int:
+    """bits per element of the tensor's dtype (helpers.py:273-285)"""
+    dt = value.dtype
+    return torch.finfo(dt).bits if dt.is_floating_point else torch.iinfo(dt).bits
+
+
+def can_quantize(value: Tensor, quant_args: QuantizationArgs) -> bool:
+    """the tensor is wider than the requested quantization (helpers.py:288-305); warns when it is narrower"""
+    depth = get_torch_bit_depth(value)
+    if depth < quant_args.num_bits:
+        import logging
+
+        logging.getLogger(__name__).warning(f"Can't quantize tensor with bit depth {depth} to {quant_args.num_bits}."
+                                            "The QuantizationArgs provided are not compatible with the input tensor.")
+    return depth > quant_args.num_bits

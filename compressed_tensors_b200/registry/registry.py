@@ -22,6 +22,8 @@ __all__ = [
     "registered_names",
     "registered_aliases",
     "standardize_lookup_name",
+    "standardize_alias_name",
+    "register_alias",
 ]
 
 _VALUES: dict[type, dict[str, Any]] = defaultdict(dict)
@@ -38,6 +40,27 @@ def _as_alias_list(alias) -> list[str]:
     if isinstance(alias, str):
         return [standardize_lookup_name(alias)]
     return [standardize_lookup_name(a) for a in alias]
+
+
+def standardize_alias_name(name):
+    """standardize_lookup_name over None / one name / a list of names (registry.py:45-53)"""
+    if name is None:
+        return None
+    return standardize_lookup_name(name) if isinstance(name, str) else [standardize_lookup_name(n) for n in name]
+
+
+def register_alias(name: str, parent_class: type, alias=None):
+    """map the alias(es), and the name itself, to `name` in the parent class's alias table (registry.py:285-318); an alias equal to
+    the name, or one that is already taken, is a KeyError"""
+    aliases = [] if alias is None else (list(alias) if isinstance(alias, (list, tuple)) else [alias])
+    if name in aliases:
+        raise KeyError(f"Attempting to register alias {name}, that is identical to the standardized name: {name}.")
+    table = _ALIASES[parent_class]
+    for a in aliases + [name]:
+        if a in table:
+            raise KeyError(f"Attempting to register alias {a} as {name} however {a} has already been registered as {table[a]}")
+    for a in aliases + [name]:
+        table[a] = name
 
 
 def _check_subclass(parent: type, value: Any):
