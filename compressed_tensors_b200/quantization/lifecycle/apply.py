@@ -18,7 +18,7 @@ from torch.nn import Module
 from ..quant_config import QuantizationConfig, QuantizationStatus
 from .initialize import initialize_module_for_quantization
 
-__all__ = ["apply_quantization_config", "is_match", "match_named_modules"]
+__all__ = ["apply_quantization_config", "is_match", "match_named_modules", "load_pretrained_quantization_parameters"]
 
 
 def _one_match(value: str, target: str) -> bool:
@@ -63,3 +63,41 @@ def apply_quantization_config(model: Module, config: QuantizationConfig | None, 
         module.quantization_scheme = target_to_scheme[first]
         initialize_module_for_quantization(module, force_zero_point=force_zero_point)
         module.quantization_status = config.quantization_status
+
+
+def load_pretrained_quantization_parameters(model: Module, model_name_or_path: str | None = None, load_weight_qparams: bool = False) -> None:
+    """Copy the quantization parameters stored in a saved checkpoint into a model that `apply_quantization_config` has already
+    initialised (apply.py:49-97, :195-236): input / output scales, zero points and g_idx always, the weight ones when asked.  A scale
+    without a stored zero point (symmetric schemes) gets zeros.  `model_name_or_path` is a local checkpoint directory (or one
+    .safetensors file): this engine has no download path."""
+    from safetensors import safe_open
+
+    from ...offload import update_offload_parameter
+    from ...utils.safetensors_load import get_quantization_parameter_to_path_mapping
+    from ..utils.helpers import is_module_quantized
+
+    mapping = get_quantization_parameter_to_path_mapping(str(model_name_or_path))
+
+    def read(full_name: str):
+        path = mapping.get(full_name)
+        if path is None:
+            return None
+        with safe_open(path, framework="pt", device="cpu") as f:
+            return f.get_tensor(full_name)
+
+    for name, module in model.named_modules():
+        if not is_module_quantized(module):
+            continue
+        scheme = module.quantization_scheme
+        bases = [b for b, on in (("input", scheme.input_activations is not None), ("output", scheme.output_activations is not None),
+                                 ("weight", load_weight_qparams and scheme.weights is not None)) if on]
+        for base in bases:
+            g_idx = read(f"{name}.{base}_g_idx")
+            if g_idx is not None:
+                update_offload_parameter(module, f"{base}_g_idx", g_idx)
+            scale = read(f"{name}.{base}_scale")
+            if scale is None:
+                continue
+            update_offload_parameter(module, f"{base}_scale", scale)
+            zp = read(f"{name}.{base}_zero_point")
+            update_offload_parameter(module, f"{base}_zero_point", zp if zp is not None else torch.zeros_like(scale, device="cpu"))

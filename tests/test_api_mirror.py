@@ -386,3 +386,23 @@ def test_module_parallel_two_ranks_gloo(tmp_path):
                         "--master-port", "29517", str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("OK") == 2
+
+
+def test_load_pretrained_quantization_parameters(tmp_path):
+    """activation qparams always, weight qparams on request, zeros for a missing zero point (apply.py:49-97, :195-236)"""
+    from safetensors.torch import save_file
+
+    from compressed_tensors_b200.quantization import QuantizationConfig, apply_quantization_config
+    from compressed_tensors_b200.quantization.lifecycle.apply import load_pretrained_quantization_parameters
+
+    model = torch.nn.Sequential(torch.nn.Linear(64, 32, bias=False), torch.nn.LayerNorm(32))
+    apply_quantization_config(model, QuantizationConfig(config_groups={"FP8": ["Linear"]}))
+    lin = model[0]
+    save_file({"0.weight_scale": torch.full_like(lin.weight_scale.data, 0.25), "0.input_scale": torch.full_like(lin.input_scale.data, 0.5),
+               "0.weight": torch.zeros(32, 64)}, str(tmp_path / "model.safetensors"))
+    lin.input_zero_point.data.fill_(3)
+    lin.weight_scale.data.fill_(9)
+    load_pretrained_quantization_parameters(model, str(tmp_path))
+    assert float(lin.input_scale) == 0.5 and float(lin.input_zero_point.float()) == 0.0 and float(lin.weight_scale.flatten()[0]) == 9.0
+    load_pretrained_quantization_parameters(model, str(tmp_path), load_weight_qparams=True)
+    assert float(lin.weight_scale.flatten()[0]) == 0.25
