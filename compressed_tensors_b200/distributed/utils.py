@@ -6,7 +6,8 @@ import os
 import torch
 import torch.distributed as dist
 
-__all__ = ["is_distributed", "init_dist", "as_broadcastable", "module_size", "set_source_process", "get_source_rank"]
+__all__ = ["is_distributed", "init_dist", "as_broadcastable", "module_size", "set_source_process", "get_source_rank", "is_source_process",
+           "wait_for_comms"]
 
 import contextlib
 
@@ -59,3 +60,16 @@ def module_size(module: torch.nn.Module) -> int:
         if t is not None:
             total += t.numel() * t.element_size()
     return total
+
+
+def is_source_process() -> bool:
+    """this rank is the one that broadcasts (rank 0 unless `set_source_process` says otherwise); always true outside torch.distributed
+    (distributed/utils.py:29-30)"""
+    return not is_distributed() or dist.get_rank() == _SRC_RANK
+
+
+def wait_for_comms(pending_comms: list) -> None:
+    """wait() on every async work handle, then empty the list in place so that it can collect the next batch (distributed/utils.py:113-127)"""
+    for work in pending_comms:
+        work.wait()
+    pending_comms.clear()

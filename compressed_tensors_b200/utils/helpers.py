@@ -14,7 +14,8 @@ from ..ops import pack_bitmasks, unpack_bitmasks
 
 __all__ = ["getattr_chain", "patch_attr", "patch_attrs", "tensor_follows_mask_structure", "pack_bitmasks", "unpack_bitmasks", "TensorStateDict",
            "find_unique_name", "get_nested_value", "ParameterizedDefaultDict", "fix_fsdp_module_name", "replace_module",
-           "is_compressed_tensors_config", "deprecated", "shard_tensor", "combine_shards"]
+           "is_compressed_tensors_config", "deprecated", "shard_tensor", "combine_shards", "Aliasable", "get_num_attn_heads",
+           "get_num_kv_heads", "get_head_dim", "is_accelerator_type"]
 
 TensorStateDict = dict[str, torch.Tensor]
 _MISSING = object()
@@ -179,3 +180,53 @@ def combine_shards(shards, dim: int = 0) -> torch.Tensor:
     if len({shard.dtype for shard in shards}) > 1:
         raise ValueError("All shards must have the same dtype.")
     return torch.cat(list(shards), dim=dim)
+
+
+class Aliasable:
+    """mixin for enums whose members have alternative spellings: equality and hashing go through `get_aliases()` (alias -> canonical
+    value), so a member equals its alias and plain strings compare by canonical value (helpers.py:210-238)"""
+
+    @staticmethod
+    def get_aliases() -> dict:
+        raise NotImplementedError()
+
+    def _canonical(self, value):
+        return self.get_aliases().get(value, value)
+
+    def __eq__(self, other):
+        other_value = other.value if isinstance(other, self.__class__) else other
+        return self._canonical(self.value) == self._canonical(other_value)
+
+    def __hash__(self):
+        return hash(self._canonical(self.value))
+
+
+def _config_value(config, what: str, direct: str, numerator: str, denominator: str) -> int:
+    if hasattr(config, direct):
+        return getattr(config, direct)
+    if numerator and hasattr(config, numerator) and hasattr(config, denominator):
+        return getattr(config, numerator) // getattr(config, denominator)
+    need = f"either `{direct}` or both `{numerator}` and `{denominator}`" if numerator else f"`{direct}`"
+    raise ValueError(f"Cannot determine {what} from config. Config must define {need}. {config}")
+
+
+def get_num_attn_heads(config) -> int:
+    """num_attention_heads, or hidden_size // head_dim (helpers.py:436-454)"""
+    return _config_value(config, "num_attention_heads", "num_attention_heads", "hidden_size", "head_dim")
+
+
+def get_num_kv_heads(config) -> int:
+    """num_key_value_heads (helpers.py:457-471)"""
+    return _config_value(config, "num_key_value_heads", "num_key_value_heads", "", "")
+
+
+def get_head_dim(config) -> int:
+    """head_dim, or hidden_size // num_attention_heads (helpers.py:474-492)"""
+    return _config_value(config, "head_dim", "head_dim", "hidden_size", "num_attention_heads")
+
+
+def is_accelerator_type(device_type: str) -> bool:
+    """the device type names the accelerator this process has; False without one (helpers.py:495-503)"""
+    if not torch.accelerator.is_available():
+        return False
+    return device_type == torch.accelerator.current_accelerator().type

@@ -17,7 +17,7 @@ __all__ = [
     "InverseWeightMap", "load_tensors_from_inverse_weight_map", "find_config_path", "get_quantization_config",
     "find_safetensors_index_path", "find_safetensors_index_file", "get_weight_map", "update_safetensors_index",
     "is_weights_file", "get_checkpoint_files", "get_safetensors_header", "match_param_name", "get_weight_mappings",
-    "get_nested_weight_mappings", "get_quantization_parameter_to_path_mapping", "is_quantization_param",
+    "get_nested_weight_mappings", "get_quantization_parameter_to_path_mapping", "is_quantization_param", "get_safetensors_folder",
 ]
 
 CONFIG_NAME = "config.json"
@@ -181,3 +181,22 @@ def is_quantization_param(name: str) -> bool:
 def get_quantization_parameter_to_path_mapping(model_path: str) -> dict[str, str]:
     """the quantization parameters of a checkpoint and the files they live in"""
     return {name: path for name, path in get_weight_mappings(model_path).items() if is_quantization_param(name)}
+
+
+def get_safetensors_folder(pretrained_model_name_or_path: str, cache_dir: Optional[str] = None) -> str:
+    """the local folder that holds a model's safetensors files (safetensors_load.py:260-299).  A path that exists is returned as is
+    (absolute); a Hub id is looked up in the local Hugging Face cache only -- this engine never downloads."""
+    path = str(pretrained_model_name_or_path)
+    if os.path.exists(path):
+        return os.path.abspath(path)
+    try:
+        from transformers.utils import cached_file
+
+        for name in (SAFE_WEIGHTS_NAME, SAFE_WEIGHTS_INDEX_NAME):
+            found = cached_file(path, name, cache_dir=cache_dir, local_files_only=True, _raise_exceptions_for_missing_entries=False,
+                                _raise_exceptions_for_connection_errors=False)
+            if found is not None:
+                return os.path.split(found)[0]
+    except Exception:  # noqa: BLE001  (no transformers, malformed id, offline cache miss)
+        pass
+    raise ValueError(f"Could not locate safetensors weight or index file from {pretrained_model_name_or_path}.")

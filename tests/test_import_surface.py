@@ -44,6 +44,16 @@ SURFACE = {
     "offload": ["update_offload_parameter", "disable_onloading", "get_execution_device", "is_distributed", "offload_module", "set_onload_device",
                 "OffloadCache", "to_meta", "as_single_threaded", "module_size"],
     "compressors.model_compressors": ["ModelCompressor"],
+    "config.dense": ["DenseSparsityConfig"],
+    "config.sparse_24_bitmask": ["Sparse24BitMaskConfig"],
+    "config.sparse_bitmask": ["BitmaskConfig"],
+    "quantization.utils.fp4_utils": ["cast_to_fp4"],
+    "quantization.lifecycle.apply": ["apply_quantization_config", "load_pretrained_quantization_parameters"],
+    "distributed.utils": ["is_source_process", "wait_for_comms", "set_source_process", "as_broadcastable"],
+    "utils.helpers": ["Aliasable", "get_num_attn_heads", "get_num_kv_heads", "get_head_dim", "is_accelerator_type", "ParameterizedDefaultDict",
+                      "patch_attrs", "get_nested_value", "deprecated", "shard_tensor", "combine_shards", "replace_module", "fix_fsdp_module_name"],
+    "utils.type": ["TorchDtype", "TensorStateDict"],
+    "registry.registry": ["RegistryMixin", "register_alias", "standardize_alias_name", "standardize_lookup_name"],
     "transform": ["TransformConfig", "TransformArgs", "TransformScheme", "TransformLocation"],
     "quantization.quant_metadata": ["KVCacheScaleType", "QuantizationMetadata"],
     "quantization.lifecycle.helpers": ["enable_quantization", "disable_quantization"],
