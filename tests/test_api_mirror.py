@@ -27,6 +27,7 @@ from compressed_tensors_b200.compressors import (
 from compressed_tensors_b200.compressors.format import infer_model_format, infer_module_format
 from compressed_tensors_b200.config import BitmaskConfig, CompressionFormat, Sparse24BitMaskConfig, SparsityCompressionConfig, SparsityStructure
 from compressed_tensors_b200.distributed import greedy_bin_packing
+from tests.util import free_port
 from compressed_tensors_b200.quantization import (
     ActivationOrdering,
     QuantizationArgs,
@@ -383,7 +384,7 @@ def test_module_parallel_two_ranks_gloo(tmp_path):
     script.write_text(_WORKER)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", CUDA_VISIBLE_DEVICES="")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29517", str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
+                        "--master-port", free_port(), str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("OK") == 2
 

@@ -10,6 +10,7 @@ import os
 import subprocess
 import sys
 import textwrap
+from tests.util import free_port
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -145,6 +146,6 @@ def test_distributed_model_compressor_two_ranks_gloo(tmp_path):
     script.write_text(_WORKER)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29543", str(script), ROOT], capture_output=True, text=True, env=env, timeout=600)
+                        "--master-port", free_port(), str(script), ROOT], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-1500:] + "\n".join(line for line in r.stderr.splitlines() if "Error" in line or "assert" in line or "File" in line)[-4000:]
     assert r.stdout.count("OK") == 2

@@ -11,6 +11,7 @@ import textwrap
 
 import pytest
 import torch
+from tests.util import free_port
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -87,6 +88,6 @@ def test_distributed_compress_two_gpus(tmp_path):
     script.write_text(_WORKER)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29531", str(script), ROOT], capture_output=True, text=True, env=env, timeout=600)
+                        "--master-port", free_port(), str(script), ROOT], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-1500:] + "\n".join(l for l in r.stderr.splitlines() if "rank" in l or "Error" in l)[-6000:]
     assert r.stdout.count("OK") == 2

@@ -61,3 +61,12 @@ def same_nan(a: torch.Tensor, b: torch.Tensor, what: str = "") -> None:
     if not torch.equal(na, nb):
         pytest.fail(f"{what}: NaN positions differ ({int(na.sum())} vs {int(nb.sum())})", pytrace=False)
     same(torch.where(na, torch.zeros_like(a), a), torch.where(nb, torch.zeros_like(b), b), what)
+
+
+def free_port() -> str:
+    """a TCP port nobody listens on right now, for torchrun's rendezvous on 127.0.0.1 (fixed ports collide when two suites run at once)"""
+    import socket
+
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sock:
+        sock.bind(("127.0.0.1", 0))
+        return str(sock.getsockname()[1])
