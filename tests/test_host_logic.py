@@ -77,6 +77,17 @@ def test_only_test_infrastructure_touches_the_oracle():
         assert re.findall(r"^def (\w+)", entry[: m.start()], flags=re.M)[-1] in ("build", "smoke")
 
 
+def test_scripts_compile():
+    """bench.py, __graft_entry__.py, tools/ and the reference-compat scripts at least parse (they only run on the GPU box / in the build container)"""
+    import glob
+
+    files = [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    files += glob.glob(os.path.join(ROOT, "tools", "*.py")) + glob.glob(os.path.join(ROOT, "tests", "reference_compat", "*.py"))
+    files += glob.glob(os.path.join(ROOT, "tests", "golden", "*.py"))
+    for f in files:
+        compile(open(f).read(), f, "exec")       # syntax only; nothing is written or executed
+
+
 def test_error_messages_match_reference():
     with pytest.raises(ValueError, match="Tensor must be quantized to torch.int8 before packing"):
         ops.pack_to_int32(torch.zeros(2, 2, dtype=torch.int32), 4)
