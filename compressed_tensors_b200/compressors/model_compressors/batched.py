@@ -183,7 +183,10 @@ def compress_modules_batched(modules, force_format: Optional[CompressionFormat] 
             args = scheme.weights
             sd = get_direct_state_dict(m)
             w, sc = sd["weight"], sd["weight_scale"]
-            zp = sd.get("weight_zero_point", None) if not args.symmetric else None
+            # the zero point goes through like in the per-module plugin path (ops.quantize): for integer codes a symmetric
+            # scheme's all-zero zero point cannot change a code (x/s + 0 only turns -0.0 into +0.0, which rounds to the same
+            # integer), so it is skipped; for fp8 codes -0.0 and +0.0 are different bytes (0x80 / 0x00), so it is added
+            zp = sd.get("weight_zero_point", None) if (not args.symmetric or args.type == "float") else None
             try:
                 p = ops._resolve(w, sc, zp, args, None)
                 qtype, bits = ops._qparams(args)

@@ -103,18 +103,18 @@ class ModelCompressor:
             self.quantization_config.quantization_status = QuantizationStatus.COMPRESSED
         self.add_decompress_hook(model)
 
-    def decompress_model(self, model: torch.nn.Module, distributed: Optional[bool] = None) -> None:
+    def decompress_model(self, model: torch.nn.Module, distributed: bool = False) -> None:
         """
-        The reference decompresses every module on every rank (model_compressor.py:196 leaves the distributed
-        version as a TODO).  Here, with `torch.distributed` initialised (or `distributed=True`), modules are dealt
-        to ranks exactly like in compress_model and the dense weights come back by NCCL broadcast.
+        Default (`distributed=False`) = the reference: every rank decompresses every module it holds, locally, no collective
+        (model_compressor.py:183-207; the decompress-on-first-forward hook always takes this path, so a rank-0-only forward
+        cannot deadlock).  `distributed=True` is an explicit opt-in to the flow the reference leaves as a TODO (:196): modules
+        are dealt to ranks exactly like in compress_model, each owner decompresses its share and the dense weights come back by
+        NCCL broadcast.  It is a COLLECTIVE call: every rank must make it, holding the same compressed modules.
         """
         modules = [m for _, m in model.named_modules(remove_duplicate=True) if is_module_quantized(m)]
-        from ...distributed import is_distributed, replace_module_parallel
+        from ...distributed import replace_module_parallel
         from .batched import decompress_modules_batched
 
-        if distributed is None:
-            distributed = is_distributed()
         if not distributed:
             decompress_modules_batched(modules, self.force_compression_format)
         else:
@@ -148,7 +148,7 @@ class ModelCompressor:
     # ---- decompress-on-first-forward hook -------------------------------------------------------
     def add_decompress_hook(self, model: torch.nn.Module):
         def ct_decompress_hook(model, args):
-            self.decompress_model(model)
+            self.decompress_model(model, distributed=False)   # never a collective: only some ranks may run forward
 
         model.ct_decompress_hook = model.register_forward_pre_hook(ct_decompress_hook)
 

@@ -102,8 +102,11 @@ static Plan plan_one(int op, const ct_quant_desc& d, const void* in, const void*
         D = d.cdiv;
     }
     if (!is_inf(D) && D % 8 != 0) return p;
-    if (zp && d.zp_dtype != CT_I8) return p;
-    const int zpk = zp ? 1 : 0;
+    // zero point: int8 everywhere; float8_e4m3fn (what the FP8 presets register) on the fp8 quantize / dequantize / fake_quantize kernels
+    const bool fp8_op = (op == CT_OP_QUANTIZE && d.qtype == CT_Q_FLOAT) || (op == CT_OP_FAKE_QUANTIZE && d.qtype == CT_Q_FLOAT) ||
+                        (op == CT_OP_DEQUANTIZE && d.q_dtype == CT_F8E4M3 && d.out_dtype == d.scale_dtype);
+    if (zp && d.zp_dtype != CT_I8 && !(d.zp_dtype == CT_F8E4M3 && fp8_op)) return p;
+    const int zpk = zp ? (d.zp_dtype == CT_I8 ? 1 : 2) : 0;
 
     int p_dt, in_bytes_per_chunk;
     FastSig sig;

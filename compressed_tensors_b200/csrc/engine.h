@@ -14,7 +14,7 @@ struct FastSig {
     int op;      // FastOp
     int p_dt;    // CT_BF16 / CT_F16 / CT_F32 (unused for F_PACK / F_UNPACK)
     int sel;     // QUANTPACK/UNPACKDEQ/PACK/UNPACK: bits (4 | 8); QUANT/DEQUANT/FAKE: QKind
-    int zp;      // 0 none, 1 int8
+    int zp;      // 0 none, 1 int8, 2 float8_e4m3fn (fp8 quantize / dequantize / fake_quantize only)
     int group;   // chunks per thread unit (1, 2 or 4): stream.cuh
     bool operator==(const FastSig& o) const { return op == o.op && p_dt == o.p_dt && sel == o.sel && zp == o.zp && group == o.group; }
 };

@@ -14,6 +14,7 @@ template <class P>
 static int fake_by(const FastSig& s, const LaunchPlan& lp, int device, cudaStream_t st) {
     if (s.sel == QF8 && s.zp == 0) return launch_stream<FakeQuantOp<P, QF8, 0>>(lp, device, st);
     if (s.sel == QF8 && s.zp == 1) return launch_stream<FakeQuantOp<P, QF8, 1>>(lp, device, st);
+    if (s.sel == QF8 && s.zp == 2) return launch_stream<FakeQuantOp<P, QF8, 2>>(lp, device, st);
     if (s.sel == QI_NARROW && s.zp == 0) return launch_stream<FakeQuantOp<P, QI_NARROW, 0>>(lp, device, st);
     if (s.sel == QI_NARROW && s.zp == 1) return launch_stream<FakeQuantOp<P, QI_NARROW, 1>>(lp, device, st);
     if (s.sel == QI_WIDE && s.zp == 0) return launch_stream<FakeQuantOp<P, QI_WIDE, 0>>(lp, device, st);
@@ -31,6 +32,7 @@ int launch_fast_fake(const FastSig& s, const LaunchPlan& lp, int device, cudaStr
         if (t.sel == QI_NARROW) t.sel = QI_WIDE;
         if (t.sel == QF8 && t.zp == 0) return launch_stream<FakeQuantOp<F32, QF8, 0>>(lp, device, st);
         if (t.sel == QF8 && t.zp == 1) return launch_stream<FakeQuantOp<F32, QF8, 1>>(lp, device, st);
+        if (t.sel == QF8 && t.zp == 2) return launch_stream<FakeQuantOp<F32, QF8, 2>>(lp, device, st);
         if (t.sel == QI_WIDE && t.zp == 0) return launch_stream<FakeQuantOp<F32, QI_WIDE, 0>>(lp, device, st);
         if (t.sel == QI_WIDE && t.zp == 1) return launch_stream<FakeQuantOp<F32, QI_WIDE, 1>>(lp, device, st);
         SIG_FAIL(s);

@@ -24,6 +24,7 @@ static int quant_p(const FastSig& s, const LaunchPlan& lp, int device, cudaStrea
     const int kind = (s.sel == QF8) ? QF8 : QI_WIDE;
     if (kind == QF8 && s.zp == 0) return quant_g<P, QF8, 0>(s, lp, device, st);
     if (kind == QF8 && s.zp == 1) return quant_g<P, QF8, 1>(s, lp, device, st);
+    if (kind == QF8 && s.zp == 2) return quant_g<P, QF8, 2>(s, lp, device, st);   // float8_e4m3fn zero point (the FP8 presets)
     if (kind == QI_WIDE && s.zp == 0) return quant_g<P, QI_WIDE, 0>(s, lp, device, st);
     if (kind == QI_WIDE && s.zp == 1) return quant_g<P, QI_WIDE, 1>(s, lp, device, st);
     SIG_FAIL(s);
@@ -47,6 +48,7 @@ static int dequant_p(const FastSig& s, const LaunchPlan& lp, int device, cudaStr
     const int kind = (s.sel == QF8) ? QF8 : QI_WIDE;
     if (kind == QF8 && s.zp == 0) return launch_stream<DequantizeOp<P, QF8, 0>>(lp, device, st);
     if (kind == QF8 && s.zp == 1) return launch_stream<DequantizeOp<P, QF8, 1>>(lp, device, st);
+    if (kind == QF8 && s.zp == 2) return launch_stream<DequantizeOp<P, QF8, 2>>(lp, device, st);
     if (kind == QI_WIDE && s.zp == 0) return launch_stream<DequantizeOp<P, QI_WIDE, 0>>(lp, device, st);
     if (kind == QI_WIDE && s.zp == 1) return launch_stream<DequantizeOp<P, QI_WIDE, 1>>(lp, device, st);
     SIG_FAIL(s);

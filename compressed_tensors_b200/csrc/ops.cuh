@@ -26,7 +26,7 @@ template <> struct ElemBytes<F32> { static constexpr int v = 4; };
 // ------------------------------------------------------------------------------------
 struct RawQP {
     uint32_t s;   // 16-bit P: the scale's bit pattern (low half); F32: float bits
-    int32_t z;    // int8 zero point (ZP == 1)
+    int32_t z;    // int8 zero point (ZP == 1) / float8_e4m3fn zero-point byte (ZP == 2: what the FP8 presets register, quant_args.py zp_dtype)
 };
 struct NoRaw {};
 
@@ -46,6 +46,7 @@ __device__ __forceinline__ RawQP fetch_qp(const Job& J, uint32_t gc) {
     else r.s = __ldg(reinterpret_cast<const unsigned short*>(J.scale) + si);
     r.z = 0;
     if constexpr (ZP == 1) r.z = __ldg(reinterpret_cast<const int8_t*>(J.zp) + si);
+    if constexpr (ZP == 2) r.z = __ldg(reinterpret_cast<const uint8_t*>(J.zp) + si);
     return r;
 }
 template <class P> __device__ __forceinline__ float scale_f32(const RawQP& r) {
@@ -58,11 +59,14 @@ template <class P> __device__ __forceinline__ uint32_t scale_t2(const RawQP& r) 
     if constexpr (P::DT == CT_F32) return r.s;
     else return r.s | (r.s << 16);
 }
-// zero_point.to(T) duplicated (16-bit P) / float bits (F32); int8 values are exact in every T
+// zero_point.to(T) duplicated (16-bit P) / float bits (F32); int8 and e4m3 values are exact in every T
 template <class P, int ZP> __device__ __forceinline__ uint32_t zp_t2(const RawQP& r) {
     if constexpr (ZP == 0) return 0u;
-    else if constexpr (P::DT == CT_F32) return __float_as_uint((float)r.z);
-    else return dup2<P>((float)r.z);
+    else {
+        const float z = (ZP == 2) ? e4m3_to_f32((uint32_t)r.z) : (float)r.z;
+        if constexpr (P::DT == CT_F32) return __float_as_uint(z);
+        else return dup2<P>(z);
+    }
 }
 
 // fp32 compute dtype: clamped, un-rounded value

@@ -8,61 +8,54 @@ module name, equals the class name, or is "re:<regex>" matching either.
 """
 from __future__ import annotations
 
-import re
+import logging
 from collections import OrderedDict
 from copy import deepcopy
 
 import torch
 from torch.nn import Module
 
+from ...utils.match import is_match, match_named_modules, match_targets
 from ..quant_config import QuantizationConfig, QuantizationStatus
 from .initialize import initialize_module_for_quantization
 
 __all__ = ["apply_quantization_config", "is_match", "match_named_modules", "load_pretrained_quantization_parameters"]
 
-
-def _one_match(value: str, target: str) -> bool:
-    if target.startswith("re:"):
-        return re.match(target[3:], value) is not None
-    return value == target
+_LOGGER = logging.getLogger(__name__)
 
 
-def is_match(name: str, module: Module, targets, ignore=()) -> bool:
-    """True when any target (and no ignore entry) matches the module's name or class name"""
-    if isinstance(targets, str):
-        targets = [targets]
-    cls_names = [c.__name__ for c in type(module).__mro__ if c is not object]
-
-    def hit(t: str) -> bool:
-        return _one_match(name, t) or any(_one_match(c, t) for c in cls_names)
-
-    if any(hit(t) for t in (ignore or ())):
-        return False
-    return any(hit(t) for t in targets)
-
-
-def match_named_modules(model: Module, targets, ignore=()):
-    for name, module in model.named_modules():
-        if is_match(name, module, targets, ignore):
-            yield name, module
+def _looks_like_attention(module: Module) -> bool:
+    """the reference's `_is_attention_module` test (quantization/lifecycle/initialize.py:123-130): class name contains "attention"
+    and the module owns k_proj / v_proj / qkv_proj"""
+    return "attention" in module.__class__.__name__.lower() and any(hasattr(module, n) for n in ("k_proj", "v_proj", "qkv_proj"))
 
 
 def apply_quantization_config(model: Module, config: QuantizationConfig | None, run_compressed: bool = False, show_progress: bool = False):
+    """quantization/lifecycle/apply.py:100-169.  A module that matches several targets takes the scheme of the most specific one
+    (`match_targets`: exact name, then regex on the name, then class name -- apply.py:149-151, :258-265), not the first in config
+    order.  KV-cache schemes and attention-module targets are outside this engine's path (OUT OF SCOPE): they raise /
+    warn instead of being dropped silently."""
     config = deepcopy(config)
     if config is None:
         return dict()
     force_zero_point = config.quantization_status < QuantizationStatus.COMPRESSED
+    if getattr(config, "kv_cache_scheme", None) is not None:
+        raise NotImplementedError(
+            "compressed_tensors_b200 does not implement KV-cache quantization (the reference's _apply_kv_cache_scheme / "
+            "initialize_hooked_kv_cache, apply.py:172-192): a checkpoint with `kv_cache_scheme` cannot be loaded by this engine")
     target_to_scheme = OrderedDict()
     for scheme in config.config_groups.values():
         for target in scheme.targets:
             target_to_scheme[target] = scheme
-    for name, module in match_named_modules(model, list(target_to_scheme), config.ignore):
-        if not isinstance(module, (torch.nn.Linear, torch.nn.Embedding)):
-            continue
-        first = next(t for t in target_to_scheme if is_match(name, module, [t]))
-        module.quantization_scheme = target_to_scheme[first]
-        initialize_module_for_quantization(module, force_zero_point=force_zero_point)
-        module.quantization_status = config.quantization_status
+    for name, module in match_named_modules(model, target_to_scheme, config.ignore, warn_on_fail=True):
+        scheme = target_to_scheme[match_targets(name, module, target_to_scheme)[0]]
+        if isinstance(module, (torch.nn.Linear, torch.nn.Embedding)):
+            module.quantization_scheme = scheme
+            initialize_module_for_quantization(module, force_zero_point=force_zero_point)
+            module.quantization_status = config.quantization_status
+        elif _looks_like_attention(module):
+            _LOGGER.warning(f"{name}: attention-module quantization targets are not supported by compressed_tensors_b200; "
+                            "no q/k/v scales are attached (the reference would run initialize_hooked_attention here)")
 
 
 def load_pretrained_quantization_parameters(model: Module, model_name_or_path: str | None = None, load_weight_qparams: bool = False) -> None:

@@ -60,7 +60,12 @@ def _divisor(value: float, like: Tensor) -> Tensor:
 
 def calculate_qparams(min_vals: Tensor, max_vals: Tensor, quantization_args: QuantizationArgs,
                       global_scale: Tensor | None = None) -> tuple[Tensor, Tensor]:
-    """observer rule of the reference (helpers.py:50-137), same op order so the scales agree bit for bit"""
+    """observer rule of the reference (helpers.py:50-137), same op order so the scales agree bit for bit.
+
+    CONTRACT: the result equals the reference's CPU result on every device.  The reference divides by a Python float; ATen's CUDA
+    kernels turn that into a multiplication by the reciprocal, so the reference ITSELF differs between CPU and CUDA by an ulp
+    now and then.  This engine pins the CPU value (the one the goldens and the reference's tests hold) and gets it on CUDA too by
+    dividing by a 0-dim tensor (`_divisor`), which keeps true IEEE division; tests/test_gpu_observe.py checks CUDA == CPU golden."""
     from .mxfp_utils import generate_mx_scales, maybe_convert_from_mx_exp, should_generate_mx_scales
 
     min_vals = torch.min(min_vals, torch.zeros_like(min_vals))

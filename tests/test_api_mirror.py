@@ -407,3 +407,48 @@ def test_load_pretrained_quantization_parameters(tmp_path):
     assert float(lin.input_scale) == 0.5 and float(lin.input_zero_point.float()) == 0.0 and float(lin.weight_scale.flatten()[0]) == 9.0
     load_pretrained_quantization_parameters(model, str(tmp_path), load_weight_qparams=True)
     assert float(lin.weight_scale.flatten()[0]) == 0.25
+
+
+def test_apply_config_prefers_the_most_specific_target():
+    """a module matching several targets takes the scheme of match_targets()[0]: exact name > regex on the name > class name
+    (reference quantization/lifecycle/apply.py:149-151, :258-265), whatever the order of the config groups"""
+    import torch
+    from compressed_tensors_b200.quantization import QuantizationConfig, apply_quantization_config
+
+    def model():
+        m = torch.nn.Sequential()
+        for n in ("fc1", "fc2", "fc3"):
+            m.add_module(n, torch.nn.Linear(64, 64))
+        return m
+
+    groups = {
+        "g0": {"targets": ["Linear"], "weights": {"num_bits": 8}},
+        "g1": {"targets": ["re:.*fc2"], "weights": {"num_bits": 4, "strategy": "group", "group_size": 32}},
+        "g2": {"targets": ["fc3"], "weights": {"num_bits": 2, "strategy": "channel"}},
+        "g3": {"targets": ["re:fc3"], "weights": {"num_bits": 6}},
+    }
+    for order in (["g0", "g1", "g2", "g3"], ["g3", "g2", "g1", "g0"]):
+        m = model()
+        apply_quantization_config(m, QuantizationConfig(config_groups={k: groups[k] for k in order}))
+        assert [getattr(m, n).quantization_scheme.weights.num_bits for n in ("fc1", "fc2", "fc3")] == [8, 4, 2], order
+        assert m.fc2.weight_scale.shape == (64, 2) and m.fc3.weight_scale.shape == (64, 1)
+
+
+def test_kv_cache_scheme_is_refused_loudly():
+    import pytest
+    import torch
+    from compressed_tensors_b200.quantization import QuantizationConfig, apply_quantization_config
+
+    cfg = QuantizationConfig(config_groups={"W8A8": ["Linear"]}, kv_cache_scheme={"num_bits": 8, "type": "float", "symmetric": True})
+    with pytest.raises(NotImplementedError, match="KV-cache"):
+        apply_quantization_config(torch.nn.Sequential(torch.nn.Linear(32, 32)), cfg)
+
+
+def test_decompress_model_is_local_unless_asked():
+    """reference behaviour: decompress_model (and the first-forward hook) never runs a collective (model_compressor.py:183-207)"""
+    import inspect
+    from compressed_tensors_b200.compressors import ModelCompressor
+
+    assert inspect.signature(ModelCompressor.decompress_model).parameters["distributed"].default is False
+    src = inspect.getsource(ModelCompressor.add_decompress_hook)
+    assert "distributed=False" in src

@@ -113,7 +113,7 @@ _WORKER = textwrap.dedent(
             model(torch.randn(2, model.proj0.in_features).to(torch.bfloat16))   # the hook decompresses on the first forward
             assert not hasattr(model, "ct_decompress_hook")
         else:
-            mc.decompress_model(model)                               # distributed decompress (the reference leaves it as a TODO)
+            mc.decompress_model(model, distributed=(preset != "FP8"))   # explicit opt-in to the collective decompress (the reference leaves it as a TODO); FP8: the default local path
         for n, m in model.named_modules():
             if n in fq:
                 assert m.weight.dtype == torch.bfloat16 and torch.equal(m.weight.data, fq[n]), f"{preset} {n}: decompress != fake_quantize"

@@ -67,7 +67,7 @@ _WORKER = textwrap.dedent(
         assert torch.equal(t, other), "ranks disagree"
         # and back: distributed decompress_model == single-process decompress, on every rank
         decompress_modules_batched(mods, None)
-        mc.decompress_model(model)
+        mc.decompress_model(model, distributed=True)
         for (n1, m1), (n2, m2) in zip(model.named_modules(), single.named_modules()):
             s1, s2 = get_direct_state_dict(m1), get_direct_state_dict(m2)
             assert set(s1) == set(s2), (n1, sorted(s1), sorted(s2))
