@@ -79,10 +79,12 @@ class ModelCompressor:
                    force_compression_format=quantization_format)
 
     # ---- compression ------------------------------------------------------------------------
-    def compress_model(self, model: torch.nn.Module, skip_compressed: bool = False, distributed: Optional[bool] = None) -> None:
+    def compress_model(self, model: torch.nn.Module, skip_compressed: bool = False, distributed: Optional[bool] = None,
+                       recouple: bool = True, stats: Optional[dict] = None) -> None:
         """
         `distributed` (extension; default None = the reference's behaviour, follow `is_distributed()`): pass False
         when every rank holds its OWN model (independent replicas / shards), so that no module is dealt to another rank.
+        `recouple` / `stats` (extensions, distributed path only): see `replace_module_parallel`.
         """
         modules = [
             m for _, m in model.named_modules(remove_duplicate=True)
@@ -98,12 +100,13 @@ class ModelCompressor:
             compress_modules_batched(modules, self.force_compression_format)
         else:
             replace_module_parallel(modules, partial(compress_module, format=self.force_compression_format), desc=None,
-                                    apply_many_fn=partial(compress_modules_batched, force_format=self.force_compression_format))
+                                    apply_many_fn=partial(compress_modules_batched, force_format=self.force_compression_format),
+                                    recouple=recouple, stats=stats)
         if self.quantization_config is not None:
             self.quantization_config.quantization_status = QuantizationStatus.COMPRESSED
         self.add_decompress_hook(model)
 
-    def decompress_model(self, model: torch.nn.Module, distributed: bool = False) -> None:
+    def decompress_model(self, model: torch.nn.Module, distributed: bool = False, recouple: bool = True, stats: Optional[dict] = None) -> None:
         """
         Default (`distributed=False`) = the reference: every rank decompresses every module it holds, locally, no collective
         (model_compressor.py:183-207; the decompress-on-first-forward hook always takes this path, so a rank-0-only forward
@@ -119,7 +122,8 @@ class ModelCompressor:
             decompress_modules_batched(modules, self.force_compression_format)
         else:
             replace_module_parallel(modules, partial(decompress_module, format=self.force_compression_format), desc=None,
-                                    apply_many_fn=partial(decompress_modules_batched, force_format=self.force_compression_format))
+                                    apply_many_fn=partial(decompress_modules_batched, force_format=self.force_compression_format),
+                                    recouple=recouple, stats=stats)
         if self.quantization_config is not None:
             self.quantization_config.quantization_status = QuantizationStatus.DECOMPRESSED
         self.remove_decompression_hook(model)

@@ -33,12 +33,26 @@ def _wire_device(dev: torch.device) -> torch.device:
     """where a tensor has to live to be broadcast: NCCL only moves device memory, so a host-resident module goes through this rank's GPU"""
     if dev.type != "cuda" and dist.get_backend() == "nccl":
         return torch.device("cuda", torch.cuda.current_device())
-    return dev
+    return torch.device("cpu") if dev.type == "meta" else dev
+
+
+def _sync(stats):
+    if stats is not None and torch.cuda.is_available():
+        torch.cuda.synchronize()
 
 
 def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callable = module_size, desc: Optional[str] = None,
-                            apply_many_fn: Optional[Callable] = None):
-    """`apply_many_fn(list_of_modules)` (extension): when given, the owner's modules are processed in one batched call"""
+                            apply_many_fn: Optional[Callable] = None, recouple: bool = True, stats: Optional[dict] = None):
+    """Extensions over the reference's signature (all optional):
+      apply_many_fn(list_of_modules): the owner's modules are processed in one batched call
+      recouple=False: skip step 4 -- every rank keeps only the results of the modules it owns (the others stay on meta); the flow for
+                      "each owner writes its own checkpoint shard"
+      stats: a dict that receives `apply_s` (this rank's own work, device-synchronised), `recouple_s`, `recouple_bytes`, `owned_modules`,
+             `owned_bytes`; asking for them adds two device synchronisations
+    A module whose tensors are on META on a non-owner rank from the start (a model sharded tensor-per-GPU: only the owner ever
+    materialised the weight) receives the owner's result on this rank's wire device (its GPU under NCCL)."""
+    import time
+
     rank, world = dist.get_rank(), dist.get_world_size()
     devices = {}
     for m in modules:
@@ -47,21 +61,29 @@ def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callab
             devices[id(m)] = tensors[0].device
     _, _, owner = greedy_bin_packing(modules, world, weight_fn)
 
+    _sync(stats)
+    t0 = time.perf_counter()
     for m in modules:
         if owner[m] != rank:
             _to_meta(m)
             apply_fn(m)
     mine = [m for m in modules if owner[m] == rank]
+    owned_bytes = sum(weight_fn(m) for m in mine)
     if apply_many_fn is not None:
         apply_many_fn(mine)
     else:
         for m in mine:
             apply_fn(m)
+    _sync(stats)
+    t1 = time.perf_counter()
 
-    for m in modules:  # same (sorted) order on every rank
+    moved = 0
+    for m in (modules if recouple else ()):  # same (sorted) order on every rank
         sd = get_direct_state_dict(m)
         home = devices.get(id(m), torch.device("cpu"))
         dev = _wire_device(home)
+        if home.type == "meta":
+            home = dev
         new = {}
         for name in sd:  # identical key order on all ranks (same compressor code path)
             t = sd[name]
@@ -78,4 +100,9 @@ def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callab
                 got = buf.view(t.dtype) if buf.dtype != t.dtype else buf
                 # tensors the shape-only path already produced for real (e.g. weight_shape, on the CPU) stay where they were
                 new[name] = got.to(home) if t.device.type == "meta" else got.to(t.device)
+            moved += t.numel() * t.element_size()
         replace_direct_state_dict(m, new)
+    _sync(stats)
+    if stats is not None:
+        stats.update(apply_s=t1 - t0, recouple_s=time.perf_counter() - t1, recouple_bytes=moved, owned_modules=len(mine),
+                     owned_bytes=int(owned_bytes), world_size=world)

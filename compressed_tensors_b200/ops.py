@@ -40,6 +40,7 @@ __all__ = [
     "bitmask_compress",
     "bitmask_decompress",
     "batched",
+    "BatchedPlan",
     "cast_to_fp4",
     "pack_fp4_to_uint8",
     "unpack_fp4_from_uint8",
@@ -830,23 +831,118 @@ def observe_quantize(x: torch.Tensor, args, pack: bool = False) -> Tuple[torch.T
 # --------------------------------------------------------------------------------------------
 # multi-tensor launch (the module loop of ModelCompressor.compress_model in one kernel)
 # --------------------------------------------------------------------------------------------
+_DT_SIZE = {0: 4, 1: 2, 2: 2, 3: 1, 4: 1, 5: 4, 6: 1, 7: 8, 8: 1}     # bytes per element of each ct_dtype_t
+
+
+def _scale_count(d: N.QuantDesc) -> int:
+    """elements of the scale / zero-point tensor that the addressing  sidx = (r / rdiv) * s_row_stride + c / cdiv  can reach"""
+    row_scaled = d.rdiv != N.INF
+    row_blocks = -(-d.rows // d.rdiv) if row_scaled else 1
+    per_row = 1 if d.cdiv == N.INF else -(-d.cols // d.cdiv)
+    return row_blocks * d.s_row_stride if (row_scaled and d.s_row_stride > 0) else per_row
+
+
+def _validate_problem(op: int, i: int, prob, on_cuda: Optional[int]) -> None:
+    """A caller-built descriptor is trusted by the kernels: rows * cols that do not match the tensors are an out-of-bounds access on
+    the device.  Cheap host-side check of every (desc, in, scale, zp, out): element counts, element sizes, placement, contiguity."""
+    d, tin, sc, zp, out = prob
+
+    def bad(msg):
+        raise ValueError(f"batched: tensor {i}: {msg}")
+
+    rows, cols, bits = int(d.rows), int(d.cols), int(d.num_bits)
+    if rows < 0 or cols < 0:
+        bad("negative shape in the descriptor")
+    n = rows * cols
+    words = rows * (-(-cols * bits // 32)) if bits > 0 else 0
+    # (input elements, input bytes/elem, output elements, output bytes/elem); None = not checked for this op
+    if op in (N.OP_QUANTIZE_PACK, N.OP_OBSERVE_QUANTIZE_PACK):
+        want = (n, _DT_SIZE.get(d.x_dtype), words, 4)
+    elif op == N.OP_UNPACK_DEQUANTIZE:
+        want = (words, 4, n, _DT_SIZE.get(d.out_dtype))
+    elif op == N.OP_QUANTIZE:
+        want = (n, _DT_SIZE.get(d.x_dtype), n, _DT_SIZE.get(d.q_dtype))
+    elif op == N.OP_DEQUANTIZE:
+        want = (n, _DT_SIZE.get(d.q_dtype), n, _DT_SIZE.get(d.out_dtype))
+    elif op == N.OP_FAKE_QUANTIZE:
+        want = (n, _DT_SIZE.get(d.x_dtype), n, _DT_SIZE.get(d.out_dtype))
+    elif op == N.OP_PACK_INT32:
+        want = (n, 1, words, 4)
+    elif op == N.OP_UNPACK_INT32:
+        want = (words, 4, n, 1)
+    elif op in (N.OP_QUANTIZE_PACK_FP4, N.OP_OBSERVE_QUANTIZE_PACK_FP4):
+        want = (n, _DT_SIZE.get(d.x_dtype), n // 2, 1)
+    elif op == N.OP_UNPACK_DEQUANTIZE_FP4:
+        want = (n // 2, 1, n, _DT_SIZE.get(d.out_dtype))
+    else:
+        bad(f"unknown op {op}")
+    for what, t, numel, size in (("input", tin, want[0], want[1]), ("output", out, want[2], want[3])):
+        if t is None:
+            bad(f"{what} tensor is missing")
+        if size is None:
+            bad(f"the descriptor names no valid dtype for the {what}")
+        if t.numel() != numel or t.element_size() != size:
+            bad(f"{what} holds {t.numel()} elements of {t.element_size()} bytes, the descriptor ({rows} x {cols}, {bits} bits) needs {numel} of {size}")
+    tensors = [("input", tin), ("output", out)]
+    if op not in (N.OP_PACK_INT32, N.OP_UNPACK_INT32):
+        if sc is None:
+            bad("scale tensor is missing")
+        ssize = _DT_SIZE.get(d.scale_dtype)
+        need = _scale_count(d)
+        if ssize is None or sc.element_size() != ssize or sc.numel() < need:
+            bad(f"scale holds {sc.numel()} elements of {sc.element_size()} bytes, the descriptor addresses {need} of {ssize}")
+        tensors.append(("scale", sc))
+        if zp is not None:
+            zsize = _DT_SIZE.get(d.zp_dtype)
+            if zsize is None or zp.element_size() != zsize or zp.numel() < need:
+                bad(f"zero point holds {zp.numel()} elements of {zp.element_size()} bytes, the descriptor addresses {need} of {zsize}")
+            tensors.append(("zero point", zp))
+    for what, t in tensors:
+        if not t.is_contiguous():
+            bad(f"{what} is not contiguous")
+        if on_cuda is not None and (not t.is_cuda or t.device.index != on_cuda):
+            bad(f"{what} lives on {t.device}, the launch runs on cuda:{on_cuda}")
+        if on_cuda is None and t.is_cuda:
+            bad(f"{what} lives on {t.device}, host_batched expects CPU tensors")
+
+
+class BatchedPlan:
+    """A validated multi-tensor launch that can be enqueued any number of times (`run()`): the descriptors are checked against their
+    tensors once, the pointer tables are built once, and `run()` is a single ct_batched call on the current stream.  The plan keeps
+    the tensors alive.  What a caller that compresses the same buffers repeatedly (benchmarks, double-buffered checkpoint
+    writers) should hold instead of calling `batched` every time."""
+
+    __slots__ = ("op", "n", "idx", "_keep", "_descs", "_ins", "_scs", "_zps", "_outs")
+
+    def __init__(self, op: int, problems, device_index: Optional[int] = None):
+        self.op, self.n = int(op), len(problems)
+        self.idx = device_index if device_index is not None else (_dev_index(problems[0][1]) if problems else 0)
+        for i, p in enumerate(problems):
+            _validate_problem(self.op, i, p, self.idx)
+        self._keep = list(problems)
+        n = self.n
+        vp = ctypes.c_void_p * max(n, 1)
+        self._descs = (N.QuantDesc * max(n, 1))(*[p[0] for p in problems])
+        self._ins = vp(*[p[1].data_ptr() for p in problems])
+        self._scs = vp(*[(p[2].data_ptr() if p[2] is not None else 0) for p in problems])
+        self._zps = vp(*[(p[3].data_ptr() if p[3] is not None else 0) for p in problems])
+        self._outs = vp(*[p[4].data_ptr() for p in problems])
+
+    def run(self) -> None:
+        if self.n == 0:
+            return
+        rc = N.lib().ct_batched(self.op, self.n, self._descs, ctypes.cast(self._ins, ctypes.c_void_p), ctypes.cast(self._scs, ctypes.c_void_p),
+                                ctypes.cast(self._zps, ctypes.c_void_p), ctypes.cast(self._outs, ctypes.c_void_p), self.idx, N.stream_ptr(self.idx))
+        N.check(rc, "ct_batched")
+
+
 @torch.no_grad()
 def batched(op: int, problems: Sequence[Tuple[N.QuantDesc, torch.Tensor, torch.Tensor, Optional[torch.Tensor], torch.Tensor]],
             device_index: Optional[int] = None) -> None:
-    """problems: (desc, in, scale, zp, out) with every tensor already on the same CUDA device."""
-    n = len(problems)
-    if n == 0:
-        return
-    idx = device_index if device_index is not None else _dev_index(problems[0][1])
-    descs = (N.QuantDesc * n)(*[p[0] for p in problems])
-    vp = ctypes.c_void_p * n
-    ins = vp(*[p[1].data_ptr() for p in problems])
-    scs = vp(*[(p[2].data_ptr() if p[2] is not None else 0) for p in problems])
-    zps = vp(*[(p[3].data_ptr() if p[3] is not None else 0) for p in problems])
-    outs = vp(*[p[4].data_ptr() for p in problems])
-    rc = N.lib().ct_batched(int(op), n, descs, ctypes.cast(ins, ctypes.c_void_p), ctypes.cast(scs, ctypes.c_void_p),
-                            ctypes.cast(zps, ctypes.c_void_p), ctypes.cast(outs, ctypes.c_void_p), idx, N.stream_ptr(idx))
-    N.check(rc, "ct_batched")
+    """problems: (desc, in, scale, zp, out) with every tensor already on the same CUDA device.  Every descriptor is checked against
+    its tensors first (ValueError, nothing launched)."""
+    if len(problems):
+        BatchedPlan(op, problems, device_index).run()
 
 
 @torch.no_grad()
@@ -857,10 +953,8 @@ def host_batched(op: int, problems: Sequence[Tuple[N.QuantDesc, torch.Tensor, to
     n = len(problems)
     if n == 0:
         return
-    for p in problems:
-        for t in (p[1], p[2], p[3], p[4]):
-            if t is not None and (t.is_cuda or not t.is_contiguous()):
-                raise ValueError("host_batched expects contiguous CPU tensors")
+    for i, p in enumerate(problems):
+        _validate_problem(int(op), i, p, None)
     idx = device_index if device_index is not None else N.require_device(None)
     descs = (N.QuantDesc * n)(*[p[0] for p in problems])
     vp = ctypes.c_void_p * n

@@ -18,8 +18,16 @@ def _check(line: str, n_gpus: int):
     assert d["unit"] == "GB/s" and d["value"] > 0 and d["warmup"] >= 3 and d["vs_baseline"] is None and d["data"] == "synthetic"
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["cores"] >= 1 and cb["sample"]
-    assert cb["cores"] == len(os.sched_getaffinity(0)), "the CPU arm must use every host thread it may (torchrun exports OMP_NUM_THREADS=1)"
+    have_ref = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "compressed_tensors", "version.py"))
+    assert cb["kind"] == ("reference" if have_ref else "port") and cb["value"] == d["value"] and cb["cores"] >= 1 and cb["sample"]
+    sys.path.insert(0, ROOT)
+    import bench
+    phys = bench.cpu_topology()[0]
+    assert cb["cores"] == len(phys) == cb["port"]["threads"], "the CPU arm must use every physical core it may (torchrun exports OMP_NUM_THREADS=1)"
+    assert cb["reps"] >= 5 and cb["cpu_model"] and cb["nproc"] == len(os.sched_getaffinity(0))
+    if have_ref:
+        assert cb["reference"]["equals_port_bit_for_bit"] is True and cb["reference"]["threads"] == len(phys)
+        assert cb["value"] == cb["reference"]["GBps"]
     e2e = d["e2e"]
     assert e2e["value"] == d["value"] and e2e["unit"] == d["unit"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
     return d

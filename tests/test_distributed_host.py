@@ -119,6 +119,40 @@ _WORKER = textwrap.dedent(
                 assert m.weight.dtype == torch.bfloat16 and torch.equal(m.weight.data, fq[n]), f"{preset} {n}: decompress != fake_quantize"
         same_on_all_ranks(model, f"{preset} decompressed")
 
+    # tensor-per-rank sharded model (BASELINE config 5): every weight exists on its owner rank only, the other rank holds meta
+    # tensors from the start; compress (owner only) + recouple gives every rank the complete compressed model, equal to the
+    # single-process result; stats are filled; recouple=False leaves the other rank's modules on meta
+    from compressed_tensors.distributed import greedy_bin_packing, module_size
+    from compressed_tensors.utils import replace_direct_state_dict
+    for recouple in (True, False):
+        full = build(6, with_extras=False)
+        quantize_config(full, "W4A16")
+        reference = copy.deepcopy(full)
+        mods = [m for m in full.modules() if getattr(m, "quantization_scheme", None) is not None]
+        owner = greedy_bin_packing(list(mods), 2, module_size)[2]
+        for m in mods:
+            if owner[m] != rank:
+                replace_direct_state_dict(m, {k: (torch.empty_like(v, device="meta") if v is not None else None) for k, v in get_direct_state_dict(m).items()})
+        stats = {}
+        ModelCompressor.from_pretrained_model(full).compress_model(full, distributed=True, recouple=recouple, stats=stats)
+        ModelCompressor.from_pretrained_model(reference).compress_model(reference, distributed=False)
+        assert stats["owned_modules"] == sum(1 for m in mods if owner[m] == rank) and stats["apply_s"] > 0 and stats["world_size"] == 2
+        assert (stats["recouple_bytes"] > 0) == recouple
+        for (n1, m1), (n2, m2) in zip(full.named_modules(), reference.named_modules()):
+            if getattr(m1, "quantization_scheme", None) is None:
+                continue
+            s1, s2 = get_direct_state_dict(m1), get_direct_state_dict(m2)
+            assert set(s1) == set(s2)
+            for k, v in s1.items():
+                if v is None:
+                    continue
+                if recouple or owner[m1] == rank or k == "weight_shape":
+                    assert v.device.type == "cpu" and v.dtype == s2[k].dtype and torch.equal(v, s2[k]), f"sharded {n1}.{k} (recouple={recouple})"
+                else:
+                    assert v.device.type == "meta" and v.shape == s2[k].shape and v.dtype == s2[k].dtype, f"sharded {n1}.{k} stays on meta"
+        if recouple:
+            same_on_all_ranks(full, "sharded compressed")
+
     # nothing to compress: no quantized modules, and an empty model
     plain = build(3)
     before = {k: v.clone() for k, v in state(plain).items()}

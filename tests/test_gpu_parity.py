@@ -320,6 +320,78 @@ def test_full_size_fp8_properties(shape):
     same_values(q[rows].cpu().view(torch.uint8), want.view(torch.uint8), "")
 
 
+LLAMA8B_LAYER = [(4096, 4096), (1024, 4096), (1024, 4096), (4096, 4096), (14336, 4096), (14336, 4096), (4096, 14336)]
+
+
+@pytest.mark.parametrize("scheme", ["w4a16_sym", "w4a16_asym", "fp8_tensor"])
+def test_full_layer_every_element_vs_oracle_through_batched(scheme):
+    """BASELINE.json's full sizes against the ORACLE, every element: all 7 Linear weights of a Llama-3-8B layer (218 M elements) go
+    through ONE multi-tensor launch (ct_batched, the entry point ModelCompressor and bench.py use) per direction, and every packed
+    word / fp8 byte / dequantized bf16 value is compared with the CPU oracle's result for the whole tensor."""
+    ws, scs, zps = [], [], []
+    for i, (R, C) in enumerate(LLAMA8B_LAYER):
+        g = torch.Generator(device=DEV).manual_seed(1000 + i)
+        w = (torch.randn(R, C, device=DEV, generator=g) * 0.02).bfloat16()
+        if scheme == "fp8_tensor":
+            sc, zp = (w.abs().max().float() / 448).bfloat16().reshape(1), None
+        else:
+            sc, zp = _group_qparams(w, 4, 128, scheme == "w4a16_sym", torch.bfloat16)
+        ws.append(w); scs.append(sc); zps.append(zp)
+    if scheme == "fp8_tensor":
+        a, op_c, op_d, qd = ns(type="float"), N.OP_QUANTIZE, N.OP_DEQUANTIZE, torch.float8_e4m3fn
+        okw_ = dict(strategy="tensor", qtype="float", dtype=torch.float8_e4m3fn)
+    else:
+        a, op_c, op_d, qd = ns(strategy="group", group_size=128, num_bits=4, symmetric=scheme == "w4a16_sym"), N.OP_QUANTIZE_PACK, N.OP_UNPACK_DEQUANTIZE, torch.int8
+        okw_ = dict(strategy="group", group_size=128, num_bits=4, dtype=torch.int8)
+    comp, cprobs, dprobs, backs = [], [], [], []
+    for w, sc, zp in zip(ws, scs, zps):
+        R, C = w.shape
+        p = ops._resolve(w, sc, zp, a, None)
+        zdt = zp.dtype if zp is not None else None
+        if scheme == "fp8_tensor":
+            out = torch.empty(R, C, dtype=qd, device=DEV)
+            d = ops._desc(p, w.dtype, sc.dtype, zdt, torch.bfloat16, qd, qd, N.Q_FLOAT, 8)
+            d2 = ops._desc(p, None, sc.dtype, zdt, None, qd, torch.bfloat16, N.Q_INT, 8)
+        else:
+            out = torch.empty(R, C // 8, dtype=torch.int32, device=DEV)
+            d = ops._desc(p, w.dtype, sc.dtype, zdt, torch.bfloat16, torch.int8, None, N.Q_INT, 4)
+            d2 = ops._desc(p, None, sc.dtype, zdt, None, torch.int8, torch.bfloat16, N.Q_INT, 4)
+        back = torch.empty(R, C, dtype=torch.bfloat16, device=DEV)
+        cprobs.append((d, w, p.scale.contiguous(), p.zp.contiguous() if p.zp is not None else None, out))
+        dprobs.append((d2, out, p.scale.contiguous(), p.zp.contiguous() if p.zp is not None else None, back))
+        comp.append(out); backs.append(back)
+    launches = N.launch_count()
+    ops.batched(op_c, cprobs)
+    ops.batched(op_d, dprobs)
+    assert N.launch_count() - launches == 2, "one multi-tensor launch per direction"
+    for i, (w, sc, zp, out, back) in enumerate(zip(ws, scs, zps, comp, backs)):
+        wc, scc, zpc = w.cpu(), sc.cpu(), (zp.cpu() if zp is not None else None)
+        q = oracle.quantize(wc, scc, zpc, **okw_)
+        if scheme == "fp8_tensor":
+            same_values(out.cpu().view(torch.uint8), q.view(torch.uint8), f"{scheme} tensor {i} {tuple(w.shape)} fp8 bytes")
+        else:
+            same_values(out.cpu(), oracle.pack_to_int32(q, 4), f"{scheme} tensor {i} {tuple(w.shape)} packed words")
+        same(back.cpu(), oracle.dequantize(q, scc, zpc), f"{scheme} tensor {i} {tuple(w.shape)} dequantized")
+
+
+def test_batched_rejects_descriptors_that_do_not_match_their_tensors():
+    """a wrong descriptor would be an out-of-bounds access on the device: ops.batched checks sizes on the host and launches nothing"""
+    a = ns(strategy="group", group_size=128, num_bits=4)
+    w = _weights((64, 256), torch.bfloat16, 1).to(DEV)
+    sc = (w.float().unflatten(-1, (-1, 128)).abs().amax(-1) / 7.5).bfloat16()
+    out = torch.zeros(64, 32, dtype=torch.int32, device=DEV)
+    p = ops._resolve(w, sc, None, a, None)
+    d = ops._desc(p, w.dtype, sc.dtype, None, torch.bfloat16, torch.int8, None, N.Q_INT, 4)
+    launches = N.launch_count()
+    for bad in [(d, w[:32], sc, None, out), (d, w, sc[:, :1].contiguous(), None, out), (d, w, sc, None, out[:32]),
+                (d, w.float(), sc, None, out), (d, w.t(), sc, None, out), (d, w.cpu(), sc, None, out), (d, w, sc, None, None)]:
+        with pytest.raises(ValueError, match="batched: tensor 0"):
+            ops.batched(N.OP_QUANTIZE_PACK, [bad])
+    assert N.launch_count() == launches
+    ops.batched(N.OP_QUANTIZE_PACK, [(d, w, sc, None, out)])
+    same_values(out, ops.quantize_pack(w, sc, None, a), "valid problem still runs")
+
+
 def test_batched_launch_equals_per_tensor():
     """one persistent launch over a table of tensors == per-tensor launches"""
     shapes = [(1024, 4096), (512, 1024), (4096, 512), (64, 128), (2048, 14336)]

@@ -60,7 +60,7 @@ def test_no_cpu_path():
 
 def test_only_test_infrastructure_touches_the_oracle():
     """oracle/ is the checker: nothing in the product package, the drop-in alias or tools/ may import it; bench.py only inside its CPU legs
-    (cpu_baseline, the reference arm), __graft_entry__ only inside build() / smoke()"""
+    (the cpu-worker subprocess of cpu_baseline / the reference arm) and as the checker of timed outputs, __graft_entry__ only inside build() / smoke()"""
     pat = re.compile(r"^\s*(import oracle\b|from oracle\b)", re.M)
     for top in ("compressed_tensors_b200", "compat", "tools", "include"):
         for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
@@ -71,7 +71,8 @@ def test_only_test_infrastructure_touches_the_oracle():
     bench = open(os.path.join(ROOT, "bench.py")).read()
     for m in pat.finditer(bench):
         fn = re.findall(r"^def (\w+)", bench[: m.start()], flags=re.M)[-1]
-        assert fn in ("cpu_baseline", "run_reference", "oracle_compress_layer"), f"bench.py imports the oracle inside {fn}()"
+        # the CPU legs (timed as the baseline) and the two places where it is the CHECKER of what the GPU arm wrote
+        assert fn in ("run_cpu_worker", "oracle_compress_layer", "run_cfg5_70b_sharded", "verify_timed_outputs"), f"bench.py imports the oracle inside {fn}()"
     entry = open(os.path.join(ROOT, "__graft_entry__.py")).read()
     for m in pat.finditer(entry):
         assert re.findall(r"^def (\w+)", entry[: m.start()], flags=re.M)[-1] in ("build", "smoke")
