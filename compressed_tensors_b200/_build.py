@@ -33,6 +33,7 @@ SOURCES = [
     "selftest.cu",
     "host_pipeline.cu",
     "sparse.cu",
+    "bitmask_onepass.cu",
     "fast_observe.cu",
     "host_many.cu",
 ]

@@ -111,6 +111,7 @@ _PROTOS = {
     "ct_bitmask_count": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp]),
     "ct_bitmask_compress": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _i64, _int, _vp]),
     "ct_bitmask_decompress": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _i64, _int, _vp]),
+    "ct_bitmask_compress_onepass": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp]),
     "ct_semi_structured_from_dense": (_int, [_vp, _int, _vp, _vp, _i64, _i64, _int, _vp]),
     "ct_semi_structured_to_dense": (_int, [_vp, _int, _vp, _vp, _i64, _i64, _int, _vp]),
     "ct_host_run": (_int, [_int, _descp, _vp, _vp, _vp, _vp, _int]),

@@ -59,4 +59,10 @@ int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in
 
 int check_device(int device);
 
+// ---- unstructured bitmask in one pass (bitmask_onepass.cu): decoupled look-back over per-tile counts ----------------
+bool bitmask_lookback_ok(int dtype, int64_t rows, int64_t cols, const void* dense, const void* mask, const void* values);
+template <bool COMPRESS>
+int launch_bitmask_lookback(const void* src, uint8_t* bitmask, void* dst, int64_t* row_offsets, int64_t* nnz_out, int64_t rows, int64_t cols,
+                            int device, cudaStream_t st);
+
 }  // namespace ctb

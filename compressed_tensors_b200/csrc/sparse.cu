@@ -669,6 +669,29 @@ int ct_bitmask_compress(const void* x, int dtype, const uint8_t* bitmask, const 
     return CT_OK;
 }
 
+/* one call, no host round trip: values has capacity rows * cols, nnz stays on the device */
+int ct_bitmask_compress_onepass(const void* x, int dtype, void* values, uint8_t* bitmask, int64_t* row_offsets, int64_t* nnz_out,
+                                int64_t rows, int64_t cols, int device, void* stream) {
+    PRECHECK(device);
+    if (!row_offsets || !nnz_out) { set_error("null pointer"); return CT_E_ARG; }
+    if (rows * cols == 0) {
+        CT_CUDA_TRY(cudaMemsetAsync(nnz_out, 0, sizeof(int64_t), st));
+        if (rows > 0) CT_CUDA_TRY(cudaMemsetAsync(row_offsets, 0, rows * sizeof(int64_t), st));
+        return CT_OK;
+    }
+    if (!x || !values || !bitmask) { set_error("null pointer"); return CT_E_ARG; }
+    if (bitmask_lookback_ok(dtype, rows, cols, x, bitmask, values) && !getenv("CT_B200_BITMASK_TWO_PHASE"))
+        return launch_bitmask_lookback<true>(x, bitmask, values, row_offsets, nnz_out, rows, cols, device, st);
+    // every other dtype / shape: the two-phase kernels with a stream-ordered workspace (still no host synchronisation)
+    void* ws = nullptr;
+    rc = scratch_alloc(&ws, (size_t)ct_bitmask_workspace_bytes(rows, cols), device, st);
+    if (rc) return rc;
+    rc = ct_bitmask_count(x, dtype, bitmask, row_offsets, nnz_out, ws, rows, cols, device, stream);
+    if (!rc) rc = ct_bitmask_compress(x, dtype, bitmask, row_offsets, values, rows, cols, device, stream);
+    cudaFreeAsync(ws, st);
+    return rc;
+}
+
 int ct_bitmask_decompress(const void* values, int dtype, const uint8_t* bitmask, const int64_t* row_offsets, void* out,
                           int64_t rows, int64_t cols, int device, void* stream) {
     PRECHECK(device);
@@ -676,6 +699,10 @@ int ct_bitmask_decompress(const void* values, int dtype, const uint8_t* bitmask,
     if (!out || !bitmask || !row_offsets) { set_error("null pointer"); return CT_E_ARG; }
     const int64_t nb = (cols + 7) / 8;
     const unsigned g = (unsigned)(rows < 148 * 8 ? rows : 148 * 8);
+    if (values && bitmask_lookback_ok(dtype, rows, cols, out, bitmask, values) && !getenv("CT_B200_BITMASK_TWO_PHASE")) {
+        // flat tiles + decoupled look-back over the mask popcounts (bitmask_onepass.cu); row_offsets is not needed
+        return launch_bitmask_lookback<false>(values, const_cast<uint8_t*>(bitmask), out, nullptr, nullptr, rows, cols, device, st);
+    }
     if (bitmask_vec16_ok(dtype, rows, cols, out, bitmask)) {
         launch_bitmask_move_vec16<false>(values, bitmask, row_offsets, out, rows, (int)(cols / 8), st);
     } else

@@ -1025,24 +1025,28 @@ def sparse24_decompress(values: torch.Tensor, bitmask: torch.Tensor, shape: Sequ
     return _back(out, values)
 
 
-def bitmask_compress(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """unstructured bitmask compression -> (values [nnz], bitmask uint8 [R, ceil(C/8)], row_offsets int64 [R])"""
+def bitmask_compress(x: torch.Tensor, exact: bool = True):
+    """unstructured bitmask compression -> (values [nnz], bitmask uint8 [R, ceil(C/8)], row_offsets int64 [R])
+
+    One ABI call, the dense tensor is read once (ct_bitmask_compress_onepass): the kernel writes into a buffer of capacity numel and
+    leaves nnz on the device.  `exact=True` (the storage format: `compressed` holds exactly nnz elements) reads nnz back at the END
+    and returns the slice; `exact=False` never synchronises and returns (values with capacity numel, bitmask, row_offsets, nnz) with
+    nnz a 1-element int64 tensor on the device -- for callers that keep going on the stream (checkpoint writers that size the file
+    record later)."""
     if x.ndim != 2:
         raise ValueError("bitmask compression expects a 2-D tensor")
     rows, cols = x.shape
     idx = _dev_index(x)
     xd = _to_dev(x, idx)
-    lib = N.lib()
     bitmask = torch.empty((rows, (cols + 7) // 8), dtype=torch.uint8, device=xd.device)
     row_offsets = torch.empty((rows,), dtype=torch.int64, device=xd.device)
-    nnz = torch.zeros((1,), dtype=torch.int64, device=xd.device)
-    ws = torch.empty((max(int(lib.ct_bitmask_workspace_bytes(rows, cols)), 256),), dtype=torch.uint8, device=xd.device)
-    N.check(lib.ct_bitmask_count(N.ptr(xd), N.DT[x.dtype], N.ptr(bitmask), N.ptr(row_offsets), N.ptr(nnz), N.ptr(ws),
-                                 rows, cols, idx, N.stream_ptr(idx)), "bitmask_count")
-    total = int(nnz.item())
-    values = torch.empty((total,), dtype=x.dtype, device=xd.device)
-    N.check(lib.ct_bitmask_compress(N.ptr(xd), N.DT[x.dtype], N.ptr(bitmask), N.ptr(row_offsets), N.ptr(values),
-                                    rows, cols, idx, N.stream_ptr(idx)), "bitmask_compress")
+    nnz = torch.empty((1,), dtype=torch.int64, device=xd.device)
+    values = torch.empty((rows * cols,), dtype=x.dtype, device=xd.device)
+    N.check(N.lib().ct_bitmask_compress_onepass(N.ptr(xd), N.DT[x.dtype], N.ptr(values), N.ptr(bitmask), N.ptr(row_offsets), N.ptr(nnz),
+                                                rows, cols, idx, N.stream_ptr(idx)), "bitmask_compress")
+    if not exact:
+        return _back(values, x), _back(bitmask, x), _back(row_offsets, x), _back(nnz, x)
+    values = values[: int(nnz.item())].clone()      # the only host read, after all device work has been enqueued
     return _back(values, x), _back(bitmask, x), _back(row_offsets, x)
 
 

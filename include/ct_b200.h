@@ -232,6 +232,13 @@ int ct_bitmask_compress(const void* x, int dtype, const uint8_t* bitmask, const 
                         int64_t rows, int64_t cols, int device, void* stream);
 int ct_bitmask_decompress(const void* values, int dtype, const uint8_t* bitmask, const int64_t* row_offsets,
                           void* out, int64_t rows, int64_t cols, int device, void* stream);
+/* The same compression in ONE call without a host round trip (BitmaskCompressor of CompressionFormat.sparse_bitmask, config/base.py:17;
+ * mask bit order of utils/helpers.py:306-317): `values` is a caller buffer of CAPACITY rows * cols elements of which the first *nnz_out
+ * (device int64) are written, row_offsets [rows] and bitmask [rows, ceil(cols/8)] as above.  bf16 / fp16 tensors with cols % 8 == 0
+ * are read exactly once (per-tile counts combined by a decoupled look-back scan inside the kernel); other dtypes / shapes run the
+ * two-phase kernels above on a stream-ordered workspace.  Enqueue-only. */
+int ct_bitmask_compress_onepass(const void* x, int dtype, void* values, uint8_t* bitmask, int64_t* row_offsets, int64_t* nnz_out,
+                                int64_t rows, int64_t cols, int device, void* stream);
 
 /* 2:4 "semi-structured" values + metadata in the CUTLASS / marlin-24 layout: replaces
  * utils/semi_structured_conversions.py:66-197 (sparse_semi_structured_from_dense_cutlass) and

@@ -458,5 +458,40 @@ def test_bitmask_compress_vs_oracle(dtype, shape):
     gv, gb, go = ops.bitmask_compress(x.to(DEV))
     same_values(gb.cpu(), bm, "")
     same(gv.cpu(), vals, "")
+    same_values(go.cpu(), offs, "row offsets")
     dense = ops.bitmask_decompress(gv, gb, go, x.shape)
     same(dense.cpu(), x.where(x != 0, torch.zeros_like(x)), "")
+
+
+@pytest.mark.parametrize("density", [0.0, 0.03, 0.5, 0.97, 1.0])
+@pytest.mark.parametrize("shape", [(8, 32), (64, 4096), (300, 1000), (1031, 2056), (4096, 14336)])
+def test_bitmask_onepass_lookback_vs_oracle(shape, density, monkeypatch):
+    """the one-pass kernels (decoupled look-back scan, csrc/bitmask_onepass.cu): every output of the format -- values, mask bytes,
+    row offsets, nnz -- against the restated oracle, the no-sync (`exact=False`) form included, for densities from empty to full, tiles
+    that hold many rows and rows that span many tiles; and the same bits as the two-phase kernels they replace"""
+    g = torch.Generator().manual_seed(shape[1] + int(density * 100))
+    x = (torch.randn(shape, generator=g) * 3).bfloat16()
+    x[torch.rand(shape, generator=g) >= density] = 0
+    x[0, 0] = -0.0                                           # -0.0 is a zero of the format
+    vals, bm, offs = oracle.bitmask_compress(x)
+    xd = x.to(DEV)
+    launches = N.launch_count()
+    cap, gb, go, nnz = ops.bitmask_compress(xd, exact=False)
+    onepass = (x.numel() // 8) % 4 == 0                      # otherwise: two-phase kernels behind the same call
+    assert N.launch_count() - launches == (1 if onepass else 3), "one kernel: the dense tensor is read once"
+    assert cap.numel() == x.numel() and nnz.is_cuda and int(nnz.item()) == vals.numel()
+    same_values(gb.cpu(), bm, "mask bytes")
+    same_values(go.cpu(), offs, "row offsets")
+    same(cap[: vals.numel()].cpu(), vals, "values")
+    gv, gb2, go2 = ops.bitmask_compress(xd)
+    assert gv.numel() == vals.numel()
+    same(gv.cpu(), vals, "values (exact)")
+    launches = N.launch_count()
+    dense = ops.bitmask_decompress(gv, gb, go, x.shape)
+    assert N.launch_count() - launches == 1
+    same(dense.cpu(), x.where(x != 0, torch.zeros_like(x)), "expand")
+    same(dense.cpu(), oracle.bitmask_decompress(vals, bm, x.shape), "expand vs oracle")
+    monkeypatch.setenv("CT_B200_BITMASK_TWO_PHASE", "1")     # count -> scan -> move
+    tv, tb, to = ops.bitmask_compress(xd)
+    same(tv, gv, "two-phase values"); same_values(tb, gb, "two-phase mask"); same_values(to, go, "two-phase offsets")
+    same(ops.bitmask_decompress(gv, gb, go, x.shape), dense, "two-phase expand")
