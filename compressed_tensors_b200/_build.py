@@ -34,6 +34,7 @@ SOURCES = [
     "host_pipeline.cu",
     "sparse.cu",
     "bitmask_onepass.cu",
+    "fast_sparse24q.cu",
     "fast_observe.cu",
     "host_many.cu",
 ]

@@ -38,7 +38,8 @@ DT = {
 
 # ct_batch_op_t
 (OP_QUANTIZE_PACK, OP_UNPACK_DEQUANTIZE, OP_QUANTIZE, OP_DEQUANTIZE, OP_FAKE_QUANTIZE, OP_PACK_INT32, OP_UNPACK_INT32,
- OP_OBSERVE_QUANTIZE_PACK, OP_QUANTIZE_PACK_FP4, OP_UNPACK_DEQUANTIZE_FP4, OP_OBSERVE_QUANTIZE_PACK_FP4) = range(11)
+ OP_OBSERVE_QUANTIZE_PACK, OP_QUANTIZE_PACK_FP4, OP_UNPACK_DEQUANTIZE_FP4, OP_OBSERVE_QUANTIZE_PACK_FP4,
+ OP_SPARSE24_QUANTIZE_PACK, OP_SPARSE24_UNPACK_DEQUANTIZE) = range(13)
 
 Q_INT, Q_FLOAT, Q_FP4 = 0, 1, 2
 DT_E8M0 = 8  # uint8 MX scale exponent as stored (CT_E8M0)
@@ -64,6 +65,7 @@ class QuantDesc(ctypes.Structure):
         ("global_scale", ctypes.c_void_p),
         ("seff_dtype", ctypes.c_int32),
         ("_reserved", ctypes.c_int32),
+        ("aux", ctypes.c_void_p),
     ]
 
 
@@ -107,6 +109,8 @@ _PROTOS = {
     "ct_unpack_bitmasks": (_int, [_vp, _vp, _i64, _i64, _int, _vp]),
     "ct_sparse24_compress": (_int, [_vp, _int, _vp, _vp, _i64, _i64, _int, _vp]),
     "ct_sparse24_decompress": (_int, [_vp, _int, _vp, _vp, _i64, _i64, _int, _vp]),
+    "ct_sparse24_quantize_pack_int4": (_int, [_descp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "ct_sparse24_unpack_dequantize_int4": (_int, [_descp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "ct_bitmask_workspace_bytes": (_i64, [_i64, _i64]),
     "ct_bitmask_count": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp]),
     "ct_bitmask_compress": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _i64, _int, _vp]),

@@ -266,6 +266,38 @@ static Plan plan_fp4(int op, const ct_quant_desc& d, const void* in, const void*
     return p;
 }
 
+// fused 2:4 select + int4 (fast_sparse24q.cu).  compress: chunk = 8 dense elements, unit = 4 chunks; decompress: chunk = 16 dense
+// elements (4 bytes of nibbles), unit = 2 chunks.  Full rows of scales only (flat scale index), cols % 32 == 0.
+static Plan plan_s24(int op, const ct_quant_desc& d, const void* in, const void* scale, const void* zp, const int32_t* g_idx, void* out) {
+    Plan p;
+    p.fast = false;
+    memset(&p.job, 0, sizeof(p.job));
+    memset(&p.cm, 0, sizeof(p.cm));
+    p.sig = FastSig{0, 0, 0, 0, 1};
+    const int64_t n = d.rows * d.cols;
+    int64_t D;
+    if (g_idx || n == 0 || n % 64 != 0 || d.cols % 32 != 0 || (n / 8) >= 0x7fffffffLL || !aligned16(in) || !aligned16(out)) return p;
+    if (!d.aux || (reinterpret_cast<uintptr_t>(d.aux) & 3u) != 0 || d.global_scale || d.qtype != CT_Q_INT || d.num_bits != 4) return p;
+    if (!flat_divisor(d, D) || (!is_inf(D) && D % 32 != 0)) return p;
+    if (zp && d.zp_dtype != CT_I8) return p;
+    const bool comp = (op == CT_OP_SPARSE24_QUANTIZE_PACK);
+    const int p_dt = comp ? d.x_dtype : d.out_dtype;
+    if (p_dt != CT_BF16 && p_dt != CT_F16) return p;
+    if (d.scale_dtype != p_dt || (comp && d.compute_dtype != p_dt)) return p;
+    const int64_t chunk = comp ? 8 : 16;
+    p.fast = true;
+    p.sig = FastSig{comp ? F_S24_QUANTPACK : F_S24_UNPACKDEQ, p_dt, 4, zp ? 1 : 0, comp ? 4 : 2};
+    p.job.in = reinterpret_cast<const uint8_t*>(in);
+    p.job.scale = scale;
+    p.job.zp = zp;
+    p.job.out = reinterpret_cast<uint8_t*>(out);
+    p.job.aux = d.aux;
+    p.job.n_chunks = (uint32_t)(n / chunk);
+    p.job.dc = make_fastdiv(is_inf(D) ? (uint64_t)0x7FFFFFFFull : (uint64_t)(D / chunk));
+    p.cm = make_common(p_dt, CT_Q_INT, 4);
+    return p;
+}
+
 // standalone pack / unpack (packed_dim 1) as a streaming job; for these ops a chunk is 16 codes
 static Plan plan_bits(bool pack, int64_t rows, int64_t cols, int bits, const void* in, void* out) {
     Plan p;
@@ -296,6 +328,8 @@ static int launch_sig(const FastSig& s, const LaunchPlan& lp, int device, cudaSt
     case F_OBSERVE_QP: return launch_fast_observe(s, lp, device, st);
     case F_FP4_QUANTPACK:
     case F_FP4_UNPACKDEQ: return launch_fast_fp4(s, lp, device, st);
+    case F_S24_QUANTPACK:
+    case F_S24_UNPACKDEQ: return launch_fast_sparse24q(s, lp, device, st);
     default: return launch_fast_bits(s, lp, device, st);
     }
 }
@@ -319,6 +353,12 @@ static int run_generic(int op, const ct_quant_desc& d, const void* in, const voi
         set_error("fused NVFP4 observe+quantize+pack supports bf16 / fp16 weights, group_size 16 with full rows of scales, cols %% 32 == 0, "
                   "a float32 global scale, 16-byte aligned contiguous tensors; run the observer and quantize_pack_fp4 separately otherwise");
         return CT_E_UNSUPPORTED;
+    case CT_OP_SPARSE24_QUANTIZE_PACK:
+    case CT_OP_SPARSE24_UNPACK_DEQUANTIZE:
+        set_error("fused 2:4 + int4 supports bf16 / fp16 weights, 4-bit integer codes, cols %% 32 == 0, rows * cols %% 64 == 0, scales in the weight dtype "
+                  "with full rows (group %% 32 == 0, channel, tensor), zero point absent or int8, 16-byte aligned contiguous tensors and a "
+                  "4-byte aligned bitmask; compose sparse24 + quantize + pack separately otherwise");
+        return CT_E_UNSUPPORTED;
     case CT_OP_OBSERVE_QUANTIZE_PACK:
         set_error("fused observe+quantize+pack supports bf16/fp16 group quantization with group_size in {32,64,128,256}, "
                   "4- or 8-bit codes, 16-byte aligned contiguous tensors; run the observer and quantize_pack separately otherwise");
@@ -330,7 +370,7 @@ static int run_generic(int op, const ct_quant_desc& d, const void* in, const voi
 
 static int check_dtypes(int op, const ct_quant_desc& d, bool has_zp) {
     const bool quantizing = (op == CT_OP_QUANTIZE_PACK || op == CT_OP_QUANTIZE || op == CT_OP_FAKE_QUANTIZE || op == CT_OP_OBSERVE_QUANTIZE_PACK ||
-                             op == CT_OP_QUANTIZE_PACK_FP4 || op == CT_OP_OBSERVE_QUANTIZE_PACK_FP4);
+                             op == CT_OP_QUANTIZE_PACK_FP4 || op == CT_OP_OBSERVE_QUANTIZE_PACK_FP4 || op == CT_OP_SPARSE24_QUANTIZE_PACK);
     const bool fp4_op = (op == CT_OP_QUANTIZE_PACK_FP4 || op == CT_OP_UNPACK_DEQUANTIZE_FP4 || op == CT_OP_OBSERVE_QUANTIZE_PACK_FP4);
     if (op == CT_OP_OBSERVE_QUANTIZE_PACK_FP4) {   // the scale is produced, as float8_e4m3fn
         if (d.qtype != CT_Q_FP4 || d.cols % 2 != 0) { set_error("fp4 ops need qtype fp4 and an even number of columns"); return CT_E_DTYPE; }
@@ -346,7 +386,8 @@ static int check_dtypes(int op, const ct_quant_desc& d, bool has_zp) {
         return CT_E_DTYPE;
     }
     if (has_zp && dt_size(d.zp_dtype) == 0) { set_error("bad zero-point dtype %d", d.zp_dtype); return CT_E_DTYPE; }
-    if ((op == CT_OP_DEQUANTIZE || op == CT_OP_UNPACK_DEQUANTIZE || op == CT_OP_FAKE_QUANTIZE || op == CT_OP_UNPACK_DEQUANTIZE_FP4) && !is_float_dt(d.out_dtype)) {
+    if ((op == CT_OP_DEQUANTIZE || op == CT_OP_UNPACK_DEQUANTIZE || op == CT_OP_FAKE_QUANTIZE || op == CT_OP_UNPACK_DEQUANTIZE_FP4 ||
+         op == CT_OP_SPARSE24_UNPACK_DEQUANTIZE) && !is_float_dt(d.out_dtype)) {
         set_error("output dtype %d is not a float dtype", d.out_dtype);
         return CT_E_DTYPE;
     }
@@ -381,6 +422,7 @@ int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in
         if (rc) return rc;
         if (descs[i].rows * descs[i].cols > 0 && (!in[i] || !scale[i] || !out[i])) { set_error("null tensor pointer (tensor %d)", i); return CT_E_ARG; }
         if (op == CT_OP_QUANTIZE_PACK_FP4 || op == CT_OP_UNPACK_DEQUANTIZE_FP4 || op == CT_OP_OBSERVE_QUANTIZE_PACK_FP4) plans[i] = plan_fp4(op, descs[i], in[i], scale[i], z, g_idx ? g_idx[i] : nullptr, out[i]);
+        else if (op == CT_OP_SPARSE24_QUANTIZE_PACK || op == CT_OP_SPARSE24_UNPACK_DEQUANTIZE) plans[i] = plan_s24(op, descs[i], in[i], scale[i], z, g_idx ? g_idx[i] : nullptr, out[i]);
         else plans[i] = plan_one(op, descs[i], in[i], scale[i], z, g_idx ? g_idx[i] : nullptr, out[i]);
     }
     // group fast jobs by kernel signature (and clamp constants), one launch per group
@@ -565,6 +607,20 @@ int ct_quantize_pack_int32(const ct_quant_desc* d, const void* x, const void* sc
 }
 int ct_unpack_dequantize_int32(const ct_quant_desc* d, const int32_t* packed, const void* scale, const void* zp, const int32_t* g_idx, void* out, int device, void* stream) {
     return run_one(CT_OP_UNPACK_DEQUANTIZE, d, packed, scale, zp, g_idx, out, device, stream);
+}
+int ct_sparse24_quantize_pack_int4(const ct_quant_desc* d, const void* x, const void* scale, const void* zp, int32_t* packed,
+                                   uint8_t* bitmask, int device, void* stream) {
+    if (!d) { set_error("null descriptor"); return CT_E_ARG; }
+    ct_quant_desc t = *d;
+    t.aux = bitmask;
+    return run_one(CT_OP_SPARSE24_QUANTIZE_PACK, &t, x, scale, zp, nullptr, packed, device, stream);
+}
+int ct_sparse24_unpack_dequantize_int4(const ct_quant_desc* d, const int32_t* packed, const uint8_t* bitmask, const void* scale,
+                                       const void* zp, void* out, int device, void* stream) {
+    if (!d) { set_error("null descriptor"); return CT_E_ARG; }
+    ct_quant_desc t = *d;
+    t.aux = const_cast<uint8_t*>(bitmask);
+    return run_one(CT_OP_SPARSE24_UNPACK_DEQUANTIZE, &t, packed, scale, zp, nullptr, out, device, stream);
 }
 int ct_observe_quantize_pack_int32(const ct_quant_desc* d, const void* x, void* scale_out, void* zp_out, int32_t* packed, int device, void* stream) {
     return run_one(CT_OP_OBSERVE_QUANTIZE_PACK, d, x, scale_out, zp_out, nullptr, packed, device, stream);

@@ -8,7 +8,7 @@ namespace ctb {
 
 // ---- fast (flat, streaming) path -------------------------------------------------------
 enum FastOp { F_QUANTPACK = 0, F_UNPACKDEQ = 1, F_QUANT = 2, F_DEQUANT = 3, F_FAKE = 4, F_PACK = 5, F_UNPACK = 6, F_OBSERVE_QP = 7,
-              F_FP4_QUANTPACK = 8, F_FP4_UNPACKDEQ = 9 };
+              F_FP4_QUANTPACK = 8, F_FP4_UNPACKDEQ = 9, F_S24_QUANTPACK = 10, F_S24_UNPACKDEQ = 11 };
 
 struct FastSig {
     int op;      // FastOp
@@ -30,6 +30,7 @@ int fast_group_quantpack(int p_dt, int bits);   // preferred unit size of the in
 int fast_group_quant(int p_dt);
 int launch_fast_fp4(const FastSig&, const LaunchPlan&, int device, cudaStream_t);       // fast_fp4.cu; sig.sel / sig.zp: see there
 int launch_fast_observe(const FastSig&, const LaunchPlan&, int device, cudaStream_t);   // fast_observe.cu; sig.group = lanes per quantization group
+int launch_fast_sparse24q(const FastSig&, const LaunchPlan&, int device, cudaStream_t); // fast_sparse24q.cu: fused 2:4 select + int4 (BASELINE config 4)
 
 // ---- generic path (any strategy, g_idx, ragged shapes, mixed dtypes) -----------------------
 enum GenericMode { G_QUANTIZE = 0, G_DEQUANTIZE = 1, G_FAKE = 2 };

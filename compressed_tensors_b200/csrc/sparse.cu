@@ -17,6 +17,7 @@
 
 #include "engine.h"
 #include "quant_core.cuh"
+#include "sparse_common.cuh"
 
 namespace ctb {
 
@@ -167,21 +168,6 @@ __global__ void __launch_bounds__(256) sparse24_decompress_kernel(const void* __
 // balances the SMs (same effect as the dynamic tile schedule of stream.cuh; see tools/ubench/mix_ceiling.cu).
 // Semantics identical to the generic kernels above (ties: lower column first; -0.0 counts as magnitude 0).
 // ---------------------------------------------------------------------------------------------
-// keep mask (bit j = element j kept) of one quad held as two packed words {e0,e1}, {e2,e3}, and the kept pair in column order
-__device__ __forceinline__ uint32_t quad_select16(uint32_t w0, uint32_t w1, uint32_t& pair) {
-    // composite = |x| bits << 2 | (3 - column): all four distinct, larger = wins (larger magnitude, or equal magnitude and lower
-    // column).  The two winners come out of a 4-input selection network of integer min / max.
-    const uint32_t c0 = ((w0 << 2) & 0x1fffcu) | 3u, c1 = ((w0 >> 14) & 0x1fffcu) | 2u;
-    const uint32_t c2 = ((w1 << 2) & 0x1fffcu) | 1u, c3 = ((w1 >> 14) & 0x1fffcu);
-    const uint32_t a = max(c0, c1), b = min(c0, c1), c = max(c2, c3), d = min(c2, c3);
-    const uint32_t first = max(a, c), second = max(min(a, c), max(b, d));
-    const uint32_t ia = 3u - (first & 3u), ib = 3u - (second & 3u);
-    const uint32_t keep = (1u << ia) | (1u << ib);
-    const uint32_t i0 = min(ia, ib), i1 = max(ia, ib);
-    pair = __byte_perm(w0, w1, 0x1010u + i0 * 0x22u + i1 * 0x2200u);   // bytes (2 i0, 2 i0 + 1, 2 i1, 2 i1 + 1)
-    return keep;
-}
-
 // Every thread handles S24_U units, all loads issued before the first use: with one 16-byte load per thread a block lives for one
 // DRAM round trip and the SM cannot keep enough bytes in flight (measured 3.9 TB/s); four loads per thread fix that.
 constexpr int S24_U = 4;

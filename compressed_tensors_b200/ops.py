@@ -39,6 +39,8 @@ __all__ = [
     "sparse24_decompress",
     "bitmask_compress",
     "bitmask_decompress",
+    "sparse24_quantize_pack",
+    "sparse24_unpack_dequantize",
     "batched",
     "BatchedPlan",
     "cast_to_fp4",
@@ -278,6 +280,7 @@ def _desc(p: _Problem, x_dt, s_dt, zp_dt, cd, q_dt, out_dt, qtype, bits, se_dt=N
     d.qtype, d.num_bits = qtype, bits
     d.global_scale = None
     d.seff_dtype = N.DT.get(se_dt, N.DT_NONE)
+    d.aux = None
     return d
 
 
@@ -874,6 +877,10 @@ def _validate_problem(op: int, i: int, prob, on_cuda: Optional[int]) -> None:
         want = (n, _DT_SIZE.get(d.x_dtype), n // 2, 1)
     elif op == N.OP_UNPACK_DEQUANTIZE_FP4:
         want = (n // 2, 1, n, _DT_SIZE.get(d.out_dtype))
+    elif op == N.OP_SPARSE24_QUANTIZE_PACK:          # kept codes [rows, cols/2] as a 4-bit stream; the bitmask (d.aux) is the caller's business
+        want = (n, _DT_SIZE.get(d.x_dtype), rows * (-(-(cols // 2) * bits // 32)), 4)
+    elif op == N.OP_SPARSE24_UNPACK_DEQUANTIZE:
+        want = (rows * (-(-(cols // 2) * bits // 32)), 4, n, _DT_SIZE.get(d.out_dtype))
     else:
         bad(f"unknown op {op}")
     for what, t, numel, size in (("input", tin, want[0], want[1]), ("output", out, want[2], want[3])):
@@ -1058,3 +1065,75 @@ def bitmask_decompress(values: torch.Tensor, bitmask: torch.Tensor, row_offsets:
     N.check(N.lib().ct_bitmask_decompress(N.ptr(v), N.DT[values.dtype], N.ptr(b), N.ptr(ro), N.ptr(out), rows, cols,
                                           idx, N.stream_ptr(idx)), "bitmask_decompress")
     return _back(out, bitmask)
+
+
+# --------------------------------------------------------------------------------------------
+# BASELINE config 4: "Sparse24BitMask + int4" (2:4 selection + pack-quantized) fused
+# --------------------------------------------------------------------------------------------
+@torch.no_grad()
+def sparse24_quantize_pack(x: torch.Tensor, scale: torch.Tensor, zero_point: Optional[torch.Tensor], args) -> Tuple[torch.Tensor, torch.Tensor]:
+    """2:4 compress + int4 quantize + pack in ONE pass over the dense weight:
+        mask    = keep the 2 of largest |x| in every 4 consecutive columns (ties: lower column), as `sparse24_compress`
+        codes   = quantize(x, scale, zero_point, args, dtype=int8)[mask].view(R, C/2)      (forward.py:36-73 on the kept columns)
+        returns (pack_to_int32(codes, num_bits) int32 [R, C * bits / 64], pack_bitmasks(mask) uint8 [R, C/8])
+    The fused kernel covers bf16 / fp16 weights, 4-bit integer codes, cols % 32 == 0 and scales with full rows; every other case
+    composes the unfused kernels (same bits).  PARITY UNPINNED as a composite: quantize, the bitstream and the mask bit order are
+    pinned by the reference's goldens, the selection rule and the composition are restated."""
+    if x.ndim != 2:
+        raise ValueError("sparse24_quantize_pack expects a 2-D weight")
+    rows, cols = x.shape
+    if cols % 4 != 0:
+        raise ValueError(f"2:4 compression needs the column count to be a multiple of 4, got {cols}")
+    _check_float(x, "input")
+    _check_float(scale, "scale")
+    qtype, bits = _qparams(args)
+    if qtype != N.Q_INT:
+        raise ValueError("pack-quantized compression needs integer quantization")
+    p = _resolve(x, scale, zero_point, args, None)
+    idx = _dev_index(x, p.scale)
+    xd, sc, zp = _to_dev(x, idx), _to_dev(p.scale, idx), _to_dev(p.zp, idx)
+    cd = torch.result_type(x, scale)
+    packed = torch.empty((rows, -(-(cols // 2) * bits // 32)), dtype=torch.int32, device=xd.device)
+    bitmask = torch.empty((rows, (cols + 7) // 8), dtype=torch.uint8, device=xd.device)
+    d = _desc(p, x.dtype, sc.dtype, zp.dtype if zp is not None else None, cd, torch.int8, None, qtype, bits)
+    rc = N.lib().ct_sparse24_quantize_pack_int4(ctypes.byref(d), N.ptr(xd), N.ptr(sc), N.ptr(zp), N.ptr(packed), N.ptr(bitmask), idx, N.stream_ptr(idx))
+    if rc == N.CT_E_UNSUPPORTED:
+        # unfused composition of the same kernels: 2:4 mask, dense codes, gather of the kept codes, bit packing
+        _, bitmask = sparse24_compress(xd)
+        q = quantize(xd, p.scale.to(xd.device), p.zp.to(xd.device) if p.zp is not None else None, args, dtype=torch.int8)
+        kept = q[unpack_bitmasks(bitmask, (rows, cols))].view(rows, cols // 2)
+        packed = pack_to_int32(kept.contiguous(), bits)
+    else:
+        N.check(rc, "sparse24_quantize_pack")
+    return _back(packed, x), _back(bitmask, x)
+
+
+@torch.no_grad()
+def sparse24_unpack_dequantize(packed: torch.Tensor, bitmask: torch.Tensor, scale: torch.Tensor, zero_point: Optional[torch.Tensor],
+                               num_bits: int, shape: Sequence[int], dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """inverse of `sparse24_quantize_pack`: kept codes back to their columns and dequantized (strategy inferred from the scale shape
+    like forward.py:99-130), dropped columns = +0; returns `dtype` (default scale.dtype) [R, C]"""
+    shape = tuple(int(v) for v in shape)
+    rows, cols = shape
+    if packed.dtype is not torch.int32:
+        raise ValueError(f"Expected {torch.int32} but got {packed.dtype}, Aborting unpack.")
+    _check_float(scale, "scale")
+    like = torch.empty(shape, dtype=torch.int8, device="meta")
+    args = _infer_dequant_args(like, scale)
+    out_dtype = (dtype or scale.dtype) if _strategy_name(args) in ("group", "tensor_group") else scale.dtype
+    p = _resolve(like, scale, zero_point, args, None)
+    idx = _dev_index(packed, bitmask)
+    pk, bm, sc, zp = _to_dev(packed, idx), _to_dev(bitmask, idx), _to_dev(p.scale, idx), _to_dev(p.zp, idx)
+    out = torch.empty(shape, dtype=out_dtype, device=pk.device)
+    d = _desc(p, None, sc.dtype, zp.dtype if zp is not None else None, None, torch.int8, out_dtype, N.Q_INT, int(num_bits))
+    rc = N.lib().ct_sparse24_unpack_dequantize_int4(ctypes.byref(d), N.ptr(pk), N.ptr(bm), N.ptr(sc), N.ptr(zp), N.ptr(out), idx, N.stream_ptr(idx))
+    if rc == N.CT_E_UNSUPPORTED:
+        kept = unpack_from_int32(pk, int(num_bits), (rows, cols // 2))
+        mask = unpack_bitmasks(bm, shape)
+        q = torch.zeros(shape, dtype=torch.int8, device=pk.device)
+        q[mask] = kept.reshape(-1)
+        out = dequantize(q, p.scale.to(pk.device), p.zp.to(pk.device) if p.zp is not None else None, args, dtype=out_dtype)
+        out = torch.where(mask, out, torch.zeros_like(out))
+    else:
+        N.check(rc, "sparse24_unpack_dequantize")
+    return _back(out, packed)

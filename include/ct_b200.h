@@ -90,6 +90,9 @@ typedef struct ct_quant_desc {
     const void* global_scale;
     int32_t seff_dtype;
     int32_t _reserved;
+    /* second tensor of the ops that have two streamed outputs / inputs (CT_OP_SPARSE24_*: the uint8 bitmask [rows, cols/8]);
+     * NULL otherwise.  A DEVICE pointer, like global_scale. */
+    void* aux;
 } ct_quant_desc;
 
 /* ---- library / device ---------------------------------------------------- */
@@ -206,7 +209,9 @@ typedef enum ct_batch_op_t {
     CT_OP_OBSERVE_QUANTIZE_PACK = 7, /* in x     -> out packed int32; scale[i] / zp[i] are OUTPUTS (see ct_observe_quantize_pack_int32) */
     CT_OP_QUANTIZE_PACK_FP4 = 8,  /* in x        -> out uint8 nibbles (ct_quantize_pack_fp4) */
     CT_OP_UNPACK_DEQUANTIZE_FP4 = 9, /* in nibbles -> out float (ct_unpack_dequantize_fp4) */
-    CT_OP_OBSERVE_QUANTIZE_PACK_FP4 = 10 /* in x -> out nibbles; scale[i] (float8_e4m3fn) is an OUTPUT (ct_observe_quantize_pack_nvfp4) */
+    CT_OP_OBSERVE_QUANTIZE_PACK_FP4 = 10, /* in x -> out nibbles; scale[i] (float8_e4m3fn) is an OUTPUT (ct_observe_quantize_pack_nvfp4) */
+    CT_OP_SPARSE24_QUANTIZE_PACK = 11,    /* in x       -> out packed int32 [rows, cols/16] + descs[i].aux = bitmask OUT (ct_sparse24_quantize_pack_int4) */
+    CT_OP_SPARSE24_UNPACK_DEQUANTIZE = 12 /* in packed  -> out float; descs[i].aux = bitmask IN (ct_sparse24_unpack_dequantize_int4) */
 } ct_batch_op_t;
 int ct_batched(int op, int n, const ct_quant_desc* descs, const void* const* in, const void* const* scale,
                const void* const* zp, void* const* out, int device, void* stream);
@@ -239,6 +244,20 @@ int ct_bitmask_decompress(const void* values, int dtype, const uint8_t* bitmask,
  * two-phase kernels above on a stream-ordered workspace.  Enqueue-only. */
 int ct_bitmask_compress_onepass(const void* x, int dtype, void* values, uint8_t* bitmask, int64_t* row_offsets, int64_t* nnz_out,
                                 int64_t rows, int64_t cols, int device, void* stream);
+
+/* BASELINE config 4, "Sparse24BitMask + int4": the composition of the 2:4 bitmask format above with pack-quantized, fused.
+ *   compress  : per quad of x keep the 2 of largest |x| (ties: lower column), quantize the KEPT values with the scale / zero point of
+ *               their original column (forward_helpers.py:523-546), pack the 4-bit codes [rows, cols/2] with pack_to_int32's bitstream
+ *               (pack_quantized/helpers.py:20-101) -> packed int32 [rows, cols/16]; bitmask = pack_bitmasks(mask) (utils/helpers.py:306-317)
+ *   decompress: codes back to their columns, dequantized (forward_helpers.py:549-572) to d->out_dtype; dropped columns are +0
+ * d as for ct_quantize_pack_int32 / ct_unpack_dequantize_int32 (num_bits = 4, CT_Q_INT).  The selection rule and the composition are
+ * restated ("parity unpinned": the compressor pair is absent from the reference snapshot).  Fast kernels: bf16 / fp16, cols % 32 == 0,
+ * scales in the weight dtype with full rows (group % 32 == 0, channel, tensor), zero point absent or int8, 16-byte aligned tensors;
+ * anything else returns CT_E_UNSUPPORTED (the Python layer then composes the unfused kernels). */
+int ct_sparse24_quantize_pack_int4(const ct_quant_desc* d, const void* x, const void* scale, const void* zp, int32_t* packed,
+                                   uint8_t* bitmask, int device, void* stream);
+int ct_sparse24_unpack_dequantize_int4(const ct_quant_desc* d, const int32_t* packed, const uint8_t* bitmask, const void* scale,
+                                       const void* zp, void* out, int device, void* stream);
 
 /* 2:4 "semi-structured" values + metadata in the CUTLASS / marlin-24 layout: replaces
  * utils/semi_structured_conversions.py:66-197 (sparse_semi_structured_from_dense_cutlass) and

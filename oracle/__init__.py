@@ -436,3 +436,28 @@ def awq_repack_zeros(qzeros: torch.Tensor) -> torch.Tensor:
 def dequantize_block_fp8(weight: torch.Tensor, scale_inv: torch.Tensor, block, dtype=torch.bfloat16) -> torch.Tensor:
     """entrypoints/convert/converters/fp8block_dequantizer.py:111-158: (w.to(f32) * s.to(f32) per block).to(dtype)"""
     return dequantize(weight, scale_inv.to(torch.float32), None, strategy="block", block_structure=list(block)).to(dtype)
+
+
+# --------------------------------------------------------------------------- #
+# BASELINE config 4: Sparse24BitMask + int4, restated as the composition of the restated / pinned pieces above
+# (parity unpinned as a composite: the compressor pair is absent from the reference snapshot)
+# --------------------------------------------------------------------------- #
+def sparse24_quantize_pack(x: torch.Tensor, scale: torch.Tensor, zero_point, *, strategy="group", group_size=None, num_bits=4):
+    """mask = 2:4 selection on |x| (sparse24_compress); codes = quantize(x)[mask] (forward.py:36-73); -> (pack_to_int32(codes), pack_bitmasks(mask))"""
+    rows, cols = x.shape
+    _, bitmask = sparse24_compress(x)
+    mask = unpack_bitmasks(bitmask, (rows, cols))
+    q = quantize(x, scale, zero_point, strategy=strategy, group_size=group_size, num_bits=num_bits, dtype=torch.int8)
+    kept = q[mask].view(rows, cols // 2).contiguous()
+    return pack_to_int32(kept, num_bits), bitmask
+
+
+def sparse24_unpack_dequantize(packed: torch.Tensor, bitmask: torch.Tensor, scale: torch.Tensor, zero_point, num_bits: int, shape):
+    """kept codes -> their columns -> dequantize (forward.py:76-145, strategy inferred); dropped columns are +0"""
+    rows, cols = int(shape[0]), int(shape[1])
+    kept = unpack_from_int32(packed, num_bits, (rows, cols // 2))
+    mask = unpack_bitmasks(bitmask, (rows, cols))
+    q = torch.zeros(rows, cols, dtype=torch.int8)
+    q[mask] = kept.reshape(-1)
+    out = dequantize(q, scale, zero_point)
+    return torch.where(mask, out, torch.zeros_like(out))
