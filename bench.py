@@ -329,6 +329,35 @@ def run_b200(a):
         extra["nvfp4_quantize_pack"] = rate(ops.BatchedPlan(N.OP_QUANTIZE_PACK_FP4, cprobs, local).run, n_elems * (2 + 2 / 16 + 0.5), weight_bytes)
         extra["nvfp4_unpack_dequantize"] = rate(ops.BatchedPlan(N.OP_UNPACK_DEQUANTIZE_FP4, uprobs, local).run, n_elems * (0.5 + 1 / 16 + 2), weight_bytes)
         del nib, nback, cprobs, uprobs, sbs, s8s
+        # BASELINE config 4: Sparse24BitMask + int4 on 2:4-pruned weights, w * mask_creator(w) (reference utils/semi_structured_conversions.py:301-330),
+        # g128 scales of the pruned weights; fused 2:4 select + quantize + pack and its inverse, one multi-tensor launch per direction.
+        # Algorithmic traffic per dense element: 2 (bf16) + 0.25 (kept nibbles) + 0.125 (mask) + 2/128 (scale) = 2.39 B.  Parity unpinned.
+        from compressed_tensors_b200.utils.semi_structured_conversions import mask_creator
+        w24 = [w * mask_creator(w).to(w.dtype) for w in ws]
+        s24 = [(w.unflatten(-1, (-1, GROUP)).abs().amax(-1).float() / 7.5).bfloat16() for w in w24]
+        pk24 = [torch.empty(w.shape[0], w.shape[1] // 16, dtype=torch.int32, device=dev) for w in w24]
+        bm24 = [torch.empty(w.shape[0], w.shape[1] // 8, dtype=torch.uint8, device=dev) for w in w24]
+        bk24 = [torch.empty_like(w) for w in w24]
+        c24, d24 = [], []
+        for w, sc, pk, bm, bk in zip(w24, s24, pk24, bm24, bk24):
+            p = ops._resolve(w, sc, None, qargs, None)
+            d = ops._desc(p, w.dtype, sc.dtype, None, torch.bfloat16, torch.int8, None, N.Q_INT, BITS)
+            d.aux = bm.data_ptr()
+            d2 = ops._desc(p, None, sc.dtype, None, None, torch.int8, torch.bfloat16, N.Q_INT, BITS)
+            d2.aux = bm.data_ptr()
+            c24.append((d, w, sc, None, pk))
+            d24.append((d2, pk, sc, None, bk))
+        b24 = n_elems * (2 + 0.25 + 0.125 + 2 / GROUP)
+        extra["cfg4_sparse24_int4_compress"] = rate(ops.BatchedPlan(N.OP_SPARSE24_QUANTIZE_PACK, c24, local).run, b24, weight_bytes)
+        extra["cfg4_sparse24_int4_decompress"] = rate(ops.BatchedPlan(N.OP_SPARSE24_UNPACK_DEQUANTIZE, d24, local).run, b24, weight_bytes)
+        # what the timed launches wrote: decompress(compress(w24)) == fake_quantize(w24) on the kept columns, 0 elsewhere, for three tensors
+        ok24 = True
+        for i in (0, 4, len(w24) - 1):
+            fq = ops.fake_quantize(w24[i], s24[i], None, qargs)
+            ok24 &= bool(torch.equal(bk24[i], torch.where(w24[i] != 0, fq, torch.zeros_like(fq))))
+        extra["cfg4_sparse24_int4_compress"]["round_trip_equals_masked_fake_quantize"] = ok24
+        extra["cfg4_sparse24_int4_compress"]["parity"] = "unpinned composite (compressor pair absent from the reference); pieces pinned, see tests/test_gpu_sparse24q.py"
+        del w24, s24, pk24, bm24, bk24, c24, d24
 
     # end to end through the plugin API on host (pinned) state dicts
     e2e = None

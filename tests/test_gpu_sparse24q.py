@@ -127,3 +127,31 @@ def test_fused_sparse24_int4_batched_llama_layer():
         wp, wb = oracle.sparse24_quantize_pack(w[rows].cpu(), sc[rows].cpu(), None, group_size=128)
         same_values(packed[rows].cpu(), wp, "slab vs oracle")
         same_values(bm[rows].cpu(), wb, "slab mask vs oracle")
+
+
+def test_composite_plugin_round_trip():
+    """the stack as ONE registry plugin with the reference's compressor interface (classmethods on local state dicts, input not mutated)"""
+    from compressed_tensors_b200.compressors import BaseCompressor
+    from compressed_tensors_b200.compressors.sparse.bitmask import SPARSE24_PACK_QUANTIZED
+    from compressed_tensors_b200.quantization import QuantizationArgs, QuantizationScheme
+
+    comp = BaseCompressor.get_value_from_registry(SPARSE24_PACK_QUANTIZED)
+    for sym in (True, False):
+        scheme = QuantizationScheme(targets=["Linear"], weights=QuantizationArgs(num_bits=4, strategy="group", group_size=128, symmetric=sym))
+        g = torch.Generator().manual_seed(5)
+        w = (torch.randn(256, 1024, generator=g) * 0.02).bfloat16()
+        w = (w.to(DEV) * mask_creator(w.to(DEV)).to(w.dtype))
+        sc, zp = _qparams(w.cpu(), "group", 128, sym)
+        sd = {"weight": w, "weight_scale": sc.to(DEV), "weight_zero_point": (zp if zp is not None else torch.zeros(sc.shape, dtype=torch.int8)).to(DEV)}
+        before = {k: v.clone() for k, v in sd.items()}
+        out = comp.compress(sd, scheme)
+        assert all(torch.equal(sd[k], before[k]) for k in sd) and set(sd) == set(before), "input state dict was mutated"
+        assert set(out) == set(comp.compression_param_names(scheme)), sorted(out)
+        wp, wb = oracle.sparse24_quantize_pack(w.cpu(), sc, zp, group_size=128)
+        same_values(out["weight_packed"].cpu(), wp, "plugin packed")
+        same_values(out["bitmask"].cpu(), wb, "plugin mask")
+        back = comp.decompress(out, scheme)
+        assert "weight_packed" not in back and back["weight"].dtype == torch.bfloat16
+        same(back["weight"].cpu(), oracle.sparse24_unpack_dequantize(wp, wb, sc, zp, 4, w.shape), "plugin decompress")
+        meta = comp.compress({k: torch.empty_like(v, device="meta") for k, v in sd.items()}, scheme)
+        assert {k: (tuple(v.shape), v.dtype) for k, v in meta.items() if k != "weight_shape"} == {k: (tuple(v.shape), v.dtype) for k, v in out.items() if k != "weight_shape"}
