@@ -35,6 +35,7 @@ SOURCES = [
     "sparse.cu",
     "bitmask_onepass.cu",
     "fast_sparse24q.cu",
+    "observe_tensor.cu",
     "fast_observe.cu",
     "host_many.cu",
 ]

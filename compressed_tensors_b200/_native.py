@@ -104,6 +104,8 @@ _PROTOS = {
     "ct_awq_repack_int4": (_int, [_vp, _vp, _i64, _i64, _int, _vp]),
     "ct_awq_repack_zeros_int4": (_int, [_vp, _vp, _i64, _i64, _int, _vp]),
     "ct_observe_quantize_channel": (_int, [_descp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "ct_observe_tensor": (_int, [_descp, _vp, _int, _vp, _vp, _int, _vp]),
+    "ct_observe_quantize_tensor": (_int, [_descp, _vp, _vp, _vp, _vp, _int, _vp]),
     "ct_batched": (_int, [_int, _int, _descp, _vp, _vp, _vp, _vp, _int, _vp]),
     "ct_pack_bitmasks": (_int, [_vp, _vp, _i64, _i64, _int, _vp]),
     "ct_unpack_bitmasks": (_int, [_vp, _vp, _i64, _i64, _int, _vp]),

@@ -53,6 +53,8 @@ __all__ = [
     "observe_quantize",
     "observe_quantize_pack",
     "observe_quantize_pack_nvfp4",
+    "observe_tensor_qparams",
+    "observe_tensor_gparam",
     "dequantize_block_fp8",
     "awq_repack",
     "awq_repack_zeros",
@@ -684,6 +686,53 @@ def awq_repack_zeros(qzeros: torch.Tensor) -> torch.Tensor:
     return _awq("ct_awq_repack_zeros_int4", qzeros, (nw, g), g, nw * 8)
 
 
+def _tensor_observer_ok(xd: torch.Tensor) -> bool:
+    return xd.dtype in _FLOAT_DTYPES and xd.is_contiguous() and xd.numel() > 0 and (xd.numel() * xd.element_size()) % 16 == 0 and xd.data_ptr() % 16 == 0
+
+
+def _tensor_desc(xd: torch.Tensor, qtype: int, bits: int, q_dt=None, asym: bool = False) -> N.QuantDesc:
+    d = N.QuantDesc()
+    cols = xd.shape[-1] if xd.ndim >= 1 else 1
+    d.rows, d.cols, d.rdiv, d.cdiv, d.s_row_stride = xd.numel() // max(cols, 1), cols, N.INF, N.INF, 0
+    d.x_dtype = d.scale_dtype = d.compute_dtype = N.DT[xd.dtype]
+    d.zp_dtype = N.DT[torch.int8] if asym else N.DT_NONE
+    d.q_dtype = N.DT[q_dt] if q_dt is not None else N.DT_NONE
+    d.out_dtype, d.qtype, d.num_bits = N.DT_NONE, qtype, bits
+    d.global_scale, d.seff_dtype, d.aux = None, N.DT_NONE, None
+    return d
+
+
+@torch.no_grad()
+def observe_tensor_qparams(x: torch.Tensor, args) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """memoryless min-max observer + calculate_qparams (utils/helpers.py:50-137) for the TENSOR strategy, entirely on the device
+    (`ct_observe_tensor`, kind 0): returns (scale [1] in x.dtype, zero point int8 [1] or None for symmetric schemes), both device
+    tensors -- nothing is read back.  Raises NotImplementedError for what the kernel declines (callers fall back to torch reductions)."""
+    qtype, bits = _qparams(args)
+    symmetric = bool(getattr(args, "symmetric", True))
+    idx = _dev_index(x)
+    xd = _to_dev(x, idx)
+    if not _tensor_observer_ok(xd) or qtype == N.Q_FP4 or (qtype == N.Q_FLOAT and not symmetric):
+        raise NotImplementedError("per-tensor observer kernel: contiguous 16-byte aligned float tensor, int or symmetric fp8 scheme")
+    scale = torch.empty((1,), dtype=x.dtype, device=xd.device)
+    zp = None if symmetric else torch.empty((1,), dtype=torch.int8, device=xd.device)
+    d = _tensor_desc(xd, qtype, bits, asym=not symmetric)
+    N.check(N.lib().ct_observe_tensor(ctypes.byref(d), N.ptr(xd), 0, N.ptr(scale), N.ptr(zp), idx, N.stream_ptr(idx)), "observe_tensor_qparams")
+    return scale, zp
+
+
+@torch.no_grad()
+def observe_tensor_gparam(x: torch.Tensor) -> torch.Tensor:
+    """generate_gparam(x.min(), x.max()) (utils/helpers.py:308-337) on the device: the float32 [1] global scale of NVFP4"""
+    idx = _dev_index(x)
+    xd = _to_dev(x, idx)
+    if not _tensor_observer_ok(xd):
+        raise NotImplementedError("per-tensor observer kernel: contiguous 16-byte aligned float tensor")
+    g = torch.empty((1,), dtype=torch.float32, device=xd.device)
+    d = _tensor_desc(xd, N.Q_FP4, 4)
+    N.check(N.lib().ct_observe_tensor(ctypes.byref(d), N.ptr(xd), 1, N.ptr(g), None, idx, N.stream_ptr(idx)), "observe_tensor_gparam")
+    return g
+
+
 @torch.no_grad()
 def observe_quantize_pack(x: torch.Tensor, args) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
     """Memoryless min-max observer + quantize + pack in ONE pass over the weight:
@@ -757,7 +806,12 @@ def observe_quantize_pack_nvfp4(x: torch.Tensor, args, global_scale: Optional[to
     rows, cols = x.shape
     idx = _dev_index(x)
     xd = _to_dev(x, idx).contiguous()
-    gs = _to_dev(global_scale, idx) if global_scale is not None else generate_gparam(xd.min(), xd.max())
+    if global_scale is not None:
+        gs = _to_dev(global_scale, idx)
+    elif _tensor_observer_ok(xd):
+        gs = observe_tensor_gparam(xd)                       # grid-wide max |x| -> generate_gparam on the device, no torch reduction
+    else:
+        gs = generate_gparam(xd.min(), xd.max())
     gs = gs.reshape(1).to(torch.float32).contiguous()
     if x.dtype in (torch.bfloat16, torch.float16) and cols % 32 == 0 and rows > 0:
         scale = torch.empty((rows, cols // 16), dtype=torch.float8_e4m3fn, device=xd.device)
@@ -784,6 +838,8 @@ def observe_quantize(x: torch.Tensor, args, pack: bool = False) -> Tuple[torch.T
 
       CHANNEL (one scale per row): bf16 / fp16, cols % 8 == 0, cols <= 16384 -> `ct_observe_quantize_channel`
                                    (int8 codes, float8_e4m3fn codes, or 4- / 8-bit packed int32)
+      TENSOR (one scale)         : `ct_observe_quantize_tensor` -- grid-wide min / max, calculate_qparams by the last CTA, then the
+                                   streaming quantize kernel with the device-resident scale; no host round trip (the FP8 preset)
       GROUP + pack               : `observe_quantize_pack`
     Everything else runs the observer with torch reductions on the device and then the quantize kernel."""
     from .quantization.utils.helpers import calculate_qparams
@@ -813,6 +869,16 @@ def observe_quantize(x: torch.Tensor, args, pack: bool = False) -> Tuple[torch.T
         d.zp_dtype = N.DT_NONE if symmetric else N.DT[torch.int8]
         d.q_dtype, d.out_dtype, d.qtype, d.num_bits = N.DT[qdt], N.DT_NONE, qtype, bits
         rc = N.lib().ct_observe_quantize_channel(ctypes.byref(d), N.ptr(xd), N.ptr(scale), N.ptr(zp), N.ptr(out), idx, N.stream_ptr(idx))
+        N.check(rc, "observe_quantize")
+        return _back(out, x), _back(scale, x), (_back(zp, x) if zp is not None else None)
+    if (strategy == "tensor" and _tensor_observer_ok(xd) and qtype in (N.Q_INT, N.Q_FLOAT) and (symmetric or qtype == N.Q_INT)
+            and (bits in (4, 8) if pack else bits == 8) and (not pack or (cols * bits) % 32 == 0)):
+        # ONE call: grid-wide min / max -> calculate_qparams on the device -> quantize (or quantize + pack) with the device-resident scale
+        scale = torch.empty((1,), dtype=x.dtype, device=xd.device)
+        zp = None if symmetric else torch.empty((1,), dtype=torch.int8, device=xd.device)
+        out = torch.empty((rows, cols * bits // 32) if pack else (rows, cols), dtype=qdt, device=xd.device)
+        d = _tensor_desc(xd, qtype, bits, q_dt=qdt, asym=not symmetric)
+        rc = N.lib().ct_observe_quantize_tensor(ctypes.byref(d), N.ptr(xd), N.ptr(scale), N.ptr(zp), N.ptr(out), idx, N.stream_ptr(idx))
         N.check(rc, "observe_quantize")
         return _back(out, x), _back(scale, x), (_back(zp, x) if zp is not None else None)
     if strategy == "group":

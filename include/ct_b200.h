@@ -190,6 +190,19 @@ int ct_awq_repack_zeros_int4(const int32_t* qzeros, int32_t* zero_point_packed, 
  * returns CT_E_UNSUPPORTED. */
 int ct_observe_quantize_channel(const ct_quant_desc* d, const void* x, void* scale_out, void* zp_out, void* out, int device, void* stream);
 
+/* ---- per-TENSOR observers without a host round trip (TENSOR strategy) -------------
+ * ct_observe_tensor: grid-wide min / max of x [rows, cols] (bf16 / fp16 / fp32, byte size % 16 == 0) and, on the device,
+ *   kind 0: calculate_qparams (quantization/utils/helpers.py:50-137) for ONE scale per tensor: scale_out = x dtype [1];
+ *           zp_out = int8 [1] for asymmetric integer schemes, NULL for symmetric ones (d->qtype / d->num_bits give the range)
+ *   kind 1: generate_gparam (helpers.py:308-337): scale_out = float32 [1], the NVFP4 global scale (448 * 6 / max|x|)
+ * ct_observe_quantize_tensor: kind 0 followed, in the same call, by ct_quantize (d->q_dtype = CT_I8 / CT_F8E4M3) or
+ *   ct_quantize_pack_int32 (d->q_dtype = CT_I32) with the fresh device-resident qparams: what
+ *   observer -> calculate_qparams -> quantize(dtype=args.pytorch_dtype()) [-> pack_to_int32] does for the FP8 preset / per-tensor INT
+ *   schemes (BASELINE config 3), with no host synchronisation and, for tensors that fit the L2, the second pass served from it.
+ * Anything else returns CT_E_UNSUPPORTED. */
+int ct_observe_tensor(const ct_quant_desc* d, const void* x, int kind, void* scale_out, void* zp_out, int device, void* stream);
+int ct_observe_quantize_tensor(const ct_quant_desc* d, const void* x, void* scale_out, void* zp_out, void* q_out, int device, void* stream);
+
 /* ---- multi-tensor (whole-model) launches -------------------------------------
  * One persistent launch over `n` independent tensors: the body of the module loop of
  * ModelCompressor.compress_model / decompress_model

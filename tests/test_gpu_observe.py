@@ -132,3 +132,85 @@ def test_channel_observer_equals_unfused_flow_at_full_size():
         assert torch.equal(s, s2) and (z is None or torch.equal(z, z2))
         q2 = ops.quantize_pack(x, s2, z2, a) if pack else ops.quantize(x, s2, z2, a, dtype=a.pytorch_dtype())
         assert torch.equal(q.view(torch.uint8) if q.dtype == torch.float8_e4m3fn else q, q2.view(torch.uint8) if q2.dtype == torch.float8_e4m3fn else q2)
+
+
+# ---- per-TENSOR fused observer (ct_observe_tensor / ct_observe_quantize_tensor) -----------------------------------------------
+def _tensor_oracle(x, qtype, bits, symmetric, pack):
+    mn, mx = x.amin().reshape(1), x.amax().reshape(1)
+    s, z = orc_qparams(mn, mx, num_bits=bits, qtype=qtype, symmetric=symmetric)        # pinned by tests/golden/qparams.pt.gz
+    z = None if symmetric else z
+    q = oracle.quantize(x, s, z, strategy="tensor", num_bits=bits, qtype=qtype, dtype=(torch.float8_e4m3fn if qtype == "float" else torch.int8))
+    return (oracle.pack_to_int32(q, bits) if pack else q), s, z
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("kind", [("float", 8, True, False), ("int", 8, True, False), ("int", 8, False, False), ("int", 4, True, True), ("int", 4, False, True)])
+@pytest.mark.parametrize("shape", [(64, 4096), (1, 8), (300, 1000), (4096, 4096), (14336, 4096)])
+def test_tensor_observer_vs_oracle(dt, kind, shape):
+    """one ABI call: grid-wide min / max -> calculate_qparams on the device (last CTA) -> quantize [+ pack] with the device-resident
+    scale == the oracle's calculate_qparams (golden-pinned) -> quantize -> pack_to_int32; no host round trip in between"""
+    from compressed_tensors_b200.quantization import QuantizationArgs
+
+    qtype, bits, sym, pack = kind
+    if dt == torch.float32 and shape[0] > 4096:
+        pytest.skip("fp32 at this size adds nothing")
+    g = torch.Generator().manual_seed(shape[1] + bits + shape[0])
+    x = (torch.randn(shape, generator=g) * 0.02).to(dt)
+    if shape[0] > 1:
+        x[shape[0] // 2, 3] = -0.31 if sym else 0.5      # the extreme sits in the middle of the tensor, one-sided for the asymmetric case
+    a = QuantizationArgs(num_bits=bits, type=qtype, symmetric=sym, strategy="tensor")
+    launches = N.launch_count()
+    q, s, z = ops.observe_quantize(x.to(DEV), a, pack=pack)
+    assert N.launch_count() - launches == 2, "min/max + qparams kernel, then the streaming quantize kernel"
+    wq, ws, wz = _tensor_oracle(x, qtype, bits, sym, pack)
+    assert s.shape == (1,) and s.dtype == dt
+    same(s.cpu(), ws, "tensor observer scale")
+    if sym:
+        assert z is None
+    else:
+        same(z.cpu(), wz, "tensor observer zero point")
+    if wq.dtype == torch.float8_e4m3fn:
+        same(q.cpu().view(torch.uint8), wq.view(torch.uint8), "tensor observer fp8 codes")
+    else:
+        same(q.cpu(), wq, "tensor observer codes")
+
+
+def test_tensor_observer_corner_cases():
+    from compressed_tensors_b200.quantization import QuantizationArgs
+    from compressed_tensors_b200.quantization.utils import calculate_qparams, generate_gparam
+
+    a8 = QuantizationArgs(num_bits=8, type="float", symmetric=True, strategy="tensor")
+    for x in (torch.zeros(32, 64, dtype=torch.bfloat16), torch.full((16, 16), -0.0, dtype=torch.float16),         # dead tensor: eps scale
+              torch.full((8, 8), 3.0e38, dtype=torch.bfloat16), -torch.rand(64, 64).bfloat16() - 1.0,                # huge; all negative
+              torch.rand(128, 8).half() * 1e-7):                                                                      # subnormal halves
+        xd = x.to(DEV)
+        s, z = ops.observe_tensor_qparams(xd, a8)
+        ws, _ = calculate_qparams(*(t.reshape(1) for t in torch.aminmax(xd)), a8)                                    # host mirror (golden-pinned)
+        same(s, ws, "qparams corner case")
+        assert z is None
+        g = ops.observe_tensor_gparam(xd)
+        same(g, generate_gparam(xd.min(), xd.max()), "gparam corner case")
+        os_, _ = orc_qparams(x.amin().reshape(1), x.amax().reshape(1), num_bits=8, qtype="float", symmetric=True)
+        same(s.cpu(), os_, "qparams corner case vs oracle")
+    # odd sizes are declined loudly (the Python layer falls back to torch reductions)
+    with pytest.raises(NotImplementedError):
+        ops.observe_tensor_qparams(torch.randn(3, 5, device=DEV).bfloat16(), a8)
+    q, s, z = ops.observe_quantize(torch.randn(3, 5, device=DEV).bfloat16(), a8)
+    assert q.dtype == torch.float8_e4m3fn and s.shape == (1,)
+
+
+def test_nvfp4_observer_uses_the_device_gparam():
+    """observe_quantize_pack_nvfp4 without a given global scale: generate_gparam comes from ct_observe_tensor (kind 1), bit-equal to
+    the host mirror's generate_gparam(min, max) (pinned by tests/golden/fp4.pt.gz), and nothing synchronises"""
+    from compressed_tensors_b200.quantization import QuantizationArgs
+    from compressed_tensors_b200.quantization.utils import generate_gparam
+
+    a = QuantizationArgs(num_bits=4, type="float", symmetric=True, strategy="tensor_group", group_size=16)
+    x = (torch.randn(512, 2048, device=DEV) * 0.02).bfloat16()
+    launches = N.launch_count()
+    packed, scale, gs = ops.observe_quantize_pack_nvfp4(x, a)
+    assert N.launch_count() - launches == 2
+    want = generate_gparam(x.min(), x.max())
+    same(gs, want, "global scale")
+    p2, s2, _ = ops.observe_quantize_pack_nvfp4(x, a, global_scale=want)
+    same_values(packed, p2, "nibbles"); same_values(scale.view(torch.uint8), s2.view(torch.uint8), "fp8 scales")
