@@ -36,6 +36,7 @@ SOURCES = [
     "bitmask_onepass.cu",
     "fast_sparse24q.cu",
     "observe_tensor.cu",
+    "cpu_twin.cu",
     "fast_observe.cu",
     "host_many.cu",
 ]
@@ -45,6 +46,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
+    # host code (the CPU twins of the ABI, cpu_twin.cu): OpenMP, and no fused multiply-add contraction -- every op rounds separately
+    "-Xcompiler", "-fopenmp", "-Xcompiler", "-ffp-contract=off",
     "--expt-relaxed-constexpr",
     # parity: never let the compiler relax IEEE semantics
     "--fmad=true", "--prec-div=true", "--prec-sqrt=true", "--ftz=false",
@@ -85,7 +88,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     with cf.ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(lambda s: _compile(s, force, verbose), SOURCES))
-    cmd = [nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
+    cmd = [nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -400,6 +400,21 @@ int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in
                 const void* const* zp, const int32_t* const* g_idx, void* const* out, int device, cudaStream_t stream) {
     const bool bits_op = (op == CT_OP_PACK_INT32 || op == CT_OP_UNPACK_INT32);
     if (n < 0 || (n > 0 && (!descs || !in || (!scale && !bits_op) || !out))) { set_error("null table"); return CT_E_ARG; }
+    if (device == CT_DEVICE_CPU) {
+        // explicit CPU twins (cpu_twin.cu): host pointers, synchronous, tensor by tensor
+        for (int i = 0; i < n; ++i) {
+            int rc;
+            if (bits_op) {
+                rc = cpu_run_bits(op == CT_OP_PACK_INT32, in[i], out[i], descs[i].rows, descs[i].cols, descs[i].num_bits, 1);
+            } else {
+                rc = validate_desc(&descs[i]);
+                if (!rc) rc = check_dtypes(op, descs[i], zp && zp[i]);
+                if (!rc) rc = cpu_run_one(op, descs[i], in[i], scale[i], zp ? zp[i] : nullptr, g_idx ? g_idx[i] : nullptr, out[i]);
+            }
+            if (rc) return rc;
+        }
+        return CT_OK;
+    }
     int rc = check_device(device);
     if (rc) return rc;
     DeviceGuard guard(device);
@@ -507,6 +522,7 @@ static int run_bits(bool pack, const void* in, void* out, int64_t rows, int64_t 
     if (bits < 1 || bits > 8) { set_error("num_bits %d outside [1, 8]", bits); return CT_E_BITS; }
     if (packed_dim != 0 && packed_dim != 1) { set_error("packed_dim must be 0 or 1"); return CT_E_ARG; }
     if (rows < 0 || cols < 0) { set_error("negative shape"); return CT_E_SHAPE; }
+    if (device == CT_DEVICE_CPU) return cpu_run_bits(pack, in, out, rows, cols, bits, packed_dim);
     int rc = check_device(device);
     if (rc) return rc;
     if (rows * cols == 0) return CT_OK;

@@ -21,43 +21,6 @@ __global__ void __launch_bounds__(256) generic_quant_kernel(const __grid_constan
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// bit packing: one thread owns a group of 32 consecutive elements along the packed dimension,
-// which maps to exactly BITS int32 words (helpers.py:62-96).  Words are sums of
-// (code + offset) << pos in wrapping int32 arithmetic, like the reference's scatter_add_.
-// ---------------------------------------------------------------------------------------------
-template <int BITS, class LoadFn>
-__device__ __forceinline__ void pack_group(uint32_t (&words)[BITS], int nvalid, LoadFn load) {
-#pragma unroll
-    for (int k = 0; k < BITS; ++k) words[k] = 0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        if (j < nvalid) {
-            const int32_t u = load(j) + (1 << (BITS - 1));
-            const int bitpos = j * BITS;
-            const int w = bitpos >> 5, sh = bitpos & 31;
-            words[w] += (uint32_t)u << sh;
-            const int ov = sh + BITS - 32;
-            if (ov > 0) words[w + 1] += (uint32_t)(u >> (BITS - ov));
-        }
-    }
-}
-
-template <int BITS, class StoreFn>
-__device__ __forceinline__ void unpack_group(const uint32_t (&words)[BITS], int nvalid, StoreFn store) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        if (j < nvalid) {
-            const int bitpos = j * BITS;
-            const int w = bitpos >> 5, sh = bitpos & 31;
-            uint32_t v = words[w] >> sh;
-            if (sh + BITS > 32) v |= words[w + 1] << (32 - sh);
-            v &= (1u << BITS) - 1u;
-            store(j, (int)v - (1 << (BITS - 1)));
-        }
-    }
-}
-
 // packed_dim == 1: in [rows, cols] -> out [rows, nw]; thread = (row, group)
 template <int BITS>
 __global__ void __launch_bounds__(256) pack_dim1_kernel(const int8_t* __restrict__ in, int32_t* __restrict__ out,

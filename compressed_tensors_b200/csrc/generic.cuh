@@ -18,7 +18,7 @@ struct GParams {
     int se_dt;         // dtype of scale / global_scale; == s_dt (for stored fp8 / E8M0 scales: the float dtype they decode to) without one
 };
 
-__device__ __forceinline__ int64_t scale_index(const GParams& p, int64_t r, int64_t c) {
+CT_HD int64_t scale_index(const GParams& p, int64_t r, int64_t c) {
     int64_t rb = (p.rdiv == 1) ? r : (p.rdiv == CT_DIV_INF ? 0 : r / p.rdiv);
     int64_t cb;
     if (p.gidx) cb = p.gidx[c];
@@ -27,13 +27,13 @@ __device__ __forceinline__ int64_t scale_index(const GParams& p, int64_t r, int6
 }
 
 // the scale every op works with: scale / global_scale in se_dt when there is a global scale (forward_helpers.py:535-536)
-__device__ __forceinline__ float eff_scale(const GParams& p, int64_t si) {
+CT_HD float eff_scale(const GParams& p, int64_t si) {
     const float s = rnd_dt(load_as_f32(p.scale, si, p.s_dt), p.se_dt);
-    return p.gs ? rnd_dt(__fdiv_rn(s, *p.gs), p.se_dt) : s;
+    return p.gs ? rnd_dt(hd_div(s, *p.gs), p.se_dt) : s;
 }
 
 // quantized value (in compute dtype, as fp32) of x[r, c]
-__device__ __forceinline__ float quant_at(const GParams& p, int64_t r, int64_t c) {
+CT_HD float quant_at(const GParams& p, int64_t r, int64_t c) {
     const int64_t si = scale_index(p, r, c);
     const float x = load_as_f32(p.in, r * p.cols + c, p.x_dt);
     const float s = eff_scale(p, si);
@@ -43,12 +43,49 @@ __device__ __forceinline__ float quant_at(const GParams& p, int64_t r, int64_t c
 }
 
 // dequantized value of code q (already widened to fp32) at [r, c], rounded per op to scale dtype
-__device__ __forceinline__ float dequant_at(const GParams& p, float q, int64_t r, int64_t c) {
+CT_HD float dequant_at(const GParams& p, float q, int64_t r, int64_t c) {
     const int64_t si = scale_index(p, r, c);
     float v = rnd_dt(q, p.se_dt);
     const float s = eff_scale(p, si);
-    if (p.zp) v = rnd_dt(__fsub_rn(v, rnd_dt(load_as_f32(p.zp, si, p.zp_dt), p.se_dt)), p.se_dt);
-    return rnd_dt(__fmul_rn(v, s), p.se_dt);
+    if (p.zp) v = rnd_dt(hd_sub(v, rnd_dt(load_as_f32(p.zp, si, p.zp_dt), p.se_dt)), p.se_dt);
+    return rnd_dt(hd_mul(v, s), p.se_dt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// bit packing: one thread owns a group of 32 consecutive elements along the packed dimension,
+// which maps to exactly BITS int32 words (helpers.py:62-96).  Words are sums of
+// (code + offset) << pos in wrapping int32 arithmetic, like the reference's scatter_add_.
+// ---------------------------------------------------------------------------------------------
+template <int BITS, class LoadFn>
+CT_HD void pack_group(uint32_t (&words)[BITS], int nvalid, LoadFn load) {
+#pragma unroll
+    for (int k = 0; k < BITS; ++k) words[k] = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (j < nvalid) {
+            const int32_t u = load(j) + (1 << (BITS - 1));
+            const int bitpos = j * BITS;
+            const int w = bitpos >> 5, sh = bitpos & 31;
+            words[w] += (uint32_t)u << sh;
+            const int ov = sh + BITS - 32;
+            if (ov > 0) words[w + 1] += (uint32_t)(u >> (BITS - ov));
+        }
+    }
+}
+
+template <int BITS, class StoreFn>
+CT_HD void unpack_group(const uint32_t (&words)[BITS], int nvalid, StoreFn store) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (j < nvalid) {
+            const int bitpos = j * BITS;
+            const int w = bitpos >> 5, sh = bitpos & 31;
+            uint32_t v = words[w] >> sh;
+            if (sh + BITS > 32) v |= words[w + 1] << (32 - sh);
+            v &= (1u << BITS) - 1u;
+            store(j, (int)v - (1 << (BITS - 1)));
+        }
+    }
 }
 
 static GParams make_params(const ct_quant_desc& d, const void* in, const void* scale, const void* zp,

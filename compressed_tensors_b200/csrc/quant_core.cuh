@@ -18,6 +18,9 @@
 // IEEE division (div.rn.f32).
 #pragma once
 
+#include <cmath>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace ctb {
@@ -185,30 +188,100 @@ __device__ __forceinline__ float e4m3_to_f32(uint32_t byte) {
 
 // ------------------------------------------------------------------------------------
 // scalar (fp32 compute dtype / generic path) helpers.  `rnd` narrows to dtype dt and widens back.
+// These are __host__ __device__: the generic kernels (generic.cu) and the CPU twins of the ABI (cpu_twin.cu, device = -1) run the
+// SAME per-element arithmetic source.  On the host the IEEE operators stand in for the round-to-nearest intrinsics (the library is
+// built without fast-math and with -ffp-contract=off) and cuda_fp8.h's software conversion for the e4m3 PTX instruction.
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ float rnd_dt(float v, int dt) {
-    if (dt == CT_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+#define CT_HD __host__ __device__ __forceinline__
+
+CT_HD float hd_div(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+CT_HD float hd_add(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+CT_HD float hd_sub(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+CT_HD float hd_mul(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+CT_HD uint8_t hd_f32_to_e4m3(float v) {
+#ifdef __CUDA_ARCH__
+    return (uint8_t)(f32x2_to_e4m3x2(v, 0.f) & 0xffu);
+#else
+    return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
+#endif
+}
+CT_HD float hd_e4m3_to_f32(uint32_t byte) {
+#ifdef __CUDA_ARCH__
+    return e4m3_to_f32(byte);
+#else
+    const __half_raw h = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)(byte & 0xffu), __NV_E4M3);
+    return __half2float(__half(h));
+#endif
+}
+// bfloat16 round-to-nearest-even on raw bits: cuda_bf16.h's host conversions are correct but ~10x slower than this on a CPU
+CT_HD uint16_t hd_bf16_bits(float v) {
+#ifdef __CUDA_ARCH__
+    return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+#else
+    uint32_t u;
+    memcpy(&u, &v, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x0040u);   // NaN stays NaN (quiet)
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+#endif
+}
+CT_HD float hd_bf16_value(uint16_t h) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float((uint32_t)h << 16);
+#else
+    const uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+CT_HD float rnd_dt(float v, int dt) {
+    if (dt == CT_BF16) return hd_bf16_value(hd_bf16_bits(v));
     if (dt == CT_F16) return __half2float(__float2half_rn(v));
     return v;
 }
-__device__ __forceinline__ float load_as_f32(const void* p, int64_t i, int dt) {
+CT_HD float load_as_f32(const void* p, int64_t i, int dt) {
     switch (dt) {
     case CT_F32: return reinterpret_cast<const float*>(p)[i];
     case CT_F16: return __half2float(reinterpret_cast<const __half*>(p)[i]);
-    case CT_BF16: return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+    case CT_BF16: return hd_bf16_value(reinterpret_cast<const uint16_t*>(p)[i]);
     case CT_I8: return (float)reinterpret_cast<const int8_t*>(p)[i];
     case CT_U8: return (float)reinterpret_cast<const uint8_t*>(p)[i];
-    case CT_F8E4M3: return e4m3_to_f32(reinterpret_cast<const uint8_t*>(p)[i]);
-    case CT_I32: return __int2float_rn(reinterpret_cast<const int32_t*>(p)[i]);
-    case CT_I64: return __ll2float_rn(reinterpret_cast<const int64_t*>(p)[i]);
+    case CT_F8E4M3: return hd_e4m3_to_f32(reinterpret_cast<const uint8_t*>(p)[i]);
+    case CT_I32: return (float)reinterpret_cast<const int32_t*>(p)[i];
+    case CT_I64: return (float)reinterpret_cast<const int64_t*>(p)[i];
     case CT_E8M0: {   // stored MX scale: 2^(e - 127) decoded through bfloat16 (mx_utils.py:43-44), so e = 255 is +inf
         const int e = (int)reinterpret_cast<const uint8_t*>(p)[i];
-        return e == 255 ? __int_as_float(0x7f800000) : ldexpf(1.0f, e - 127);
+        return e == 255 ? INFINITY : ldexpf(1.0f, e - 127);
     }
     default: return 0.f;
     }
 }
-__device__ __forceinline__ float clamp_nan(float v, float lo, float hi) {
+CT_HD float clamp_nan(float v, float lo, float hi) {
     // torch.clamp propagates NaN
     return (v != v) ? v : fminf(fmaxf(v, lo), hi);
 }
@@ -216,7 +289,7 @@ __device__ __forceinline__ uint8_t f32_to_e4m3_byte(float v) { return (uint8_t)(
 
 // FP4_E2M1_DATA.cast_to_fp4 (quantization/utils/fp4_utils.py:77-98) on one value: |x| snapped by the closed / open
 // interval ladder, times torch.sign(x) -- so +-0 -> +0, small negatives -> -0, NaN stays NaN
-__device__ __forceinline__ float fp4_round(float v) {
+CT_HD float fp4_round(float v) {
     const float a = fabsf(v);
     float r = a <= 0.25f ? 0.0f : a < 0.75f ? 0.5f : a <= 1.25f ? 1.0f : a < 1.75f ? 1.5f : a <= 2.5f ? 2.0f : a < 3.5f ? 3.0f : a <= 5.0f ? 4.0f : 6.0f;
     if (v != v) return v;
@@ -235,22 +308,22 @@ __device__ __forceinline__ float fp4_value(uint32_t nib) {
 }
 
 // value of `quantized_ground` before the final .to(dtype), in compute dtype cd
-__device__ __forceinline__ float quant_scalar(float x, float s, bool has_zp, float zp_in_xdt, int cd, int qtype, float qmin, float qmax) {
-    float t = rnd_dt(__fdiv_rn(x, s), cd);
-    if (has_zp) t = rnd_dt(__fadd_rn(t, zp_in_xdt), cd);
+CT_HD float quant_scalar(float x, float s, bool has_zp, float zp_in_xdt, int cd, int qtype, float qmin, float qmax) {
+    float t = rnd_dt(hd_div(x, s), cd);
+    if (has_zp) t = rnd_dt(hd_add(t, zp_in_xdt), cd);
     t = clamp_nan(t, qmin, qmax);
     if (qtype == CT_Q_INT) t = rintf(t);
     else if (qtype == CT_Q_FP4) t = fp4_round(t);
-    else t = (t != t) ? t : e4m3_to_f32(f32_to_e4m3_byte(t));
+    else t = (t != t) ? t : hd_e4m3_to_f32(hd_f32_to_e4m3(t));
     return t;
 }
-__device__ __forceinline__ void store_from_f32(void* p, int64_t i, int dt, float v) {
+CT_HD void store_from_f32(void* p, int64_t i, int dt, float v) {
     switch (dt) {
     case CT_F32: reinterpret_cast<float*>(p)[i] = v; break;
     case CT_F16: reinterpret_cast<__half*>(p)[i] = __float2half_rn(v); break;
-    case CT_BF16: reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v); break;
-    case CT_I8: reinterpret_cast<int8_t*>(p)[i] = (v != v || isinf(v)) ? (int8_t)0 : (int8_t)(int)v; break;
-    case CT_F8E4M3: reinterpret_cast<uint8_t*>(p)[i] = f32_to_e4m3_byte(v); break;
+    case CT_BF16: reinterpret_cast<uint16_t*>(p)[i] = hd_bf16_bits(v); break;
+    case CT_I8: reinterpret_cast<int8_t*>(p)[i] = (v != v || v - v != 0.f) ? (int8_t)0 : (int8_t)(int)v; break;   // NaN / inf -> 0
+    case CT_F8E4M3: reinterpret_cast<uint8_t*>(p)[i] = hd_f32_to_e4m3(v); break;
     case CT_I32: reinterpret_cast<int32_t*>(p)[i] = (int)v; break;
     default: break;
     }

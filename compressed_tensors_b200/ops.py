@@ -18,7 +18,9 @@ no eager / CPU fallback.  Meta tensors only get their output shape and dtype com
 from __future__ import annotations
 
 import ctypes
+import functools
 import math
+import threading
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -68,7 +70,15 @@ _HOST_PIPELINE_MIN_BYTES = 8 << 20
 # --------------------------------------------------------------------------------------------
 # device staging
 # --------------------------------------------------------------------------------------------
+_CPU = -1              # CT_DEVICE_CPU: the explicit host twins of the seven per-tensor hot-path entry points (csrc/cpu_twin.cu)
+_mode = threading.local()
+
+
 def _dev_index(*tensors: Optional[torch.Tensor]) -> int:
+    """where the call runs: a CUDA device index, or _CPU when the eager body was selected (ImplBackend: no usable CUDA device, or
+    CT_ENFORCE_EAGER).  Never a silent fallback: the CUDA backend on a GPU-less host raises."""
+    if getattr(_mode, "cpu", False):
+        return _CPU
     for t in tensors:
         if t is not None and t.is_cuda:
             return N.require_device(t.device)
@@ -78,6 +88,8 @@ def _dev_index(*tensors: Optional[torch.Tensor]) -> int:
 def _to_dev(t: Optional[torch.Tensor], idx: int) -> Optional[torch.Tensor]:
     if t is None:
         return None
+    if idx == _CPU:
+        return t.detach().cpu().contiguous()
     if t.is_cuda:
         if t.device.index != idx:
             raise ValueError(f"tensors live on different CUDA devices ({t.device} vs cuda:{idx})")
@@ -86,7 +98,11 @@ def _to_dev(t: Optional[torch.Tensor], idx: int) -> Optional[torch.Tensor]:
 
 
 def _back(out: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
-    return out if like.is_cuda else out.cpu()
+    return out if like.device == out.device else out.to(like.device)
+
+
+def _stream(idx: int):
+    return None if idx == _CPU else N.stream_ptr(idx)
 
 
 # --------------------------------------------------------------------------------------------
@@ -115,7 +131,7 @@ def pack_to_int32(value: torch.Tensor, num_bits: int, packed_dim: int = 1) -> to
     idx = _dev_index(value)
     v = _to_dev(value, idx)
     out = torch.empty(out_shape, dtype=torch.int32, device=v.device)
-    rc = N.lib().ct_pack_int32(N.ptr(v), N.ptr(out), rows, cols, int(num_bits), int(packed_dim), idx, N.stream_ptr(idx))
+    rc = N.lib().ct_pack_int32(N.ptr(v), N.ptr(out), rows, cols, int(num_bits), int(packed_dim), idx, _stream(idx))
     N.check(rc, "pack_to_int32")
     out = _back(out, value)
     if packed_dim == 0:
@@ -155,7 +171,7 @@ def unpack_from_int32(value: torch.Tensor, num_bits: int, shape: Sequence[int], 
     idx = _dev_index(value)
     v = _to_dev(value, idx)
     out = torch.empty((rows, cols), dtype=torch.int8, device=v.device)
-    rc = N.lib().ct_unpack_int32(N.ptr(v), N.ptr(out), rows, cols, int(num_bits), int(packed_dim), idx, N.stream_ptr(idx))
+    rc = N.lib().ct_unpack_int32(N.ptr(v), N.ptr(out), rows, cols, int(num_bits), int(packed_dim), idx, _stream(idx))
     N.check(rc, "unpack_from_int32")
     return _back(out, value)
 
@@ -293,7 +309,8 @@ def _run(fn_name: str, op: int, d: N.QuantDesc, p: _Problem, src: torch.Tensor, 
     idx = _dev_index(src, p.scale)
     gs = getattr(p, "gs", None)
     if (
-        on_cpu
+        idx != _CPU
+        and on_cpu
         and p.g_idx is None
         and gs is None
         and op not in (N.OP_QUANTIZE_PACK_FP4, N.OP_UNPACK_DEQUANTIZE_FP4)
@@ -315,9 +332,9 @@ def _run(fn_name: str, op: int, d: N.QuantDesc, p: _Problem, src: torch.Tensor, 
     gs_dev = _to_dev(gs, idx)   # one float32 on the device, read by the kernel (kept alive until the call returns)
     d.global_scale = gs_dev.data_ptr() if gs_dev is not None else None
     out = torch.empty(out_shape, dtype=out_dtype, device=s_dev.device)
-    rc = getattr(lib, fn_name)(ctypes.byref(d), N.ptr(s_dev), N.ptr(sc), N.ptr(zp), N.ptr(gi), N.ptr(out), idx, N.stream_ptr(idx))
+    rc = getattr(lib, fn_name)(ctypes.byref(d), N.ptr(s_dev), N.ptr(sc), N.ptr(zp), N.ptr(gi), N.ptr(out), idx, _stream(idx))
     N.check(rc, fn_name)
-    return out.cpu() if on_cpu else out
+    return _back(out, src)
 
 
 def _global_scale(scale, global_scale):
@@ -1203,3 +1220,40 @@ def sparse24_unpack_dequantize(packed: torch.Tensor, bitmask: torch.Tensor, scal
     else:
         N.check(rc, "sparse24_unpack_dequantize")
     return _back(out, packed)
+
+
+# --------------------------------------------------------------------------------------------
+# ImplBackend wiring (reference utils/impl_backend.py:23-134): the seven per-tensor hot-path ops are entrypoints.
+#   backend "<op>_sm100": the CUDA kernels; req = a CUDA device is usable (CPU tensors are then staged through it, as before)
+#   eager body "<op>_eager": the library's own host code (device = -1 twins, csrc/cpu_twin.cu) -- what a GPU-less host and
+#                            CT_ENFORCE_EAGER=1 get.  Results are bit-identical (same per-element source as the generic kernels).
+# --------------------------------------------------------------------------------------------
+def _cuda_usable(*args, **kwargs) -> bool:
+    return torch.cuda.is_available()
+
+
+def _wire_impl_backend():
+    from .utils.impl_backend import ImplBackend
+
+    for name in ("pack_to_int32", "unpack_from_int32", "quantize", "dequantize", "fake_quantize", "quantize_pack", "unpack_dequantize"):
+        fn = globals()[name]
+
+        def cuda_fn(*a, _fn=fn, **k):
+            return _fn(*a, **k)
+
+        def eager_fn(*a, _fn=fn, **k):
+            prev = getattr(_mode, "cpu", False)
+            _mode.cpu = True
+            try:
+                return _fn(*a, **k)
+            finally:
+                _mode.cpu = prev
+
+        functools.update_wrapper(cuda_fn, fn)
+        functools.update_wrapper(eager_fn, fn)
+        cuda_fn.__name__, eager_fn.__name__ = f"{name}_sm100", f"{name}_eager"
+        ImplBackend.register(name, req=_cuda_usable, priority=0)(cuda_fn)
+        globals()[name] = ImplBackend.entrypoint(name)(eager_fn)
+
+
+_wire_impl_backend()

@@ -19,8 +19,13 @@
  *   - reentrant, no global mutable state besides per-device lazily created scratch
  *     guarded by a mutex (the reference's convert_checkpoint calls decompress from a
  *     thread pool: entrypoints/convert/convert_checkpoint.py:110-134).
- *   - there is NO CPU implementation behind this ABI: with no usable CUDA device every
- *     compute entry point fails with CT_E_NODEV.
+ *   - NO SILENT CPU FALLBACK: `device` >= 0 without a usable B200 fails with CT_E_NODEV, always.  The seven per-tensor
+ *     entry points of the hot path (ct_pack_int32, ct_unpack_int32, ct_quantize, ct_dequantize, ct_fake_quantize,
+ *     ct_quantize_pack_int32, ct_unpack_dequantize_int32, and ct_batched over them) have an EXPLICIT CPU twin: pass
+ *     device = CT_DEVICE_CPU (-1) with HOST pointers and the call runs synchronously in host code of this library
+ *     (csrc/cpu_twin.cu; same per-element source as the generic CUDA kernels), `stream` ignored.  That is the body the reference
+ *     calls "eager" (utils/impl_backend.py:98-123): what a GPU-less host and CT_ENFORCE_EAGER=1 get.  Every other entry point
+ *     answers CT_E_NODEV / CT_E_UNSUPPORTED for device = -1.
  */
 #ifndef CT_B200_H
 #define CT_B200_H
@@ -60,6 +65,7 @@ typedef enum ct_dtype_t {
 typedef enum ct_qtype_t { CT_Q_INT = 0, CT_Q_FLOAT = 1, CT_Q_FP4 = 2 } ct_qtype_t;
 
 #define CT_DIV_INF INT64_MAX
+#define CT_DEVICE_CPU (-1)   /* explicit CPU twin of the per-tensor entry points (see the conventions above) */
 
 /*
  * One 2-D quantization problem: x is [rows, cols] row-major contiguous.

@@ -203,11 +203,14 @@ def test_impl_backend_surface():
         return x
 
     assert op(3) == 6 and op(-3) == -3 and calls == ["fast", "body"]
-    assert ImplBackend.call("_ct_b200_test_op", 2) == 4
+    assert ImplBackend.call("fast", 2) == 4 and ImplBackend.call("op", 2) == 2     # by function name, bypassing the checks
+    with pytest.raises(KeyError):
+        ImplBackend.call("disabled", 1)
+    with pytest.raises(ValueError, match="already registered"):
+        ImplBackend.register("_ct_b200_other", lambda x: True, "0")(fast)
     os.environ["CT_ENFORCE_EAGER"] = "1"
     try:
-        with pytest.raises(RuntimeError):
-            op(1)
+        assert op(1) == 1, "CT_ENFORCE_EAGER: the entrypoint's own (eager) body runs even though a backend accepts the arguments"
     finally:
         del os.environ["CT_ENFORCE_EAGER"]
 

@@ -79,7 +79,7 @@ def test_fused_sparse24_int4_vs_oracle(shape, dtype, strategy, group, sym, fused
     same_values(got_p.cpu(), want_p, "packed words")
     if shape[0] >= 64:
         # (row 0 holds an all-zero quad, where topk's choice inside mask_creator is implementation-defined)
-        same_values(ops.unpack_bitmasks(got_b, shape).cpu()[1:], mask_creator(w)[1:], "on 2:4-pruned input the mask is mask_creator's (golden-pinned)")
+        same_values(ops.unpack_bitmasks(got_b, shape).cpu()[1:], mask_creator(w)[1:].bool(), "on 2:4-pruned input the mask is mask_creator's (golden-pinned)")
     # the way back
     want_d = oracle.sparse24_unpack_dequantize(want_p, want_b, sc, zp, 4, shape)
     launches = N.launch_count()

@@ -44,18 +44,25 @@ def test_every_declared_symbol_cites_the_reference_and_is_mapped_in_integration_
     assert len(re.findall(r"\.py:\d+", hdr)) >= 20, "the header should cite reference file:line for its entry points"
 
 
-def test_no_cpu_path():
-    """without a GPU every compute entry point must refuse (never fall back)"""
+def test_no_silent_cpu_fallback():
+    """without a GPU a CUDA entry point (device >= 0) refuses; host code runs only when asked for explicitly (device = -1 /
+    ImplBackend's eager body), and only for the seven per-tensor hot-path ops -- everything else still raises"""
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     assert N.lib().ct_device_count() == 0
     q = torch.zeros(4, 32, dtype=torch.int8)
-    with pytest.raises(N.NativeLibraryError):
-        ops.pack_to_int32(q, 4)
     out = torch.zeros(4, 4, dtype=torch.int32)
     rc = N.lib().ct_pack_int32(N.ptr(q), N.ptr(out), 4, 32, 4, 1, 0, None)
     assert rc == N.CT_E_NODEV
     assert "no CPU path" in N.last_error() or "CUDA" in N.last_error()
+    from compressed_tensors_b200.utils import ImplBackend
+
+    with pytest.raises(N.NativeLibraryError):
+        ImplBackend.call("pack_to_int32_sm100", q, 4)
+    for fn, args in ((ops.sparse24_compress, (torch.zeros(4, 32, dtype=torch.bfloat16),)), (ops.cast_to_fp4, (torch.zeros(4, 32),)),
+                     (ops.pack_bitmasks, (torch.zeros(4, 32, dtype=torch.bool),)), (ops.bitmask_compress, (torch.zeros(4, 32, dtype=torch.bfloat16),))):
+        with pytest.raises(N.NativeLibraryError):
+            fn(*args)
 
 
 def test_only_test_infrastructure_touches_the_oracle():
