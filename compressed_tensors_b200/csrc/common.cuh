@@ -106,6 +106,11 @@ __device__ __forceinline__ uint32_t ldg_stream4(const void* p) {
 __device__ __forceinline__ void stg_stream16(void* p, const uint4& v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// 256-bit store (sm_100: STG.E.NA.ENL2.256): one thread writes 32 contiguous bytes, p 32-byte aligned
+__device__ __forceinline__ void stg_stream32(void* p, const uint32_t (&o)[8]) {
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+                 "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+}
 __device__ __forceinline__ void stg_stream8(void* p, const uint2& v) {
     asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }

@@ -38,6 +38,15 @@ static int validate_desc(const ct_quant_desc* d) {
     return CT_OK;
 }
 
+// Job tables of multi-tensor launches normally reach the device with one cudaMemcpyAsync from a host image -- a pageable-memory copy,
+// which a stream capture rejects.  While the stream is being captured the table travels as KERNEL PARAMETERS instead (32 jobs = 3.3 KB
+// per launch of this one-warp kernel; parameters are copied into the graph node at capture time), so a whole-model ct_batched call can
+// be captured once and replayed.
+struct JobBlock { Job j[32]; };
+static __global__ void upload_jobs_kernel(Job* dst, const __grid_constant__ JobBlock blk, int n) {
+    if ((int)threadIdx.x < n) dst[threadIdx.x] = blk.j[threadIdx.x];
+}
+
 struct Plan {
     bool fast;
     FastSig sig;
@@ -267,7 +276,7 @@ static Plan plan_fp4(int op, const ct_quant_desc& d, const void* in, const void*
 }
 
 // fused 2:4 select + int4 (fast_sparse24q.cu).  compress: chunk = 8 dense elements, unit = 4 chunks; decompress: chunk = 16 dense
-// elements (4 bytes of nibbles), unit = 2 chunks.  Full rows of scales only (flat scale index), cols % 32 == 0.
+// elements (4 bytes of nibbles) = one unit.  Full rows of scales only (flat scale index), cols % 32 == 0.
 static Plan plan_s24(int op, const ct_quant_desc& d, const void* in, const void* scale, const void* zp, const int32_t* g_idx, void* out) {
     Plan p;
     p.fast = false;
@@ -281,12 +290,13 @@ static Plan plan_s24(int op, const ct_quant_desc& d, const void* in, const void*
     if (!flat_divisor(d, D) || (!is_inf(D) && D % 32 != 0)) return p;
     if (zp && d.zp_dtype != CT_I8) return p;
     const bool comp = (op == CT_OP_SPARSE24_QUANTIZE_PACK);
+    if (!comp && (reinterpret_cast<uintptr_t>(out) & 31u) != 0) return p;   // the expansion writes with 256-bit stores
     const int p_dt = comp ? d.x_dtype : d.out_dtype;
     if (p_dt != CT_BF16 && p_dt != CT_F16) return p;
     if (d.scale_dtype != p_dt || (comp && d.compute_dtype != p_dt)) return p;
     const int64_t chunk = comp ? 8 : 16;
     p.fast = true;
-    p.sig = FastSig{comp ? F_S24_QUANTPACK : F_S24_UNPACKDEQ, p_dt, 4, zp ? 1 : 0, comp ? 4 : 2};
+    p.sig = FastSig{comp ? F_S24_QUANTPACK : F_S24_UNPACKDEQ, p_dt, 4, zp ? 1 : 0, comp ? 4 : 1};
     p.job.in = reinterpret_cast<const uint8_t*>(in);
     p.job.scale = scale;
     p.job.zp = zp;
@@ -488,7 +498,20 @@ int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in
             const size_t tbl_bytes = many ? jobs.size() * sizeof(Job) : 0;
             rc = scratch_alloc(reinterpret_cast<void**>(&scratch), 16 + tbl_bytes, device, stream);
             if (rc) return rc;
-            if (many) {
+            cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+            if (many) cudaStreamIsCapturing(stream, &capturing);
+            if (many && capturing == cudaStreamCaptureStatusActive) {
+                CT_CUDA_TRY(cudaMemsetAsync(scratch, 0, 16, stream));
+                for (size_t o = 0; o < jobs.size(); o += 32) {
+                    JobBlock blk;
+                    const int cnt = (int)(jobs.size() - o < 32 ? jobs.size() - o : 32);
+                    memcpy(blk.j, jobs.data() + o, (size_t)cnt * sizeof(Job));
+                    upload_jobs_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<Job*>(scratch + 16) + o, blk, cnt);
+                }
+                count_launch((int)((jobs.size() + 31) / 32));
+                CT_CUDA_TRY(cudaGetLastError());
+                lp.tbl.jobs = reinterpret_cast<const Job*>(scratch + 16);
+            } else if (many) {
                 std::vector<uint8_t> img(16 + tbl_bytes, 0);
                 memcpy(img.data() + 16, jobs.data(), tbl_bytes);
                 CT_CUDA_TRY(cudaMemcpyAsync(scratch, img.data(), img.size(), cudaMemcpyHostToDevice, stream));

@@ -14,8 +14,8 @@
 //
 // Both directions are functors on the streaming pipelines of stream.cuh (TMA ring + dynamic tile claims):
 //   Sparse24QuantPackOp    chunk = 8 dense elements (16 B in), unit = 4 chunks: 8 quads -> 8 B of nibbles + 4 mask bytes
-//   Sparse24UnpackDequantOp chunk = 16 dense elements (4 B of nibbles in, streamed through the ring; the 2 mask bytes come with the
-//                           scale prefetch), unit = 2 chunks: 64 B out
+//   Sparse24UnpackDequantOp chunk = unit = 16 dense elements (4 B of nibbles in, streamed through the ring; the 2 mask bytes come with
+//                           the scale prefetch): 32 B out as one 256-bit store
 // The second tensor (the bitmask) travels in Job::aux.
 #include "engine.h"
 #include "ops.cuh"
@@ -67,15 +67,17 @@ struct Sparse24QuantPackOp {
 template <class P, int ZP>
 struct Sparse24UnpackDequantOp {
     static constexpr int IN_BYTES = 4;    // per chunk of 16 dense elements: 8 kept codes
-    static constexpr int GROUP = 2;
+    static constexpr int GROUP = 1;       // one thread = one chunk = 32 contiguous output bytes = ONE 256-bit store: consecutive lanes write
+                                          // consecutive 32-byte sectors (two 16-byte stores per lane would leave every store instruction
+                                          // with half-filled sectors)
     struct Raw {
         RawQP qp;
-        uint32_t mask;   // the unit's 4 mask bytes
+        uint32_t mask;   // the chunk's 2 mask bytes
     };
     __device__ static __forceinline__ Raw prefetch(const Job& J, uint32_t gc) {
         Raw r;
         r.qp = fetch_qp<P, ZP>(J, gc);
-        r.mask = __ldg(reinterpret_cast<const uint32_t*>(J.aux) + (gc >> 1));
+        r.mask = __ldg(reinterpret_cast<const unsigned short*>(J.aux) + gc);
         return r;
     }
     // kept pair v = {first kept, second kept} of a quad, b = its 4 mask bits -> the quad's 4 elements in two words.
@@ -90,24 +92,18 @@ struct Sparse24UnpackDequantOp {
         o01 = __byte_perm(v, 0u, s0 | (s1 << 8));
         o23 = __byte_perm(v, 0u, s2 | (s3 << 8));
     }
-    __device__ static __forceinline__ void run(const Job& J, const Common&, const Raw& r, uint32_t gc0, const uint32_t (&w)[2][1], int) {
+    __device__ static __forceinline__ void run(const Job& J, const Common&, const Raw& r, uint32_t gc, const uint32_t (&w)[1][1], int) {
         const uint32_t s2 = scale_t2<P>(r.qp), zp2 = zp_t2<P, ZP>(r.qp);
+        const uint32_t word = w[0][0];
+        uint32_t o[8];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const uint32_t word = w[c][0];
-            const uint32_t m16 = (r.mask >> (16 * c)) & 0xffffu;
-            uint32_t o[8];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                // nibble u = code + 8 in [0, 15]; (EXP | u) is the T value EXPVAL + u exactly; subtract EXPVAL + 8 (UnpackDequantOp's trick)
-                const uint32_t lo = (word >> (8 * q)) & 0xfu, hi = (word >> (8 * q + 4)) & 0xfu;
-                const uint32_t v = dq_tail2<P, ZP>(sub2<P>(P::ONE_TWENTY_EIGHT2 | lo | (hi << 16), P::OFF8_2), zp2, s2);
-                scatter_quad(v, (m16 >> (4 * q)) & 0xfu, o[2 * q], o[2 * q + 1]);
-            }
-            uint8_t* dst = J.out + (size_t)(gc0 + c) * 32;
-            stg_stream16(dst, make_uint4(o[0], o[1], o[2], o[3]));
-            stg_stream16(dst + 16, make_uint4(o[4], o[5], o[6], o[7]));
+        for (int q = 0; q < 4; ++q) {
+            // nibble u = code + 8 in [0, 15]; (EXP | u) is the T value EXPVAL + u exactly; subtract EXPVAL + 8 (UnpackDequantOp's trick)
+            const uint32_t lo = (word >> (8 * q)) & 0xfu, hi = (word >> (8 * q + 4)) & 0xfu;
+            const uint32_t v = dq_tail2<P, ZP>(sub2<P>(P::ONE_TWENTY_EIGHT2 | lo | (hi << 16), P::OFF8_2), zp2, s2);
+            scatter_quad(v, (r.mask >> (4 * q)) & 0xfu, o[2 * q], o[2 * q + 1]);
         }
+        stg_stream32(J.out + (size_t)gc * 32, o);
     }
 };
 

@@ -214,9 +214,9 @@ int ct_observe_quantize_tensor(const ct_quant_desc* d, const void* x, void* scal
  * ModelCompressor.compress_model / decompress_model
  * (compressors/model_compressors/model_compressor.py:153-172, :183-207).
  * descs / pointer tables are HOST arrays of length n; tensor i uses descs[i], x[i], ...
- * Enqueue-only like every device entry point, with one caveat for CUDA graphs: when more than one tensor shares a launch, the
- * job table is uploaded with a host-to-device copy from pageable memory, which a stream capture rejects; the single-tensor entry
- * points (no table) can be captured and replayed (tests/test_gpu_robust.py). */
+ * Enqueue-only like every device entry point, and capturable into a CUDA graph: when `stream` is being captured the job table of
+ * a multi-tensor launch travels as kernel parameters (one small upload kernel per 32 tensors) instead of a host-to-device copy from
+ * pageable memory, so a whole-model call can be captured once and replayed on the same buffers (tests/test_gpu_robust.py). */
 typedef enum ct_batch_op_t {
     CT_OP_QUANTIZE_PACK = 0,      /* in x        -> out packed int32 */
     CT_OP_UNPACK_DEQUANTIZE = 1,  /* in packed   -> out float */

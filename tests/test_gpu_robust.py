@@ -149,6 +149,40 @@ def test_per_tensor_launches_are_cuda_graph_capturable():
     assert not torch.equal(outs[0], want[0])
 
 
+def test_multi_tensor_launch_is_cuda_graph_capturable():
+    """a whole-model ct_batched call (job table + dynamic tile counter) captured once and replayed on new data in the same buffers"""
+    a = _w4()
+    shapes = [(1024, 4096), (4096, 4096), (14336, 4096)] * 14          # 42 tensors: two upload kernels (32 + 10 jobs), dynamic schedule
+    ws = [(torch.randn(sh, device=DEV) * 0.02).to(torch.bfloat16) for sh in shapes]
+    ss = [(w.float().unflatten(-1, (-1, 128)).abs().amax(-1) / 7.5).to(torch.bfloat16) for w in ws]
+    outs = [torch.zeros(w.shape[0], w.shape[1] // 8, dtype=torch.int32, device=DEV) for w in ws]
+    probs = []
+    for w, s, o in zip(ws, ss, outs):
+        p = ops._resolve(w, s, None, a, None)
+        probs.append((ops._desc(p, w.dtype, s.dtype, None, torch.bfloat16, torch.int8, None, N.Q_INT, 4), w, s, None, o))
+    plan = ops.BatchedPlan(N.OP_QUANTIZE_PACK, probs)
+    plan.run()
+    torch.cuda.synchronize()
+    first = [o.clone() for o in outs]
+    side = torch.cuda.Stream(device=DEV)
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        plan.run()
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            plan.run()
+    for w in ws:
+        w.mul_(-1.0)
+    for o in outs:
+        o.zero_()
+    graph.replay()
+    graph.replay()
+    torch.cuda.synchronize()
+    for o, w, s, f in zip(outs[::5], ws[::5], ss[::5], first[::5]):
+        assert torch.equal(o, ops.quantize_pack(w, s, None, a)) and not torch.equal(o, f)
+
+
 # ---- error behaviour of the newer entry points: the reference's exception types, never a silent fallback ---------------------------
 def test_error_paths_raise_like_the_reference():
     from compressed_tensors_b200.compressors import NVFP4PackedCompressor
