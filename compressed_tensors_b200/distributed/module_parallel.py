@@ -26,7 +26,9 @@ __all__ = ["replace_module_parallel"]
 def _to_meta(module: torch.nn.Module):
     """data -> meta; `*_shape` bookkeeping tensors hold VALUES the shape-only path reads (decompress), they stay real"""
     sd = get_direct_state_dict(module)
-    replace_direct_state_dict(module, {k: (v if v is None or k.endswith("shape") else torch.empty_like(v, device="meta")) for k, v in sd.items()})
+    # torch.empty(shape, ...) rather than empty_like(device="meta"): the latter goes through torch._refs and drags sympy in (2 s on first use)
+    replace_direct_state_dict(module, {k: (v if v is None or k.endswith("shape") else torch.empty(v.shape, dtype=v.dtype, device="meta"))
+                                       for k, v in sd.items()})
 
 
 def _wire_device(dev: torch.device) -> torch.device:
@@ -47,8 +49,9 @@ def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callab
       apply_many_fn(list_of_modules): the owner's modules are processed in one batched call
       recouple=False: skip step 4 -- every rank keeps only the results of the modules it owns (the others stay on meta); the flow for
                       "each owner writes its own checkpoint shard"
-      stats: a dict that receives `apply_s` (this rank's own work, device-synchronised), `recouple_s`, `recouple_bytes`, `owned_modules`,
-             `owned_bytes`; asking for them adds two device synchronisations
+      stats: a dict that receives `apply_s` (this rank's own work + the meta mirror of the others', device-synchronised), its parts
+             `owner_host_s` (incl. the final device wait) / `mirror_host_s` / `device_ms` (CUDA events around the owner's launches), `recouple_s`, `recouple_bytes`,
+             `owned_modules`, `owned_bytes`; asking for them adds two device synchronisations
     A module whose tensors are on META on a non-owner rank from the start (a model sharded tensor-per-GPU: only the owner ever
     materialised the weight) receives the owner's result on this rank's wire device (its GPU under NCCL)."""
     import time
@@ -63,17 +66,39 @@ def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callab
 
     _sync(stats)
     t0 = time.perf_counter()
-    for m in modules:
-        if owner[m] != rank:
+    mine = [m for m in modules if owner[m] == rank]
+    others = [m for m in modules if owner[m] != rank]
+    owned_bytes = sum(weight_fn(m) for m in mine)
+    ev = None
+    t_mirror = 0.0
+
+    def mirror():
+        nonlocal t_mirror
+        t = time.perf_counter()
+        for m in others:
             _to_meta(m)
             apply_fn(m)
-    mine = [m for m in modules if owner[m] == rank]
-    owned_bytes = sum(weight_fn(m) for m in mine)
+        t_mirror = time.perf_counter() - t
+
+    # Mirroring the other ranks' modules on meta is host-only bookkeeping (the larger share of the host time at 8 ranks).  When those
+    # modules hold real tensors here (every rank loaded the whole model) it comes FIRST: it releases their memory before this rank's
+    # outputs are allocated.  When they are on meta already (a model sharded tensor-per-rank) the owner's kernels are enqueued first
+    # and the mirror runs while the GPU is busy.
+    mirror_first = any(devices.get(id(m), torch.device("meta")).type != "meta" for m in others)
+    if mirror_first:
+        mirror()
+    if stats is not None and torch.cuda.is_available():
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     if apply_many_fn is not None:
         apply_many_fn(mine)
     else:
         for m in mine:
             apply_fn(m)
+    if ev is not None:
+        ev[1].record()
+    if not mirror_first:
+        mirror()
     _sync(stats)
     t1 = time.perf_counter()
 
@@ -105,4 +130,5 @@ def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callab
     _sync(stats)
     if stats is not None:
         stats.update(apply_s=t1 - t0, recouple_s=time.perf_counter() - t1, recouple_bytes=moved, owned_modules=len(mine),
-                     owned_bytes=int(owned_bytes), world_size=world)
+                     owned_bytes=int(owned_bytes), world_size=world, mirror_host_s=t_mirror, owner_host_s=t1 - t0 - t_mirror,
+                     device_ms=(ev[0].elapsed_time(ev[1]) if ev is not None else None))

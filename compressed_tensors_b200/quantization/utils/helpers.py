@@ -111,7 +111,9 @@ def generate_gparam(updated_min_val: Tensor, updated_max_val: Tensor, scale_data
     hi = torch.max(updated_max_val, torch.zeros_like(updated_max_val))
     top = torch.max(torch.abs(lo), torch.abs(hi))
     top = torch.clamp(top, min=torch.finfo(top.dtype).tiny)
-    g = scale_data.max * quant_data.max / top
+    # Python float / tensor: ATen's CUDA kernel evaluates it as  float * reciprocal(tensor), which loses bits when 1 / top is a float32
+    # subnormal (top ~ 3e38 in bf16); the CPU kernel -- the pinned result -- divides.  A tensor numerator keeps IEEE division on both.
+    g = torch.tensor(scale_data.max * quant_data.max, dtype=top.dtype, device=top.device) / top
     g = torch.nan_to_num(g, nan=1.0, posinf=1.0, neginf=1.0)
     return g.to(dtype).reshape([1])
 
