@@ -81,6 +81,24 @@ def sparse_family(rows, cols, dt):
     ops.bitmask_decompress(v, m, o, (rows, cols))
     b = torch.rand(rows, cols, device=DEV) < 0.3
     ops.unpack_bitmasks(ops.pack_bitmasks(b), (rows, cols))
+    # round 2: one-pass bitmask (ring kernel + look-back; also the v1 look-back kernel), fused 2:4 + int4
+    for density in (0.0, 0.07, 1.0):
+        u = torch.where(torch.rand(rows, cols, device=DEV) < density, x, torch.zeros_like(x))
+        for v1 in (False, True):
+            if v1:
+                os.environ["CT_B200_BITMASK_V1"] = "1"
+            v, m, o, n = ops.bitmask_compress(u, exact=False)
+            os.environ.pop("CT_B200_BITMASK_V1", None)
+        ops.bitmask_decompress(v[: int(n.item())].clone(), m, o, (rows, cols))
+    if cols % 4 == 0 and dt != torch.float32:
+        for a, shape in ((qa(num_bits=4, type="int", strategy="channel"), (rows, 1)), (qa(num_bits=4, type="int", strategy="group", group_size=32), (rows, max(cols // 32, 1)))):
+            if a.strategy == "group" and cols % 32 != 0:
+                continue
+            s = scale_for(x, shape, 7.5)
+            z = torch.randint(-4, 4, shape, device=DEV, dtype=torch.int8)
+            for zz in (None, z):
+                pk, bm = ops.sparse24_quantize_pack(x, s, zz, a)
+                ops.sparse24_unpack_dequantize(pk, bm, s, zz, 4, (rows, cols))
 
 
 def observer_family(rows, cols, dt):
@@ -93,6 +111,11 @@ def observer_family(rows, cols, dt):
         for kw, pack in ((dict(num_bits=8, type="int"), False), (dict(num_bits=4, type="int"), True)):
             ops.observe_quantize(x, qa(strategy="channel", symmetric=sym, **kw), pack=pack)
     ops.observe_quantize(x, qa(strategy="channel", num_bits=8, type="float"))
+    # round 2: per-tensor observers (grid-wide reduction + last-CTA qparams), NVFP4 global scale on the device
+    for kw, pack in ((dict(num_bits=8, type="float"), False), (dict(num_bits=8, type="int", symmetric=False), False), (dict(num_bits=4, type="int"), True)):
+        ops.observe_quantize(x, qa(strategy="tensor", **kw), pack=pack)
+    if (rows * cols) % 8 == 0:
+        ops.observe_tensor_gparam(x)
 
 
 def converter_family(rows, cols):
@@ -119,6 +142,22 @@ def batched_family(dt):
         N.set_tuning(pipe, 4, 3)
         ops.batched(N.OP_QUANTIZE_PACK, probs, 0)
     N.set_tuning(1, 4, 3)
+    # round 2: the fused 2:4 + int4 ops as multi-tensor launches (bitmask in desc.aux)
+    c24, d24, keep = [], [], []
+    for d, x, s, _, _ in probs:
+        rows, cols = x.shape
+        if cols % 32 or (rows * cols) % 64:
+            continue
+        pk = torch.empty(rows, cols // 16, dtype=torch.int32, device=DEV)
+        bm = torch.empty(rows, cols // 8, dtype=torch.uint8, device=DEV)
+        bk = torch.empty_like(x)
+        p = ops._resolve(x, s, None, a, None)
+        d1 = ops._desc(p, dt, dt, None, dt, torch.int8, None, N.Q_INT, 4)
+        d2 = ops._desc(p, None, dt, None, None, torch.int8, dt, N.Q_INT, 4)
+        d1.aux = d2.aux = bm.data_ptr()
+        c24.append((d1, x, s, None, pk)); d24.append((d2, pk, s, None, bk)); keep.append(bm)
+    ops.batched(N.OP_SPARSE24_QUANTIZE_PACK, c24, 0)
+    ops.batched(N.OP_SPARSE24_UNPACK_DEQUANTIZE, d24, 0)
 
 
 FAILED = []
