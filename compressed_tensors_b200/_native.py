@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libct_b200.so")
+LIB_PATH = os.environ.get("CT_B200_LIB") or os.path.join(_HERE, "libct_b200.so")   # CT_B200_LIB: an A/B build variant (_build.build_variant)
 
 INF = (1 << 63) - 1  # CT_DIV_INF
 

@@ -241,24 +241,24 @@ __global__ void __launch_bounds__(256) bitmask_lookback_kernel(const void* __res
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
-// v2 of the compressing direction: the same scan, restructured for latency.  v1 above keeps a tile in REGISTERS between its load and its
-// write-out, so a CTA has nothing in flight while it waits for its predecessors (4 CTAs / SM at 64 registers: 213 us for 235 MB, slower
-// than the two-phase kernels), and a first wave of ~1200 simultaneous CTAs resolves its chain 32 descriptors at a time (~40 us).
-//   * a producer lane claims tiles from the ticket counter and streams them with 1-D bulk copies (TMA engine) into a shared-memory
-//     ring; the input of the next tile is in flight whatever the consumers are waiting for
-//   * 4 consumer warps read their units from shared memory (no 16-byte values held in registers), scan, compact into a staging
-//     buffer, RELEASE the ring slot, and only then look back -- 128 descriptors per step (one per consumer thread)
-//   * the compact run leaves the staging buffer as 16-byte vectors aligned to GLOBAL 16-byte boundaries: the run starts at an arbitrary
-//     element, so every output vector is cut out of two aligned shared-memory vectors with a funnel shift (tile-uniform shift)
+// The shipped kernels.  What the first versions taught (B200, 235 MB tensor, 50 % zeros; two-phase kernels: 155 us / 111 us):
+//   * v1 above (tile in registers, 64 registers -> 4 CTAs / SM, one warp looks back 32 descriptors per step): 213 us.  The prefix
+//     "frontier" advances one look-back window per L2 round trip, i.e. 32 tiles x 16 KB per ~0.5 us = 1.05 TB/s -- exactly what was
+//     measured.  The window, not the memory system, set the speed.
+//   * widening the window to every thread of the CTA with a plain spin made it WORSE (346 / 176 us): ~300 000 threads re-reading
+//     their descriptor as fast as they can saturate the L2 and stretch the very round trip the frontier depends on.
+//   * a persistent CTA whose producer claims tickets AHEAD of the consumers (TMA ring) is wrong for a chained scan: a claimed tile
+//     that waits in the ring publishes nothing, and every successor in ticket order waits for it.
+// Hence: one tile per CTA, claimed when the CTA starts (processing order = ticket order); the tile lives in SHARED memory (one bulk
+// copy), so the kernel needs 40 registers and 6 CTAs / SM are resident; all 128 threads look back, but POLITELY -- one read per
+// descriptor per round, a round is repeated (after a nanosleep) only while a descriptor that is actually needed is unpublished.
 // ------------------------------------------------------------------------------------------------------------------------------
-constexpr int B2_CW = 4;                       // consumer warps
-constexpr int B2_CT = 32 * B2_CW;              // consumer threads
-constexpr int B2_TILE = 1024;                  // units per tile (8192 elements, 16 KB)
-constexpr int B2_UPT = B2_TILE / B2_CT;        // units per consumer thread (8)
-constexpr int B2_STAGES = 2;
-constexpr uint32_t B2_HDR = 128;               // full[2] | empty[2] | ids[2] | pad
-constexpr uint32_t B2_STAGE_BYTES = 8 * B2_TILE * 2 + 32;   // compact elements of a tile + one vector of slack for the funnel
-constexpr uint32_t B2_SMEM = B2_HDR + B2_STAGES * (B2_TILE * 16) + B2_STAGE_BYTES;
+constexpr int B3_T = 128;                      // threads
+constexpr int B3_W = B3_T / 32;                // warps
+constexpr int B3_TILE = 1024;                  // units per tile (8192 elements, 16 KB)
+constexpr int B3_UPT = B3_TILE / B3_T;         // units per thread (8)
+constexpr uint32_t B3_STAGE_BYTES = 8 * B3_TILE * 2 + 32;   // compact elements of a tile + one vector of slack for the funnel
+constexpr uint32_t B3_SMEM = 16 + B3_TILE * 16 + B3_STAGE_BYTES;
 
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
     uint4 v;
@@ -266,230 +266,270 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
     return v;
 }
 __device__ __forceinline__ void sts16(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"((unsigned short)v) : "memory"); }
-__device__ __forceinline__ uint32_t lds16(uint32_t saddr) {
-    unsigned short v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
-    return v;
+
+// exclusive prefix of `tile` (sum of the counts of all tiles before it); every thread of the 128-thread CTA takes part and returns it.
+// Thread t inspects tile base - t; warp w therefore covers distances 32 w .. 32 w + 31, nearest first.
+__device__ __forceinline__ unsigned long long lookback128(unsigned long long* desc, uint32_t tile, uint32_t total, unsigned long long* lb_sum, int* lb_p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) st_desc(desc + tile, (tile == 0 ? DESC_P : DESC_A) | (unsigned long long)total);
+    unsigned long long excl = 0;
+    if (tile == 0) return 0;
+    int64_t base = (int64_t)tile - 1;
+    while (true) {
+        const int64_t idx = base - (int64_t)threadIdx.x;
+        unsigned long long d = DESC_P;                 // before the first tile: prefix 0
+        if (idx >= 0) d = ld_desc(desc + idx);
+        // a descriptor matters only if no nearer one already holds a prefix: nearer lanes of this warp, or any nearer warp
+        while (true) {
+            const uint32_t has_p = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+            const uint32_t is_x = __ballot_sync(0xffffffffu, (d >> 62) == 0);
+            const uint32_t needed = has_p ? ((2u << (__ffs(has_p) - 1)) - 1u) : 0xffffffffu;     // lanes up to the nearest prefix
+            if ((is_x & needed) == 0) break;
+            __nanosleep(40);
+            if ((d >> 62) == 0) d = ld_desc(desc + idx);   // only the unpublished ones are read again
+        }
+        const uint32_t has_p = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+        const int stop = has_p ? (__ffs(has_p) - 1) : 31;
+        unsigned long long part = (lane <= stop) ? (d & DESC_VAL) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) { lb_sum[warp] = part; lb_p[warp] = has_p != 0; }
+        __syncthreads();
+        bool found = false;
+#pragma unroll
+        for (int w = 0; w < B3_W; ++w) {
+            if (!found) { excl += lb_sum[w]; found = lb_p[w] != 0; }
+        }
+        __syncthreads();
+        if (found) break;
+        base -= B3_T;
+    }
+    if (threadIdx.x == 0) st_desc(desc + tile, DESC_P | (excl + (unsigned long long)total));
+    return excl;
 }
 
-__global__ void __launch_bounds__(32 * (B2_CW + 1)) bitmask_compress_ring_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ bitmask,
-                                                                                  uint16_t* __restrict__ values, int64_t* __restrict__ row_offsets,
-                                                                                  int64_t* __restrict__ nnz_out, unsigned long long* __restrict__ desc,
-                                                                                  uint32_t* __restrict__ ticket, uint32_t n_units, uint32_t n_tiles, FastDiv upr) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ int warp_tot[B2_UPT][B2_CW];
-    __shared__ unsigned long long lb_sum[B2_CW];
-    __shared__ int lb_p[B2_CW];
-    const uint32_t sbase = smem_u32(smem_raw);
-    const uint32_t full0 = sbase, empty0 = sbase + 16, ids0 = sbase + 32;
-    const uint32_t ring0 = sbase + B2_HDR;
-    const uint32_t stage0 = ring0 + B2_STAGES * (B2_TILE * 16);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < B2_STAGES; ++s) {
-            mbar_init_a(full0 + 8 * s, 1);
-            mbar_init_a(empty0 + 8 * s, B2_CW);
+// per-thread scan bookkeeping shared by both directions: counts of the thread's 8 units (unit k * 128 + t, scan order = unit order)
+// -> off[k] = first slot of unit k in the tile's compact run; returns the tile's total
+__device__ __forceinline__ int tile_scan(const int (&cnt)[B3_UPT], int (&off)[B3_UPT], int (*warp_tot)[B3_W]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl[B3_UPT];
+#pragma unroll
+    for (int k = 0; k < B3_UPT; ++k) incl[k] = cnt[k];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int k = 0; k < B3_UPT; ++k) {
+            const int n = __shfl_up_sync(0xffffffffu, incl[k], o);
+            if (lane >= o) incl[k] += n;
         }
-        mbar_fence_init();
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int k = 0; k < B3_UPT; ++k) warp_tot[k][warp] = incl[k];
     }
     __syncthreads();
-
-    if (warp == B2_CW) {
-        // ---------------- producer ----------------
-        if (lane == 0) {
-            const uint64_t policy = l2_evict_first_policy();
-            int s = 0;
-            uint32_t ph = 0;
-            while (true) {
-                const uint32_t tile = atomicAdd(ticket, 1u);
-                mbar_wait_a(empty0 + 8 * s, ph ^ 1u);
-                if (tile >= n_tiles) {                                  // nothing left: tell the consumers
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(ids0 + 4 * s), "r"(0xffffffffu) : "memory");
-                    mbar_arrive_a(full0 + 8 * s);
-                    break;
-                }
-                const uint32_t nu = min((uint32_t)B2_TILE, n_units - tile * B2_TILE);
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(ids0 + 4 * s), "r"(tile) : "memory");
-                mbar_expect_tx_a(full0 + 8 * s, nu * 16);
-                bulk_g2s_a(ring0 + (uint32_t)s * (B2_TILE * 16), src + (size_t)tile * (B2_TILE * 16), nu * 16, full0 + 8 * s, policy);
-                if (++s == B2_STAGES) { s = 0; ph ^= 1u; }
-            }
+    int total = 0;
+#pragma unroll
+    for (int k = 0; k < B3_UPT; ++k) {
+        int before = 0, seg = 0;
+#pragma unroll
+        for (int w = 0; w < B3_W; ++w) {
+            const int t = warp_tot[k][w];
+            if (w < warp) before += t;
+            seg += t;
         }
-        return;
+        off[k] = total + before + incl[k] - cnt[k];
+        total += seg;
     }
+    return total;
+}
 
-    // ---------------- consumers ----------------
-    const int ctid = threadIdx.x;      // 0 .. 127
-    int s = 0;
-    uint32_t ph = 0;
-    while (true) {
-        mbar_wait_a(full0 + 8 * s, ph);
-        uint32_t tile;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tile) : "r"(ids0 + 4 * s) : "memory");
-        if (tile == 0xffffffffu) break;
-        const uint32_t u0 = tile * B2_TILE;
-        const uint32_t nu = min((uint32_t)B2_TILE, n_units - u0);
-        const uint32_t ring = ring0 + (uint32_t)s * (B2_TILE * 16);
-
-        // ---- A: mask bytes, counts, scan (unit order: segment k of 128 units, then thread) ----
-        uint32_t bytes_lo = 0, bytes_hi = 0;      // mask bytes of units k = 0..3 / 4..7
-        int incl[B2_UPT];
+// the compact run [excl, excl + total) <-> the staging buffer, as 16-byte vectors aligned to GLOBAL 16-byte boundaries.  The run starts at
+// an arbitrary element, so global vector c corresponds to stage elements [8c - shift, 8c - shift + 8): cut out of the aligned shared
+// vectors c - 1 and c with a funnel shift (shift is tile-uniform).  TO_GLOBAL: stage -> values; else values -> stage (shifted copy:
+// global vector c lands at stage vector c, i.e. run element j at stage element j + shift).
+__device__ __forceinline__ void run_to_global(uint16_t* values, unsigned long long excl, int total, uint32_t stage0) {
+    const uint32_t shift = (uint32_t)(excl & 7ull);               // elements of the first global vector that belong to earlier tiles
+    const unsigned long long g0 = excl - shift;
+    const uint32_t span = shift + (uint32_t)total;
+    const uint32_t nvec = (span + 7) >> 3;
+    uint4* gv = reinterpret_cast<uint4*>(values + g0);
+    const uint32_t h0 = 8u - shift;                                // first half of the (vector c - 1, vector c) pair: 1 .. 8
+    const uint32_t wo = h0 >> 1, odd = h0 & 1u;
+    for (uint32_t c = threadIdx.x; c < nvec; c += B3_T) {
+        const bool first = (c == 0), last = (8 * c + 8 > span);
+        uint32_t o[4];
+        if (shift == 0) {
+            const uint4 A = lds128(stage0 + 16u * c);
+            o[0] = A.x; o[1] = A.y; o[2] = A.z; o[3] = A.w;
+        } else {
+            uint4 A = make_uint4(0, 0, 0, 0);
+            if (c > 0) A = lds128(stage0 + 16u * (c - 1));
+            const uint4 B = lds128(stage0 + 16u * c);
+            const uint32_t W[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
 #pragma unroll
-        for (int k = 0; k < B2_UPT; ++k) {
-            const uint32_t i = k * B2_CT + ctid;
-            uint32_t b = 0;
-            if (i < nu) b = nz_byte16(lds128(ring + i * 16));
-            if (k < 4) bytes_lo |= b << (8 * k);
-            else bytes_hi |= b << (8 * (k - 4));
-            incl[k] = __popc(b);
-            // four neighbouring lanes combine their bytes into one aligned 32-bit store (n_units % 4 == 0)
-            uint32_t w = b;
-            w |= __shfl_down_sync(0xffffffffu, w, 1) << 8;
-            w |= __shfl_down_sync(0xffffffffu, w, 2) << 16;
-            if ((ctid & 3) == 0 && i < nu) reinterpret_cast<uint32_t*>(bitmask)[(u0 + i) >> 2] = w;
-        }
-        int cnt_packed_lo = 0, cnt_packed_hi = 0;   // the per-unit counts (<= 8: 4 bits each)
-#pragma unroll
-        for (int k = 0; k < B2_UPT; ++k) {
-            if (k < 4) cnt_packed_lo |= incl[k] << (4 * k);
-            else cnt_packed_hi |= incl[k] << (4 * (k - 4));
-        }
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-            for (int k = 0; k < B2_UPT; ++k) {
-                const int n = __shfl_up_sync(0xffffffffu, incl[k], o);
-                if (lane >= o) incl[k] += n;
+            for (int i = 0; i < 4; ++i) {
+                uint32_t lo, hi;
+                switch (wo) {                                       // tile-uniform; h0 in 1 .. 7 here, so wo in 0 .. 3
+                case 0: lo = W[i]; hi = W[i + 1]; break;
+                case 1: lo = W[i + 1]; hi = W[i + 2]; break;
+                case 2: lo = W[i + 2]; hi = W[i + 3]; break;
+                default: lo = W[i + 3]; hi = W[i + 4]; break;
+                }
+                o[i] = odd ? __funnelshift_r(lo, hi, 16) : lo;
             }
         }
-        if (lane == 31) {
+        if (!first && !last) stg_stream16(gv + c, make_uint4(o[0], o[1], o[2], o[3]));
+        else {
+            // partial vector: the elements before the run belong to the previous tile, those after it to the next one
+            uint16_t* ge = values + g0 + 8ull * c;
 #pragma unroll
-            for (int k = 0; k < B2_UPT; ++k) warp_tot[k][warp] = incl[k];
-        }
-        named_bar_sync(1, B2_CT);
-        int total = 0;
-        int off[B2_UPT];
-#pragma unroll
-        for (int k = 0; k < B2_UPT; ++k) {
-            int before = 0, seg = 0;
-#pragma unroll
-            for (int w = 0; w < B2_CW; ++w) {
-                const int t = warp_tot[k][w];
-                if (w < warp) before += t;
-                seg += t;
+            for (int e = 0; e < 8; ++e) {
+                const uint32_t pos = 8 * c + e;
+                if (pos >= shift && pos < span) ge[e] = (uint16_t)(o[e >> 1] >> (16 * (e & 1)));
             }
-            const int c = ((k < 4 ? cnt_packed_lo >> (4 * k) : cnt_packed_hi >> (4 * (k - 4))) & 15);
-            off[k] = total + before + incl[k] - c;
-            total += seg;
         }
+    }
+}
 
-        // ---- B: compaction into the staging buffer (element j of the tile's run at stage[j]) ----
+__global__ void __launch_bounds__(B3_T) bitmask_compress_tile_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ bitmask,
+                                                                     uint16_t* __restrict__ values, int64_t* __restrict__ row_offsets,
+                                                                     int64_t* __restrict__ nnz_out, unsigned long long* __restrict__ desc,
+                                                                     uint32_t* __restrict__ ticket, uint32_t n_units, uint32_t n_tiles, FastDiv upr) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ int warp_tot[B3_UPT][B3_W];
+    __shared__ unsigned long long lb_sum[B3_W];
+    __shared__ int lb_p[B3_W];
+    __shared__ uint32_t tile_s;
+    const uint32_t sbase = smem_u32(smem_raw);
+    const uint32_t bar = sbase, data = sbase + 16, stage0 = data + B3_TILE * 16;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        // the ticket is taken when the CTA starts running: processing order = ticket order, every predecessor is resident or done
+        const uint32_t tile = atomicAdd(ticket, 1u);
+        tile_s = tile;
+        mbar_init_a(bar, 1);
+        mbar_fence_init();
+        const uint32_t nu = min((uint32_t)B3_TILE, n_units - tile * B3_TILE);
+        mbar_expect_tx_a(bar, nu * 16);
+        bulk_g2s_a(data, src + (size_t)tile * (B3_TILE * 16), nu * 16, bar, l2_evict_first_policy());
+    }
+    __syncthreads();
+    const uint32_t tile = tile_s;
+    const uint32_t u0 = tile * B3_TILE;
+    const uint32_t nu = min((uint32_t)B3_TILE, n_units - u0);
+    mbar_wait_a(bar, 0);
+
+    // ---- mask bytes, counts, scan ----
+    uint32_t bytes_lo = 0, bytes_hi = 0;      // mask bytes of units k = 0..3 / 4..7
+    int cnt[B3_UPT], off[B3_UPT];
 #pragma unroll
-        for (int k = 0; k < B2_UPT; ++k) {
-            const uint32_t i = k * B2_CT + ctid;
+    for (int k = 0; k < B3_UPT; ++k) {
+        const uint32_t i = k * B3_T + tid;
+        uint32_t b = 0;
+        if (i < nu) b = nz_byte16(lds128(data + i * 16));
+        if (k < 4) bytes_lo |= b << (8 * k);
+        else bytes_hi |= b << (8 * (k - 4));
+        cnt[k] = __popc(b);
+        // four neighbouring lanes combine their bytes into one aligned 32-bit store (n_units % 4 == 0)
+        uint32_t w = b;
+        w |= __shfl_down_sync(0xffffffffu, w, 1) << 8;
+        w |= __shfl_down_sync(0xffffffffu, w, 2) << 16;
+        if ((tid & 3) == 0 && i < nu) reinterpret_cast<uint32_t*>(bitmask)[(u0 + i) >> 2] = w;
+    }
+    const int total = tile_scan(cnt, off, warp_tot);
+
+    // ---- compaction into the staging buffer (element j of the tile's run at stage[j]) ----
+#pragma unroll
+    for (int k = 0; k < B3_UPT; ++k) {
+        const uint32_t i = k * B3_T + tid;
+        const uint32_t b = (k < 4 ? bytes_lo >> (8 * k) : bytes_hi >> (8 * (k - 4))) & 0xffu;
+        if (b) {
+            const uint4 v = lds128(data + i * 16);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            uint32_t o = stage0 + 2u * (uint32_t)off[k];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if ((b >> e) & 1u) { sts16(o, w[e >> 1] >> (16 * (e & 1))); o += 2; }
+        }
+    }
+    // (the look-back's barriers also order the staging writes before the write-out)
+    const unsigned long long excl = lookback128(desc, tile, (uint32_t)total, lb_sum, lb_p);
+    if (tid == 0 && tile == n_tiles - 1) *nnz_out = (int64_t)(excl + (unsigned long long)total);
+    if (tile == 0) __syncthreads();            // tile 0 skips the look-back's barriers
+
+    if (row_offsets) {
+#pragma unroll
+        for (int k = 0; k < B3_UPT; ++k) {
+            const uint32_t i = k * B3_T + tid;
+            if (i < nu) {
+                const uint32_t gu = u0 + i, r = fd_div(gu, upr);
+                if (r * upr.d == gu) row_offsets[r] = (int64_t)(excl + (unsigned long long)off[k]);
+            }
+        }
+    }
+    run_to_global(values, excl, total, stage0);
+}
+
+// expansion: mask bytes -> counts -> scan -> look-back -> the tile's run of `values` into shared memory (aligned 16-byte loads, so that
+// run element j sits at stage element j + shift) -> dense tile, 16-byte stores
+__global__ void __launch_bounds__(B3_T) bitmask_expand_tile_kernel(const uint16_t* __restrict__ values, const uint8_t* __restrict__ bitmask,
+                                                                   uint4* __restrict__ dense, unsigned long long* __restrict__ desc,
+                                                                   uint32_t* __restrict__ ticket, uint32_t n_units, uint32_t n_tiles) {
+    __shared__ __align__(16) uint16_t stage[8 * B3_TILE + 16];
+    __shared__ uint32_t mask_s[B3_TILE / 4];
+    __shared__ int warp_tot[B3_UPT][B3_W];
+    __shared__ unsigned long long lb_sum[B3_W];
+    __shared__ int lb_p[B3_W];
+    __shared__ uint32_t tile_s;
+    const int tid = threadIdx.x;
+    if (tid == 0) tile_s = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = tile_s;
+    const uint32_t u0 = tile * B3_TILE;
+    const uint32_t nu = min((uint32_t)B3_TILE, n_units - u0);
+    // the tile's mask bytes: 2 coalesced words per thread (n_units % 4 == 0)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const uint32_t wi = j * B3_T + tid;
+        mask_s[wi] = (wi * 4 < nu) ? __ldg(reinterpret_cast<const uint32_t*>(bitmask + u0) + wi) : 0u;
+    }
+    __syncthreads();
+    uint32_t bytes_lo = 0, bytes_hi = 0;
+    int cnt[B3_UPT], off[B3_UPT];
+#pragma unroll
+    for (int k = 0; k < B3_UPT; ++k) {
+        const uint32_t i = k * B3_T + tid;
+        const uint32_t b = (i < nu) ? reinterpret_cast<const uint8_t*>(mask_s)[i] : 0u;
+        if (k < 4) bytes_lo |= b << (8 * k);
+        else bytes_hi |= b << (8 * (k - 4));
+        cnt[k] = __popc(b);
+    }
+    const int total = tile_scan(cnt, off, warp_tot);
+    const unsigned long long excl = lookback128(desc, tile, (uint32_t)total, lb_sum, lb_p);
+
+    const uint32_t shift = (uint32_t)(excl & 7ull);
+    const uint32_t nvec = (shift + (uint32_t)total + 7) >> 3;
+    const uint4* gv = reinterpret_cast<const uint4*>(values + (excl - shift));
+    const uint32_t span = shift + (uint32_t)total;
+    for (uint32_t c = tid; c < nvec; c += B3_T) {
+        if (8 * c + 8 <= span) reinterpret_cast<uint4*>(stage)[c] = ldg_stream16(gv + c);    // c == 0 may include up to 7 elements of the previous tile's run
+        else {
+            for (uint32_t pos = 8 * c; pos < span; ++pos) stage[pos] = values[excl - shift + pos];   // the last vector: never read past the run (= past `values`)
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < B3_UPT; ++k) {
+        const uint32_t i = k * B3_T + tid;
+        if (i < nu) {
             const uint32_t b = (k < 4 ? bytes_lo >> (8 * k) : bytes_hi >> (8 * (k - 4))) & 0xffu;
-            if (b) {
-                const uint4 v = lds128(ring + i * 16);
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                uint32_t o = stage0 + 2u * (uint32_t)off[k];
+            uint32_t e[8];
+            int o = (int)shift + off[k];
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    if ((b >> e) & 1u) { sts16(o, w[e >> 1] >> (16 * (e & 1))); o += 2; }
-            }
+            for (int q = 0; q < 8; ++q) e[q] = ((b >> q) & 1u) ? (uint32_t)stage[o++] : 0u;
+            stg_stream16(dense + u0 + i, make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16)));
         }
-        named_bar_sync(1, B2_CT);
-        if (lane == 0) mbar_arrive_a(empty0 + 8 * s);      // the producer may refill this slot while we look back
-
-        // ---- C: exclusive prefix of the tile, 128 descriptors per step ----
-        if (ctid == 0) st_desc(desc + tile, (tile == 0 ? DESC_P : DESC_A) | (unsigned long long)total);
-        unsigned long long excl = 0;
-        if (tile > 0) {
-            int64_t base = (int64_t)tile - 1;
-            while (true) {
-                const int64_t idx = base - ctid;
-                unsigned long long d = DESC_P;                 // before the first tile: prefix 0
-                if (idx >= 0) {
-                    do { d = ld_desc(desc + idx); } while ((d >> 62) == 0);
-                }
-                const uint32_t has_p = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-                const int stop = has_p ? (__ffs(has_p) - 1) : 31;
-                unsigned long long part = (lane <= stop) ? (d & DESC_VAL) : 0ull;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                if (lane == 0) { lb_sum[warp] = part; lb_p[warp] = has_p != 0; }
-                named_bar_sync(1, B2_CT);
-                bool found = false;
-#pragma unroll
-                for (int w = 0; w < B2_CW; ++w) {
-                    if (!found) { excl += lb_sum[w]; found = lb_p[w] != 0; }
-                }
-                named_bar_sync(1, B2_CT);
-                if (found) break;
-                base -= B2_CT;
-            }
-        }
-        if (ctid == 0) {
-            st_desc(desc + tile, DESC_P | (excl + (unsigned long long)total));
-            if (tile == n_tiles - 1) *nnz_out = (int64_t)(excl + (unsigned long long)total);
-        }
-
-        // ---- D: row offsets, then the compact run [excl, excl + total) as global-aligned 16-byte vectors ----
-        if (row_offsets) {
-#pragma unroll
-            for (int k = 0; k < B2_UPT; ++k) {
-                const uint32_t i = k * B2_CT + ctid;
-                if (i < nu) {
-                    const uint32_t gu = u0 + i, r = fd_div(gu, upr);
-                    if (r * upr.d == gu) row_offsets[r] = (int64_t)(excl + (unsigned long long)off[k]);
-                }
-            }
-        }
-        {
-            const uint32_t shift = (uint32_t)(excl & 7ull);               // elements of the first global vector that belong to earlier tiles
-            const unsigned long long g0 = excl - shift;                    // first element of the first global vector we touch
-            const uint32_t span = shift + (uint32_t)total;                 // elements from g0 to the end of the run
-            const uint32_t nvec = (span + 7) >> 3;
-            uint4* gv = reinterpret_cast<uint4*>(values + g0);
-            // vector c holds stage elements [8c - shift, 8c - shift + 8): halves (8 - shift) .. of the pair (stage vector c - 1, stage vector c)
-            const uint32_t h0 = 8u - shift;                                // 1 .. 8
-            const uint32_t wo = h0 >> 1, odd = h0 & 1u;
-            for (uint32_t c = ctid; c < nvec; c += B2_CT) {
-                const bool first = (c == 0), last = (8 * c + 8 > span);
-                uint4 A = make_uint4(0, 0, 0, 0);
-                if (c > 0 || shift == 0) A = lds128(stage0 + 16u * (c - (shift ? 1u : 0u)));   // shift == 0: the vector is stage vector c itself
-                uint4 B = A;
-                if (shift) B = lds128(stage0 + 16u * c);
-                uint32_t o[4];
-                if (shift == 0) { o[0] = A.x; o[1] = A.y; o[2] = A.z; o[3] = A.w; }
-                else {
-                    const uint32_t W[9] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, 0u};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint32_t lo = 0, hi = 0;
-                        switch (wo) {                                       // tile-uniform
-                        case 0: lo = W[i]; hi = W[i + 1]; break;
-                        case 1: lo = W[i + 1]; hi = W[i + 2]; break;
-                        case 2: lo = W[i + 2]; hi = W[i + 3]; break;
-                        case 3: lo = W[i + 3]; hi = W[i + 4]; break;
-                        default: lo = W[i + 4]; hi = W[i + 5 > 8 ? 8 : i + 5]; break;
-                        }
-                        o[i] = odd ? __funnelshift_r(lo, hi, 16) : lo;
-                    }
-                }
-                if (!first && !last) gv[c] = make_uint4(o[0], o[1], o[2], o[3]);
-                else {
-                    // partial vector: elements before the run belong to another tile, elements after it to the next one
-                    uint16_t* ge = values + g0 + 8ull * c;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const uint32_t pos = 8 * c + e;
-                        if (pos >= shift && pos < span) ge[e] = (uint16_t)(o[e >> 1] >> (16 * (e & 1)));
-                    }
-                }
-            }
-        }
-        named_bar_sync(1, B2_CT);      // the staging buffer is reused by the next tile
-        if (++s == B2_STAGES) { s = 0; ph ^= 1u; }
     }
 }
 
@@ -510,14 +550,18 @@ int launch_bitmask_lookback(const void* src, uint8_t* bitmask, void* dst, int64_
     int rc = scratch_alloc(reinterpret_cast<void**>(&scratch), bytes, device, st);
     if (rc) return rc;
     CT_CUDA_TRY(cudaMemsetAsync(scratch, 0, bytes, st));
-    if (COMPRESS && !getenv("CT_B200_BITMASK_V1")) {
-        auto kfn = bitmask_compress_ring_kernel;
-        CT_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2_SMEM));
-        uint32_t grid = (uint32_t)sm_count(device) * 4;
-        if (grid > n_tiles) grid = n_tiles;
-        kfn<<<grid, 32 * (B2_CW + 1), B2_SMEM, st>>>(reinterpret_cast<const uint8_t*>(src), bitmask, reinterpret_cast<uint16_t*>(dst), row_offsets, nnz_out,
-                                                     reinterpret_cast<unsigned long long*>(scratch + 16), reinterpret_cast<uint32_t*>(scratch),
-                                                     (uint32_t)n_units, n_tiles, make_fastdiv((uint64_t)(cols / 8)));
+    if (!getenv("CT_B200_BITMASK_V1")) {
+        if (COMPRESS) {
+            auto kfn = bitmask_compress_tile_kernel;
+            CT_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B3_SMEM));
+            kfn<<<n_tiles, B3_T, B3_SMEM, st>>>(reinterpret_cast<const uint8_t*>(src), bitmask, reinterpret_cast<uint16_t*>(dst), row_offsets, nnz_out,
+                                                reinterpret_cast<unsigned long long*>(scratch + 16), reinterpret_cast<uint32_t*>(scratch),
+                                                (uint32_t)n_units, n_tiles, make_fastdiv((uint64_t)(cols / 8)));
+        } else {
+            bitmask_expand_tile_kernel<<<n_tiles, B3_T, 0, st>>>(reinterpret_cast<const uint16_t*>(src), bitmask, reinterpret_cast<uint4*>(dst),
+                                                                 reinterpret_cast<unsigned long long*>(scratch + 16), reinterpret_cast<uint32_t*>(scratch),
+                                                                 (uint32_t)n_units, n_tiles);
+        }
     } else {
         bitmask_lookback_kernel<COMPRESS><<<n_tiles, 256, 0, st>>>(src, bitmask, dst, row_offsets, nnz_out,
                                                                    reinterpret_cast<unsigned long long*>(scratch + 16), reinterpret_cast<uint32_t*>(scratch),

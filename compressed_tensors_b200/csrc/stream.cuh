@@ -25,7 +25,10 @@
 
 namespace ctb {
 
-constexpr int TILE_CHUNKS = 1024;   // 8192 elements
+#ifndef CT_TILE_CHUNKS
+#define CT_TILE_CHUNKS 1024
+#endif
+constexpr int TILE_CHUNKS = CT_TILE_CHUNKS;   // 1024: 8192 elements (build-time knob for the tile-size A/B, tools/ab_tile.sh)
 constexpr int CHUNK_ELEMS = 8;
 constexpr int NCW = 8;              // consumer warps (tma pipeline)
 constexpr int DIRECT_THREADS = 256;
