@@ -471,9 +471,10 @@ int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in
         }
         std::vector<Job> jobs;
         uint32_t tiles = 0;
+        const uint32_t tc = (uint32_t)sig_tile_chunks(plans[i].sig);
         for (int k = i; k < n; ++k) {
             if (done[k] || !plans[k].fast || !(plans[k].sig == plans[i].sig) || plans[k].cm.bits != plans[i].cm.bits) continue;
-            const uint32_t nt = (plans[k].job.n_chunks + TILE_CHUNKS - 1) / TILE_CHUNKS;
+            const uint32_t nt = (plans[k].job.n_chunks + tc - 1) / tc;
             if ((uint64_t)tiles + nt >= 0xffffffffull) break;
             Job j = plans[k].job;
             j.tile_begin = tiles;
@@ -485,6 +486,7 @@ int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in
         LaunchPlan lp;
         lp.cm = plans[i].cm;
         lp.total_tiles = tiles;
+        lp.tile_chunks = (int)tc;
         lp.tbl.n = (int)jobs.size();
         lp.tbl.jobs = nullptr;
         lp.tbl.one = jobs[0];
@@ -493,7 +495,7 @@ int run_batched(int op, int n, const ct_quant_desc* descs, const void* const* in
         // Launches with few tiles per CTA keep the static deal and need no scratch at all.
         uint8_t* scratch = nullptr;
         const bool many = jobs.size() > 1;
-        const bool dynamic = tuning().dynamic && tiles >= (uint32_t)(DYNAMIC_MIN_TILES_PER_SM * sm_count(device));
+        const bool dynamic = tuning().dynamic && (uint64_t)tiles * tc >= (uint64_t)DYNAMIC_MIN_TILES_PER_SM * TILE_CHUNKS * sm_count(device);
         if (many || dynamic) {
             const size_t tbl_bytes = many ? jobs.size() * sizeof(Job) : 0;
             rc = scratch_alloc(reinterpret_cast<void**>(&scratch), 16 + tbl_bytes, device, stream);

@@ -19,6 +19,13 @@ struct FastSig {
     bool operator==(const FastSig& o) const { return op == o.op && p_dt == o.p_dt && sel == o.sel && zp == o.zp && group == o.group; }
 };
 
+// chunks per tile of the kernel a signature selects (stream.cuh: TileOf<Op>): the 16-bit quantize+pack, unpack+dequantize, quantize and
+// dequantize functors run on the big tile
+static inline int sig_tile_chunks(const FastSig& s) {
+    const bool p16 = (s.p_dt == CT_BF16 || s.p_dt == CT_F16);
+    return (p16 && (s.op == F_QUANTPACK || s.op == F_UNPACKDEQ || s.op == F_QUANT || s.op == F_DEQUANT)) ? BIG_TILE_CHUNKS : TILE_CHUNKS;
+}
+
 // defined in fast_pack.cu / fast_quant.cu / fast_fake.cu
 int launch_fast_quantpack(const FastSig&, const LaunchPlan&, int device, cudaStream_t);
 int launch_fast_unpackdeq(const FastSig&, const LaunchPlan&, int device, cudaStream_t);

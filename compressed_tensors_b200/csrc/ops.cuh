@@ -118,6 +118,9 @@ __device__ __forceinline__ void store_words(uint8_t* p, const uint32_t (&o)[N]) 
 template <class P, int BITS, int ZP, int G>
 struct QuantPackOp {
     static_assert(BITS == 4 || BITS == 8, "fast path packs 4- and 8-bit codes");
+    static constexpr int TILE = (P::DT == CT_F32) ? TILE_CHUNKS : BIG_TILE_CHUNKS;   // engine.h: sig_tile_chunks
+    static constexpr int PREF_STAGES = (P::DT == CT_F32) ? 4 : 3;
+    static constexpr int PREF_CTAS = (P::DT == CT_F32) ? 3 : 2;
     static constexpr int IN_BYTES = 8 * ElemBytes<P>::v;
     static constexpr int GROUP = G;
     static constexpr int OUT_WORDS = BITS / 4;   // per chunk
@@ -179,6 +182,9 @@ struct QuantPackOp {
 // ------------------------------------------------------------------------------------
 template <class P, int KIND, int ZP, int G>
 struct QuantizeOp {
+    static constexpr int TILE = (P::DT == CT_F32) ? TILE_CHUNKS : BIG_TILE_CHUNKS;   // engine.h: sig_tile_chunks
+    static constexpr int PREF_STAGES = (P::DT == CT_F32) ? 4 : 3;
+    static constexpr int PREF_CTAS = (P::DT == CT_F32) ? 3 : 2;
     static constexpr int IN_BYTES = 8 * ElemBytes<P>::v;
     static constexpr int GROUP = G;
     using Raw = RawQP;
@@ -267,6 +273,9 @@ __device__ __forceinline__ void store_out8(uint8_t* out, uint32_t gc, const uint
 // ------------------------------------------------------------------------------------
 template <class P, int KIND /* QI_* = int8 codes, QF8 = e4m3 codes */, int ZP>
 struct DequantizeOp {
+    static constexpr int TILE = (P::DT == CT_F32) ? TILE_CHUNKS : BIG_TILE_CHUNKS;   // engine.h: sig_tile_chunks
+    static constexpr int PREF_STAGES = (P::DT == CT_F32) ? 4 : 3;
+    static constexpr int PREF_CTAS = (P::DT == CT_F32) ? 3 : 2;
     static constexpr int IN_BYTES = 8;
     static constexpr int GROUP = 1;
     using Raw = RawQP;
@@ -312,6 +321,9 @@ struct DequantizeOp {
 // ------------------------------------------------------------------------------------
 template <class P>
 struct DequantF32ScaleOp {
+    static constexpr int TILE = (P::DT == CT_F32) ? TILE_CHUNKS : BIG_TILE_CHUNKS;   // engine.h: sig_tile_chunks
+    static constexpr int PREF_STAGES = (P::DT == CT_F32) ? 4 : 3;
+    static constexpr int PREF_CTAS = (P::DT == CT_F32) ? 3 : 2;
     static constexpr int IN_BYTES = 8;
     static constexpr int GROUP = 1;
     struct Raw { uint32_t s; };
@@ -339,6 +351,9 @@ struct DequantF32ScaleOp {
 template <class P, int BITS, int ZP>
 struct UnpackDequantOp {
     static_assert(BITS == 4 || BITS == 8, "fast path unpacks 4- and 8-bit codes");
+    static constexpr int TILE = (P::DT == CT_F32) ? TILE_CHUNKS : BIG_TILE_CHUNKS;   // engine.h: sig_tile_chunks
+    static constexpr int PREF_STAGES = (P::DT == CT_F32) ? 4 : 3;
+    static constexpr int PREF_CTAS = (P::DT == CT_F32) ? 3 : 2;
     static constexpr int IN_BYTES = BITS;
     static constexpr int GROUP = 1;
     using Raw = RawQP;

@@ -28,7 +28,15 @@ namespace ctb {
 #ifndef CT_TILE_CHUNKS
 #define CT_TILE_CHUNKS 1024
 #endif
-constexpr int TILE_CHUNKS = CT_TILE_CHUNKS;   // 1024: 8192 elements (build-time knob for the tile-size A/B, tools/ab_tile.sh)
+constexpr int TILE_CHUNKS = CT_TILE_CHUNKS;   // default tile: 1024 chunks = 8192 elements (16 KB of bf16); build-time knob for A/B variants
+#ifndef CT_BIG_TILE_CHUNKS
+#define CT_BIG_TILE_CHUNKS 2048
+#endif
+// An op may ask for another tile size (`static constexpr int TILE`).  The four headline 16-bit ops run on 2048-chunk tiles with a
+// 3-stage x 2-CTA ring: half the per-tile bookkeeping of the consumer warps for the same bytes in flight; +2.2 % / +1.4 % / +2.5 % / +2.5 %
+// on quantize+pack / unpack+dequantize / fp8 quantize / fp8 dequantize (profiles/ops_r2.md).  The host side must count tiles with the
+// same number: sig_tile_chunks() in engine.h, checked at every launch.
+constexpr int BIG_TILE_CHUNKS = CT_BIG_TILE_CHUNKS;
 constexpr int CHUNK_ELEMS = 8;
 constexpr int NCW = 8;              // consumer warps (tma pipeline)
 constexpr int DIRECT_THREADS = 256;
@@ -88,6 +96,8 @@ template <class Op, class = void> struct HasTile { static constexpr bool value =
 template <class Op> struct HasTile<Op, decltype((void)sizeof(typename Op::Tile))> { static constexpr bool value = true; };
 template <class Op, class = void> struct HasShape { static constexpr bool value = false; };
 template <class Op> struct HasShape<Op, decltype((void)Op::PREF_CTAS)> { static constexpr bool value = true; };
+template <class Op, class = void> struct TileOf { static constexpr int value = TILE_CHUNKS; };
+template <class Op> struct TileOf<Op, decltype((void)Op::TILE)> { static constexpr int value = Op::TILE; };
 struct NoTile {};
 template <class Op> __device__ __forceinline__ auto op_tile(const Job& J) {
     if constexpr (HasTile<Op>::value) return Op::tile(J);
@@ -192,6 +202,7 @@ template <class Op>
 __global__ void __launch_bounds__(32 * (NCW + 1)) stream_tma_kernel(const __grid_constant__ JobTable tbl,
                                                                    const __grid_constant__ Common cm,
                                                                    uint32_t total_tiles, int stages, uint32_t* sched) {
+    constexpr int TILE_CHUNKS = TileOf<Op>::value;     // shadows the default on purpose: everything below is per-op
     constexpr int TILE_BYTES = TILE_CHUNKS * Op::IN_BYTES;
     constexpr int CTHREADS = NCW * 32;
     constexpr int G = Op::GROUP;
@@ -337,6 +348,7 @@ template <class Op>
 __global__ void __launch_bounds__(DIRECT_THREADS) stream_direct_kernel(const __grid_constant__ JobTable tbl,
                                                                        const __grid_constant__ Common cm,
                                                                        uint32_t total_tiles) {
+    constexpr int TILE_CHUNKS = TileOf<Op>::value;
     constexpr int G = Op::GROUP;
     constexpr int UNITS = TILE_CHUNKS / G;
     constexpr int ITERS = UNITS / DIRECT_THREADS;
@@ -376,16 +388,21 @@ struct LaunchPlan {
     JobTable tbl;
     Common cm;
     uint32_t total_tiles;
+    int tile_chunks = TILE_CHUNKS;   // the tile size the host counted tiles with; must equal TileOf<Op>::value of the kernel launched
     uint32_t* sched = nullptr;   // zeroed device counter for the dynamic tile schedule (nullptr = static deal); owned by dispatch.cu
 };
 
 template <class Op>
 int launch_stream(const LaunchPlan& lp, int device, cudaStream_t stream) {
     if (lp.total_tiles == 0) return CT_OK;
+    if (lp.tile_chunks != TileOf<Op>::value) {
+        set_error("internal: tiles counted with %d chunks, the kernel uses %d", lp.tile_chunks, TileOf<Op>::value);
+        return CT_E_ARG;
+    }
     const Tuning tn = tuning();
     const int sms = sm_count(device);
     if (tn.pipe == 1) {
-        constexpr int TILE_BYTES = TILE_CHUNKS * Op::IN_BYTES;
+        constexpr int TILE_BYTES = TileOf<Op>::value * Op::IN_BYTES;
         int stages = tn.stages;
         int ctas = tn.ctas_per_sm;
         if constexpr (HasShape<Op>::value) {   // an op's measured preference, unless the caller tuned explicitly
