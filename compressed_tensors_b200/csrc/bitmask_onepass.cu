@@ -471,6 +471,171 @@ __global__ void __launch_bounds__(B3_T) bitmask_compress_tile_kernel(const uint8
     run_to_global(values, excl, total, stage0);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// v4 of the compressing direction: the same tile / ticket / look-back structure, but the compaction is a GATHER.
+// v3 (bitmask_compress_tile_kernel above) spends 25 instructions per input element (ncu: 92 M warp instructions for 117 M elements,
+// 37 % issue-slot utilisation, i.e. >= 81 us even at full issue rate): 8 units per thread in STRIDED order cost 40 scan shuffles and
+// 8 offset computations per thread, the non-zero byte 3 instructions per element, and every kept element is extracted, stored to a
+// staging buffer with a predicated 16-bit store, and read again for the write-out.
+//   * a thread owns 8 CONSECUTIVE units (64 elements): one count per thread -> 5 scan shuffles; its 8 mask bytes are one 8-byte store
+//   * non-zero byte of a unit: |x| != 0 per half with the packed 16-bit integer min (VIMNMX.U16x2 against 0x00010001): 13 instructions
+//   * no staging buffer: after the look-back every thread knows where the tile's run starts in `values`; OUTPUT vector v (8 kept
+//     elements, 16 bytes, aligned in global memory) is produced by one thread that walks the tile's bit mask from the position of the
+//     vector's first element (a 2 KB table filled by the threads that own those positions) and fetches the kept halves straight from
+//     the tile in shared memory
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t B4_SMEM = 16 + B3_TILE * 16;
+
+// non-zero byte of 8 halves: per word  min(|x| per half, 1)  ->  bit 0 / bit 16; folded into 8 bits
+__device__ __forceinline__ uint32_t nz_byte16_fast(const uint4& v) {
+    const uint32_t r0 = __vminu2(v.x & 0x7fff7fffu, 0x00010001u), r1 = __vminu2(v.y & 0x7fff7fffu, 0x00010001u);
+    const uint32_t r2 = __vminu2(v.z & 0x7fff7fffu, 0x00010001u), r3 = __vminu2(v.w & 0x7fff7fffu, 0x00010001u);
+    const uint32_t t = r0 + r1 * 4u + r2 * 16u + r3 * 64u;        // even elements at bits 0,2,4,6; odd ones at 16,18,20,22
+    return (t | (t >> 15)) & 0xffu;
+}
+// position of the n-th (0-based) set bit of x; x has more than n set bits
+__device__ __forceinline__ uint32_t select32(uint32_t x, uint32_t n) {
+    uint32_t pos = 0;
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const uint32_t c = __popc(x & ((1u << w) - 1u));
+        if (n >= c) { n -= c; x >>= w; pos += w; }
+    }
+    return pos;
+}
+
+__global__ void __launch_bounds__(B3_T) bitmask_compress_gather_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ bitmask,
+                                                                       uint16_t* __restrict__ values, int64_t* __restrict__ row_offsets,
+                                                                       int64_t* __restrict__ nnz_out, unsigned long long* __restrict__ desc,
+                                                                       uint32_t* __restrict__ ticket, uint32_t n_units, uint32_t n_tiles, FastDiv upr) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(16) uint32_t mask_w[B3_TILE / 4 + 4];   // the tile's mask bytes (+ zero padding for the walkers' look-ahead)
+    __shared__ uint16_t start_s[B3_TILE + 8];                     // element index (within the tile) of the first element of output vector v
+    __shared__ int warp_tot[B3_W];
+    __shared__ unsigned long long lb_sum[B3_W];
+    __shared__ int lb_p[B3_W];
+    __shared__ uint32_t tile_s;
+    const uint32_t sbase = smem_u32(smem_raw);
+    const uint32_t bar = sbase, data = sbase + 16;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        const uint32_t tile = atomicAdd(ticket, 1u);
+        tile_s = tile;
+        mbar_init_a(bar, 1);
+        mbar_fence_init();
+        const uint32_t nu = min((uint32_t)B3_TILE, n_units - tile * B3_TILE);
+        mbar_expect_tx_a(bar, nu * 16);
+        bulk_g2s_a(data, src + (size_t)tile * (B3_TILE * 16), nu * 16, bar, l2_evict_first_policy());
+    }
+    if (tid < 4) mask_w[B3_TILE / 4 + tid] = 0u;
+    __syncthreads();
+    const uint32_t tile = tile_s;
+    const uint32_t u0 = tile * B3_TILE;
+    const uint32_t nu = min((uint32_t)B3_TILE, n_units - u0);
+    mbar_wait_a(bar, 0);
+
+    // ---- A: mask bytes of the thread's 8 consecutive units (read in a lane-dependent order: bank-conflict free), counts, scan ----
+    const uint32_t uf = 8u * (uint32_t)tid;
+    uint8_t* mask_b = reinterpret_cast<uint8_t*>(mask_w);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t i = uf + (uint32_t)(k ^ (tid & 7));
+        uint32_t b = 0;
+        if (i < nu) b = nz_byte16_fast(lds128(data + i * 16));
+        mask_b[i] = (uint8_t)b;
+    }
+    const uint32_t lo = mask_w[2 * tid], hi = mask_w[2 * tid + 1];       // written by this thread: no barrier needed
+    if (uf + 4 <= nu) reinterpret_cast<uint32_t*>(bitmask + u0 + uf)[0] = lo;        // n_units % 4 == 0; the mask is 4-byte aligned
+    if (uf + 8 <= nu) reinterpret_cast<uint32_t*>(bitmask + u0 + uf)[1] = hi;
+    const int clo = __popc(lo), cnt = clo + __popc(hi);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();                                                       // also publishes every thread's mask bytes
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < B3_W; ++w) {
+        const int t = warp_tot[w];
+        if (w < warp) before += t;
+        total += t;
+    }
+    const int toff = before + incl - cnt;          // first slot of this thread's elements in the tile's run
+
+    const unsigned long long excl = lookback128(desc, tile, (uint32_t)total, lb_sum, lb_p);
+    if (tid == 0 && tile == n_tiles - 1) *nnz_out = (int64_t)(excl + (unsigned long long)total);
+
+    // ---- row offsets: a row starts in this thread's units at most once when a row has >= 8 units ----
+    if (row_offsets && uf < nu) {
+        const uint32_t g = u0 + uf;
+        uint32_t r = fd_div(g, upr);
+        uint32_t k = (r * upr.d == g) ? 0u : (r + 1) * upr.d - g;          // units until the next row start
+        if (k != 0) ++r;
+        while (k < 8 && uf + k < nu) {
+            const uint32_t below = (k < 4) ? __popc(lo & ((1u << (8 * k)) - 1u)) : (uint32_t)clo + __popc(hi & ((1u << (8 * (k - 4))) - 1u));
+            row_offsets[r] = (int64_t)(excl + (unsigned long long)toff + below);
+            k += upr.d;
+            ++r;
+        }
+    }
+
+    // ---- B: where does output vector v start?  run element j0(v) = max(8 v - shift, 0); the thread that owns it records its position ----
+    const uint32_t shift = (uint32_t)(excl & 7ull);
+    const uint32_t span = shift + (uint32_t)total;
+    const uint32_t nvec = (span + 7) >> 3;
+    if (cnt > 0) {
+        uint32_t v = ((uint32_t)toff + shift + 7) >> 3;                     // first vector whose first element is at or after toff
+        if (toff == 0) v = 0;
+        while (true) {
+            const uint32_t j0 = (v == 0) ? 0u : 8 * v - shift;
+            if (j0 >= (uint32_t)(toff + cnt)) break;
+            const uint32_t n = j0 - (uint32_t)toff;
+            const uint32_t bit = (n < (uint32_t)clo) ? select32(lo, n) : 32u + select32(hi, n - (uint32_t)clo);
+            start_s[v] = (uint16_t)(uf * 8 + bit);
+            ++v;
+        }
+    }
+    __syncthreads();
+
+    // ---- C: one thread per output vector walks the mask from the vector's first element and gathers 8 kept halves from the tile ----
+    const unsigned long long g0 = excl - shift;
+    for (uint32_t v = tid; v < nvec; v += B3_T) {
+        if (((v == 0) ? shift : 0u) >= min(8u, span - 8 * v)) continue;      // an empty tile's only vector: nothing of it belongs to this run
+        uint32_t bit = start_s[v];
+        uint32_t wi = bit >> 5;
+        const uint32_t s = bit & 31u;
+        uint32_t cur = __funnelshift_r(mask_w[wi], mask_w[wi + 1], s);      // kept-flags of elements bit .. bit + 31
+        const uint32_t p_lo = (v == 0) ? shift : 0u;                         // positions of this vector that belong to the run
+        const uint32_t p_hi = min(8u, span - 8 * v);
+        uint32_t o[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if ((uint32_t)e >= p_lo && (uint32_t)e < p_hi) {
+                while (cur == 0u) {                                          // the next kept element is further than 32 positions away
+                    bit += 32;
+                    ++wi;
+                    cur = __funnelshift_r(mask_w[wi], mask_w[wi + 1], s);
+                }
+                const uint32_t idx = bit + (uint32_t)__ffs(cur) - 1u;
+                cur &= cur - 1u;
+                uint32_t h;
+                asm volatile("{ .reg .b16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(h) : "r"(data + idx * 2));
+                o[e >> 1] |= h << (16 * (e & 1));
+            }
+        }
+        if (p_lo == 0 && p_hi == 8) stg_stream16(reinterpret_cast<uint4*>(values + g0) + v, make_uint4(o[0], o[1], o[2], o[3]));
+        else {
+            uint16_t* ge = values + g0 + 8ull * v;
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if ((uint32_t)e >= p_lo && (uint32_t)e < p_hi) ge[e] = (uint16_t)(o[e >> 1] >> (16 * (e & 1)));
+        }
+    }
+}
+
 // expansion: mask bytes -> counts -> scan -> look-back -> the tile's run of `values` into shared memory (aligned 16-byte loads, so that
 // run element j sits at stage element j + shift) -> dense tile, 16-byte stores
 __global__ void __launch_bounds__(B3_T) bitmask_expand_tile_kernel(const uint16_t* __restrict__ values, const uint8_t* __restrict__ bitmask,
@@ -551,7 +716,12 @@ int launch_bitmask_lookback(const void* src, uint8_t* bitmask, void* dst, int64_
     if (rc) return rc;
     CT_CUDA_TRY(cudaMemsetAsync(scratch, 0, bytes, st));
     if (!getenv("CT_B200_BITMASK_V1")) {
-        if (COMPRESS) {
+        if (COMPRESS && !getenv("CT_B200_BITMASK_V3")) {
+            bitmask_compress_gather_kernel<<<n_tiles, B3_T, B4_SMEM, st>>>(reinterpret_cast<const uint8_t*>(src), bitmask, reinterpret_cast<uint16_t*>(dst),
+                                                                            row_offsets, nnz_out, reinterpret_cast<unsigned long long*>(scratch + 16),
+                                                                            reinterpret_cast<uint32_t*>(scratch), (uint32_t)n_units, n_tiles,
+                                                                            make_fastdiv((uint64_t)(cols / 8)));
+        } else if (COMPRESS) {
             auto kfn = bitmask_compress_tile_kernel;
             CT_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B3_SMEM));
             kfn<<<n_tiles, B3_T, B3_SMEM, st>>>(reinterpret_cast<const uint8_t*>(src), bitmask, reinterpret_cast<uint16_t*>(dst), row_offsets, nnz_out,

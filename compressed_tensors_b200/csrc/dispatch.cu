@@ -570,6 +570,7 @@ static int run_bits(bool pack, const void* in, void* out, int64_t rows, int64_t 
         lp.tbl.one.tile_end = (lp.tbl.one.n_chunks + TILE_CHUNKS - 1) / TILE_CHUNKS;
         lp.tbl.one.dc = make_fastdiv(0x7FFFFFFFull);
         lp.total_tiles = lp.tbl.one.tile_end;
+        lp.tile_chunks = TILE_CHUNKS;
         lp.cm = make_common(CT_F32, CT_Q_INT, bits);
         FastSig s{pack ? F_PACK : F_UNPACK, CT_I8, bits, 0, 1};
         return launch_fast_bits(s, lp, device, stream);
