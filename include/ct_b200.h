@@ -260,7 +260,9 @@ int ct_bitmask_decompress(const void* values, int dtype, const uint8_t* bitmask,
  * mask bit order of utils/helpers.py:306-317): `values` is a caller buffer of CAPACITY rows * cols elements of which the first *nnz_out
  * (device int64) are written, row_offsets [rows] and bitmask [rows, ceil(cols/8)] as above.  bf16 / fp16 tensors with cols % 8 == 0
  * are read exactly once (per-tile counts combined by a decoupled look-back scan inside the kernel); other dtypes / shapes run the
- * two-phase kernels above on a stream-ordered workspace.  Enqueue-only. */
+ * two-phase kernels above on a stream-ordered workspace.  Enqueue-only.
+ * (ct_bitmask_decompress is one pass either way: with row_offsets every row knows where its values start; row_offsets = NULL is
+ * accepted for bf16 / fp16, cols % 8 == 0: the scan is then recomputed from the mask popcounts with the same look-back.) */
 int ct_bitmask_compress_onepass(const void* x, int dtype, void* values, uint8_t* bitmask, int64_t* row_offsets, int64_t* nnz_out,
                                 int64_t rows, int64_t cols, int device, void* stream);
 

@@ -494,4 +494,5 @@ def test_bitmask_onepass_lookback_vs_oracle(shape, density, monkeypatch):
     monkeypatch.setenv("CT_B200_BITMASK_TWO_PHASE", "1")     # count -> scan -> move
     tv, tb, to = ops.bitmask_compress(xd)
     same(tv, gv, "two-phase values"); same_values(tb, gb, "two-phase mask"); same_values(to, go, "two-phase offsets")
-    same(ops.bitmask_decompress(gv, gb, go, x.shape), dense, "two-phase expand")
+    monkeypatch.setenv("CT_B200_BITMASK_LOOKBACK", "1")      # expansion without row_offsets: the scan recomputed from the mask popcounts
+    same(ops.bitmask_decompress(gv, gb, go, x.shape), dense, "look-back expand == row_offsets expand")

@@ -49,10 +49,12 @@ for density in (0.5, 0.1):
     b_alg = n * (2 + 2 * d + 0.125)
     os.environ.pop("CT_B200_BITMASK_TWO_PHASE", None)
     report("bitmask_compress_onepass", med(lambda: ops.bitmask_compress(un, exact=False)), b_alg, density=round(d, 3))
+    report("bitmask_expand_row_offsets", med(lambda: ops.bitmask_decompress(vals, mask, offs, un.shape)), b_alg, density=round(d, 3))
+    os.environ["CT_B200_BITMASK_LOOKBACK"] = "1"
     report("bitmask_expand_lookback", med(lambda: ops.bitmask_decompress(vals, mask, offs, un.shape)), b_alg, density=round(d, 3))
+    os.environ.pop("CT_B200_BITMASK_LOOKBACK", None)
     os.environ["CT_B200_BITMASK_TWO_PHASE"] = "1"
     report("bitmask_compress_two_phase", med(lambda: ops.bitmask_compress(un, exact=False)), b_alg, density=round(d, 3))
-    report("bitmask_expand_two_phase", med(lambda: ops.bitmask_decompress(vals, mask, offs, un.shape)), b_alg, density=round(d, 3))
     os.environ.pop("CT_B200_BITMASK_TWO_PHASE", None)
     del un, vals, mask, offs
 
