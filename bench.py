@@ -490,6 +490,7 @@ def run_cfg5_70b_sharded(a, rank: int, world: int, dev):
         mc.compress_model(model, distributed=True, stats=st)
         torch.cuda.synchronize()
         total = time.perf_counter() - t0
+        recouple_how = st.get("recouple_how")
         if k > 0:
             runs.append(reduce_max([st["apply_s"], st["recouple_s"], total, st["device_ms"] or 0.0, st["mirror_host_s"]]) + [st["recouple_bytes"]])
     best = min(runs, key=lambda r: r[2])
@@ -543,6 +544,7 @@ def run_cfg5_70b_sharded(a, rank: int, world: int, dev):
             torch.cuda.synchronize()
             total = time.perf_counter() - t0
             d_runs.append(reduce_max([st["apply_s"], st["recouple_s"], total, st["device_ms"] or 0.0]) + [st["recouple_bytes"]])
+            d_how = st.get("recouple_how")
         d_apply, d_rec, d_total, d_dev, d_bytes = d_runs[-1]
         dsums = torch.stack([m.weight.view(torch.int16).sum(dtype=torch.int64) for m in mods])
         hi, lo = dsums.clone(), dsums.clone()
@@ -559,7 +561,7 @@ def run_cfg5_70b_sharded(a, rank: int, world: int, dev):
         dec = {"decompress_ms": round(d_apply * 1e3, 2), "decompress_device_ms": round(d_dev, 2), "recouple_ms": round(d_rec * 1e3, 2),
                "total_ms": round(d_total * 1e3, 2), "weight_GBps_decompress_only": round(dense_total / d_apply / 1e9, 1),
                "weight_GBps_decompress_device_time": round(dense_total / (d_dev * 1e-3) / 1e9, 1) if d_dev else None,
-               "recouple_GBps_per_rank": round(d_bytes / d_rec / 1e9, 1), "first_pass_total_ms": round(d_runs[0][2] * 1e3, 1),
+               "recouple_GBps_per_rank": round(d_bytes / d_rec / 1e9, 1), "recouple_how": d_how, "first_pass_total_ms": round(d_runs[0][2] * 1e3, 1),
                "ranks_agree": bool(torch.equal(hi, lo)), "sample_equals_fake_quantize": bool(okd.item())}
     else:
         dec = {"skipped": f"{free_b / 2**30:.0f} GiB free, the recoupled dense model needs {dense_total / 2**30:.0f} GiB"}
@@ -578,7 +580,7 @@ def run_cfg5_70b_sharded(a, rank: int, world: int, dev):
         "weight_GBps_compress_device_time": round(dense_total / (dev_ms * 1e-3) / 1e9, 1) if dev_ms else None,
         "note": "compress_ms = host clock of the owners' launches + the meta mirror of the other ranks' modules (Python, per module), device-synchronised; "
                 "compress_device_ms = CUDA events around the slowest rank's kernels alone",
-        "recouple_bytes_per_rank": int(rec_bytes), "recouple_GBps_per_rank": round(rec_bytes / rec_s / 1e9, 1),
+        "recouple_bytes_per_rank": int(rec_bytes), "recouple_GBps_per_rank": round(rec_bytes / rec_s / 1e9, 1), "recouple_how": recouple_how,
         "reps": len(runs), "timing": "host clock around the call with device synchronisation on both sides, max over ranks (the call includes the Python module loop)",
         "generate_s": round(gen_s, 2),
         "parity": {"ranks_agree_on_all_checksums": ranks_agree, "sample_equals_single_rank": sample_ok, "sample": sample, "oracle_tensor_1": oracle_ok},

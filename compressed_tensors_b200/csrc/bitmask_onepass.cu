@@ -253,9 +253,15 @@ __global__ void __launch_bounds__(256) bitmask_lookback_kernel(const void* __res
 // copy), so the kernel needs 40 registers and 6 CTAs / SM are resident; all 128 threads look back, but POLITELY -- one read per
 // descriptor per round, a round is repeated (after a nanosleep) only while a descriptor that is actually needed is unpublished.
 // ------------------------------------------------------------------------------------------------------------------------------
-constexpr int B3_T = 128;                      // threads
+#ifndef CT_BITMASK_THREADS
+#define CT_BITMASK_THREADS 256
+#endif
+// 256 threads x 8 units = 2048 units = 32 KB of input per tile: the chained scan advances one look-back window (one descriptor per
+// thread) per ~1.2 us hop whatever the tile size, so the bytes per hop -- 256 tiles x 32 KB = 8 MB -- set the ceiling (128 x 16 KB
+// tiles: ~2 TB/s of input, measured)
+constexpr int B3_T = CT_BITMASK_THREADS;       // threads
 constexpr int B3_W = B3_T / 32;                // warps
-constexpr int B3_TILE = 1024;                  // units per tile (8192 elements, 16 KB)
+constexpr int B3_TILE = 8 * B3_T;              // units per tile
 constexpr int B3_UPT = B3_TILE / B3_T;         // units per thread (8)
 constexpr uint32_t B3_STAGE_BYTES = 8 * B3_TILE * 2 + 32;   // compact elements of a tile + one vector of slack for the funnel
 constexpr uint32_t B3_SMEM = 16 + B3_TILE * 16 + B3_STAGE_BYTES;
@@ -267,9 +273,9 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
 }
 __device__ __forceinline__ void sts16(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"((unsigned short)v) : "memory"); }
 
-// exclusive prefix of `tile` (sum of the counts of all tiles before it); every thread of the 128-thread CTA takes part and returns it.
+// exclusive prefix of `tile` (sum of the counts of all tiles before it); every thread of the CTA takes part and returns it.
 // Thread t inspects tile base - t; warp w therefore covers distances 32 w .. 32 w + 31, nearest first.
-__device__ __forceinline__ unsigned long long lookback128(unsigned long long* desc, uint32_t tile, uint32_t total, unsigned long long* lb_sum, int* lb_p) {
+__device__ __forceinline__ unsigned long long lookback_cta(unsigned long long* desc, uint32_t tile, uint32_t total, unsigned long long* lb_sum, int* lb_p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) st_desc(desc + tile, (tile == 0 ? DESC_P : DESC_A) | (unsigned long long)total);
     unsigned long long excl = 0;
@@ -454,7 +460,7 @@ __global__ void __launch_bounds__(B3_T) bitmask_compress_tile_kernel(const uint8
         }
     }
     // (the look-back's barriers also order the staging writes before the write-out)
-    const unsigned long long excl = lookback128(desc, tile, (uint32_t)total, lb_sum, lb_p);
+    const unsigned long long excl = lookback_cta(desc, tile, (uint32_t)total, lb_sum, lb_p);
     if (tid == 0 && tile == n_tiles - 1) *nnz_out = (int64_t)(excl + (unsigned long long)total);
     if (tile == 0) __syncthreads();            // tile 0 skips the look-back's barriers
 
@@ -565,7 +571,7 @@ __global__ void __launch_bounds__(B3_T) bitmask_compress_gather_kernel(const uin
     }
     const int toff = before + incl - cnt;          // first slot of this thread's elements in the tile's run
 
-    const unsigned long long excl = lookback128(desc, tile, (uint32_t)total, lb_sum, lb_p);
+    const unsigned long long excl = lookback_cta(desc, tile, (uint32_t)total, lb_sum, lb_p);
     if (tid == 0 && tile == n_tiles - 1) *nnz_out = (int64_t)(excl + (unsigned long long)total);
 
     // ---- row offsets: a row starts in this thread's units at most once when a row has >= 8 units ----
@@ -671,7 +677,7 @@ __global__ void __launch_bounds__(B3_T) bitmask_expand_tile_kernel(const uint16_
         cnt[k] = __popc(b);
     }
     const int total = tile_scan(cnt, off, warp_tot);
-    const unsigned long long excl = lookback128(desc, tile, (uint32_t)total, lb_sum, lb_p);
+    const unsigned long long excl = lookback_cta(desc, tile, (uint32_t)total, lb_sum, lb_p);
 
     const uint32_t shift = (uint32_t)(excl & 7ull);
     const uint32_t nvec = (shift + (uint32_t)total + 7) >> 3;
@@ -709,14 +715,17 @@ template <bool COMPRESS>
 int launch_bitmask_lookback(const void* src, uint8_t* bitmask, void* dst, int64_t* row_offsets, int64_t* nnz_out, int64_t rows, int64_t cols,
                             int device, cudaStream_t st) {
     const int64_t n_units = rows * cols / 8;
-    const uint32_t n_tiles = (uint32_t)((n_units + BM_TILE - 1) / BM_TILE);
+    const bool v1 = getenv("CT_B200_BITMASK_V1") != nullptr;
+    const int64_t tile_units = v1 ? BM_TILE : B3_TILE;
+    const uint32_t n_tiles = (uint32_t)((n_units + tile_units - 1) / tile_units);
     uint8_t* scratch = nullptr;
     const size_t bytes = 16 + (size_t)n_tiles * sizeof(unsigned long long);
     int rc = scratch_alloc(reinterpret_cast<void**>(&scratch), bytes, device, st);
     if (rc) return rc;
     CT_CUDA_TRY(cudaMemsetAsync(scratch, 0, bytes, st));
-    if (!getenv("CT_B200_BITMASK_V1")) {
+    if (!v1) {
         if (COMPRESS && !getenv("CT_B200_BITMASK_V3")) {
+            CT_CUDA_TRY(cudaFuncSetAttribute(bitmask_compress_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B4_SMEM));
             bitmask_compress_gather_kernel<<<n_tiles, B3_T, B4_SMEM, st>>>(reinterpret_cast<const uint8_t*>(src), bitmask, reinterpret_cast<uint16_t*>(dst),
                                                                             row_offsets, nnz_out, reinterpret_cast<unsigned long long*>(scratch + 16),
                                                                             reinterpret_cast<uint32_t*>(scratch), (uint32_t)n_units, n_tiles,

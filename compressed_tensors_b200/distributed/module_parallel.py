@@ -38,6 +38,110 @@ def _wire_device(dev: torch.device) -> torch.device:
     return torch.device("cpu") if dev.type == "meta" else dev
 
 
+_ALIGN = 256
+
+
+def _layout(modules, owner, world):
+    """byte layout of every owner's results inside its slot of the gathered buffer; identical on every rank (the meta mirror gave every
+    rank the same names / shapes / dtypes)"""
+    entries = {r: [] for r in range(world)}
+    sizes = [0] * world
+    for m in modules:
+        o = owner[m]
+        for name, t in get_direct_state_dict(m).items():
+            if t is None:
+                continue
+            nbytes = t.numel() * t.element_size()
+            entries[o].append((m, name, sizes[o], nbytes, tuple(t.shape), t.dtype))
+            sizes[o] = (sizes[o] + nbytes + _ALIGN - 1) // _ALIGN * _ALIGN
+    return entries, max(sizes) if sizes else 0
+
+
+def _allgather_fits(modules, owner, world) -> bool:
+    """the gathered buffer (every owner's results, once) fits comfortably on EVERY rank -- agreed collectively, or some ranks would
+    enter an all_gather and others a broadcast"""
+    _, slot = _layout(modules, owner, world)
+    total = slot * world
+    nccl = dist.get_backend() == "nccl" and torch.cuda.is_available()
+    if nccl:
+        free_b, _ = torch.cuda.mem_get_info()
+        ok = total <= free_b // 2
+    else:
+        ok = total <= (4 << 30)
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=_wire_device(torch.device("meta")))
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item())
+
+
+def _recouple_allgather(modules, owner, rank, world, devices) -> int:
+    entries, slot = _layout(modules, owner, world)
+    if slot == 0:
+        return 0
+    wire = _wire_device(torch.device("meta"))
+    out = torch.empty(world * slot, dtype=torch.uint8, device=wire)
+    mine = out[rank * slot:(rank + 1) * slot]
+    for m, name, off, nbytes, _, _ in entries[rank]:
+        if nbytes:
+            t = get_direct_state_dict(m)[name]
+            mine[off:off + nbytes].copy_(as_broadcastable(t.contiguous()).reshape(-1).view(torch.uint8), non_blocking=True)
+    dist.all_gather_into_tensor(out, mine)          # in place: this rank's slot is its own contribution
+    received = {}
+    for r in range(world):
+        if r == rank:
+            continue                                 # the owner keeps its own tensors
+        base = r * slot
+        for m, name, off, nbytes, shape, dtype in entries[r]:
+            v = out[base + off: base + off + nbytes]
+            v = v.view(dtype).reshape(shape) if nbytes else torch.empty(shape, dtype=dtype, device=wire)   # offsets are 256-byte aligned
+            received.setdefault(id(m), (m, {}))[1][name] = v
+    moved = 0
+    for m, got in received.values():
+        sd = get_direct_state_dict(m)
+        home = devices.get(id(m), torch.device("cpu"))
+        if home.type == "meta":
+            home = wire
+        new = {}
+        for name, t in sd.items():
+            if t is None:
+                new[name] = None
+                continue
+            v = got[name]
+            # tensors the shape-only path already produced for real (e.g. weight_shape, on the CPU) stay where they were
+            new[name] = v.to(home) if t.device.type == "meta" else v.to(t.device)
+            moved += v.numel() * v.element_size()
+        replace_direct_state_dict(m, new)
+    return moved
+
+
+def _recouple_broadcast(modules, owner, rank, devices) -> int:
+    moved = 0
+    for m in modules:  # same (sorted) order on every rank
+        sd = get_direct_state_dict(m)
+        home = devices.get(id(m), torch.device("cpu"))
+        dev = _wire_device(home)
+        if home.type == "meta":
+            home = dev
+        new = {}
+        for name in sd:  # identical key order on all ranks (same compressor code path)
+            t = sd[name]
+            if t is None:
+                new[name] = None
+                continue
+            if owner[m] == rank:
+                buf = as_broadcastable(t.contiguous().to(dev))
+                dist.broadcast(buf, src=owner[m])
+                new[name] = t                                   # the owner keeps its own tensors
+            else:
+                buf = as_broadcastable(torch.empty(t.shape, dtype=t.dtype, device=dev))
+                dist.broadcast(buf, src=owner[m])
+                got = buf.view(t.dtype) if buf.dtype != t.dtype else buf
+                # tensors the shape-only path already produced for real (e.g. weight_shape, on the CPU) stay where they were
+                new[name] = got.to(home) if t.device.type == "meta" else got.to(t.device)
+            moved += t.numel() * t.element_size()
+        replace_direct_state_dict(m, new)
+    return moved
+
+
 def _sync(stats):
     if stats is not None and torch.cuda.is_available():
         torch.cuda.synchronize()
@@ -48,7 +152,11 @@ def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callab
     """Extensions over the reference's signature (all optional):
       apply_many_fn(list_of_modules): the owner's modules are processed in one batched call
       recouple=False: skip step 4 -- every rank keeps only the results of the modules it owns (the others stay on meta); the flow for
-                      "each owner writes its own checkpoint shard"
+                      "each owner writes its own checkpoint shard".  True (default) picks between "allgather" -- every owner packs its
+                      results into one flat byte buffer and ONE all_gather_into_tensor moves everything (all owners send at once: the
+                      NVSwitch is used from every GPU, where per-tensor broadcasts have one sender at a time) -- and "broadcast" (one
+                      dist.broadcast per tensor, frees memory incrementally; chosen when the gathered buffer would not fit comfortably);
+                      either can be forced by name
       stats: a dict that receives `apply_s` (this rank's own work + the meta mirror of the others', device-synchronised), its parts
              `owner_host_s` (incl. the final device wait) / `mirror_host_s` / `device_ms` (CUDA events around the owner's launches), `recouple_s`, `recouple_bytes`,
              `owned_modules`, `owned_bytes`; asking for them adds two device synchronisations
@@ -102,33 +210,17 @@ def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callab
     _sync(stats)
     t1 = time.perf_counter()
 
-    moved = 0
-    for m in (modules if recouple else ()):  # same (sorted) order on every rank
-        sd = get_direct_state_dict(m)
-        home = devices.get(id(m), torch.device("cpu"))
-        dev = _wire_device(home)
-        if home.type == "meta":
-            home = dev
-        new = {}
-        for name in sd:  # identical key order on all ranks (same compressor code path)
-            t = sd[name]
-            if t is None:
-                new[name] = None
-                continue
-            if owner[m] == rank:
-                buf = as_broadcastable(t.contiguous().to(dev))
-                dist.broadcast(buf, src=owner[m])
-                new[name] = t                                   # the owner keeps its own tensors
-            else:
-                buf = as_broadcastable(torch.empty(t.shape, dtype=t.dtype, device=dev))
-                dist.broadcast(buf, src=owner[m])
-                got = buf.view(t.dtype) if buf.dtype != t.dtype else buf
-                # tensors the shape-only path already produced for real (e.g. weight_shape, on the CPU) stay where they were
-                new[name] = got.to(home) if t.device.type == "meta" else got.to(t.device)
-            moved += t.numel() * t.element_size()
-        replace_direct_state_dict(m, new)
+    moved, how = 0, "none"
+    if recouple:
+        how = recouple if isinstance(recouple, str) else "auto"
+        if how == "auto":
+            how = "allgather" if _allgather_fits(modules, owner, world) else "broadcast"
+        if how == "allgather":
+            moved = _recouple_allgather(modules, owner, rank, world, devices)
+        else:
+            moved = _recouple_broadcast(modules, owner, rank, devices)
     _sync(stats)
     if stats is not None:
         stats.update(apply_s=t1 - t0, recouple_s=time.perf_counter() - t1, recouple_bytes=moved, owned_modules=len(mine),
-                     owned_bytes=int(owned_bytes), world_size=world, mirror_host_s=t_mirror, owner_host_s=t1 - t0 - t_mirror,
+                     owned_bytes=int(owned_bytes), world_size=world, mirror_host_s=t_mirror, owner_host_s=t1 - t0 - t_mirror, recouple_how=how,
                      device_ms=(ev[0].elapsed_time(ev[1]) if ev is not None else None))

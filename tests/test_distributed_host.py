@@ -124,7 +124,7 @@ _WORKER = textwrap.dedent(
     # single-process result; stats are filled; recouple=False leaves the other rank's modules on meta
     from compressed_tensors.distributed import greedy_bin_packing, module_size
     from compressed_tensors.utils import replace_direct_state_dict
-    for recouple in (True, False):
+    for recouple in (True, "broadcast", "allgather", False):
         full = build(6, with_extras=False)
         quantize_config(full, "W4A16")
         reference = copy.deepcopy(full)
@@ -137,7 +137,8 @@ _WORKER = textwrap.dedent(
         ModelCompressor.from_pretrained_model(full).compress_model(full, distributed=True, recouple=recouple, stats=stats)
         ModelCompressor.from_pretrained_model(reference).compress_model(reference, distributed=False)
         assert stats["owned_modules"] == sum(1 for m in mods if owner[m] == rank) and stats["apply_s"] > 0 and stats["world_size"] == 2
-        assert (stats["recouple_bytes"] > 0) == recouple
+        assert (stats["recouple_bytes"] > 0) == bool(recouple)
+        assert stats["recouple_how"] == {True: "allgather", False: "none"}.get(recouple, recouple)
         for (n1, m1), (n2, m2) in zip(full.named_modules(), reference.named_modules()):
             if getattr(m1, "quantization_scheme", None) is None:
                 continue
