@@ -384,6 +384,8 @@ def run_b200(a):
                        "launch": "one multi-tensor persistent launch per step", "pipe": os.environ.get("CT_B200_PIPE", "tma")},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic_per_launch("quantize_pack", n_elems), "peak_source": peak_src,
+                         "traffic_source": "NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture of "
+                                           "this kernel (" + str((profile_traffic("quantize_pack") or {}).get("source")) + "), scaled by element count",
                          "algorithmic_bytes_per_launch": alg_bytes, "frac_of_8TBps_nominal": round(achieved / 8000.0, 4)},
             "gpu_launches": int(launches), "clocks": clocks,
             "verified": verified, "verified_against": f"oracle (CPU) on every packed word of tensors {verified_idx} written by the timed launches",

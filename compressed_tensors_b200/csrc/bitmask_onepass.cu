@@ -543,12 +543,25 @@ __global__ void __launch_bounds__(B3_T) bitmask_compress_gather_kernel(const uin
     // ---- A: mask bytes of the thread's 8 consecutive units (read in a lane-dependent order: bank-conflict free), counts, scan ----
     const uint32_t uf = 8u * (uint32_t)tid;
     uint8_t* mask_b = reinterpret_cast<uint8_t*>(mask_w);
+    {
+        const uint32_t sw = (uint32_t)(tid & 7);
+        const uint32_t tdata = data + uf * 16;
+        uint8_t* tmask = mask_b + uf;
+        if (nu == (uint32_t)B3_TILE) {                 // a full tile (all but the last one): no bounds checks
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const uint32_t i = uf + (uint32_t)(k ^ (tid & 7));
-        uint32_t b = 0;
-        if (i < nu) b = nz_byte16_fast(lds128(data + i * 16));
-        mask_b[i] = (uint8_t)b;
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t p = (uint32_t)k ^ sw;
+                tmask[p] = (uint8_t)nz_byte16_fast(lds128(tdata + p * 16));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t p = (uint32_t)k ^ sw;
+                uint32_t b = 0;
+                if (uf + p < nu) b = nz_byte16_fast(lds128(tdata + p * 16));
+                tmask[p] = (uint8_t)b;
+            }
+        }
     }
     const uint32_t lo = mask_w[2 * tid], hi = mask_w[2 * tid + 1];       // written by this thread: no barrier needed
     if (uf + 4 <= nu) reinterpret_cast<uint32_t*>(bitmask + u0 + uf)[0] = lo;        // n_units % 4 == 0; the mask is 4-byte aligned
@@ -609,35 +622,47 @@ __global__ void __launch_bounds__(B3_T) bitmask_compress_gather_kernel(const uin
     // ---- C: one thread per output vector walks the mask from the vector's first element and gathers 8 kept halves from the tile ----
     const unsigned long long g0 = excl - shift;
     for (uint32_t v = tid; v < nvec; v += B3_T) {
-        if (((v == 0) ? shift : 0u) >= min(8u, span - 8 * v)) continue;      // an empty tile's only vector: nothing of it belongs to this run
+        const uint32_t p_lo = (v == 0) ? shift : 0u;                         // positions of this vector that belong to the run
+        const uint32_t p_hi = min(8u, span - 8 * v);
+        if (p_lo >= p_hi) continue;                                          // an empty tile's only vector: nothing of it belongs to this run
         uint32_t bit = start_s[v];
         uint32_t wi = bit >> 5;
         const uint32_t s = bit & 31u;
         uint32_t cur = __funnelshift_r(mask_w[wi], mask_w[wi + 1], s);      // kept-flags of elements bit .. bit + 31
-        const uint32_t p_lo = (v == 0) ? shift : 0u;                         // positions of this vector that belong to the run
-        const uint32_t p_hi = min(8u, span - 8 * v);
-        uint32_t o[4] = {0u, 0u, 0u, 0u};
+        uint32_t ebase = data + bit * 2;                                     // shared address of element `bit`
+        if (p_lo == 0 && p_hi == 8) {
+            // the common case: a whole vector.  Per element: isolate the lowest kept flag, its position, one 16-bit shared load
+            uint32_t h[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            if ((uint32_t)e >= p_lo && (uint32_t)e < p_hi) {
+            for (int e = 0; e < 8; ++e) {
                 while (cur == 0u) {                                          // the next kept element is further than 32 positions away
-                    bit += 32;
                     ++wi;
+                    ebase += 64;
                     cur = __funnelshift_r(mask_w[wi], mask_w[wi + 1], s);
                 }
-                const uint32_t idx = bit + (uint32_t)__ffs(cur) - 1u;
+                const uint32_t pos = (uint32_t)__ffs(cur) - 1u;
                 cur &= cur - 1u;
-                uint32_t h;
-                asm volatile("{ .reg .b16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(h) : "r"(data + idx * 2));
-                o[e >> 1] |= h << (16 * (e & 1));
+                unsigned short t;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(t) : "r"(ebase + 2 * pos));
+                h[e] = t;
             }
-        }
-        if (p_lo == 0 && p_hi == 8) stg_stream16(reinterpret_cast<uint4*>(values + g0) + v, make_uint4(o[0], o[1], o[2], o[3]));
-        else {
+            stg_stream16(reinterpret_cast<uint4*>(values + g0) + v,
+                         make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16)));
+        } else {
+            // the run's first / last vector: only positions [p_lo, p_hi) are ours
             uint16_t* ge = values + g0 + 8ull * v;
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-                if ((uint32_t)e >= p_lo && (uint32_t)e < p_hi) ge[e] = (uint16_t)(o[e >> 1] >> (16 * (e & 1)));
+            for (uint32_t e = p_lo; e < p_hi; ++e) {
+                while (cur == 0u) {
+                    ++wi;
+                    ebase += 64;
+                    cur = __funnelshift_r(mask_w[wi], mask_w[wi + 1], s);
+                }
+                const uint32_t pos = (uint32_t)__ffs(cur) - 1u;
+                cur &= cur - 1u;
+                unsigned short t;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(t) : "r"(ebase + 2 * pos));
+                ge[e] = t;
+            }
         }
     }
 }

@@ -65,6 +65,7 @@ def _allgather_fits(modules, owner, world) -> bool:
     nccl = dist.get_backend() == "nccl" and torch.cuda.is_available()
     if nccl:
         free_b, _ = torch.cuda.mem_get_info()
+        free_b += torch.cuda.memory_reserved() - torch.cuda.memory_allocated()      # blocks the caching allocator holds but does not use
         ok = total <= free_b // 2
     else:
         ok = total <= (4 << 30)
@@ -94,7 +95,6 @@ def _recouple_allgather(modules, owner, rank, world, devices) -> int:
             v = out[base + off: base + off + nbytes]
             v = v.view(dtype).reshape(shape) if nbytes else torch.empty(shape, dtype=dtype, device=wire)   # offsets are 256-byte aligned
             received.setdefault(id(m), (m, {}))[1][name] = v
-    moved = 0
     for m, got in received.values():
         sd = get_direct_state_dict(m)
         home = devices.get(id(m), torch.device("cpu"))
@@ -108,9 +108,8 @@ def _recouple_allgather(modules, owner, rank, world, devices) -> int:
             v = got[name]
             # tensors the shape-only path already produced for real (e.g. weight_shape, on the CPU) stay where they were
             new[name] = v.to(home) if t.device.type == "meta" else v.to(t.device)
-            moved += v.numel() * v.element_size()
         replace_direct_state_dict(m, new)
-    return moved
+    return sum(e[3] for r in range(world) for e in entries[r])      # bytes that went through the collective (like the broadcast path counts)
 
 
 def _recouple_broadcast(modules, owner, rank, devices) -> int:

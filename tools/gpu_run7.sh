@@ -1,7 +1,3 @@
 cd $GRAFT_REPO_ROOT
-for K in 1 2 4; do for S in 0 20 100; do
-echo "== K=$K sleep=$S"; CT_B200_BITMASK_LB_K=$K CT_B200_BITMASK_LB_SLEEP=$S python tools/sparse_bench.py 2>/dev/null | grep -E "onepass|expand_lookback" | python -c "
-import sys,json
-for l in sys.stdin:
-    d=json.loads(l); print('  ', d['op'], d['density'], d['us'])"
-done; done
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_compressors.py tests/test_gpu_large.py -m gpu -q -k "bitmask or Bitmask or sparse" 2>&1 | tail -3
+python tools/sparse_bench.py 2>/dev/null | grep -E "bitmask"
