@@ -147,7 +147,8 @@ def _sync(stats):
 
 
 def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callable = module_size, desc: Optional[str] = None,
-                            apply_many_fn: Optional[Callable] = None, recouple: bool = True, stats: Optional[dict] = None):
+                            apply_many_fn: Optional[Callable] = None, recouple: bool = True, stats: Optional[dict] = None,
+                            mirror_cache: bool = True):
     """Extensions over the reference's signature (all optional):
       apply_many_fn(list_of_modules): the owner's modules are processed in one batched call
       recouple=False: skip step 4 -- every rank keeps only the results of the modules it owns (the others stay on meta); the flow for
@@ -180,11 +181,32 @@ def replace_module_parallel(modules: list, apply_fn: Callable, weight_fn: Callab
     t_mirror = 0.0
 
     def mirror():
+        """the other ranks' modules, shape-only.  `apply_fn` runs for real on the first module of every signature (class, scheme
+        object, names / shapes / dtypes of its tensors, values of the `*_shape` bookkeeping tensors the shape-only path reads); its
+        effect -- the resulting meta state dict and quantization_status -- is replayed for the other modules of that signature
+        (a 70B model has 560 modules and 4 signatures).  Valid for compress_module / decompress_module, whose meta path is a pure
+        function of exactly that signature."""
         nonlocal t_mirror
         t = time.perf_counter()
+        plans = {}
         for m in others:
-            _to_meta(m)
-            apply_fn(m)
+            sd = get_direct_state_dict(m)
+            key = (type(m), id(getattr(m, "quantization_scheme", None)), getattr(m, "quantization_status", None),
+                   tuple((k, tuple(v.shape), v.dtype, tuple(v.reshape(-1).tolist()) if k.endswith("shape") else None) for k, v in sd.items() if v is not None))
+            plan = plans.get(key) if mirror_cache else None
+            if plan is None:
+                _to_meta(m)
+                apply_fn(m)
+                if mirror_cache:
+                    out = get_direct_state_dict(m)
+                    plans[key] = ({k: (None if v is None else ((tuple(v.shape), v.dtype) if v.device.type == "meta" else v)) for k, v in out.items()},
+                                  getattr(m, "quantization_status", None))
+            else:
+                spec, status = plan
+                replace_direct_state_dict(m, {k: (None if v is None else (torch.empty(v[0], dtype=v[1], device="meta") if isinstance(v, tuple) else v.clone()))
+                                              for k, v in spec.items()})
+                if status is not None:
+                    m.quantization_status = status
         t_mirror = time.perf_counter() - t
 
     # Mirroring the other ranks' modules on meta is host-only bookkeeping (the larger share of the host time at 8 ranks).  When those
