@@ -102,9 +102,11 @@ __global__ void __launch_bounds__(256) minmax_qparams_kernel(const uint4* __rest
     lo = -dec_f32(atomicMax(slots + 0, 0u));                     // min(min_vals, 0)
     hi = dec_f32(atomicMax(slots + 1, 0u));                      // max(max_vals, 0)
     if (prm.kind == 1) {
-        // generate_gparam (helpers.py:308-337): 448 * 6 / clamp(max|x|, tiny) in x's dtype, NaN / inf -> 1, as float32
+        // generate_gparam (helpers.py:308-337): 448 * 6 / clamp(max|x|, tiny) in x's dtype, NaN / inf -> 1, as float32.
+        // `python_float / tensor` is Tensor.__rtruediv__ = tensor.reciprocal() * python_float: TWO roundings to x's dtype (1 / top, then
+        // the product), not one division -- 2688 / 1.745 is 1541 in fp16 this way, 1540 by a correctly rounded quotient.
         float top = fmaxf(fmaxf(fabsf(lo), fabsf(hi)), tiny_t<P>());
-        float g = to_t<P>(__fdiv_rn(2688.0f, top));
+        float g = to_t<P>(__fmul_rn(to_t<P>(__frcp_rn(top)), 2688.0f));
         if (g != g || fabsf(g) == __int_as_float(0x7f800000)) g = 1.0f;
         *reinterpret_cast<float*>(scale_out) = g;
         return;

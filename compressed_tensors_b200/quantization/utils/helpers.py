@@ -111,9 +111,10 @@ def generate_gparam(updated_min_val: Tensor, updated_max_val: Tensor, scale_data
     hi = torch.max(updated_max_val, torch.zeros_like(updated_max_val))
     top = torch.max(torch.abs(lo), torch.abs(hi))
     top = torch.clamp(top, min=torch.finfo(top.dtype).tiny)
-    # Python float / tensor: ATen's CUDA kernel evaluates it as  float * reciprocal(tensor), which loses bits when 1 / top is a float32
-    # subnormal (top ~ 3e38 in bf16); the CPU kernel -- the pinned result -- divides.  A tensor numerator keeps IEEE division on both.
-    g = torch.tensor(scale_data.max * quant_data.max, dtype=top.dtype, device=top.device) / top
+    # Python float / tensor is Tensor.__rtruediv__ = top.reciprocal() * float: the reciprocal is rounded to top's dtype before the
+    # product (2688 / 1.745 -> 1541 in fp16, where a correctly rounded quotient is 1540).  The value is pinned by the reference's
+    # behaviour (fuzz_host_mirror.py); ct_observe_tensor (kind 1) restates exactly these two roundings.
+    g = (scale_data.max * quant_data.max) / top
     g = torch.nan_to_num(g, nan=1.0, posinf=1.0, neginf=1.0)
     return g.to(dtype).reshape([1])
 

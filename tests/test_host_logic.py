@@ -165,3 +165,17 @@ def test_dequant_strategy_inference():
     assert b.strategy == "block" and b.block_structure == [4, 32]
     with pytest.raises(ValueError, match="Could not infer"):
         ops._infer_dequant_args(x, torch.ones(2, 2, 2))
+
+
+def test_generate_gparam_rounds_like_the_reference():
+    """`float / tensor` is reciprocal-then-multiply, each rounded to the tensor's dtype (reference helpers.py:328).  Known answers
+    produced by the reference in the build container (tests/reference_compat/fuzz_host_mirror.py found the 1541 / 1540 split)."""
+    import torch
+
+    from compressed_tensors_b200.quantization.utils import generate_gparam
+
+    cases = [(torch.float16, -1.7451171875, 1.68359375, 1541.0), (torch.float16, -484.0, 131.625, 5.55078125),
+             (torch.bfloat16, -0.59765625, 13.5, 200.0), (torch.float16, -224.125, 207.25, 12.0)]
+    for dt, lo, hi, want in cases:
+        g = generate_gparam(torch.tensor(lo, dtype=dt), torch.tensor(hi, dtype=dt))
+        assert g.dtype == torch.float32 and g.shape == (1,) and g.item() == want, (dt, lo, hi, g)
