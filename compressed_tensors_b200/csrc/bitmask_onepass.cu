@@ -275,9 +275,14 @@ __device__ __forceinline__ void sts16(uint32_t saddr, uint32_t v) { asm volatile
 
 // exclusive prefix of `tile` (sum of the counts of all tiles before it); every thread of the CTA takes part and returns it.
 // Thread t inspects tile base - t; warp w therefore covers distances 32 w .. 32 w + 31, nearest first.
+// PUBLISH = false: the caller published the aggregate itself (lookback_publish), earlier.
+__device__ __forceinline__ void lookback_publish(unsigned long long* desc, uint32_t tile, uint32_t total) {
+    if (threadIdx.x == 0) st_desc(desc + tile, (tile == 0 ? DESC_P : DESC_A) | (unsigned long long)total);
+}
+template <bool PUBLISH = true>
 __device__ __forceinline__ unsigned long long lookback_cta(unsigned long long* desc, uint32_t tile, uint32_t total, unsigned long long* lb_sum, int* lb_p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) st_desc(desc + tile, (tile == 0 ? DESC_P : DESC_A) | (unsigned long long)total);
+    if (PUBLISH) lookback_publish(desc, tile, total);
     unsigned long long excl = 0;
     if (tile == 0) return 0;
     int64_t base = (int64_t)tile - 1;
@@ -667,6 +672,177 @@ __global__ void __launch_bounds__(B3_T) bitmask_compress_gather_kernel(const uin
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// v5 (shipped): v4 with the look-back moved BEHIND the gather.  ncu on v4 (profiles/ncu_sparse_r2.md): 45 % of all stall samples sit
+// in lookback_cta -- a CTA finishes its counts and then waits until every predecessor of its window has finished ITS counts, i.e.
+// for the slowest of up to 256 bulk loads that were issued at about the same time; nothing of the tile's own work can proceed,
+// because v4 lays its output vectors on GLOBAL 16-byte boundaries and therefore needs (prefix mod 8) before it gathers.
+// Here the vectors are laid on the boundaries of the tile's OWN run: the aggregate is published as soon as it is known, the gather
+// compacts the tile in place in shared memory (vector v of the run over elements 8 v .. 8 v + 7 of the tile; sources are never below
+// their destination, one barrier per pass of 256 vectors separates a pass's reads from its writes), and only then the prefix is
+// collected -- by now it is there -- and the run leaves through the funnel-shifted, globally aligned write-out of v3.
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t B5_SMEM = 16 + B3_TILE * 16 + 32;    // + two vectors of slack: the write-out reads up to one vector past the run
+
+__global__ void __launch_bounds__(B3_T) bitmask_compress_late_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ bitmask,
+                                                                     uint16_t* __restrict__ values, int64_t* __restrict__ row_offsets,
+                                                                     int64_t* __restrict__ nnz_out, unsigned long long* __restrict__ desc,
+                                                                     uint32_t* __restrict__ ticket, uint32_t n_units, uint32_t n_tiles, FastDiv upr) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(16) uint32_t mask_w[B3_TILE / 4 + 4];   // the tile's mask bytes (+ zero padding for the walkers' look-ahead)
+    __shared__ uint16_t start_s[B3_TILE + 8];                     // element index (within the tile) of the first element of run vector v
+    __shared__ int warp_tot[B3_W];
+    __shared__ unsigned long long lb_sum[B3_W];
+    __shared__ int lb_p[B3_W];
+    __shared__ uint32_t tile_s;
+    const uint32_t sbase = smem_u32(smem_raw);
+    const uint32_t bar = sbase, data = sbase + 16;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        const uint32_t tile = atomicAdd(ticket, 1u);
+        tile_s = tile;
+        mbar_init_a(bar, 1);
+        mbar_fence_init();
+        const uint32_t nu = min((uint32_t)B3_TILE, n_units - tile * B3_TILE);
+        mbar_expect_tx_a(bar, nu * 16);
+        bulk_g2s_a(data, src + (size_t)tile * (B3_TILE * 16), nu * 16, bar, l2_evict_first_policy());
+    }
+    if (tid < 4) mask_w[B3_TILE / 4 + tid] = 0u;
+    __syncthreads();
+    const uint32_t tile = tile_s;
+    const uint32_t u0 = tile * B3_TILE;
+    const uint32_t nu = min((uint32_t)B3_TILE, n_units - u0);
+    mbar_wait_a(bar, 0);
+
+    // ---- A: mask bytes of the thread's 8 consecutive units, counts, scan (as v4) ----
+    const uint32_t uf = 8u * (uint32_t)tid;
+    uint8_t* mask_b = reinterpret_cast<uint8_t*>(mask_w);
+    {
+        const uint32_t sw = (uint32_t)(tid & 7);
+        const uint32_t tdata = data + uf * 16;
+        uint8_t* tmask = mask_b + uf;
+        if (nu == (uint32_t)B3_TILE) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t p = (uint32_t)k ^ sw;
+                tmask[p] = (uint8_t)nz_byte16_fast(lds128(tdata + p * 16));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t p = (uint32_t)k ^ sw;
+                uint32_t b = 0;
+                if (uf + p < nu) b = nz_byte16_fast(lds128(tdata + p * 16));
+                tmask[p] = (uint8_t)b;
+            }
+        }
+    }
+    const uint32_t lo = mask_w[2 * tid], hi = mask_w[2 * tid + 1];
+    if (uf + 4 <= nu) reinterpret_cast<uint32_t*>(bitmask + u0 + uf)[0] = lo;
+    if (uf + 8 <= nu) reinterpret_cast<uint32_t*>(bitmask + u0 + uf)[1] = hi;
+    const int clo = __popc(lo), cnt = clo + __popc(hi);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < B3_W; ++w) {
+        const int t = warp_tot[w];
+        if (w < warp) before += t;
+        total += t;
+    }
+    const int toff = before + incl - cnt;
+    lookback_publish(desc, tile, (uint32_t)total);        // the successors' look-back can pass this tile from here on
+
+    // ---- B: run vector v starts at run element 8 v; the thread that owns that element records where it sits in the tile ----
+    const uint32_t nvec = ((uint32_t)total + 7) >> 3;
+    if (cnt > 0) {
+        for (uint32_t v = ((uint32_t)toff + 7) >> 3; 8 * v < (uint32_t)(toff + cnt); ++v) {
+            const uint32_t n = 8 * v - (uint32_t)toff;
+            const uint32_t bit = (n < (uint32_t)clo) ? select32(lo, n) : 32u + select32(hi, n - (uint32_t)clo);
+            start_s[v] = (uint16_t)(uf * 8 + bit);
+        }
+    }
+    __syncthreads();
+
+    // ---- C: gather, in place.  Pass k: vectors 256 k .. 256 k + 255 are read into registers, barrier, written to elements 8 v .. 8 v + 7.
+    // A source element is never below its destination, and the sources of LATER passes lie at or above the end of this pass's
+    // destinations, so one barrier per pass is enough.
+    for (uint32_t vb = 0; vb < nvec; vb += B3_T) {
+        const uint32_t v = vb + (uint32_t)tid;
+        uint32_t h[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) h[e] = 0u;
+        if (v < nvec) {
+            const uint32_t bit = start_s[v];
+            uint32_t wi = bit >> 5;
+            const uint32_t s = bit & 31u;
+            uint32_t cur = __funnelshift_r(mask_w[wi], mask_w[wi + 1], s);      // kept-flags of elements bit .. bit + 31
+            uint32_t ebase = data + bit * 2;                                     // shared address of element `bit`
+            if (8 * v + 8 <= (uint32_t)total) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    while (cur == 0u) {                                          // the next kept element is further than 32 positions away
+                        ++wi;
+                        ebase += 64;
+                        cur = __funnelshift_r(mask_w[wi], mask_w[wi + 1], s);
+                    }
+                    const uint32_t pos = (uint32_t)__ffs(cur) - 1u;
+                    cur &= cur - 1u;
+                    unsigned short t;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(t) : "r"(ebase + 2 * pos));
+                    h[e] = t;
+                }
+            } else {
+                const uint32_t ne = (uint32_t)total - 8 * v;                     // the run's last vector: 1 .. 7 elements
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if ((uint32_t)e < ne) {
+                        while (cur == 0u) {
+                            ++wi;
+                            ebase += 64;
+                            cur = __funnelshift_r(mask_w[wi], mask_w[wi + 1], s);
+                        }
+                        const uint32_t pos = (uint32_t)__ffs(cur) - 1u;
+                        cur &= cur - 1u;
+                        unsigned short t;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(t) : "r"(ebase + 2 * pos));
+                        h[e] = t;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (v < nvec)
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(data + 16u * v), "r"(h[0] | (h[1] << 16)), "r"(h[2] | (h[3] << 16)),
+                         "r"(h[4] | (h[5] << 16)), "r"(h[6] | (h[7] << 16))
+                         : "memory");
+    }
+    __syncthreads();
+
+    // ---- D: the prefix (published long ago by now), row offsets, write-out ----
+    const unsigned long long excl = lookback_cta<false>(desc, tile, (uint32_t)total, lb_sum, lb_p);
+    if (tid == 0 && tile == n_tiles - 1) *nnz_out = (int64_t)(excl + (unsigned long long)total);
+    if (row_offsets && uf < nu) {
+        const uint32_t g = u0 + uf;
+        uint32_t r = fd_div(g, upr);
+        uint32_t k = (r * upr.d == g) ? 0u : (r + 1) * upr.d - g;          // units until the next row start
+        if (k != 0) ++r;
+        while (k < 8 && uf + k < nu) {
+            const uint32_t below = (k < 4) ? __popc(lo & ((1u << (8 * k)) - 1u)) : (uint32_t)clo + __popc(hi & ((1u << (8 * (k - 4))) - 1u));
+            row_offsets[r] = (int64_t)(excl + (unsigned long long)toff + below);
+            k += upr.d;
+            ++r;
+        }
+    }
+    run_to_global(values, excl, total, data);
+}
+
 // expansion: mask bytes -> counts -> scan -> look-back -> the tile's run of `values` into shared memory (aligned 16-byte loads, so that
 // run element j sits at stage element j + shift) -> dense tile, 16-byte stores
 __global__ void __launch_bounds__(B3_T) bitmask_expand_tile_kernel(const uint16_t* __restrict__ values, const uint8_t* __restrict__ bitmask,
@@ -749,7 +925,13 @@ int launch_bitmask_lookback(const void* src, uint8_t* bitmask, void* dst, int64_
     if (rc) return rc;
     CT_CUDA_TRY(cudaMemsetAsync(scratch, 0, bytes, st));
     if (!v1) {
-        if (COMPRESS && !getenv("CT_B200_BITMASK_V3")) {
+        if (COMPRESS && !getenv("CT_B200_BITMASK_V3") && !getenv("CT_B200_BITMASK_V4")) {
+            CT_CUDA_TRY(cudaFuncSetAttribute(bitmask_compress_late_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B5_SMEM));
+            bitmask_compress_late_kernel<<<n_tiles, B3_T, B5_SMEM, st>>>(reinterpret_cast<const uint8_t*>(src), bitmask, reinterpret_cast<uint16_t*>(dst),
+                                                                          row_offsets, nnz_out, reinterpret_cast<unsigned long long*>(scratch + 16),
+                                                                          reinterpret_cast<uint32_t*>(scratch), (uint32_t)n_units, n_tiles,
+                                                                          make_fastdiv((uint64_t)(cols / 8)));
+        } else if (COMPRESS && !getenv("CT_B200_BITMASK_V3")) {
             CT_CUDA_TRY(cudaFuncSetAttribute(bitmask_compress_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B4_SMEM));
             bitmask_compress_gather_kernel<<<n_tiles, B3_T, B4_SMEM, st>>>(reinterpret_cast<const uint8_t*>(src), bitmask, reinterpret_cast<uint16_t*>(dst),
                                                                             row_offsets, nnz_out, reinterpret_cast<unsigned long long*>(scratch + 16),
