@@ -511,7 +511,7 @@ def run_cfg5_70b_sharded(a, rank: int, world: int, dev):
         got = get_direct_state_dict(mods[i])
         sample_ok &= bool(torch.equal(got["weight_packed"], want["weight_packed"]) and torch.equal(got["weight_scale"], want["weight_scale"])
                           and got["weight_shape"].tolist() == list(w.shape) and got["weight_packed"].device == dev)
-        del w, sc, want
+        del w, sc, want, got            # `got` holds views of a gathered recouple buffer: a survivor would keep that buffer alive
     oracle_ok = None
     if rank == 0:
         import oracle   # checker only

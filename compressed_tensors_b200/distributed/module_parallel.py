@@ -39,29 +39,46 @@ def _wire_device(dev: torch.device) -> torch.device:
 
 
 _ALIGN = 256
+_BUCKET = 256 << 20      # bytes one owner contributes to one gathered buffer (a tensor larger than this gets a bucket of its own)
 
 
 def _layout(modules, owner, world):
-    """byte layout of every owner's results inside its slot of the gathered buffer; identical on every rank (the meta mirror gave every
-    rank the same names / shapes / dtypes)"""
-    entries = {r: [] for r in range(world)}
-    sizes = [0] * world
+    """byte layout of every owner's results inside the gathered buffers; identical on every rank (the meta mirror gave every rank the
+    same names / shapes / dtypes).  The results travel in BUCKETS: bucket k is one flat buffer of `world` equal slots, slot r holding the
+    k-th <= 256 MB run of owner r's tensors in module order.  One buffer for everything would be one collective fewer, but every
+    received tensor is a view of its buffer, and a single surviving view (a caller that keeps one weight) would pin all of it; with
+    buckets a later decompress_model also returns the memory progressively, bucket by bucket, as it walks the modules.
+    Returns (buckets, total_bytes): buckets[k] = (slot_bytes, {rank: [(module, name, offset, nbytes, shape, dtype), ...]})"""
+    cur = [0] * world          # bucket an owner is filling
+    fill = [0] * world         # bytes it has put there
+    slots, entries = [], []
+
+    def bucket(k):
+        while len(slots) <= k:
+            slots.append(0)
+            entries.append({r: [] for r in range(world)})
+        return entries[k]
+
     for m in modules:
         o = owner[m]
         for name, t in get_direct_state_dict(m).items():
             if t is None:
                 continue
             nbytes = t.numel() * t.element_size()
-            entries[o].append((m, name, sizes[o], nbytes, tuple(t.shape), t.dtype))
-            sizes[o] = (sizes[o] + nbytes + _ALIGN - 1) // _ALIGN * _ALIGN
-    return entries, max(sizes) if sizes else 0
+            if fill[o] and fill[o] + nbytes > _BUCKET:
+                cur[o] += 1
+                fill[o] = 0
+            bucket(cur[o])[o].append((m, name, fill[o], nbytes, tuple(t.shape), t.dtype))
+            fill[o] = (fill[o] + nbytes + _ALIGN - 1) // _ALIGN * _ALIGN
+            slots[cur[o]] = max(slots[cur[o]], fill[o])
+    buckets = [(slots[k], entries[k]) for k in range(len(slots)) if slots[k]]
+    return buckets, sum(sl for sl, _ in buckets) * world
 
 
 def _allgather_fits(modules, owner, world) -> bool:
-    """the gathered buffer (every owner's results, once) fits comfortably on EVERY rank -- agreed collectively, or some ranks would
+    """the gathered buffers (every owner's results, once) fit comfortably on EVERY rank -- agreed collectively, or some ranks would
     enter an all_gather and others a broadcast"""
-    _, slot = _layout(modules, owner, world)
-    total = slot * world
+    _, total = _layout(modules, owner, world)
     nccl = dist.get_backend() == "nccl" and torch.cuda.is_available()
     if nccl:
         free_b, _ = torch.cuda.mem_get_info()
@@ -75,26 +92,29 @@ def _allgather_fits(modules, owner, world) -> bool:
 
 
 def _recouple_allgather(modules, owner, rank, world, devices) -> int:
-    entries, slot = _layout(modules, owner, world)
-    if slot == 0:
+    buckets, _ = _layout(modules, owner, world)
+    if not buckets:
         return 0
     wire = _wire_device(torch.device("meta"))
-    out = torch.empty(world * slot, dtype=torch.uint8, device=wire)
-    mine = out[rank * slot:(rank + 1) * slot]
-    for m, name, off, nbytes, _, _ in entries[rank]:
-        if nbytes:
-            t = get_direct_state_dict(m)[name]
-            mine[off:off + nbytes].copy_(as_broadcastable(t.contiguous()).reshape(-1).view(torch.uint8), non_blocking=True)
-    dist.all_gather_into_tensor(out, mine)          # in place: this rank's slot is its own contribution
     received = {}
-    for r in range(world):
-        if r == rank:
-            continue                                 # the owner keeps its own tensors
-        base = r * slot
-        for m, name, off, nbytes, shape, dtype in entries[r]:
-            v = out[base + off: base + off + nbytes]
-            v = v.view(dtype).reshape(shape) if nbytes else torch.empty(shape, dtype=dtype, device=wire)   # offsets are 256-byte aligned
-            received.setdefault(id(m), (m, {}))[1][name] = v
+    moved = 0
+    for slot, entries in buckets:
+        out = torch.empty(world * slot, dtype=torch.uint8, device=wire)
+        mine = out[rank * slot:(rank + 1) * slot]
+        for m, name, off, nbytes, _, _ in entries[rank]:
+            if nbytes:
+                t = get_direct_state_dict(m)[name]
+                mine[off:off + nbytes].copy_(as_broadcastable(t.contiguous()).reshape(-1).view(torch.uint8), non_blocking=True)
+        dist.all_gather_into_tensor(out, mine)          # in place: this rank's slot is its own contribution
+        for r in range(world):
+            moved += sum(e[3] for e in entries[r])      # bytes that went through the collective (like the broadcast path counts)
+            if r == rank:
+                continue                                 # the owner keeps its own tensors
+            base = r * slot
+            for m, name, off, nbytes, shape, dtype in entries[r]:
+                v = out[base + off: base + off + nbytes]
+                v = v.view(dtype).reshape(shape) if nbytes else torch.empty(shape, dtype=dtype, device=wire)   # offsets are 256-byte aligned
+                received.setdefault(id(m), (m, {}))[1][name] = v
     for m, got in received.values():
         sd = get_direct_state_dict(m)
         home = devices.get(id(m), torch.device("cpu"))
@@ -109,7 +129,7 @@ def _recouple_allgather(modules, owner, rank, world, devices) -> int:
             # tensors the shape-only path already produced for real (e.g. weight_shape, on the CPU) stay where they were
             new[name] = v.to(home) if t.device.type == "meta" else v.to(t.device)
         replace_direct_state_dict(m, new)
-    return sum(e[3] for r in range(world) for e in entries[r])      # bytes that went through the collective (like the broadcast path counts)
+    return moved
 
 
 def _recouple_broadcast(modules, owner, rank, devices) -> int:

@@ -124,7 +124,10 @@ _WORKER = textwrap.dedent(
     # single-process result; stats are filled; recouple=False leaves the other rank's modules on meta
     from compressed_tensors.distributed import greedy_bin_packing, module_size
     from compressed_tensors.utils import replace_direct_state_dict
-    for recouple in (True, "broadcast", "allgather", False):
+    import compressed_tensors.distributed.module_parallel as mp
+    default_bucket = mp._BUCKET
+    for recouple, bucket in ((True, None), ("broadcast", None), ("allgather", None), ("allgather", 4096), (False, None)):
+        mp._BUCKET = bucket or default_bucket            # 4096: every tensor beyond the first few opens a new gathered buffer
         full = build(6, with_extras=False)
         quantize_config(full, "W4A16")
         reference = copy.deepcopy(full)
@@ -153,6 +156,12 @@ _WORKER = textwrap.dedent(
                     assert v.device.type == "meta" and v.shape == s2[k].shape and v.dtype == s2[k].dtype, f"sharded {n1}.{k} stays on meta"
         if recouple:
             same_on_all_ranks(full, "sharded compressed")
+        if recouple == "allgather":
+            # received tensors are views of the gathered buffers: one buffer with the default bucket size, several with small buckets
+            # (so that one surviving view cannot pin everything that was received)
+            stores = {get_direct_state_dict(m)["weight_packed"].untyped_storage().data_ptr() for m in mods if owner[m] != rank}
+            assert (len(stores) > 1) == (bucket is not None), (bucket, len(stores))
+    mp._BUCKET = default_bucket
 
     # nothing to compress: no quantized modules, and an empty model
     plain = build(3)
