@@ -482,6 +482,230 @@ __global__ void __launch_bounds__(256) bitmask_move_vec16_kernel(const void* __r
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Expansion with row_offsets, pipelined (round 2).  The per-row kernel above is not issue-bound (23 M warp instructions for a 235 MB
+// tensor = 20 us of issue time) but takes 109 us: a CTA lives for one row and goes through two DEPENDENT trips to DRAM (mask bytes ->
+// counts -> the row's values) with nothing else in flight.  Both loads depend only on row_offsets, so here persistent CTAs walk the
+// rows (r = blockIdx.x + k * gridDim.x); a PRODUCER warp keeps the next rows' mask bytes and value runs coming with bulk copies
+// into a BYTE ring in shared memory (an entry is as large as the row's run actually is, so a sparse tensor has many rows in flight
+// and a CTA needs only 1.5 worst-case rows of shared memory: 8 CTAs / SM for 8192 columns), eight consumer warps expand the current
+// row out of shared memory.  Entries are released in order (`empty` barriers), the producer allocates behind the oldest one.
+//   entry = [ values run, from the 16-byte boundary at or below row_offsets[r] to the one at or above row_offsets[r + 1] | mask bytes ]
+// The over-read at the end of a run (< 16 bytes) is only done where it provably stays inside `values` (it ends at or before
+// row_offsets[rows - 1] <= nnz); the last row and rows ending within 8 elements of it get a worst-case entry and fetch their values
+// after the scan instead.
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr int EXR_SLOTS = 8;                 // rows in flight per CTA (barrier pairs)
+constexpr int EXR_CONSUMERS = 256;
+constexpr int EXR_THREADS = EXR_CONSUMERS + 32;
+
+__device__ __forceinline__ void exr_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EXR_CONSUMERS) : "memory"); }
+
+template <int U>
+__global__ void __launch_bounds__(EXR_THREADS, (U <= 4 ? 6 : 4)) bitmask_expand_rows_kernel(const uint16_t* __restrict__ values, const uint8_t* __restrict__ bitmask,
+                                                                          const int64_t* __restrict__ row_offsets, uint4* __restrict__ dense,
+                                                                          int units, int rows, uint32_t ring_bytes, uint32_t vcap) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];     // [full barriers][empty barriers][ring]
+    constexpr int NP = (U + 1) / 2;                          // two 16-bit segment counters per register (a segment holds <= 2048 elements)
+    __shared__ uint32_t warp_tot[NP][8];
+    __shared__ long long pos_s[EXR_SLOTS];
+    __shared__ uint32_t off_s[EXR_SLOTS];                    // entry start in the ring; bit 31: the values are already there
+    __shared__ uint32_t vpart_s[EXR_SLOTS];                  // bytes of the entry's values part (the mask bytes follow it)
+    const uint32_t sbase = smem_u32(smem_raw);
+    const uint32_t full0 = sbase, empty0 = sbase + 8u * EXR_SLOTS, ring0 = sbase + 16u * EXR_SLOTS;
+    uint8_t* ring = smem_raw + 16 * EXR_SLOTS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < EXR_SLOTS; ++s) {
+            mbar_init_a(full0 + 8u * s, 1);
+            mbar_init_a(empty0 + 8u * s, 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == EXR_CONSUMERS / 32) {
+        // ---------------- producer ----------------
+        if (lane != 0) return;
+        const uint64_t policy = l2_evict_first_policy();
+        const int64_t safe_end = row_offsets[rows - 1];
+        uint32_t tail = 0, used = 0;                          // FIFO ring: outstanding bytes are [tail - used, tail) circularly
+        uint32_t size_q[EXR_SLOTS];                           // bytes each outstanding entry holds (incl. the gap skipped when wrapping)
+        uint32_t issued = 0, released = 0;
+        for (int64_t r = blockIdx.x; r < rows; r += gridDim.x, ++issued) {
+            const int64_t pos = row_offsets[r];
+            const int64_t a0 = pos & ~7LL;
+            uint32_t vb = 0;
+            bool fast = false;
+            if (r + 1 < rows) {
+                const int64_t a1 = (row_offsets[r + 1] + 7) & ~7LL;
+                if (a1 <= safe_end) { fast = true; vb = (uint32_t)(a1 - a0) * 2u; }
+            }
+            const uint32_t need = (fast ? vb : vcap) + (uint32_t)units;
+            uint32_t start, size;
+            while (true) {
+                bool ok = issued - released < (uint32_t)EXR_SLOTS;
+                if (ok) {
+                    if (used == 0) { start = 0; size = need; }
+                    else {
+                        const uint32_t head = (tail + ring_bytes - used) % ring_bytes;
+                        if (head < tail) {                    // outstanding entries do not wrap: free = [tail, end) and [0, head)
+                            if (tail + need <= ring_bytes) { start = tail; size = need; }
+                            else if (need <= head) { start = 0; size = need + (ring_bytes - tail); }
+                            else ok = false;
+                        } else {                              // they wrap (or the ring is full): free = [tail, head)
+                            if (used < ring_bytes && need <= head - tail) { start = tail; size = need; }
+                            else ok = false;
+                        }
+                    }
+                }
+                if (ok) break;
+                // wait for the oldest outstanding entry
+                const uint32_t q = released % EXR_SLOTS;
+                mbar_wait_a(empty0 + 8u * q, (released / EXR_SLOTS) & 1u);
+                used -= size_q[q];
+                ++released;
+            }
+            const uint32_t q = issued % EXR_SLOTS;
+            size_q[q] = size;
+            used += size;
+            tail = start + need;
+            pos_s[q] = pos;
+            off_s[q] = start | (fast ? 0x80000000u : 0u);
+            const uint32_t bar = full0 + 8u * q, dst = ring0 + start;
+            const uint32_t vpart = fast ? vb : vcap;          // the mask bytes follow the values part
+            vpart_s[q] = vpart;
+            mbar_expect_tx_a(bar, (uint32_t)units + vb);
+            bulk_g2s_a(dst + vpart, bitmask + r * units, (uint32_t)units, bar, policy);
+            if (vb) bulk_g2s_a(dst, values + a0, vb, bar, policy);
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    uint32_t it = 0;
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x, ++it) {
+        const uint32_t q = it % EXR_SLOTS;
+        mbar_wait_a(full0 + 8u * q, (it / EXR_SLOTS) & 1u);
+        const uint32_t o = off_s[q];
+        const bool fast = (o >> 31) != 0;
+        const int64_t pos = pos_s[q];
+        const int shift = (int)(pos & 7);                  // run element j sits at entry element shift + j
+        uint16_t* sv = reinterpret_cast<uint16_t*>(ring + (o & 0x7fffffffu));
+        uint32_t byte[U];
+        int cnt[U], off[U];
+        uint32_t pk[NP];                                   // segment u's count in the (u & 1) half of pk[u >> 1]
+        {
+            const uint8_t* mask = reinterpret_cast<const uint8_t*>(sv) + vpart_s[q];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) pk[i] = 0u;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = u * 256 + tid;
+                byte[u] = (i < units) ? mask[i] : 0u;
+                cnt[u] = __popc(byte[u]);
+                pk[u >> 1] |= (uint32_t)cnt[u] << (16 * (u & 1));
+            }
+        }
+        // inclusive scan over the warp, two segments per shuffle
+#pragma unroll
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, pk[i], o2);
+                if (lane >= o2) pk[i] += n;
+            }
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) warp_tot[i][warp] = pk[i];
+        }
+        exr_consumer_sync();
+        // the eight warp totals of every segment: lanes 0 .. 7 scan them (three shuffle rounds), everybody reads its warp's exclusive
+        // prefix from lane warp - 1 and the segment totals from lane 7
+        int total = 0;
+        {
+            uint32_t t[NP], before[NP], seg[NP];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) t[i] = (lane < 8) ? warp_tot[i][lane] : 0u;
+#pragma unroll
+            for (int o2 = 1; o2 < 8; o2 <<= 1) {
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    const uint32_t n = __shfl_up_sync(0xffffffffu, t[i], o2);
+                    if (lane >= o2) t[i] += n;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                before[i] = __shfl_sync(0xffffffffu, t[i], (warp + 7) & 7);
+                if (warp == 0) before[i] = 0u;
+                seg[i] = __shfl_sync(0xffffffffu, t[i], 7);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int sh = 16 * (u & 1);
+                off[u] = total + (int)((before[u >> 1] >> sh) & 0xffffu) + (int)((pk[u >> 1] >> sh) & 0xffffu) - cnt[u];
+                total += (int)((seg[u >> 1] >> sh) & 0xffffu);
+            }
+        }
+        if (!fast) {                                       // CTA-uniform: the last rows of the tensor
+            for (int j = tid; j < total; j += EXR_CONSUMERS) sv[shift + j] = values[pos + j];
+            exr_consumer_sync();
+        }
+        uint4* dout = dense + r * units;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = u * 256 + tid;
+            if (i < units) {
+                uint32_t e[8];
+                int o2 = shift + off[u];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) e[k] = ((byte[u] >> k) & 1u) ? (uint32_t)sv[o2++] : 0u;
+                stg_stream16(dout + i, make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16)));
+            }
+        }
+        exr_consumer_sync();                               // every consumer is done with the entry and with warp_tot
+        if (tid == 0) mbar_arrive_a(empty0 + 8u * q);
+    }
+}
+
+static bool bitmask_expand_rows_ok(int64_t rows, int units, const void* values) {
+    return rows >= 2 && units % 16 == 0 && units <= 2048 && aligned16(values) && !getenv("CT_B200_BITMASK_ROWS_V1");
+}
+
+template <int U>
+static int launch_bitmask_expand_rows_u(const void* values, const uint8_t* bitmask, const int64_t* row_offsets, void* dst, int64_t rows, int units,
+                                        int device, cudaStream_t st) {
+    const uint32_t vcap = (uint32_t)units * 16u + 32u;
+    const uint32_t worst = vcap + (uint32_t)units;                 // an entry of a full row
+    int pct = 150;                                                 // ring = 1.5 worst-case rows
+    if (const char* e = getenv("CT_B200_BITMASK_RING_PCT")) pct = atoi(e);   // measurement aid
+    if (pct < 100) pct = 100;
+    if (pct > 600) pct = 600;
+    const uint32_t ring = (uint32_t)((uint64_t)worst * pct / 100 + 15) / 16 * 16;
+    const int smem = 16 * EXR_SLOTS + (int)ring;
+    if (smem > 200 * 1024) { set_error("bitmask expand: ring too large"); return CT_E_SHAPE; }
+    auto kfn = bitmask_expand_rows_kernel<U>;
+    CT_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int occ = 0;
+    CT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, EXR_THREADS, smem));
+    if (occ < 1) { set_error("bitmask expand: no occupancy"); return CT_E_CUDA; }
+    int64_t grid = (int64_t)occ * sm_count(device);
+    if (grid > rows) grid = rows;
+    kfn<<<(unsigned)grid, EXR_THREADS, smem, st>>>(reinterpret_cast<const uint16_t*>(values), bitmask, row_offsets, reinterpret_cast<uint4*>(dst), units,
+                                                   (int)rows, ring, vcap);
+    return CT_OK;
+}
+
+static int launch_bitmask_expand_rows(const void* values, const uint8_t* bitmask, const int64_t* row_offsets, void* dst, int64_t rows, int units,
+                                      int device, cudaStream_t st) {
+    if (units <= 256) return launch_bitmask_expand_rows_u<1>(values, bitmask, row_offsets, dst, rows, units, device, st);
+    if (units <= 512) return launch_bitmask_expand_rows_u<2>(values, bitmask, row_offsets, dst, rows, units, device, st);
+    if (units <= 1024) return launch_bitmask_expand_rows_u<4>(values, bitmask, row_offsets, dst, rows, units, device, st);
+    return launch_bitmask_expand_rows_u<8>(values, bitmask, row_offsets, dst, rows, units, device, st);
+}
+
 // rows shorter than one 4-segment iteration keep the single-segment shape (less shared memory, more blocks per SM)
 template <bool COMPRESS>
 static void launch_bitmask_move_vec16(const void* src, const uint8_t* bitmask, const int64_t* row_offsets, void* dst, int64_t rows, int units, cudaStream_t st) {
@@ -691,7 +915,11 @@ int ct_bitmask_decompress(const void* values, int dtype, const uint8_t* bitmask,
     if (values && (!row_offsets || getenv("CT_B200_BITMASK_LOOKBACK")) && bitmask_lookback_ok(dtype, rows, cols, out, bitmask, values))
         return launch_bitmask_lookback<false>(values, const_cast<uint8_t*>(bitmask), out, nullptr, nullptr, rows, cols, device, st);
     if (!row_offsets) { set_error("bitmask_decompress without row_offsets needs a 2-byte dtype, cols %% 8 == 0 and aligned tensors"); return CT_E_UNSUPPORTED; }
-    if (bitmask_vec16_ok(dtype, rows, cols, out, bitmask)) {
+    if (bitmask_vec16_ok(dtype, rows, cols, out, bitmask) && (reinterpret_cast<uintptr_t>(bitmask) & 15u) == 0 &&
+        bitmask_expand_rows_ok(rows, (int)(cols / 8), values)) {
+        const int rc = launch_bitmask_expand_rows(values, bitmask, row_offsets, out, rows, (int)(cols / 8), device, st);
+        if (rc) return rc;
+    } else if (bitmask_vec16_ok(dtype, rows, cols, out, bitmask)) {
         launch_bitmask_move_vec16<false>(values, bitmask, row_offsets, out, rows, (int)(cols / 8), st);
     } else
     switch (esize_of(dtype)) {

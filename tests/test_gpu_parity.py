@@ -463,6 +463,36 @@ def test_bitmask_compress_vs_oracle(dtype, shape):
     same(dense.cpu(), x.where(x != 0, torch.zeros_like(x)), "")
 
 
+@pytest.mark.parametrize("shape", [(2, 128), (5, 16384), (3, 16512), (1, 8192), (37, 8192), (700, 4096), (150, 14336)])
+def test_bitmask_expand_rows_pipeline(shape, monkeypatch):
+    """the pipelined row expansion (persistent CTAs, bulk-copy ring; csrc/sparse.cu bitmask_expand_rows_kernel) against the oracle and
+    against the per-row kernel it replaces: rows that are empty, full, and mixed; more rows than one CTA's ring holds; the last rows of
+    the tensor (values fetched after the scan, because the run's 16-byte over-read would leave `values`); shapes the pipeline declines
+    (one row, more than 2048 units per row)"""
+    g = torch.Generator().manual_seed(shape[0] * 7 + shape[1])
+    x = (torch.randn(shape, generator=g) * 3).bfloat16()
+    x[torch.rand(shape, generator=g) < 0.5] = 0
+    R = shape[0]
+    if R >= 5:
+        x[1] = 0                                             # an empty row
+        x[2] = 1.5                                           # a full row
+        x[R - 2] = 0                                         # the last row's predecessor is empty: its run ends where the last row starts
+        x[R - 1, : shape[1] // 2] = 0
+    vals, bm, offs = oracle.bitmask_compress(x)
+    want = oracle.bitmask_decompress(vals, bm, x.shape)
+    gv, gb, go = vals.to(DEV), bm.to(DEV), offs.to(DEV)
+    launches = N.launch_count()
+    dense = ops.bitmask_decompress(gv, gb, go, x.shape)
+    assert N.launch_count() - launches == 1
+    same(dense.cpu(), want, "pipelined expand vs oracle")
+    monkeypatch.setenv("CT_B200_BITMASK_ROWS_V1", "1")
+    same(ops.bitmask_decompress(gv, gb, go, x.shape), dense, "per-row kernel == pipelined kernel")
+    monkeypatch.delenv("CT_B200_BITMASK_ROWS_V1")
+    for pct in ("100", "400"):                              # ring of exactly one worst-case row (no prefetch at full density) / a deep one
+        monkeypatch.setenv("CT_B200_BITMASK_RING_PCT", pct)
+        same(ops.bitmask_decompress(gv, gb, go, x.shape), dense, f"ring {pct} %")
+
+
 @pytest.mark.parametrize("density", [0.0, 0.03, 0.5, 0.97, 1.0])
 @pytest.mark.parametrize("shape", [(8, 32), (64, 4096), (300, 1000), (1031, 2056), (4096, 14336)])
 def test_bitmask_onepass_lookback_vs_oracle(shape, density, monkeypatch):
