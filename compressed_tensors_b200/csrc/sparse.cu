@@ -909,9 +909,10 @@ int ct_bitmask_decompress(const void* values, int dtype, const uint8_t* bitmask,
     if (!out || !bitmask) { set_error("null pointer"); return CT_E_ARG; }
     const int64_t nb = (cols + 7) / 8;
     const unsigned g = (unsigned)(rows < 148 * 8 ? rows : 148 * 8);
-    // With the format's row_offsets the expansion is ONE pass already (every row knows where its values start: the per-row kernel
-    // below, 109 us for 235 MB at 50 % density, 66 us at 10 %).  The look-back kernel (flat tiles, the scan recomputed from the mask
-    // popcounts, 144 / 119 us) serves callers that do not have row_offsets, and CT_B200_BITMASK_LOOKBACK=1 for measurements.
+    // With the format's row_offsets the expansion is ONE pass already (every row knows where its values start): the pipelined row
+    // kernel (70 us for 235 MB at 50 % density, 62 us at 10 %), or the per-row kernel for shapes it declines (111 / 66 us).  The
+    // look-back kernel (flat tiles, the scan recomputed from the mask popcounts, 140 / 115 us) serves callers that do not have
+    // row_offsets, and CT_B200_BITMASK_LOOKBACK=1 for measurements.
     if (values && (!row_offsets || getenv("CT_B200_BITMASK_LOOKBACK")) && bitmask_lookback_ok(dtype, rows, cols, out, bitmask, values))
         return launch_bitmask_lookback<false>(values, const_cast<uint8_t*>(bitmask), out, nullptr, nullptr, rows, cols, device, st);
     if (!row_offsets) { set_error("bitmask_decompress without row_offsets needs a 2-byte dtype, cols %% 8 == 0 and aligned tensors"); return CT_E_UNSUPPORTED; }
