@@ -254,11 +254,13 @@ __global__ void __launch_bounds__(256) bitmask_lookback_kernel(const void* __res
 // descriptor per round, a round is repeated (after a nanosleep) only while a descriptor that is actually needed is unpublished.
 // ------------------------------------------------------------------------------------------------------------------------------
 #ifndef CT_BITMASK_THREADS
-#define CT_BITMASK_THREADS 256
+#define CT_BITMASK_THREADS 128
 #endif
-// 256 threads x 8 units = 2048 units = 32 KB of input per tile: the chained scan advances one look-back window (one descriptor per
-// thread) per ~1.2 us hop whatever the tile size, so the bytes per hop -- 256 tiles x 32 KB = 8 MB -- set the ceiling (128 x 16 KB
-// tiles: ~2 TB/s of input, measured)
+// 128 threads x 8 units = 1024 units = 16 KB of input per tile.  With v4's EARLY look-back the tile size set the ceiling (the chained
+// scan advances one window of one descriptor per thread per ~1.2 us hop) and 256-thread tiles were better; with v5's LATE look-back a
+// tile lives ~10 us of mostly serial latencies (ticket, bulk load, barriers, descriptor read, write-out), what counts is how many
+// tiles an SM has in flight, and smaller tiles win: 64 / 96 / 128 / 192 / 224 / 256 threads = 127 / 121 / 117 / 123 / 127 / 130 us at
+// 50 % density, 107 / 105 / 95 / 103 / 99 / 107 us at 10 % (tools/gpu_run13.sh, gpu_run21.sh, gpu_run22.sh)
 constexpr int B3_T = CT_BITMASK_THREADS;       // threads
 constexpr int B3_W = B3_T / 32;                // warps
 constexpr int B3_TILE = 8 * B3_T;              // units per tile
@@ -679,7 +681,7 @@ __global__ void __launch_bounds__(B3_T) bitmask_compress_gather_kernel(const uin
 // because v4 lays its output vectors on GLOBAL 16-byte boundaries and therefore needs (prefix mod 8) before it gathers.
 // Here the vectors are laid on the boundaries of the tile's OWN run: the aggregate is published as soon as it is known, the gather
 // compacts the tile in place in shared memory (vector v of the run over elements 8 v .. 8 v + 7 of the tile; sources are never below
-// their destination, one barrier per pass of 256 vectors separates a pass's reads from its writes), and only then the prefix is
+// their destination, one barrier per pass of one vector per thread separates a pass's reads from its writes), and only then the prefix is
 // collected -- by now it is there -- and the run leaves through the funnel-shifted, globally aligned write-out of v3.
 // ------------------------------------------------------------------------------------------------------------------------------
 constexpr uint32_t B5_SMEM = 16 + B3_TILE * 16 + 32;    // + two vectors of slack: the write-out reads up to one vector past the run
@@ -770,7 +772,7 @@ __global__ void __launch_bounds__(B3_T) bitmask_compress_late_kernel(const uint8
     }
     __syncthreads();
 
-    // ---- C: gather, in place.  Pass k: vectors 256 k .. 256 k + 255 are read into registers, barrier, written to elements 8 v .. 8 v + 7.
+    // ---- C: gather, in place.  Pass k: vectors T k .. T k + T - 1 (T threads) are read into registers, barrier, written to elements 8 v .. 8 v + 7.
     // A source element is never below its destination, and the sources of LATER passes lie at or above the end of this pass's
     // destinations, so one barrier per pass is enough.
     for (uint32_t vb = 0; vb < nvec; vb += B3_T) {
@@ -841,6 +843,165 @@ __global__ void __launch_bounds__(B3_T) bitmask_compress_late_kernel(const uint8
         }
     }
     run_to_global(values, excl, total, data);
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// v6 (NOT shipped; CT_B200_BITMASK_V6=1): what the expanding direction taught (csrc/sparse.cu, bitmask_expand_rows_kernel), applied here.  v5 is bound by
+// instruction issue, and 62 % of its instructions serve the GATHER formulation (a table of where every output vector starts, then a
+// walk over the bit mask per kept element: ~19 instructions per kept element).  A SCATTER needs ~3 per input element whatever the
+// density (extract the half, predicated 16-bit shared store, bump the offset) -- v3 did that and drowned in scan bookkeeping.  Here:
+//   * the tile never sits in shared memory: a thread loads its 8 units (i = u * 256 + tid: consecutive lanes own consecutive units, so
+//     their kept runs are ~2 words apart in the staging buffer and the 16-bit stores do not collide in the banks) with 8 independent
+//     16-byte loads and keeps them in registers (32 KB in flight per CTA, as the bulk copy had)
+//   * the eight per-slot warp scans run two 16-bit counters per register (20 shuffles instead of 40); the eight warp totals of every
+//     slot are scanned by lanes 0-7 with three shuffle rounds, not by 32 loads + selects in every thread
+//   * the aggregate is published as soon as it is known, the look-back runs BEHIND the compaction (v5), the run leaves through v3's
+//     funnel-shifted, globally aligned write-out
+//   * persistent CTAs: the next tile's ticket is taken and its loads are issued before the current tile's look-back and write-out
+// Measured (B200, 235 MB, 50 % / 10 % density): one tile per CTA 162 / 146 us, persistent 209 / 199 us -- against v5's 130 / 103.
+// Fewer instructions (14 per element instead of 21) do not help: a tile lives ~10 us of mostly serial latencies (ticket, load, two
+// barriers, descriptor read, write-out), 64-78 registers allow 3-4 CTAs / SM instead of 5, and the persistent form repeats v2's
+// lesson -- a ticket taken ahead of the work publishes its aggregate late and every successor in ticket order waits for it.
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr int B6_NP = B3_UPT / 2;
+constexpr uint32_t B6_SMEM = 8 * B3_TILE * 2 + 64;     // the compact run of a full tile + the vector the write-out may read past it
+static_assert(B3_W <= 8 && B3_UPT == 8, "the warp-total scan runs on lanes 0 .. 7");
+
+__global__ void __launch_bounds__(B3_T, 3) bitmask_compress_regs_kernel(const uint4* __restrict__ src, uint8_t* __restrict__ bitmask,
+                                                                        uint16_t* __restrict__ values, int64_t* __restrict__ row_offsets,
+                                                                        int64_t* __restrict__ nnz_out, unsigned long long* __restrict__ desc,
+                                                                        uint32_t* __restrict__ ticket, uint32_t n_units, uint32_t n_tiles, FastDiv upr) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(16) uint32_t mask_w[B3_TILE / 4];
+    __shared__ uint32_t warp_tot[B6_NP][B3_W];
+    __shared__ unsigned long long lb_sum[B3_W];
+    __shared__ int lb_p[B3_W];
+    __shared__ uint32_t tile_s[2];
+    const uint32_t stage0 = smem_u32(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) tile_s[0] = atomicAdd(ticket, 1u);   // taken when the work on it starts: processing order = ticket order
+    __syncthreads();
+    uint32_t tile = tile_s[0];
+    if (tile >= n_tiles) return;
+    uint32_t u0 = tile * B3_TILE;
+    uint32_t nu = min((uint32_t)B3_TILE, n_units - u0);
+
+    // ---- the tile: 8 independent 16-byte loads per thread ----
+    uint4 v[B3_UPT];
+#pragma unroll
+    for (int u = 0; u < B3_UPT; ++u) {
+        const uint32_t i = (uint32_t)u * B3_T + (uint32_t)tid;
+        v[u] = (i < nu) ? ldg_stream16(src + u0 + i) : make_uint4(0, 0, 0, 0);
+    }
+    for (uint32_t it = 0;; ++it) {
+        // ---- mask bytes, counts (two per register), warp scans ----
+        uint32_t blo = 0, bhi = 0, pk[B6_NP];
+        uint8_t* mask_b = reinterpret_cast<uint8_t*>(mask_w);
+#pragma unroll
+        for (int i = 0; i < B6_NP; ++i) pk[i] = 0u;
+#pragma unroll
+        for (int u = 0; u < B3_UPT; ++u) {
+            const uint32_t b = nz_byte16_fast(v[u]);
+            mask_b[u * B3_T + tid] = (uint8_t)b;
+            if (u < 4) blo |= b << (8 * u);
+            else bhi |= b << (8 * (u - 4));
+            pk[u >> 1] |= (uint32_t)__popc(b) << (16 * (u & 1));
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int i = 0; i < B6_NP; ++i) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, pk[i], o);
+                if (lane >= o) pk[i] += n;
+            }
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int i = 0; i < B6_NP; ++i) warp_tot[i][warp] = pk[i];
+        }
+        __syncthreads();                                   // warp totals and every thread's mask bytes
+        // the NEXT tile's ticket: its latency hides behind the compaction; every thread reads it after the barrier below
+        if (tid == 0) tile_s[(it + 1) & 1] = atomicAdd(ticket, 1u);
+        // the tile's mask bytes leave as two coalesced 4-byte words per thread (n_units % 4 == 0)
+        {
+            const uint32_t uf = 8u * (uint32_t)tid;
+            if (uf + 4 <= nu) reinterpret_cast<uint32_t*>(bitmask + u0 + uf)[0] = mask_w[2 * tid];
+            if (uf + 8 <= nu) reinterpret_cast<uint32_t*>(bitmask + u0 + uf)[1] = mask_w[2 * tid + 1];
+        }
+        int off[B3_UPT];
+        int total = 0;
+        {
+            uint32_t t[B6_NP], before[B6_NP], seg[B6_NP];
+#pragma unroll
+            for (int i = 0; i < B6_NP; ++i) t[i] = (lane < B3_W) ? warp_tot[i][lane] : 0u;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+                for (int i = 0; i < B6_NP; ++i) {
+                    const uint32_t n = __shfl_up_sync(0xffffffffu, t[i], o);
+                    if (lane >= o) t[i] += n;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < B6_NP; ++i) {
+                before[i] = __shfl_sync(0xffffffffu, t[i], (warp + 31) & 31);
+                if (warp == 0) before[i] = 0u;
+                seg[i] = __shfl_sync(0xffffffffu, t[i], B3_W - 1);
+            }
+#pragma unroll
+            for (int u = 0; u < B3_UPT; ++u) {
+                const int sh = 16 * (u & 1);
+                const uint32_t b = (u < 4 ? blo >> (8 * u) : bhi >> (8 * (u - 4))) & 0xffu;
+                off[u] = total + (int)((before[u >> 1] >> sh) & 0xffffu) + (int)((pk[u >> 1] >> sh) & 0xffffu) - __popc(b);
+                total += (int)((seg[u >> 1] >> sh) & 0xffffu);
+            }
+        }
+        lookback_publish(desc, tile, (uint32_t)total);        // the successors' look-back can pass this tile from here on
+
+        // ---- compaction from the registers into the staging buffer (element j of the tile's run at stage[j]) ----
+#pragma unroll
+        for (int u = 0; u < B3_UPT; ++u) {
+            const uint32_t b = (u < 4 ? blo >> (8 * u) : bhi >> (8 * (u - 4))) & 0xffu;
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            uint32_t o = stage0 + 2u * (uint32_t)off[u];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if ((b >> e) & 1u) { sts16(o, w[e >> 1] >> (16 * (e & 1))); o += 2; }
+        }
+        __syncthreads();
+
+        // ---- the registers are free: the next tile's loads fly while this tile's prefix is collected and its run written out ----
+        const uint32_t next = tile_s[(it + 1) & 1];
+        const uint32_t nu0 = u0, nun = nu;
+        const bool more = next < n_tiles;
+        if (more) {
+            u0 = next * B3_TILE;
+            nu = min((uint32_t)B3_TILE, n_units - u0);
+#pragma unroll
+            for (int u = 0; u < B3_UPT; ++u) {
+                const uint32_t i = (uint32_t)u * B3_T + (uint32_t)tid;
+                v[u] = (i < nu) ? ldg_stream16(src + u0 + i) : make_uint4(0, 0, 0, 0);
+            }
+        }
+
+        // ---- the prefix (published long ago by now), row offsets, write-out ----
+        const unsigned long long excl = lookback_cta<false>(desc, tile, (uint32_t)total, lb_sum, lb_p);
+        if (tid == 0 && tile == n_tiles - 1) *nnz_out = (int64_t)(excl + (unsigned long long)total);
+        if (row_offsets) {
+#pragma unroll
+            for (int u = 0; u < B3_UPT; ++u) {
+                const uint32_t i = (uint32_t)u * B3_T + (uint32_t)tid;
+                if (i < nun) {
+                    const uint32_t gu = nu0 + i, r = fd_div(gu, upr);
+                    if (r * upr.d == gu) row_offsets[r] = (int64_t)(excl + (unsigned long long)off[u]);
+                }
+            }
+        }
+        run_to_global(values, excl, total, stage0);
+        if (!more) break;
+        tile = next;
+        __syncthreads();                                   // the staging buffer, mask_w and the look-back arrays are reused
+    }
 }
 
 // expansion: mask bytes -> counts -> scan -> look-back -> the tile's run of `values` into shared memory (aligned 16-byte loads, so that
@@ -925,7 +1086,19 @@ int launch_bitmask_lookback(const void* src, uint8_t* bitmask, void* dst, int64_
     if (rc) return rc;
     CT_CUDA_TRY(cudaMemsetAsync(scratch, 0, bytes, st));
     if (!v1) {
-        if (COMPRESS && !getenv("CT_B200_BITMASK_V3") && !getenv("CT_B200_BITMASK_V4")) {
+        if (COMPRESS && getenv("CT_B200_BITMASK_V6")) {       // the register-tile scatter experiment: slower than v5, kept for the record
+            CT_CUDA_TRY(cudaFuncSetAttribute(bitmask_compress_regs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B6_SMEM));
+            int occ = 0;
+            CT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bitmask_compress_regs_kernel, B3_T, B6_SMEM));
+            uint32_t grid = (uint32_t)(occ > 0 ? occ : 1) * (uint32_t)sm_count(device);
+            if (const char* e = getenv("CT_B200_BITMASK_GRID")) grid = (uint32_t)atoi(e);    // measurement aid
+            if (grid > n_tiles) grid = n_tiles;
+            if (grid < 1) grid = 1;
+            bitmask_compress_regs_kernel<<<grid, B3_T, B6_SMEM, st>>>(reinterpret_cast<const uint4*>(src), bitmask, reinterpret_cast<uint16_t*>(dst),
+                                                                          row_offsets, nnz_out, reinterpret_cast<unsigned long long*>(scratch + 16),
+                                                                          reinterpret_cast<uint32_t*>(scratch), (uint32_t)n_units, n_tiles,
+                                                                          make_fastdiv((uint64_t)(cols / 8)));
+        } else if (COMPRESS && !getenv("CT_B200_BITMASK_V3") && !getenv("CT_B200_BITMASK_V4")) {
             CT_CUDA_TRY(cudaFuncSetAttribute(bitmask_compress_late_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B5_SMEM));
             bitmask_compress_late_kernel<<<n_tiles, B3_T, B5_SMEM, st>>>(reinterpret_cast<const uint8_t*>(src), bitmask, reinterpret_cast<uint16_t*>(dst),
                                                                           row_offsets, nnz_out, reinterpret_cast<unsigned long long*>(scratch + 16),
