@@ -83,14 +83,15 @@ struct Sparse24UnpackDequantOp {
     // kept pair v = {first kept, second kept} of a quad, b = its 4 mask bits -> the quad's 4 elements in two words.
     // element e takes the first kept value if it is the lowest set bit, the second if any lower bit is set, zero if its bit is clear
     __device__ static __forceinline__ void scatter_quad(uint32_t v, uint32_t b, uint32_t& o01, uint32_t& o23) {
-        const uint32_t b0 = b & 1u, b1 = (b >> 1) & 1u, b2 = (b >> 2) & 1u, b3 = (b >> 3) & 1u;
-        // byte selectors: first = bytes (0,1) = 0x10, second = (2,3) = 0x32, zero = (4,4) = 0x44 (second prmt operand = 0)
-        const uint32_t s0 = b0 ? 0x10u : 0x44u;
-        const uint32_t s1 = b1 ? (b0 ? 0x32u : 0x10u) : 0x44u;
-        const uint32_t s2 = b2 ? ((b0 | b1) ? 0x32u : 0x10u) : 0x44u;
-        const uint32_t s3 = b3 ? ((b0 | b1 | b2) ? 0x32u : 0x10u) : 0x44u;
-        o01 = __byte_perm(v, 0u, s0 | (s1 << 8));
-        o23 = __byte_perm(v, 0u, s2 | (s3 << 8));
+        // byte selectors per element: first kept = bytes (0,1) = 0x10, second = (2,3) = 0x32, zero = (4,4) = 0x44 (second prmt operand = 0):
+        //   sel_e = 0x44 - 0x34 * bit_e + 0x22 * (bit_e and a lower bit is set)
+        // all four at once: the bits that have a lower set bit are b & (b - 1); a multiply by 1 + 2^7 + 2^14 + 2^21 and a mask move bit e
+        // of a nibble to byte e (no two partial products meet, so nothing carries)
+        const uint32_t later = b & (b - 1u);
+        const uint32_t B = (b * 0x00204081u) & 0x01010101u, L = (later * 0x00204081u) & 0x01010101u;
+        const uint32_t S = 0x44444444u - B * 0x34u + L * 0x22u;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(o01) : "r"(v), "r"(0u), "r"(S));          // PRMT reads the selector's low 16 bits
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(o23) : "r"(v), "r"(0u), "r"(S >> 16));
     }
     __device__ static __forceinline__ void run(const Job& J, const Common&, const Raw& r, uint32_t gc, const uint32_t (&w)[1][1], int) {
         const uint32_t s2 = scale_t2<P>(r.qp), zp2 = zp_t2<P, ZP>(r.qp);
