@@ -405,6 +405,39 @@ __device__ __forceinline__ void run_to_global(uint16_t* values, unsigned long lo
     }
 }
 
+// The same write-out with the window of a global vector fetched as five 4-byte words from the 4-byte boundary at or below its first
+// element (one funnel shift by 16 when the run position is odd) instead of two 16-byte vectors and a tile-uniform `switch` over the
+// word offset, which the compiler turns into a select tree (8 % of v5's instructions).  May read up to 16 bytes BELOW stage0 (vector 0
+// of a run that does not start on a 16-byte boundary; those halves are never stored): the caller's buffer is preceded by >= 16 bytes
+// of its own shared memory.
+__device__ __forceinline__ void run_to_global_words(uint16_t* values, unsigned long long excl, int total, uint32_t stage0) {
+    const uint32_t shift = (uint32_t)(excl & 7ull);
+    const unsigned long long g0 = excl - shift;
+    const uint32_t span = shift + (uint32_t)total;
+    const uint32_t nvec = (span + 7) >> 3;
+    uint4* gv = reinterpret_cast<uint4*>(values + g0);
+    const uint32_t sh = (shift & 1u) << 4;
+    const uint32_t base = stage0 - 2u * shift - 2u * (shift & 1u);        // word that holds stage element -shift (4-byte aligned)
+    for (uint32_t c = threadIdx.x; c < nvec; c += B3_T) {
+        const bool first = (c == 0), last = (8 * c + 8 > span);
+        const uint32_t a = base + 16u * c;
+        uint32_t w[5], o[4];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[i]) : "r"(a + 4u * i));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = __funnelshift_r(w[i], w[i + 1], sh);
+        if (!first && !last) stg_stream16(gv + c, make_uint4(o[0], o[1], o[2], o[3]));
+        else {
+            uint16_t* ge = values + g0 + 8ull * c;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const uint32_t pos = 8 * c + e;
+                if (pos >= shift && pos < span) ge[e] = (uint16_t)(o[e >> 1] >> (16 * (e & 1)));
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(B3_T) bitmask_compress_tile_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ bitmask,
                                                                      uint16_t* __restrict__ values, int64_t* __restrict__ row_offsets,
                                                                      int64_t* __restrict__ nnz_out, unsigned long long* __restrict__ desc,
@@ -505,6 +538,12 @@ __device__ __forceinline__ uint32_t nz_byte16_fast(const uint4& v) {
     const uint32_t r2 = __vminu2(v.z & 0x7fff7fffu, 0x00010001u), r3 = __vminu2(v.w & 0x7fff7fffu, 0x00010001u);
     const uint32_t t = r0 + r1 * 4u + r2 * 16u + r3 * 64u;        // even elements at bits 0,2,4,6; odd ones at 16,18,20,22
     return (t | (t >> 15)) & 0xffu;
+}
+// popcount of every byte of x, in that byte
+__device__ __forceinline__ uint32_t byte_popc4(uint32_t x) {
+    x = x - ((x >> 1) & 0x55555555u);
+    x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
+    return (x + (x >> 4)) & 0x0f0f0f0fu;
 }
 // position of the n-th (0-based) set bit of x; x has more than n set bits
 __device__ __forceinline__ uint32_t select32(uint32_t x, uint32_t n) {
@@ -762,12 +801,29 @@ __global__ void __launch_bounds__(B3_T) bitmask_compress_late_kernel(const uint8
     lookback_publish(desc, tile, (uint32_t)total);        // the successors' look-back can pass this tile from here on
 
     // ---- B: run vector v starts at run element 8 v; the thread that owns that element records where it sits in the tile ----
+    // Unit by unit (8 fixed steps, no data-dependent trip count): a unit holds <= 8 kept elements, so at most one vector boundary
+    // (run index = 0 mod 8) falls into it -- r kept elements into the unit, an 8-bit select.  The per-unit counts and their running sums
+    // come from one byte-wise popcount and one multiply per mask word.  (The first form looped over the thread's boundaries with a
+    // 32-bit select each: 28 % of the kernel's instructions, and a warp ran as long as its busiest lane.)
     const uint32_t nvec = ((uint32_t)total + 7) >> 3;
     if (cnt > 0) {
-        for (uint32_t v = ((uint32_t)toff + 7) >> 3; 8 * v < (uint32_t)(toff + cnt); ++v) {
-            const uint32_t n = 8 * v - (uint32_t)toff;
-            const uint32_t bit = (n < (uint32_t)clo) ? select32(lo, n) : 32u + select32(hi, n - (uint32_t)clo);
-            start_s[v] = (uint16_t)(uf * 8 + bit);
+        const uint32_t clo4 = byte_popc4(lo), chi4 = byte_popc4(hi);
+        const uint32_t plo = clo4 * 0x01010101u, phi = chi4 * 0x01010101u + (uint32_t)clo * 0x01010101u;   // inclusive, <= 64 per byte
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int sh = 8 * (k & 3);
+            const uint32_t cntk = ((k < 4 ? clo4 : chi4) >> sh) & 0xffu;
+            const uint32_t first = (uint32_t)toff + (((k < 4 ? plo : phi) >> sh) & 0xffu) - cntk;   // run index of the unit's first kept element
+            const uint32_t r = (0u - first) & 7u;
+            if (r < cntk) {
+                uint32_t x = ((k < 4 ? lo : hi) >> sh) & 0xffu, n = r, pos = 0;
+#pragma unroll
+                for (int w = 4; w >= 1; w >>= 1) {
+                    const uint32_t c = __popc(x & ((1u << w) - 1u));
+                    if (n >= c) { n -= c; x >>= w; pos += w; }
+                }
+                start_s[(first + r) >> 3] = (uint16_t)((uf + k) * 8 + pos);
+            }
         }
     }
     __syncthreads();
@@ -842,7 +898,7 @@ __global__ void __launch_bounds__(B3_T) bitmask_compress_late_kernel(const uint8
             ++r;
         }
     }
-    run_to_global(values, excl, total, data);
+    run_to_global_words(values, excl, total, data);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
