@@ -179,3 +179,43 @@ def test_generate_gparam_rounds_like_the_reference():
     for dt, lo, hi, want in cases:
         g = generate_gparam(torch.tensor(lo, dtype=dt), torch.tensor(hi, dtype=dt))
         assert g.dtype == torch.float32 and g.shape == (1,) and g.item() == want, (dt, lo, hi, g)
+
+
+def test_recouple_bucket_layout():
+    """the all-gather recouple's byte layout (distributed/module_parallel.py::_layout): every owner's tensors in module order, cut
+    into buckets of <= _BUCKET bytes per owner (a larger tensor gets a bucket of its own), offsets 256-byte aligned, slot = the
+    largest owner's fill; identical for every rank by construction (pure function of shapes / dtypes / owners)"""
+    import torch
+
+    import compressed_tensors_b200.distributed.module_parallel as mp
+
+    class M(torch.nn.Module):
+        def __init__(self, n):
+            super().__init__()
+            self.weight_packed = torch.nn.Parameter(torch.empty(n, dtype=torch.int32, device="meta"), requires_grad=False)
+            self.weight_scale = torch.nn.Parameter(torch.empty(max(n // 16, 1), dtype=torch.bfloat16, device="meta"), requires_grad=False)
+
+    sizes = [1000, 70000, 10, 300000, 5000, 64, 90000, 1]
+    mods = [M(n) for n in sizes]
+    owner = {m: i % 3 for i, m in enumerate(mods)}
+    old = mp._BUCKET
+    try:
+        mp._BUCKET = 256 << 10
+        buckets, total = mp._layout(mods, owner, 3)
+    finally:
+        mp._BUCKET = old
+    assert total == sum(slot for slot, _ in buckets) * 3
+    seen = []
+    for slot, entries in buckets:
+        assert slot > 0 and slot % mp._ALIGN == 0
+        for r in range(3):
+            end = 0
+            for m, name, off, nbytes, shape, dtype in entries[r]:
+                assert owner[m] == r and off % mp._ALIGN == 0 and off >= end and off + nbytes <= slot
+                assert nbytes == getattr(m, name).numel() * getattr(m, name).element_size()
+                end = off + nbytes
+                seen.append((id(m), name))
+            # a bucket holds more than _BUCKET bytes of one owner only when it is a single oversized tensor
+            assert end <= (256 << 10) or len(entries[r]) == 1
+    assert sorted(seen) == sorted((id(m), n) for m in mods for n in ("weight_packed", "weight_scale"))   # every tensor exactly once
+    assert len(buckets) > 1                                                                              # 1.2 MB tensor: several buckets
