@@ -787,11 +787,15 @@ def cpu_sample():
     return ws, scs, tmp
 
 
-def _median_time(fn, budget_s: float, min_reps: int, max_reps: int):
-    fn()                                    # warm-up
+def _median_time(fn, budget_s: float, min_reps: int, max_reps: int, warmup: int = 1):
+    """median of the timed repetitions.  min_reps == max_reps = the exact count the reference arm was asked for (--steps K), which the
+    time budget may only cut short after 5 repetitions"""
+    for _ in range(max(warmup, 1)):
+        fn()                                # warm-up
     times = []
     t_start = time.perf_counter()
-    while len(times) < max_reps and (len(times) < min_reps or time.perf_counter() - t_start < budget_s):
+    exact = min_reps == max_reps
+    while len(times) < max_reps and (len(times) < (5 if exact else min_reps) or time.perf_counter() - t_start < budget_s):
         t0 = time.perf_counter()
         fn()
         times.append(time.perf_counter() - t0)
@@ -815,14 +819,21 @@ def run_cpu_worker(a):
     ws, scs, tmp = cpu_sample()
     wbytes = sum(w.numel() * 2 for w in ws)
     budget = float(a.cpu_seconds)
-    med, times = _median_time(lambda: oracle_compress_layer(ws, scs, tmp), budget * 0.4, 5, 40)
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    have_ref = os.path.exists(os.path.join(ref_dir, "compressed_tensors", "version.py"))
+    # --impl reference --steps K --warmup W: the MAIN leg (the reference when it is installed, else the port) does W warm-ups and
+    # exactly K timed repetitions, cut short only by a 300 s budget; the other leg stays a short time-bounded sample
+    k, wup = int(a.cpu_steps), max(int(a.cpu_warmup), 1)
+    if k > 0 and not have_ref:
+        med, times = _median_time(lambda: oracle_compress_layer(ws, scs, tmp), 300.0, k, k, wup)
+    else:
+        med, times = _median_time(lambda: oracle_compress_layer(ws, scs, tmp), (8.0 if k > 0 else budget * 0.4), 5, 40)
     out = {"nproc": len(allowed), "threads": len(phys), "cpu_model": model, "numa_nodes": len(nodes), "memory_interleaved": bool(interleaved),
            "sample_bytes": wbytes,
            "port": {"GBps": round(wbytes / med / 1e9, 3), "ms_median": round(med * 1e3, 1), "ms_min": round(times[0] * 1e3, 1),
                     "ms_max": round(times[-1] * 1e3, 1), "reps": len(times), "threads": oracle.num_threads()},
            "reference": None}
-    ref_dir = os.path.join(ROOT, "baseline", "_ref")
-    if os.path.exists(os.path.join(ref_dir, "compressed_tensors", "version.py")):
+    if have_ref:
         try:
             sys.path.insert(0, ref_dir)
             import compressed_tensors                                   # the reference itself, not site-packages' older release
@@ -840,7 +851,7 @@ def run_cpu_worker(a):
                     for sd in sds:
                         got.append(PackedQuantizationCompressor.compress(sd, scheme)["weight_packed"])
 
-            rmed, rtimes = _median_time(ref_layer, budget * 0.6, 5, 20)
+            rmed, rtimes = _median_time(ref_layer, 300.0, k, k, wup) if k > 0 else _median_time(ref_layer, budget * 0.6, 5, 20)
             same = all(torch.equal(g, t[1]) for g, t in zip(got, tmp))     # the oracle port reproduces the reference's words on the sample
             out["reference"] = {"GBps": round(wbytes / rmed / 1e9, 3), "ms_median": round(rmed * 1e3, 1), "ms_min": round(rtimes[0] * 1e3, 1),
                                 "ms_max": round(rtimes[-1] * 1e3, 1), "reps": len(rtimes), "threads": torch.get_num_threads(),
@@ -851,16 +862,18 @@ def run_cpu_worker(a):
     print("CPUWORKER " + json.dumps(out))
 
 
-def cpu_arm(seconds: float):
-    """run the CPU legs in a fresh, pinned subprocess and shape the `cpu_baseline` object"""
+def cpu_arm(seconds: float, steps: int = 0, warmup: int = 1):
+    """run the CPU legs in a fresh, pinned subprocess and shape the `cpu_baseline` object (steps > 0: the main leg runs exactly that
+    many timed repetitions after `warmup` warm-ups -- the reference arm's --steps / --warmup)"""
     phys, allowed, nodes, model = cpu_topology()
     env = {k: v for k, v in os.environ.items() if not k.startswith(("OMP_", "MKL_", "GOMP_", "KMP_")) and k not in
            ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID")}
     env.update(OMP_NUM_THREADS=str(len(phys)), MKL_NUM_THREADS=str(len(phys)), OMP_PROC_BIND="close",
                OMP_PLACES=",".join("{%d}" % c for c in phys), CUDA_VISIBLE_DEVICES="")
     r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu-worker", "--cpu-seconds", str(seconds),
-                        "--cpu-list", ",".join(str(c) for c in phys), "--nproc", str(len(allowed))],
-                       capture_output=True, text=True, env=env, timeout=600)
+                        "--cpu-list", ",".join(str(c) for c in phys), "--nproc", str(len(allowed)),
+                        "--cpu-steps", str(steps), "--cpu-warmup", str(warmup)],
+                       capture_output=True, text=True, env=env, timeout=900)
     line = next((ln for ln in r.stdout.splitlines() if ln.startswith("CPUWORKER ")), None)
     if r.returncode != 0 or line is None:
         raise RuntimeError(f"cpu worker failed (rc {r.returncode}): {r.stderr[-1500:]}")
@@ -884,8 +897,10 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_arm(seconds=max(10.0, min(60.0, 2.0 * (a.steps + a.warmup))))
+    cb = cpu_arm(seconds=20.0, steps=a.steps, warmup=a.warmup)          # exactly --steps timed repetitions after --warmup warm-ups
     v = cb["value"]
+    if cb["reps"] != a.steps:
+        cb["sample"] += f"; {a.steps} steps were asked for, the 300 s budget allowed {cb['reps']}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": cb["reps"], "warmup": max(a.warmup, 1),
         "ms_per_step": cb["ms_median"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -904,6 +919,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu-worker"])
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="time budget of the CPU legs (bounded sample)")
     ap.add_argument("--cpu-list", default="", help=argparse.SUPPRESS)   # cpu-worker only: one hardware thread per physical core
+    ap.add_argument("--cpu-steps", type=int, default=0, help=argparse.SUPPRESS)    # cpu-worker only: exact repetition count of the main leg
+    ap.add_argument("--cpu-warmup", type=int, default=1, help=argparse.SUPPRESS)
     ap.add_argument("--nproc", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--layers", type=int, default=32, help="Llama-3-8B layers per GPU (32 = the full model)")
     ap.add_argument("--e2e-layers", type=int, default=32)
