@@ -824,6 +824,8 @@ def run_cpu_worker(a):
     # --impl reference --steps K --warmup W: the MAIN leg (the reference when it is installed, else the port) does W warm-ups and
     # exactly K timed repetitions, cut short only by a 300 s budget; the other leg stays a short time-bounded sample
     k, wup = int(a.cpu_steps), max(int(a.cpu_warmup), 1)
+    if k > 0:
+        k = max(k, 5)                       # a median needs at least 5 repetitions; --steps below that is raised
     if k > 0 and not have_ref:
         med, times = _median_time(lambda: oracle_compress_layer(ws, scs, tmp), 300.0, k, k, wup)
     else:
@@ -900,7 +902,8 @@ def run_reference(a):
     cb = cpu_arm(seconds=20.0, steps=a.steps, warmup=a.warmup)          # exactly --steps timed repetitions after --warmup warm-ups
     v = cb["value"]
     if cb["reps"] != a.steps:
-        cb["sample"] += f"; {a.steps} steps were asked for, the 300 s budget allowed {cb['reps']}"
+        cb["sample"] += (f"; {a.steps} steps were asked for, {cb['reps']} were timed "
+                         + ("(a median needs 5)" if a.steps < 5 else "(300 s budget)"))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": cb["reps"], "warmup": max(a.warmup, 1),
         "ms_per_step": cb["ms_median"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
