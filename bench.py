@@ -530,7 +530,9 @@ def run_cfg5_70b_sharded(a, rank: int, world: int, dev):
     free_b, _ = torch.cuda.mem_get_info()
     packed_here = sum(m.weight_packed.numel() * 4 for m in mods)
     dec = None
-    if free_b + packed_here > dense_total + (12 << 30):
+    fits = torch.tensor([int(free_b + packed_here > dense_total + (12 << 30))], device=dev)
+    dist.all_reduce(fits, op=dist.ReduceOp.MIN)          # one decision for all ranks: the leg is full of collectives
+    if bool(fits.item()):
         from compressed_tensors_b200 import ops
 
         d_runs = []
